@@ -1,0 +1,130 @@
+/*
+ * nnfac_b200 -- C ABI of the B200-native (sm_100a) factor-update path of nn-fac.
+ *
+ * The reference (ax-le/nn-fac v0.3.4) is pure Python/numpy and has no FFI: its
+ * "plugin interface" for this path is a set of module functions.  Each entry
+ * point below names the reference expression it replaces (paths relative to the
+ * reference root).  A maintainer binds them with ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every matrix pointer is a DEVICE pointer, row-major, with an explicit
+ *     leading dimension (elements, not bytes);
+ *   - dtype: NNFAC_F32 or NNFAC_F64 (all operands of one call share it);
+ *   - stream: a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - return value: 0 on success, negative nnfac_status otherwise; the message
+ *     is available from nnfac_last_error() (thread-local).  Nothing throws.
+ *   - calls are asynchronous on `stream` unless stated otherwise.
+ */
+#ifndef NNFAC_B200_H
+#define NNFAC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NNFAC_ABI_VERSION 1
+
+typedef enum { NNFAC_F32 = 0, NNFAC_F64 = 1 } nnfac_dtype;
+
+typedef enum {
+  NNFAC_OK = 0,
+  NNFAC_ERR_ARG = -1,      /* invalid argument                                   */
+  NNFAC_ERR_CUDA = -2,     /* CUDA runtime / driver error                        */
+  NNFAC_ERR_UNSUPPORTED = -3, /* shape or option outside what this build covers  */
+  NNFAC_ERR_ALLOC = -4
+} nnfac_status;
+
+/* flags of nnfac_hals_nnls */
+#define NNFAC_HALS_NORMALIZE 1u /* nnls.py:179-185 */
+#define NNFAC_HALS_NONZERO 2u   /* nnls.py:173-177 */
+
+typedef struct nnfac_ctx nnfac_ctx; /* per-device workspace + launch limits; not thread-safe */
+
+int nnfac_abi_version(void);
+const char* nnfac_last_error(void);
+int nnfac_ctx_create(int device, nnfac_ctx** out);
+int nnfac_ctx_destroy(nnfac_ctx* ctx);
+int nnfac_ctx_sm_count(const nnfac_ctx* ctx);
+/* Number of kernels this library has launched on behalf of `ctx` since creation. */
+int64_t nnfac_ctx_launch_count(const nnfac_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------------
+ * HALS NNLS solver: replaces nn_fac/update_rules/nnls.py:156-198 (hals_nnls_acc sweep loop with
+ * the deterministic stop rule, i.e. alpha = inf).  V (r x n) is updated IN PLACE; the caller
+ * makes the copy that nnls.py:147 makes.  Rows k >= r of UtU/V are never touched
+ * (tests/nnls_tests.py:40-47).
+ *   sparsity : value subtracted in the numerator (0 = no sparsity term, nnls.py:162-167)
+ *   result   : device double[4] = { eps, cnt, zero_diag_row (-1 if none, only with NONZERO), sweeps }
+ * -------------------------------------------------------------------------------------------*/
+int nnfac_hals_nnls(nnfac_ctx* ctx, int dtype, const void* UtM, int64_t ld_utm, const void* UtU,
+                    int64_t ld_utu, void* V, int64_t ld_v, int r, int64_t n, int maxiter,
+                    double delta, double sparsity, unsigned flags, double* result, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Strided, batched, K-blocked GEMM on CUDA cores (fp32 or fp64 accumulate in the operand type):
+ *   C[b][i][j] = sum_{q<kb} sum_{k<K} A[b*sa_b + q*sa_q + i*sa_i + k*sa_k] * B[b*sb_b + q*sb_q + k*sb_k + j*sb_j]
+ * written to C[b*sc_b + i*ldc + j].  Covers the dense call sites the reference hands to numpy:
+ * Grams and cross products (nmf.py:407-408,432-433; ntf.py:442-445,449), K = U V (mu.py:82),
+ * mode products (mu.py:141,159; ntd.py:672).  Deterministic (fixed summation order).
+ * -------------------------------------------------------------------------------------------*/
+int nnfac_gemm_strided(nnfac_ctx* ctx, int dtype, void* C, int64_t ldc, int64_t sc_b, const void* A,
+                       int64_t sa_i, int64_t sa_k, int64_t sa_q, int64_t sa_b, const void* B,
+                       int64_t sb_k, int64_t sb_j, int64_t sb_q, int64_t sb_b, int64_t M, int64_t N,
+                       int64_t K, int64_t kb, int64_t batch, void* stream);
+
+/* Multiplicative-update element-wise terms, mu.py:84-97 / mu.py:143-155:
+ *   P = K^(beta-2) * X   and   Q = K^(beta-1)   (either output may be NULL; in-place on K allowed) */
+int nnfac_mu_terms(nnfac_ctx* ctx, int dtype, double beta, const void* K, const void* X, void* P,
+                   void* Q, int64_t count, void* stream);
+
+/* F_out[i][k] = max(F_in[i][k] * (num[i][k] / den)^gamma, floor), mu.py:88,91,94,97,159.
+ * den = den_mat[i][k] when den_vec is NULL; else the beta=1 row-sum form (mu.py:85-87):
+ * den_vec[k] (vec_per_row = 0, F is m x r) or den_vec[i] (vec_per_row = 1, F is r x n). */
+int nnfac_mu_apply(nnfac_ctx* ctx, int dtype, void* F_out, const void* F_in, const void* num,
+                   const void* den_mat, const void* den_vec, int vec_per_row, int64_t rows,
+                   int64_t cols, double gamma, double floor_value, void* stream);
+
+/* out[0] = beta_divergence(A, B, beta) summed over `count` elements, beta_divergence.py:42-52.
+ * fp64 accumulation, deterministic two-stage reduction. */
+int nnfac_beta_divergence(nnfac_ctx* ctx, int dtype, double beta, const void* A, const void* B,
+                          int64_t count, double* out, void* stream);
+
+/* out[0] = sum (A - B)^2  (the Frobenius term of nmf.py:452); B may be NULL (-> sum A^2). */
+int nnfac_sq_diff(nnfac_ctx* ctx, int dtype, const void* A, const void* B, int64_t count,
+                  double* out, void* stream);
+
+/* out[0] = sum A*B  (ntf.py:470 inner product) */
+int nnfac_dot(nnfac_ctx* ctx, int dtype, const void* A, const void* B, int64_t count, double* out,
+              void* stream);
+
+/* out[i] = sum_j A[i][j]  (mu.py:86) */
+int nnfac_row_sums(nnfac_ctx* ctx, int dtype, const void* A, int64_t lda, int64_t rows,
+                   int64_t cols, void* out, void* stream);
+
+/* out[0] = max_j sum_i |A[i][j]|  (numpy's matrix 1-norm used by nmf.py:452, ntf.py:466) */
+int nnfac_norm1(nnfac_ctx* ctx, int dtype, const void* A, int64_t lda, int64_t rows, int64_t cols,
+                double* out, void* stream);
+
+/* out (cols x rows) = in (rows x cols)^T */
+int nnfac_transpose(nnfac_ctx* ctx, int dtype, void* out, int64_t ld_out, const void* in,
+                    int64_t ld_in, int64_t rows, int64_t cols, void* stream);
+
+/* Khatri-Rao product of two factors (ntf.py:448): out[(i*J + j)][q] = A[i][q] * B[j][q]. */
+int nnfac_khatri_rao(nnfac_ctx* ctx, int dtype, void* out, const void* A, int64_t I, const void* B,
+                     int64_t J, int64_t r, void* stream);
+
+/* out[i][j] = A[i][j] * B[i][j] (Hadamard of Grams, ntf.py:445); in place allowed. */
+int nnfac_hadamard(nnfac_ctx* ctx, int dtype, void* out, const void* A, const void* B,
+                   int64_t count, void* stream);
+
+/* Row-wise L2 normalisation of the Tucker core unfolding (ntd.py:676-681), in place. */
+int nnfac_normalize_rows(nnfac_ctx* ctx, int dtype, void* A, int64_t lda, int64_t rows,
+                         int64_t cols, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNFAC_B200_H */

@@ -1,0 +1,89 @@
+// Shared host/device helpers for the nnfac_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/nnfac_b200.h"
+
+struct nnfac_ctx {
+  int device;
+  int sm_count;
+  int64_t launches;
+  void* ws;         // scratch (split-K partials, reduction partials)
+  size_t ws_bytes;
+  double* red;      // small scratch for two-stage reductions / sweep barrier partials
+  size_t red_count;
+  unsigned* sync;   // grid-barrier counters (zeroed before each cooperative launch)
+};
+
+void nnfac_set_error(const char* fmt, ...);
+int nnfac_ws_reserve(nnfac_ctx* ctx, size_t bytes, cudaStream_t st);
+
+#define NNFAC_CUDA(call)                                                                   \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      nnfac_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return NNFAC_ERR_CUDA;                                                               \
+    }                                                                                      \
+  } while (0)
+
+#define NNFAC_ARG(cond, ...)      \
+  do {                            \
+    if (!(cond)) {                \
+      nnfac_set_error(__VA_ARGS__); \
+      return NNFAC_ERR_ARG;       \
+    }                             \
+  } while (0)
+
+#define NNFAC_LAUNCH_CHECK(ctx)                 \
+  do {                                          \
+    (ctx)->launches++;                          \
+    NNFAC_CUDA(cudaGetLastError());             \
+  } while (0)
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- device reductions ---------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum; result valid in every thread. `sh` must hold >= 33 doubles.
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    double t = lane < nw ? sh[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) sh[32] = t;
+  }
+  __syncthreads();
+  return sh[32];
+}
+__device__ __forceinline__ double block_max(double v, double* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    double t = lane < nw ? sh[lane] : -1.0e300;
+    t = warp_max(t);
+    if (lane == 0) sh[32] = t;
+  }
+  __syncthreads();
+  return sh[32];
+}

@@ -1,0 +1,310 @@
+// Element-wise terms, reductions and small layout kernels of the factor-update path.
+// Reference call sites: mu.py:84-97,143-159 (ratio / power terms and the multiplicative apply),
+// beta_divergence.py:42-52, nmf.py:452 (Frobenius term, matrix 1-norm), ntf.py:445,448,466,470,
+// ntd.py:676-681.
+#include "common.cuh"
+
+namespace {
+
+constexpr int RB = 256;        // reduction block size
+constexpr int RMAX_BLOCKS = 1184;  // 8 x 148: two-stage reductions use at most this many partials
+
+template <typename T> __device__ __forceinline__ T t_pow(T a, T b);
+template <> __device__ __forceinline__ float t_pow<float>(float a, float b) { return powf(a, b); }
+template <> __device__ __forceinline__ double t_pow<double>(double a, double b) { return pow(a, b); }
+template <typename T> __device__ __forceinline__ T t_log(T a);
+template <> __device__ __forceinline__ float t_log<float>(float a) { return logf(a); }
+template <> __device__ __forceinline__ double t_log<double>(double a) { return log(a); }
+
+// ---- mu terms --------------------------------------------------------------------------------
+// mode: 0 beta==1 (P = X / K), 1 beta==2 (P = X, Q = K), 2 beta==3 (P = K X, Q = K^2), 3 general
+template <typename T>
+__global__ void mu_terms_kernel(int mode, T beta, const T* __restrict__ K, const T* __restrict__ X,
+                                T* P, T* Q, int64_t count) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const T k = K[i];
+    const T x = X ? X[i] : T(1);
+    T p, q;
+    if (mode == 0) { p = x / k; q = T(1); }
+    else if (mode == 1) { p = x; q = k; }
+    else if (mode == 2) { p = k * x; q = k * k; }
+    else { p = t_pow<T>(k, beta - T(2)) * x; q = t_pow<T>(k, beta - T(1)); }
+    if (P) P[i] = p;
+    if (Q) Q[i] = q;
+  }
+}
+
+template <typename T>
+__global__ void mu_apply_kernel(T* out, const T* __restrict__ F, const T* __restrict__ num,
+                                const T* __restrict__ den_mat, const T* __restrict__ den_vec,
+                                int vec_per_row, int64_t rows, int64_t cols, T gamma, T floor_value) {
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const T d = den_vec ? den_vec[vec_per_row ? i / cols : i % cols] : den_mat[i];
+    T ratio = num[i] / d;
+    if (gamma != T(1)) ratio = t_pow<T>(ratio, gamma);
+    const T v = F[i] * ratio;
+    out[i] = v > floor_value ? v : floor_value;   // np.maximum(., epsilon); NaN propagates like numpy
+    if (v != v) out[i] = v;
+  }
+}
+
+// ---- reductions --------------------------------------------------------------------------------
+// op: 0 beta-div beta==1, 1 beta==0, 2 general beta, 3 squared difference, 4 dot, 5 sum of squares
+template <typename T>
+__device__ __forceinline__ double red_term(int op, double beta, const T* A, const T* B, int64_t i) {
+  const double a = (double)A[i];
+  if (op == 5) return a * a;
+  const double b = (double)B[i];
+  switch (op) {
+    case 0: return a * log(a / b) - a + b;
+    case 1: { const double q = a / b; return q - log(q) - 1.0; }
+    case 2: return (pow(a, beta) + (beta - 1.0) * pow(b, beta) - beta * a * pow(b, beta - 1.0)) / (beta * (beta - 1.0));
+    case 3: { const double d = a - b; return d * d; }
+    default: return a * b;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RB) reduce_stage1(int op, double beta, const T* __restrict__ A,
+                                                    const T* __restrict__ B, int64_t count, double* part) {
+  __shared__ double sh[33];
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * RB + threadIdx.x; i < count; i += (int64_t)gridDim.x * RB)
+    s += red_term<T>(op, beta, A, B, i);
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(RB) reduce_stage2(const double* part, int nparts, double* out, int is_max) {
+  __shared__ double sh[33];
+  double s = is_max ? -1.0e300 : 0.0;
+  for (int i = threadIdx.x; i < nparts; i += RB) s = is_max ? fmax(s, part[i]) : s + part[i];
+  s = is_max ? block_max(s, sh) : block_sum(s, sh);
+  if (threadIdx.x == 0) out[0] = s;
+}
+
+template <typename T>
+int run_reduce(nnfac_ctx* ctx, int op, double beta, const T* A, const T* B, int64_t count, double* out,
+               cudaStream_t st) {
+  int blocks = (int)(ceil_div64(count, RB * 4) < RMAX_BLOCKS ? ceil_div64(count, RB * 4) : RMAX_BLOCKS);
+  if (blocks < 1) blocks = 1;
+  reduce_stage1<T><<<blocks, RB, 0, st>>>(op, beta, A, B, count, ctx->red);
+  NNFAC_LAUNCH_CHECK(ctx);
+  reduce_stage2<<<1, RB, 0, st>>>(ctx->red, blocks, out, 0);
+  NNFAC_LAUNCH_CHECK(ctx);
+  return NNFAC_OK;
+}
+
+// row sums: one warp per row
+template <typename T>
+__global__ void row_sums_kernel(const T* __restrict__ A, int64_t lda, int64_t rows, int64_t cols, T* out) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  double s = 0.0;
+  for (int64_t j = threadIdx.x & 31; j < cols; j += 32) s += (double)A[row * lda + j];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) out[row] = (T)s;
+}
+
+// column abs sums -> per-block maxima (matrix 1-norm)
+template <typename T>
+__global__ void __launch_bounds__(RB) norm1_stage1(const T* __restrict__ A, int64_t lda, int64_t rows,
+                                                   int64_t cols, double* part) {
+  __shared__ double sh[33];
+  double best = 0.0;
+  for (int64_t j = (int64_t)blockIdx.x * RB + threadIdx.x; j < cols; j += (int64_t)gridDim.x * RB) {
+    double s = 0.0;
+    for (int64_t i = 0; i < rows; ++i) s += fabs((double)A[i * lda + j]);
+    best = fmax(best, s);
+  }
+  best = block_max(best, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = best;
+}
+
+template <typename T>
+__global__ void transpose_kernel(T* out, int64_t ld_out, const T* __restrict__ in, int64_t ld_in,
+                                 int64_t rows, int64_t cols) {
+  __shared__ T tile[32][33];
+  const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? in[r * ld_in + c] : T(0);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[c * ld_out + r] = tile[threadIdx.x][i];
+  }
+}
+
+template <typename T>
+__global__ void khatri_rao_kernel(T* out, const T* __restrict__ A, int64_t I, const T* __restrict__ B,
+                                  int64_t J, int64_t r) {
+  const int64_t total = I * J * r;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = idx % r, ij = idx / r;
+    out[idx] = A[(ij / J) * r + q] * B[(ij % J) * r + q];
+  }
+}
+
+template <typename T>
+__global__ void hadamard_kernel(T* out, const T* A, const T* B, int64_t count) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = A[i] * B[i];
+}
+
+// one block per row: row /= ||row||_2 when the norm is non-zero (ntd.py:678-680)
+template <typename T>
+__global__ void __launch_bounds__(RB) normalize_rows_kernel(T* A, int64_t lda, int64_t cols) {
+  __shared__ double sh[33];
+  T* row = A + (int64_t)blockIdx.x * lda;
+  double s = 0.0;
+  for (int64_t j = threadIdx.x; j < cols; j += RB) s += (double)row[j] * (double)row[j];
+  s = block_sum(s, sh);
+  const double nrm = sqrt(s);
+  if (nrm != 0.0)
+    for (int64_t j = threadIdx.x; j < cols; j += RB) row[j] = (T)((double)row[j] / nrm);
+}
+
+inline int grid_for(int64_t count, int sm) {
+  int64_t b = ceil_div64(count, 256);
+  const int64_t cap = (int64_t)sm * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+#define DISPATCH_T(dtype, CALL_F, CALL_D) \
+  if ((dtype) == NNFAC_F32) { CALL_F; } else if ((dtype) == NNFAC_F64) { CALL_D; } else { \
+    nnfac_set_error("bad dtype %d", (int)(dtype)); return NNFAC_ERR_ARG; }
+
+}  // namespace
+
+extern "C" {
+
+int nnfac_mu_terms(nnfac_ctx* ctx, int dtype, double beta, const void* K, const void* X, void* P,
+                   void* Q, int64_t count, void* stream) {
+  NNFAC_ARG(ctx && K && count > 0, "nnfac_mu_terms: bad argument");
+  NNFAC_ARG(beta >= 0, "nnfac_mu_terms: negative beta");
+  const int mode = beta == 1.0 ? 0 : beta == 2.0 ? 1 : beta == 3.0 ? 2 : 3;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(count, ctx->sm_count);
+  DISPATCH_T(dtype,
+             (mu_terms_kernel<float><<<grid, 256, 0, st>>>(mode, (float)beta, (const float*)K, (const float*)X, (float*)P, (float*)Q, count)),
+             (mu_terms_kernel<double><<<grid, 256, 0, st>>>(mode, beta, (const double*)K, (const double*)X, (double*)P, (double*)Q, count)));
+  NNFAC_LAUNCH_CHECK(ctx);
+  return NNFAC_OK;
+}
+
+int nnfac_mu_apply(nnfac_ctx* ctx, int dtype, void* F_out, const void* F_in, const void* num,
+                   const void* den_mat, const void* den_vec, int vec_per_row, int64_t rows,
+                   int64_t cols, double gamma, double floor_value, void* stream) {
+  NNFAC_ARG(ctx && F_out && F_in && num && (den_mat || den_vec) && rows > 0 && cols > 0, "nnfac_mu_apply: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(rows * cols, ctx->sm_count);
+  DISPATCH_T(dtype,
+             (mu_apply_kernel<float><<<grid, 256, 0, st>>>((float*)F_out, (const float*)F_in, (const float*)num, (const float*)den_mat, (const float*)den_vec, vec_per_row, rows, cols, (float)gamma, (float)floor_value)),
+             (mu_apply_kernel<double><<<grid, 256, 0, st>>>((double*)F_out, (const double*)F_in, (const double*)num, (const double*)den_mat, (const double*)den_vec, vec_per_row, rows, cols, gamma, floor_value)));
+  NNFAC_LAUNCH_CHECK(ctx);
+  return NNFAC_OK;
+}
+
+int nnfac_beta_divergence(nnfac_ctx* ctx, int dtype, double beta, const void* A, const void* B,
+                          int64_t count, double* out, void* stream) {
+  NNFAC_ARG(ctx && A && B && out && count > 0, "nnfac_beta_divergence: bad argument");
+  NNFAC_ARG(beta >= 0, "nnfac_beta_divergence: negative beta");
+  const int op = beta == 1.0 ? 0 : beta == 0.0 ? 1 : 2;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_T(dtype, return run_reduce<float>(ctx, op, beta, (const float*)A, (const float*)B, count, out, st),
+             return run_reduce<double>(ctx, op, beta, (const double*)A, (const double*)B, count, out, st));
+}
+
+int nnfac_sq_diff(nnfac_ctx* ctx, int dtype, const void* A, const void* B, int64_t count,
+                  double* out, void* stream) {
+  NNFAC_ARG(ctx && A && out && count > 0, "nnfac_sq_diff: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int op = B ? 3 : 5;
+  DISPATCH_T(dtype, return run_reduce<float>(ctx, op, 0.0, (const float*)A, (const float*)B, count, out, st),
+             return run_reduce<double>(ctx, op, 0.0, (const double*)A, (const double*)B, count, out, st));
+}
+
+int nnfac_dot(nnfac_ctx* ctx, int dtype, const void* A, const void* B, int64_t count, double* out,
+              void* stream) {
+  NNFAC_ARG(ctx && A && B && out && count > 0, "nnfac_dot: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_T(dtype, return run_reduce<float>(ctx, 4, 0.0, (const float*)A, (const float*)B, count, out, st),
+             return run_reduce<double>(ctx, 4, 0.0, (const double*)A, (const double*)B, count, out, st));
+}
+
+int nnfac_row_sums(nnfac_ctx* ctx, int dtype, const void* A, int64_t lda, int64_t rows,
+                   int64_t cols, void* out, void* stream) {
+  NNFAC_ARG(ctx && A && out && rows > 0 && cols > 0, "nnfac_row_sums: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = (int)ceil_div64(rows, 8);
+  DISPATCH_T(dtype, (row_sums_kernel<float><<<grid, 256, 0, st>>>((const float*)A, lda, rows, cols, (float*)out)),
+             (row_sums_kernel<double><<<grid, 256, 0, st>>>((const double*)A, lda, rows, cols, (double*)out)));
+  NNFAC_LAUNCH_CHECK(ctx);
+  return NNFAC_OK;
+}
+
+int nnfac_norm1(nnfac_ctx* ctx, int dtype, const void* A, int64_t lda, int64_t rows, int64_t cols,
+                double* out, void* stream) {
+  NNFAC_ARG(ctx && A && out && rows > 0 && cols > 0, "nnfac_norm1: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = (int)(ceil_div64(cols, RB) < RMAX_BLOCKS ? ceil_div64(cols, RB) : RMAX_BLOCKS);
+  DISPATCH_T(dtype, (norm1_stage1<float><<<blocks, RB, 0, st>>>((const float*)A, lda, rows, cols, ctx->red)),
+             (norm1_stage1<double><<<blocks, RB, 0, st>>>((const double*)A, lda, rows, cols, ctx->red)));
+  NNFAC_LAUNCH_CHECK(ctx);
+  reduce_stage2<<<1, RB, 0, st>>>(ctx->red, blocks, out, 1);
+  NNFAC_LAUNCH_CHECK(ctx);
+  return NNFAC_OK;
+}
+
+int nnfac_transpose(nnfac_ctx* ctx, int dtype, void* out, int64_t ld_out, const void* in,
+                    int64_t ld_in, int64_t rows, int64_t cols, void* stream) {
+  NNFAC_ARG(ctx && out && in && rows > 0 && cols > 0, "nnfac_transpose: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  NNFAC_ARG(ceil_div64(rows, 32) <= 65535, "nnfac_transpose: too many rows");
+  dim3 grid((unsigned)ceil_div64(cols, 32), (unsigned)ceil_div64(rows, 32)), block(32, 8);
+  DISPATCH_T(dtype, (transpose_kernel<float><<<grid, block, 0, st>>>((float*)out, ld_out, (const float*)in, ld_in, rows, cols)),
+             (transpose_kernel<double><<<grid, block, 0, st>>>((double*)out, ld_out, (const double*)in, ld_in, rows, cols)));
+  NNFAC_LAUNCH_CHECK(ctx);
+  return NNFAC_OK;
+}
+
+int nnfac_khatri_rao(nnfac_ctx* ctx, int dtype, void* out, const void* A, int64_t I, const void* B,
+                     int64_t J, int64_t r, void* stream) {
+  NNFAC_ARG(ctx && out && A && B && I > 0 && J > 0 && r > 0, "nnfac_khatri_rao: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(I * J * r, ctx->sm_count);
+  DISPATCH_T(dtype, (khatri_rao_kernel<float><<<grid, 256, 0, st>>>((float*)out, (const float*)A, I, (const float*)B, J, r)),
+             (khatri_rao_kernel<double><<<grid, 256, 0, st>>>((double*)out, (const double*)A, I, (const double*)B, J, r)));
+  NNFAC_LAUNCH_CHECK(ctx);
+  return NNFAC_OK;
+}
+
+int nnfac_hadamard(nnfac_ctx* ctx, int dtype, void* out, const void* A, const void* B,
+                   int64_t count, void* stream) {
+  NNFAC_ARG(ctx && out && A && B && count > 0, "nnfac_hadamard: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(count, ctx->sm_count);
+  DISPATCH_T(dtype, (hadamard_kernel<float><<<grid, 256, 0, st>>>((float*)out, (const float*)A, (const float*)B, count)),
+             (hadamard_kernel<double><<<grid, 256, 0, st>>>((double*)out, (const double*)A, (const double*)B, count)));
+  NNFAC_LAUNCH_CHECK(ctx);
+  return NNFAC_OK;
+}
+
+int nnfac_normalize_rows(nnfac_ctx* ctx, int dtype, void* A, int64_t lda, int64_t rows,
+                         int64_t cols, void* stream) {
+  NNFAC_ARG(ctx && A && rows > 0 && cols > 0, "nnfac_normalize_rows: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_T(dtype, (normalize_rows_kernel<float><<<(unsigned)rows, RB, 0, st>>>((float*)A, lda, cols)),
+             (normalize_rows_kernel<double><<<(unsigned)rows, RB, 0, st>>>((double*)A, lda, cols)));
+  NNFAC_LAUNCH_CHECK(ctx);
+  return NNFAC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+// Strided / batched / K-blocked GEMM on CUDA cores, fp32 or fp64.
+//
+// This is the general-shape dense kernel of the library: it serves the fp64 validation mode, odd
+// shapes, and every small contraction of the tensor models (Grams, mode products, MTTKRP on a
+// materialised Khatri-Rao block).  The two X-streaming cross products and the fused multiplicative
+// update of the fp32 headline path have their own tcgen05 kernels (tc_*.cu).
+//
+// Replaces the numpy dgemm call sites listed in include/nnfac_b200.h (nmf.py:407-408,432-433,
+// mu.py:82, ntf.py:442-449, mu.py:141,159, ntd.py:672).
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+
+template <typename T>
+struct GemmArgs {
+  T* C;
+  const T* A;
+  const T* B;
+  T* partial;  // [splits][batch][M][N] when splits > 1
+  int64_t ldc, sc_b;
+  int64_t sa_i, sa_k, sa_q, sa_b;
+  int64_t sb_k, sb_j, sb_q, sb_b;
+  int64_t M, N, K, kb, batch;
+  int splits;
+  int64_t kblocks_per_q;   // ceil(K / BK)
+  int64_t blocks_per_split;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(NT) gemm_strided_kernel(GemmArgs<T> g) {
+  __shared__ T As[BK][BM + 4];
+  __shared__ T Bs[BK][BN + 4];
+  const int t = threadIdx.x;
+  const int tx = t & 15, ty = t >> 4;
+  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+  const int64_t bz = blockIdx.z;
+  const int64_t b = bz / g.splits;
+  const int split = (int)(bz % g.splits);
+  const T* __restrict__ A = g.A + b * g.sa_b;
+  const T* __restrict__ B = g.B + b * g.sb_b;
+
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+
+  const int64_t nblk = g.kb * g.kblocks_per_q;
+  const int64_t blk0 = (int64_t)split * g.blocks_per_split;
+  int64_t blk1 = blk0 + g.blocks_per_split;
+  if (blk1 > nblk) blk1 = nblk;
+  const bool a_kcontig = (g.sa_k == 1);
+  const bool b_jcontig = (g.sb_j == 1);
+
+  for (int64_t blk = blk0; blk < blk1; ++blk) {
+    const int64_t q = blk / g.kblocks_per_q;
+    const int64_t k0 = (blk % g.kblocks_per_q) * BK;
+    const T* Aq = A + q * g.sa_q;
+    const T* Bq = B + q * g.sb_q;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int i, k;
+      if (a_kcontig) { k = t & 15; i = (t >> 4) + 16 * j; }
+      else           { i = t & 63; k = (t >> 6) + 4 * j; }
+      const int64_t gi = m0 + i, gk = k0 + k;
+      As[k][i] = (gi < g.M && gk < g.K) ? Aq[gi * g.sa_i + gk * g.sa_k] : T(0);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c, k;
+      if (b_jcontig) { c = t & 63; k = (t >> 6) + 4 * j; }
+      else           { k = t & 15; c = (t >> 4) + 16 * j; }
+      const int64_t gc = n0 + c, gk = k0 + k;
+      Bs[k][c] = (gc < g.N && gk < g.K) ? Bq[gk * g.sb_k + gc * g.sb_j] : T(0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      T a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  T* out;
+  int64_t ld;
+  if (g.splits == 1) { out = g.C + b * g.sc_b; ld = g.ldc; }
+  else { out = g.partial + ((int64_t)split * g.batch + b) * g.M * g.N; ld = g.N; }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t gi = m0 + ty * 4 + i;
+    if (gi >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t gj = n0 + tx * 4 + j;
+      if (gj < g.N) out[gi * ld + gj] = acc[i][j];
+    }
+  }
+}
+
+template <typename T>
+__global__ void splitk_reduce_kernel(T* C, int64_t ldc, int64_t sc_b, const T* partial, int64_t M,
+                                     int64_t N, int64_t batch, int splits) {
+  const int64_t total = batch * M * N;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    T s = T(0);
+    for (int sp = 0; sp < splits; ++sp) s += partial[(int64_t)sp * total + idx];  // fixed order
+    const int64_t b = idx / (M * N), rem = idx % (M * N);
+    C[b * sc_b + (rem / N) * ldc + (rem % N)] = s;
+  }
+}
+
+template <typename T>
+int run_gemm(nnfac_ctx* ctx, T* C, int64_t ldc, int64_t sc_b, const T* A, int64_t sa_i, int64_t sa_k,
+             int64_t sa_q, int64_t sa_b, const T* B, int64_t sb_k, int64_t sb_j, int64_t sb_q,
+             int64_t sb_b, int64_t M, int64_t N, int64_t K, int64_t kb, int64_t batch, cudaStream_t st) {
+  GemmArgs<T> g;
+  g.C = C; g.A = A; g.B = B; g.ldc = ldc; g.sc_b = sc_b;
+  g.sa_i = sa_i; g.sa_k = sa_k; g.sa_q = sa_q; g.sa_b = sa_b;
+  g.sb_k = sb_k; g.sb_j = sb_j; g.sb_q = sb_q; g.sb_b = sb_b;
+  g.M = M; g.N = N; g.K = K; g.kb = kb; g.batch = batch;
+  g.kblocks_per_q = ceil_div64(K, BK);
+  const int64_t nblk = kb * g.kblocks_per_q;
+  const int64_t tm = ceil_div64(M, BM), tn = ceil_div64(N, BN);
+  const int64_t tiles = tm * tn * batch;
+  int64_t splits = 1;
+  if (tiles < 2 * (int64_t)ctx->sm_count) {
+    splits = ceil_div64(2 * (int64_t)ctx->sm_count, tiles);
+    const int64_t max_by_work = nblk / 8 > 0 ? nblk / 8 : 1;  // at least 8 k-blocks per split
+    if (splits > max_by_work) splits = max_by_work;
+    if (splits > 256) splits = 256;
+  }
+  g.blocks_per_split = ceil_div64(nblk, splits);
+  splits = ceil_div64(nblk, g.blocks_per_split);
+  g.splits = (int)splits;
+  g.partial = nullptr;
+  if (splits > 1) {
+    const size_t need = (size_t)splits * batch * M * N * sizeof(T);
+    int rc = nnfac_ws_reserve(ctx, need, st);
+    if (rc) return rc;
+    g.partial = (T*)ctx->ws;
+  }
+  NNFAC_ARG(tm <= 65535 && batch * splits <= 65535, "nnfac_gemm_strided: grid too large (M tiles %lld, batch*splits %lld)",
+            (long long)tm, (long long)(batch * splits));
+  dim3 grid((unsigned)tn, (unsigned)tm, (unsigned)(batch * splits));
+  gemm_strided_kernel<T><<<grid, NT, 0, st>>>(g);
+  NNFAC_LAUNCH_CHECK(ctx);
+  if (splits > 1) {
+    const int64_t total = batch * M * N;
+    int blocks = (int)(ceil_div64(total, 256) < 4096 ? ceil_div64(total, 256) : 4096);
+    splitk_reduce_kernel<T><<<blocks, 256, 0, st>>>(C, ldc, sc_b, g.partial, M, N, batch, (int)splits);
+    NNFAC_LAUNCH_CHECK(ctx);
+  }
+  return NNFAC_OK;
+}
+
+}  // namespace
+
+extern "C" int nnfac_gemm_strided(nnfac_ctx* ctx, int dtype, void* C, int64_t ldc, int64_t sc_b,
+                                  const void* A, int64_t sa_i, int64_t sa_k, int64_t sa_q,
+                                  int64_t sa_b, const void* B, int64_t sb_k, int64_t sb_j,
+                                  int64_t sb_q, int64_t sb_b, int64_t M, int64_t N, int64_t K,
+                                  int64_t kb, int64_t batch, void* stream) {
+  NNFAC_ARG(ctx && C && A && B, "nnfac_gemm_strided: NULL argument");
+  NNFAC_ARG(M > 0 && N > 0 && K > 0 && kb > 0 && batch > 0, "nnfac_gemm_strided: empty dimension");
+  NNFAC_ARG(dtype == NNFAC_F32 || dtype == NNFAC_F64, "nnfac_gemm_strided: bad dtype %d", dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == NNFAC_F32)
+    return run_gemm<float>(ctx, (float*)C, ldc, sc_b, (const float*)A, sa_i, sa_k, sa_q, sa_b,
+                           (const float*)B, sb_k, sb_j, sb_q, sb_b, M, N, K, kb, batch, st);
+  return run_gemm<double>(ctx, (double*)C, ldc, sc_b, (const double*)A, sa_i, sa_k, sa_q, sa_b,
+                          (const double*)B, sb_k, sb_j, sb_q, sb_b, M, N, K, kb, batch, st);
+}

@@ -1,0 +1,55 @@
+// C-ABI entry of the HALS NNLS solver; dispatches on dtype and padded rank.
+#include "hals_sweep.cuh"
+
+#define DECL(tag, T, rp) int nnfac_sweep_##tag##_##rp(nnfac_ctx*, hals::SweepArgs<T>, cudaStream_t);
+DECL(f32, float, 16) DECL(f32, float, 32) DECL(f32, float, 64) DECL(f32, float, 128)
+DECL(f64, double, 16) DECL(f64, double, 32) DECL(f64, double, 64) DECL(f64, double, 128)
+#undef DECL
+
+namespace {
+template <typename T>
+hals::SweepArgs<T> make_args(const void* UtM, int64_t ld_utm, const void* UtU, int64_t ld_utu, void* V,
+                             int64_t ld_v, int r, int64_t n, int maxiter, double delta, double sparsity,
+                             unsigned flags, double* result) {
+  hals::SweepArgs<T> a;
+  a.b = (const T*)UtM; a.G = (const T*)UtU; a.V = (T*)V;
+  a.ld_b = ld_utm; a.ld_g = ld_utu; a.ld_v = ld_v; a.n = n;
+  a.r = r; a.maxiter = maxiter; a.delta = delta; a.sp = (T)sparsity; a.flags = flags;
+  a.nbatch = 1; a.part = nullptr; a.counter = nullptr; a.result = result;
+  return a;
+}
+}  // namespace
+
+extern "C" int nnfac_hals_nnls(nnfac_ctx* ctx, int dtype, const void* UtM, int64_t ld_utm,
+                               const void* UtU, int64_t ld_utu, void* V, int64_t ld_v, int r,
+                               int64_t n, int maxiter, double delta, double sparsity, unsigned flags,
+                               double* result, void* stream) {
+  NNFAC_ARG(ctx && UtM && UtU && V && result, "nnfac_hals_nnls: NULL argument");
+  NNFAC_ARG(r > 0 && n > 0, "nnfac_hals_nnls: empty problem (r=%d, n=%lld)", r, (long long)n);
+  NNFAC_ARG(ld_utm >= n && ld_v >= n && ld_utu >= r, "nnfac_hals_nnls: leading dimension too small");
+  if (r > 128) {
+    nnfac_set_error("nnfac_hals_nnls: rank %d > 128 is not covered by this build", r);
+    return NNFAC_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rp = r <= 16 ? 16 : r <= 32 ? 32 : r <= 64 ? 64 : 128;
+  if (dtype == NNFAC_F32) {
+    auto a = make_args<float>(UtM, ld_utm, UtU, ld_utu, V, ld_v, r, n, maxiter, delta, sparsity, flags, result);
+    switch (rp) {
+      case 16: return nnfac_sweep_f32_16(ctx, a, st);
+      case 32: return nnfac_sweep_f32_32(ctx, a, st);
+      case 64: return nnfac_sweep_f32_64(ctx, a, st);
+      default: return nnfac_sweep_f32_128(ctx, a, st);
+    }
+  } else if (dtype == NNFAC_F64) {
+    auto a = make_args<double>(UtM, ld_utm, UtU, ld_utu, V, ld_v, r, n, maxiter, delta, sparsity, flags, result);
+    switch (rp) {
+      case 16: return nnfac_sweep_f64_16(ctx, a, st);
+      case 32: return nnfac_sweep_f64_32(ctx, a, st);
+      case 64: return nnfac_sweep_f64_64(ctx, a, st);
+      default: return nnfac_sweep_f64_128(ctx, a, st);
+    }
+  }
+  nnfac_set_error("nnfac_hals_nnls: bad dtype %d", dtype);
+  return NNFAC_ERR_ARG;
+}

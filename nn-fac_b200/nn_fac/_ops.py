@@ -1,0 +1,198 @@
+"""Device operators: torch CUDA tensors in, torch CUDA tensors out, every FLOP in libnnfac_b200.
+
+These are the building blocks the drop-in modules (nmf, ntf, ntd, update_rules.*) are written
+with.  torch allocates the buffers; it never computes.
+"""
+import torch
+
+from . import _lib as L
+
+
+def _lib():
+    return L.load_library()
+
+
+def gemm(A, a_str, B, b_str, M, N, K, kb=1, batch=1, out=None, ldc=None, sc_b=0):
+    """C[b][i][j] = sum_{q<kb} sum_{k<K} A[b*sa_b + q*sa_q + i*sa_i + k*sa_k] * B[b*sb_b + q*sb_q + k*sb_k + j*sb_j].
+
+    a_str = (sa_i, sa_k, sa_q, sa_b); b_str = (sb_k, sb_j, sb_q, sb_b), in elements.
+    """
+    if out is None:
+        out = torch.empty((batch, M, N) if batch > 1 else (M, N), dtype=A.dtype, device=A.device)
+        ldc, sc_b = N, M * N
+    sa = tuple(a_str) + (0,) * (4 - len(a_str))
+    sb = tuple(b_str) + (0,) * (4 - len(b_str))
+    L.check(_lib().nnfac_gemm_strided(L.ctx(A.device), L.code_of(A.dtype), L.ptr(out), ldc, sc_b, L.ptr(A), *sa,
+                                      L.ptr(B), *sb, M, N, K, kb, batch, L.stream_ptr()))
+    return out
+
+
+def matmul(A, B):
+    """Row-major A (M x K) @ B (K x N)."""
+    M, K = A.shape
+    K2, N = B.shape
+    assert K == K2
+    return gemm(A, (A.stride(0), A.stride(1)), B, (B.stride(0), B.stride(1)), M, N, K)
+
+
+def transpose(A):
+    rows, cols = A.shape
+    out = torch.empty((cols, rows), dtype=A.dtype, device=A.device)
+    L.check(_lib().nnfac_transpose(L.ctx(A.device), L.code_of(A.dtype), L.ptr(out), rows, L.ptr(A), A.stride(0),
+                                   rows, cols, L.stream_ptr()))
+    return out
+
+
+def hals_nnls(UtM, UtU, V, r, maxiter, delta, sparsity, normalize, nonzero, result=None):
+    """In-place accelerated HALS on V (r x n).  Returns the device double[4] result vector."""
+    n = UtM.shape[1]
+    if result is None:
+        result = torch.empty(4, dtype=torch.float64, device=V.device)
+    flags = (L.HALS_NORMALIZE if normalize else 0) | (L.HALS_NONZERO if nonzero else 0)
+    L.check(_lib().nnfac_hals_nnls(L.ctx(V.device), L.code_of(V.dtype), L.ptr(UtM), UtM.stride(0), L.ptr(UtU),
+                                   UtU.stride(0), L.ptr(V), V.stride(0), r, n, maxiter, float(delta),
+                                   float(sparsity), flags, L.ptr(result), L.stream_ptr()))
+    return result
+
+
+def mu_terms(K, X, beta, want_q=True, out_p=None, out_q=None):
+    """P = K^(beta-2) * X, Q = K^(beta-1).  P may alias K when Q is not wanted."""
+    P = out_p if out_p is not None else torch.empty_like(K)
+    Q = None
+    if want_q:
+        Q = out_q if out_q is not None else torch.empty_like(K)
+    L.check(_lib().nnfac_mu_terms(L.ctx(K.device), L.code_of(K.dtype), float(beta), L.ptr(K), L.ptr(X), L.ptr(P),
+                                  L.ptr(Q), K.numel(), L.stream_ptr()))
+    return P, Q
+
+
+def mu_apply(F, num, den_mat=None, den_vec=None, vec_per_row=False, gamma=1.0, floor=1e-12):
+    out = torch.empty_like(F)
+    rows = F.shape[0]
+    cols = F.numel() // rows
+    L.check(_lib().nnfac_mu_apply(L.ctx(F.device), L.code_of(F.dtype), L.ptr(out), L.ptr(F), L.ptr(num),
+                                  L.ptr(den_mat), L.ptr(den_vec), 1 if vec_per_row else 0, rows, cols,
+                                  float(gamma), float(floor), L.stream_ptr()))
+    return out
+
+
+def _scalar(device):
+    return torch.empty(1, dtype=torch.float64, device=device)
+
+
+def beta_divergence(A, B, beta, out=None):
+    out = out if out is not None else _scalar(A.device)
+    L.check(_lib().nnfac_beta_divergence(L.ctx(A.device), L.code_of(A.dtype), float(beta), L.ptr(A), L.ptr(B),
+                                         A.numel(), L.ptr(out), L.stream_ptr()))
+    return out
+
+
+def sq_diff(A, B=None, out=None):
+    out = out if out is not None else _scalar(A.device)
+    L.check(_lib().nnfac_sq_diff(L.ctx(A.device), L.code_of(A.dtype), L.ptr(A), L.ptr(B), A.numel(), L.ptr(out),
+                                 L.stream_ptr()))
+    return out
+
+
+def dot(A, B, out=None):
+    out = out if out is not None else _scalar(A.device)
+    L.check(_lib().nnfac_dot(L.ctx(A.device), L.code_of(A.dtype), L.ptr(A), L.ptr(B), A.numel(), L.ptr(out),
+                             L.stream_ptr()))
+    return out
+
+
+def row_sums(A):
+    rows, cols = A.shape
+    out = torch.empty(rows, dtype=A.dtype, device=A.device)
+    L.check(_lib().nnfac_row_sums(L.ctx(A.device), L.code_of(A.dtype), L.ptr(A), A.stride(0), rows, cols, L.ptr(out),
+                                  L.stream_ptr()))
+    return out
+
+
+def norm1(A):
+    rows, cols = A.shape
+    out = _scalar(A.device)
+    L.check(_lib().nnfac_norm1(L.ctx(A.device), L.code_of(A.dtype), L.ptr(A), A.stride(0), rows, cols, L.ptr(out),
+                               L.stream_ptr()))
+    return out
+
+
+def khatri_rao(A, B):
+    I, r = A.shape
+    J = B.shape[0]
+    out = torch.empty((I * J, r), dtype=A.dtype, device=A.device)
+    L.check(_lib().nnfac_khatri_rao(L.ctx(A.device), L.code_of(A.dtype), L.ptr(out), L.ptr(A), I, L.ptr(B), J, r,
+                                    L.stream_ptr()))
+    return out
+
+
+def hadamard_(A, B):
+    L.check(_lib().nnfac_hadamard(L.ctx(A.device), L.code_of(A.dtype), L.ptr(A), L.ptr(A), L.ptr(B), A.numel(),
+                                  L.stream_ptr()))
+    return A
+
+
+def normalize_rows_(A):
+    rows, cols = A.shape
+    L.check(_lib().nnfac_normalize_rows(L.ctx(A.device), L.code_of(A.dtype), L.ptr(A), A.stride(0), rows, cols,
+                                        L.stream_ptr()))
+    return A
+
+
+# ---- tensor helpers (C-order N-way tensors, no unfolding copies) ---------------------------------
+def _split(shape, mode):
+    left = 1
+    for s in shape[:mode]:
+        left *= s
+    right = 1
+    for s in shape[mode + 1:]:
+        right *= s
+    return left, shape[mode], right
+
+
+def mode_dot(T, M, mode, transpose=False):
+    """fold(M @ unfold(T, mode)) (tensorly.tenalg.mode_dot); with transpose=True uses M^T."""
+    shape = list(T.shape)
+    left, I, right = _split(shape, mode)
+    if transpose:
+        R, si, sk = M.shape[1], M.stride(1), M.stride(0)
+    else:
+        R, si, sk = M.shape[0], M.stride(0), M.stride(1)
+    shape[mode] = R
+    out = torch.empty(shape, dtype=T.dtype, device=T.device)
+    if right == 1:
+        # out[l, a] = sum_i T[l, i] M[a, i]
+        gemm(T, (I, 1), M, (sk, si), left, R, I, out=out, ldc=R, sc_b=0)
+    else:
+        # out[l, a, rr] = sum_i M[a, i] T[l, i, rr], batched over l (chunked to respect the grid limit)
+        step = 16384
+        for l0 in range(0, left, step):
+            nb = min(step, left - l0)
+            gemm(M, (si, sk, 0, 0), T.reshape(-1)[l0 * I * right:], (right, 1, 0, I * right), R, right, I,
+                 batch=nb, out=out.reshape(-1)[l0 * R * right:], ldc=right, sc_b=R * right)
+    return out
+
+
+def multi_mode_dot(T, mats, skip=None, transpose=False):
+    out = T
+    for mode, M in enumerate(mats):
+        if mode == skip:
+            continue
+        out = mode_dot(out, M, mode, transpose=transpose)
+    return out
+
+
+def unfold_times(P, B, mode):
+    """unfold(P, mode) @ unfold(B, mode)^T for tensors that differ only along `mode`
+    (P: I along mode, B: R along mode).  Result I x R.  P may be a 0-d 'ones' marker (shape ())."""
+    shape = list(B.shape)
+    left, R, right = _split(shape, mode)
+    if P.dim() == 0:
+        # ones^T @ unfold(B, mode)^T : row sums of the unfolding
+        if right == 1:
+            return gemm(P.reshape(1), (0, 0, 0, 0), B, (R, 1, 0, 0), 1, R, left).reshape(R)
+        return gemm(P.reshape(1), (0, 0, 0, 0), B, (1, right, R * right, 0), 1, R, right, kb=left).reshape(R)
+    I = P.shape[mode]
+    if right == 1:
+        return gemm(P, (1, I, 0, 0), B, (R, 1, 0, 0), I, R, left)
+    return gemm(P, (right, 1, I * right, 0), B, (1, right, R * right, 0), I, R, right, kb=left)

@@ -1,0 +1,176 @@
+"""Nonnegative Tucker decomposition (NTD), B200 path (reference: nn_fac/ntd.py).
+
+Covered: the multiplicative-update algorithm (``update_rule="mu"``, any beta >= 0), i.e.
+``one_ntd_step_mu`` = per-mode ``mu_betadivmin`` on the implicit unfoldings followed by
+``mu_tensorial`` on the core and the beta-divergence cost (ntd.py:658-698).
+Not covered yet: ``update_rule="hals"`` (the projected-gradient core update of ntd.py:436-645 is
+row N2 of SURVEY.md section 8(f)); it raises NotImplementedError rather than falling back to a CPU.
+"""
+import time
+import warnings
+
+import numpy as np
+import torch
+
+import nn_fac.update_rules.mu as mu
+import nn_fac.utils.errors as err
+import nn_fac.utils.initialize_factors as init_factors
+from nn_fac import _lib as L
+from nn_fac import _ops as ops
+from nn_fac.utils.beta_divergence import gamma_beta
+
+
+def ntd(tensor, ranks, init="random", core_0=None, factors_0=[], n_iter_max=100, tol=1e-6,
+        update_rule="hals", beta=2,
+        sparsity_coefficients=[], fixed_modes=[], normalize=[], mode_core_norm=None,
+        verbose=False, return_costs=False, deterministic=False, seed=0):
+    """Arguments, defaults, checks and returns follow nn_fac.ntd.ntd (ntd.py:27-246):
+    returns (core, factors) or (core, factors, cost_fct_vals, toc)."""
+    nb_modes = len(tensor.shape)
+    if deterministic:
+        np.random.seed(seed)                                                # ntd.py:206-207
+    if type(ranks) is int:
+        ranks = [ranks for _ in range(nb_modes)]
+    elif len(ranks) != nb_modes:
+        raise err.InvalidRanksException(
+            "The number of ranks is different than the dim of the tensor, which is incorrect.") from None
+    for i in range(nb_modes):
+        if ranks[i] > tensor.shape[i]:                                      # ntd.py:215-219 (mutates the caller's list)
+            ranks[i] = tensor.shape[i]
+            warnings.warn(f"The {i}-th mode rank was larger than the shape of the tensor, which is incorrect "
+                          f"(rank: {ranks[i]}, tensor shape: {tensor.shape[i]}). The rank was then set to the shape of the tensor.")
+    if update_rule == "hals":
+        assert beta == 2, ("Beta parameter is only used for MU update rule. Please set update_rule to 'mu' to use "
+                           f"another beta value than 2. (Current setting: beta = {beta} and update_rule = {update_rule}).")
+    if init.lower() == "custom":                                            # ntd.py:224-234
+        factors = factors_0
+        core = core_0
+        if len(factors) != nb_modes:
+            raise err.CustomNotEngouhFactors("Custom initialization, but not enough factors")
+        for array in factors:
+            if array is None:
+                raise err.CustomNotValidFactors("Custom initialization, but (at least) one factor is set to 'None'")
+        if core is None:
+            raise err.CustomNotValidCore("Custom initialization, but the core is set to 'None'")
+    else:
+        host = tensor.detach().cpu().numpy() if isinstance(tensor, torch.Tensor) else tensor
+        core, factors = init_factors.ntd_initialization(host, ranks, init, deterministic=deterministic, seed=seed)
+    if init.lower() == "chromas" and 0 not in fixed_modes:
+        fixed_modes.append(0)
+    return compute_ntd(tensor, ranks, core, factors, n_iter_max=n_iter_max, tol=tol, update_rule=update_rule,
+                       beta=beta, sparsity_coefficients=sparsity_coefficients, fixed_modes=fixed_modes,
+                       normalize=normalize, mode_core_norm=mode_core_norm, verbose=verbose,
+                       return_costs=return_costs, deterministic=deterministic, seed=seed)
+
+
+class DeviceNTD:
+    """Tensor, core and factors resident on one GPU; one call of step_mu = one outer iteration."""
+
+    def __init__(self, tensor, core, factors, dtype, device=None):
+        self.T = L.to_device(tensor, dtype, device)
+        self.core = L.to_device(core, dtype, device)
+        self.factors = [L.to_device(f, dtype, device) for f in factors]
+
+    def factor_update(self, mode, beta):
+        """mu_betadivmin(F, unfold(G x_{j != mode} F_j, mode), unfold(T, mode), beta), ntd.py:672."""
+        F = self.factors[mode]
+        B = ops.multi_mode_dot(self.core, self.factors, skip=mode)          # shape of T except R_mode along `mode`
+        K = ops.mode_dot(B, F, mode)                                        # = F @ unfold(B, mode), folded (mu.py:82)
+        g = gamma_beta(beta)
+        if beta == 2:
+            P, Q = self.T, K
+        elif beta == 1:
+            P, Q = ops.mu_terms(K, self.T, beta, want_q=False, out_p=K)[0], None
+        else:
+            P, Q = ops.mu_terms(K, self.T, beta, want_q=True, out_p=torch.empty_like(K), out_q=K)
+        num = ops.unfold_times(P, B, mode)
+        if Q is None:
+            ones = torch.ones((), dtype=self.T.dtype, device=self.T.device)
+            den_vec = ops.unfold_times(ones, B, mode)                       # row sums of unfold(B, mode), mu.py:86
+            return ops.mu_apply(F, num, den_vec=den_vec, vec_per_row=False, gamma=g, floor=mu.epsilon)
+        return ops.mu_apply(F, num, den_mat=ops.unfold_times(Q, B, mode), gamma=g, floor=mu.epsilon)
+
+    def step_mu(self, beta, fixed_modes, normalize, mode_core_norm):
+        for mode in [m for m in range(self.T.dim()) if m not in fixed_modes]:
+            self.factors[mode] = self.factor_update(mode, beta)
+        self.core = mu.mu_tensorial_device(self.core, self.factors, self.T, beta)   # ntd.py:674
+        if normalize[-1]:                                                    # ntd.py:676-681
+            moved = self.core.movedim(mode_core_norm, 0).contiguous()
+            flat = moved.reshape(moved.shape[0], -1)
+            ops.normalize_rows_(flat)
+            self.core = moved.movedim(0, mode_core_norm).contiguous()
+        K = ops.multi_mode_dot(self.core, self.factors)
+        return float(ops.beta_divergence(self.T, K, beta).item())           # ntd.py:694-696 (not normalised)
+
+
+def compute_ntd(tensor_in, ranks, core_in, factors_in, n_iter_max=100, tol=1e-6,
+                update_rule="hals", beta=2,
+                sparsity_coefficients=[], fixed_modes=[], normalize=[], mode_core_norm=None,
+                verbose=False, return_costs=False, deterministic=False, seed=0):
+    """Outer loop of ntd.py:248-433."""
+    nb_modes = len(tensor_in.shape)
+    if sparsity_coefficients is None or len(sparsity_coefficients) != nb_modes + 1:   # ntd.py:364-378
+        print("Irrelevant number of sparsity coefficient (different from the number of modes + 1 for the core), they have been set to None.")
+        sparsity_coefficients = [None for _ in range(nb_modes + 1)]
+    if fixed_modes is None:
+        fixed_modes = []
+    if normalize is None or len(normalize) != nb_modes + 1:
+        print("Irrelevant number of normalization booleans (different from the number of modes + 1 for the core), they have been set to False.")
+        normalize = [False for _ in range(nb_modes + 1)]
+    if normalize[-1] and (mode_core_norm is None or mode_core_norm < 0 or mode_core_norm >= nb_modes):
+        print("The core was asked to be normalized, but an invalid mode was specified. Normalization has been set to False.")
+        normalize[-1] = False
+    if not normalize[-1] and (mode_core_norm is not None and 0 <= mode_core_norm < nb_modes):
+        print("The core was asked NOT to be normalized, but mode_core_norm was set to a valid norm. Is this a mistake?")
+    if update_rule == "hals":
+        raise NotImplementedError("ntd(update_rule='hals') is not part of this build yet (SURVEY.md 8(f) N2); "
+                                  "use update_rule='mu'. There is no CPU fallback.")
+    if update_rule != "mu":
+        raise err.InvalidArgumentValue(
+            f"The update rule provided is not valid. Please choose between 'hals' and 'mu' (Got {update_rule}).")
+    if beta < 0:
+        raise err.InvalidArgumentValue("Invalid value for beta: negative one.") from None
+    dt = L.resolve_dtype(tensor_in, core_in, *factors_in)
+    state = DeviceNTD(tensor_in, core_in, factors_in, dt)
+    cost_fct_vals, toc = [], []
+    tic = time.time()
+    for iteration in range(n_iter_max):
+        cost = state.step_mu(beta, fixed_modes, normalize, mode_core_norm)
+        toc.append(time.time() - tic)
+        cost_fct_vals.append(cost)
+        if verbose:
+            if iteration == 0:
+                print('Normalized cost function value={}'.format(cost))
+            else:
+                gain = cost_fct_vals[-2] - cost_fct_vals[-1]
+                line = 'Normalized cost function value={}, variation={}.'.format(cost_fct_vals[-1], gain)
+                print(line if gain > 0 else '\033[91m' + line + '\033[0m')
+        if iteration > 0 and abs(cost_fct_vals[-2] - cost_fct_vals[-1]) < tol:
+            if verbose:
+                print('Converged in {} iterations.'.format(iteration))
+            break
+    if isinstance(tensor_in, torch.Tensor):
+        core, factors = state.core, state.factors
+    else:
+        core, factors = state.core.cpu().numpy(), [f.cpu().numpy() for f in state.factors]
+    if return_costs:
+        return core, factors, cost_fct_vals, toc
+    return core, factors
+
+
+def one_ntd_step_mu(tensor, ranks, in_core, in_factors, beta, norm_tensor,
+                    fixed_modes, normalize, mode_core_norm):
+    """ntd.py:658-698: returns (core, factors, cost).  Host arrays are uploaded on every call."""
+    if beta < 0:
+        raise err.InvalidArgumentValue("Invalid value for beta: negative one.") from None
+    dt = L.resolve_dtype(tensor, in_core, *in_factors)
+    state = DeviceNTD(tensor, in_core, in_factors, dt)
+    cost = state.step_mu(beta, fixed_modes, normalize, mode_core_norm)
+    if isinstance(tensor, torch.Tensor):
+        return state.core, state.factors, cost
+    return state.core.cpu().numpy(), [f.cpu().numpy() for f in state.factors], cost
+
+
+def ntd_mu(*args, **kwargs):
+    """Deprecated in the reference as well (ntd.py:649-656)."""
+    raise DeprecationWarning("The ntd_mu function is deprecated. Please use the ntd function with update_rule='mu' instead.")

@@ -1,0 +1,231 @@
+"""Nonnegative PARAFAC / CP (NTF), B200 path (reference: nn_fac/ntf.py).
+
+``ntf`` / ``compute_ntf`` keep the tensor resident on the GPU; the per-mode MTTKRP contracts the
+tensor in place through strided access (no unfolded copies: the reference makes one copy of the
+tensor per mode, ntf.py:309-311).  HALS uses the deterministic inner stopping rule.
+
+Reference quirk kept: ``ntf`` returns ``np.array(factors)`` (ntf.py:342-344), which numpy >= 1.24
+rejects for non-cubic tensors; here a non-cubic result is returned as an object array of factors.
+"""
+import time
+
+import numpy as np
+import torch
+
+import nn_fac.update_rules.mu as mu
+import nn_fac.update_rules.nnls as nnls
+import nn_fac.utils.errors as err
+import nn_fac.utils.initialize_factors as init_factors
+from nn_fac import _lib as L
+from nn_fac import _ops as ops
+
+
+def ntf(tensor, rank, init="random", factors_0=[], n_iter_max=100, tol=1e-8,
+        update_rule="hals", beta=2,
+        sparsity_coefficients=[], fixed_modes=[], normalize=[],
+        verbose=False, return_costs=False):
+    """Arguments, defaults and returns follow nn_fac.ntf.ntf (ntf.py:19-199)."""
+    nb_modes = len(tensor.shape)
+    if init.lower() == "custom":                                            # ntf.py:184-191
+        factors = factors_0
+        if len(factors) != nb_modes:
+            raise err.CustomNotEngouhFactors("Custom initialization, but not enough factors")
+        for array in factors:
+            if array is None:
+                raise err.CustomNotValidFactors("Custom initialization, but one factor is set to 'None'")
+    else:
+        host = tensor.detach().cpu().numpy() if isinstance(tensor, torch.Tensor) else tensor
+        factors = init_factors.ntf_initialization(host, rank, init, deterministic=False, seed=0)   # ntf.py:194
+    return compute_ntf(tensor, rank, factors, n_iter_max=n_iter_max, tol=tol, update_rule=update_rule, beta=beta,
+                       sparsity_coefficients=sparsity_coefficients, fixed_modes=fixed_modes, normalize=normalize,
+                       verbose=verbose, return_costs=return_costs)
+
+
+def _check_step_arguments(update_rule, beta):
+    if update_rule not in ("hals", "mu"):                                   # ntf.py:422-425
+        raise err.InvalidArgumentValue(f"Invalid update rule: {update_rule}") from None
+    if update_rule == "hals" and beta != 2:
+        raise err.InvalidArgumentValue(
+            "The hals is only valid for the frobenius norm, corresponding to the beta divergence with beta = 2. "
+            f"Here, beta was set to {beta}. To compute NMF with this value of beta, please use the mu update_rule."
+        ) from None
+
+
+class DeviceNTF:
+    """Tensor (C order) and factors resident on one GPU."""
+
+    def __init__(self, tensor, factors, dtype, device=None):
+        self.T = L.to_device(tensor, dtype, device)
+        self.shape = tuple(self.T.shape)
+        self.factors = [L.to_device(f, dtype, device) for f in factors]
+        self.norm_sq = None
+        self.stats = torch.zeros(4, dtype=torch.float64, device=self.T.device)
+
+    def khatri_rao(self, skip):
+        kept = [f for i, f in enumerate(self.factors) if i != skip]
+        out = kept[0]
+        for f in kept[1:]:
+            out = ops.khatri_rao(out, f)                                    # ntf.py:448
+        return out
+
+    def mttkrp(self, mode, krao):
+        """unfold(T, mode) @ krao without forming the unfolding (ntf.py:449)."""
+        left, I, right = ops._split(list(self.shape), mode)
+        r = krao.shape[1]
+        if right == 1:
+            return ops.gemm(self.T, (1, I), krao, (r, 1), I, r, left)
+        return ops.gemm(self.T, (right, 1, I * right, 0), krao, (r, 1, right * r, 0), I, r, right, kb=left)
+
+    def reconstruct_unfolded(self, mode, krao):
+        """factors[mode] @ krao^T laid out as the C-order tensor (only for the MU path)."""
+        F = self.factors[mode]
+        left, I, right = ops._split(list(self.shape), mode)
+        r = F.shape[1]
+        K = torch.empty(self.shape, dtype=self.T.dtype, device=self.T.device)
+        if right == 1:
+            # K[l, i] = sum_q krao[l, q] F[i, q]
+            ops.gemm(krao, (r, 1), F, (1, r), left, I, r, out=K, ldc=I, sc_b=0)
+        else:
+            step = 16384
+            for l0 in range(0, left, step):
+                nb = min(step, left - l0)
+                # K[l, i, rr] = sum_q F[i, q] krao[l*right + rr, q]
+                ops.gemm(F, (r, 1, 0, 0), krao.reshape(-1)[l0 * right * r:], (1, r, 0, right * r), I, right, r,
+                         batch=nb, out=K.reshape(-1)[l0 * I * right:], ldc=right, sc_b=I * right)
+        return K
+
+    def step(self, rank, norm_tensor, update_rule, beta, sparsity, fixed_modes, normalize):
+        modes = [m for m in range(len(self.shape)) if m not in fixed_modes]
+        rhs = krao = cross = None
+        mode = None
+        for mode in modes:
+            krao = self.khatri_rao(mode)
+            if update_rule == "hals":
+                cross = None
+                for i, f in enumerate(self.factors):
+                    if i != mode:
+                        gram = ops.gemm(f, (1, f.shape[1]), f, (f.shape[1], 1), rank, rank, f.shape[0])  # ntf.py:445
+                        cross = gram if cross is None else ops.hadamard_(cross, gram)
+                rhs = self.mttkrp(mode, krao)
+                rhs_t = ops.transpose(rhs)
+                Ft = ops.transpose(self.factors[mode])
+                nnls.hals_nnls_device(rhs_t, cross, Ft, rank, maxiter=100, delta=0.01,
+                                      sparsity_coefficient=sparsity[mode], normalize=normalize[mode],
+                                      nonzero=False, result=self.stats)    # ntf.py:454-456
+                self.factors[mode] = ops.transpose(Ft)
+            else:
+                F = self.factors[mode]
+                K = self.reconstruct_unfolded(mode, krao)
+                self.factors[mode] = self._mu_factor(F, krao, K, mode, beta)   # ntf.py:459-460
+        sparsity_error = 0.0
+        for idx, s in enumerate(sparsity):
+            if s:
+                sparsity_error += 2 * (s * float(ops.norm1(self.factors[idx]).item()))   # ntf.py:463-466
+        F = self.factors[mode]
+        if update_rule == "hals":
+            # ntf.py:470; ||F krao^T||^2 = <F^T F, krao^T krao> and krao^T krao = cross (Hadamard of Grams)
+            ftf = ops.gemm(F, (1, rank), F, (rank, 1), rank, rank, F.shape[0])
+            parts = torch.cat([ops.dot(F, rhs), ops.dot(ftf, cross)]).cpu().numpy()
+            rec_error = norm_tensor ** 2 - 2 * parts[0] + parts[1]
+        else:
+            K = self.reconstruct_unfolded(mode, krao)
+            rec_error = float(ops.beta_divergence(self.T, K, beta).item())  # ntf.py:473
+        return float((rec_error + sparsity_error) / (norm_tensor ** 2))     # ntf.py:475
+
+    def _mu_factor(self, F, krao, K, mode, beta):
+        """mu_betadivmin(F, krao.T, unfold(T, mode), beta) with the unfolding kept implicit."""
+        from nn_fac.utils.beta_divergence import gamma_beta
+        left, I, right = ops._split(list(self.shape), mode)
+        r = F.shape[1]
+        g = gamma_beta(beta)
+        if beta == 2:
+            P, Q = self.T, K
+        elif beta == 1:
+            P, Q = ops.mu_terms(K, self.T, beta, want_q=False, out_p=K)[0], None
+        else:
+            P, Q = ops.mu_terms(K, self.T, beta, want_q=True, out_p=torch.empty_like(K), out_q=K)
+
+        def contract(Z):
+            if right == 1:
+                return ops.gemm(Z, (1, I), krao, (r, 1), I, r, left)
+            return ops.gemm(Z, (right, 1, I * right, 0), krao, (r, 1, right * r, 0), I, r, right, kb=left)
+
+        num = contract(P)
+        if Q is None:
+            den_vec = ops.row_sums(ops.transpose(krao))                     # column sums of krao = row sums of krao^T
+            return ops.mu_apply(F, num, den_vec=den_vec, vec_per_row=False, gamma=g, floor=mu.epsilon)
+        return ops.mu_apply(F, num, den_mat=contract(Q), gamma=g, floor=mu.epsilon)
+
+
+def _pack(factors, like):
+    if isinstance(like, torch.Tensor):
+        return factors
+    host = [f.cpu().numpy() for f in factors]
+    if len({f.shape for f in host}) == 1:
+        return np.array(host)                                               # ntf.py:342-344
+    out = np.empty(len(host), dtype=object)
+    for i, f in enumerate(host):
+        out[i] = f
+    return out
+
+
+def compute_ntf(tensor_in, rank, factors_in, n_iter_max=100, tol=1e-8,
+                update_rule="hals", beta=2,
+                sparsity_coefficients=[], fixed_modes=[], normalize=[],
+                verbose=False, return_costs=False):
+    """Outer loop of ntf.py:201-344.  The cost is normalised by ||tensor||^2 (ntf.py:475)."""
+    nb_modes = len(tensor_in.shape)
+    if sparsity_coefficients is None or len(sparsity_coefficients) != nb_modes:      # ntf.py:292-301
+        print("Irrelevant number of sparsity coefficient (different from the number of modes), they have been set to None.")
+        sparsity_coefficients = [None for _ in range(nb_modes)]
+    if fixed_modes is None:
+        fixed_modes = []
+    if normalize is None or len(normalize) != nb_modes:
+        print("Irrelevant number of normalization booleans (different from the number of modes), they have been set to False.")
+        normalize = [False for _ in range(nb_modes)]
+    _check_step_arguments(update_rule, beta)
+    for fixed_value in fixed_modes:
+        sparsity_coefficients[fixed_value] = None                           # ntf.py:428-429 (caller's list, as in the reference)
+    dt = L.resolve_dtype(tensor_in, *factors_in)
+    state = DeviceNTF(tensor_in, factors_in, dt)
+    norm_tensor = float(np.sqrt(ops.sq_diff(state.T).item()))              # ntf.py:290
+    cost_fct_vals, toc = [], []
+    tic = time.time()
+    for iteration in range(n_iter_max):
+        cost = state.step(rank, norm_tensor, update_rule, beta, sparsity_coefficients, fixed_modes, normalize)
+        toc.append(time.time() - tic)
+        cost_fct_vals.append(cost)
+        if verbose:
+            if iteration == 0:
+                print('Normalized cost function value={}'.format(cost))
+            else:
+                gain = cost_fct_vals[-2] - cost_fct_vals[-1]
+                line = 'Normalized cost function value={}, variation={}.'.format(cost_fct_vals[-1], gain)
+                print(line if gain > 0 else '\033[91m' + line + '\033[0m')
+        if iteration > 0 and abs(cost_fct_vals[-2] - cost_fct_vals[-1]) < tol:
+            if verbose:
+                print('Converged in {} iterations.'.format(iteration))
+            break
+    out = _pack(state.factors, tensor_in)
+    if return_costs:
+        return out, cost_fct_vals, toc
+    return out
+
+
+def one_ntf_step(unfolded_tensors, rank, in_factors, norm_tensor, update_rule, beta,
+                 sparsity_coefficients, fixed_modes, normalize,
+                 alpha=0.5, delta=0.01):
+    """One pass over the modes (ntf.py:347-477).  Takes the reference's list of mode unfoldings;
+    only unfolded_tensors[0] (I_0 x prod(others), C order) and the factor shapes are needed to
+    rebuild the tensor.  `alpha` is ignored (deterministic rule); `delta` must be 0.01."""
+    _check_step_arguments(update_rule, beta)
+    for fixed_value in fixed_modes:
+        sparsity_coefficients[fixed_value] = None
+    shape = tuple(int(f.shape[0]) for f in in_factors)
+    first = unfolded_tensors[0]
+    tensor = first.reshape(shape) if isinstance(first, torch.Tensor) else np.reshape(first, shape)
+    dt = L.resolve_dtype(first, *in_factors)
+    state = DeviceNTF(tensor, in_factors, dt)
+    cost = state.step(rank, float(norm_tensor), update_rule, beta, sparsity_coefficients, fixed_modes, normalize)
+    factors = state.factors if isinstance(first, torch.Tensor) else [f.cpu().numpy() for f in state.factors]
+    return factors, cost
