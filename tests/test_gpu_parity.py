@@ -283,9 +283,9 @@ def test_nmf_early_stop_and_rank_clamp():
     rng = np.random.RandomState(2)
     data = rng.rand(30, 6) @ rng.rand(6, 20) + 1e-3
     U0, V0 = rng.rand(30, 6), rng.rand(6, 20)
-    _, _, costs, toc = nmf.nmf(data, 6, init="custom", U_0=U0, V_0=V0, n_iter_max=200, tol=1e-3, update_rule="mu",
+    _, _, costs, toc = nmf.nmf(data, 6, init="custom", U_0=U0, V_0=V0, n_iter_max=200, tol=5e-2, update_rule="mu",
                                beta=2, return_costs=True, deterministic=True)
-    _, _, costs_o, _ = orc.compute_nmf(data, U0, V0, n_iter_max=200, tol=1e-3, update_rule="mu", beta=2)
+    _, _, costs_o, _ = orc.compute_nmf(data, U0, V0, n_iter_max=200, tol=5e-2, update_rule="mu", beta=2)
     assert len(costs) == len(costs_o) < 200                           # data-dependent break (nmf.py:320)
     with pytest.warns(UserWarning):
         U, V = nmf.nmf(data, 50, n_iter_max=2, deterministic=True)    # rank clamped to min(shape) (nmf.py:175-178)
