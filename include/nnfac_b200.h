@@ -124,6 +124,26 @@ int nnfac_hadamard(nnfac_ctx* ctx, int dtype, void* out, const void* A, const vo
 int nnfac_normalize_rows(nnfac_ctx* ctx, int dtype, void* A, int64_t lda, int64_t rows,
                          int64_t cols, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * NMF plan: the fp32 headline path (tcgen05 / TMA).  The data matrix X (m x n) is kept resident as
+ * bf16 hi/lo planes (4 bytes per element, ~17 mantissa bits) in both orientations so that each of
+ * the two X passes of an outer iteration (nmf.py:408 and nmf.py:433) streams K-major tiles.
+ * Rank <= 128.  A plan is bound to one context and one stream at a time.
+ * -------------------------------------------------------------------------------------------*/
+typedef struct nnfac_nmf_plan nnfac_nmf_plan;
+int nnfac_nmf_plan_create(nnfac_ctx* ctx, int64_t m, int64_t n, int r, nnfac_nmf_plan** out);
+int nnfac_nmf_plan_destroy(nnfac_nmf_plan* plan);
+/* Ingest X (device fp32, row-major, leading dimension ldx >= n): one read of X, two plane writes. */
+int nnfac_nmf_plan_load_x(nnfac_nmf_plan* plan, const float* X, int64_t ldx, void* stream);
+/* which = 0: out (r x m) = F X^T with F = V (r x n)      -- VMt, nmf.py:408
+ * which = 1: out (r x n) = F X   with F = U^T (r x m)    -- UtM, nmf.py:433
+ * F and out are device fp32, row-major.  Deterministic. */
+int nnfac_nmf_plan_cross(nnfac_nmf_plan* plan, int which, const float* F, int64_t ldf, float* out,
+                         int64_t ld_out, void* stream);
+/* Work decomposition chosen for one side (for benchmarks / DESIGN.md); any pointer may be NULL. */
+int nnfac_nmf_plan_info(const nnfac_nmf_plan* plan, int which, int* splits, int* stages_per_unit,
+                        int* num_units, int* num_stages, int* grid);
+
 #ifdef __cplusplus
 }
 #endif

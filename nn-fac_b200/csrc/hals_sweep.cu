@@ -15,7 +15,7 @@ hals::SweepArgs<T> make_args(const void* UtM, int64_t ld_utm, const void* UtU, i
   a.b = (const T*)UtM; a.G = (const T*)UtU; a.V = (T*)V;
   a.ld_b = ld_utm; a.ld_g = ld_utu; a.ld_v = ld_v; a.n = n;
   a.r = r; a.maxiter = maxiter; a.delta = delta; a.sp = (T)sparsity; a.flags = flags;
-  a.nbatch = 1; a.part = nullptr; a.counter = nullptr; a.result = result;
+  a.nbatch = 1; a.slab_ld = 0; a.part = nullptr; a.counter = nullptr; a.result = result;
   return a;
 }
 }  // namespace

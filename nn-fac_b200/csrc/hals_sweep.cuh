@@ -32,6 +32,7 @@ struct SweepArgs {
   T sp;
   unsigned flags;
   int64_t nbatch;
+  int slab_ld;        // > 0: the CTA keeps its r x slab_ld slice of UtM in shared memory
   double* part;       // [2][2 * gridDim.x] barrier partials
   unsigned* counter;  // zeroed before launch
   double* result;     // {eps, cnt, zero_diag_row, sweeps}
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(MAXT, 1) hals_sweep_kernel(SweepArgs<T> a) {
   T* Gs = reinterpret_cast<T*>(smem_raw);
   T* diag = Gs + RP * RP;
   double* sh = reinterpret_cast<double*>(diag + RP);  // 40 doubles
+  T* bs = reinterpret_cast<T*>(sh + 40);              // optional r x slab_ld slice of UtM
 
   const int t = threadIdx.x;
   const int lane_l = t % L;
@@ -132,6 +134,17 @@ __global__ void __launch_bounds__(MAXT, 1) hals_sweep_kernel(SweepArgs<T> a) {
       }
   };
 
+  if (a.slab_ld > 0) {
+    // stage this CTA's columns of UtM once: the sweep re-reads them every sweep, and a global
+    // load in the middle of the row loop is a ~700-cycle bubble that 7 warps cannot hide
+    const int64_t cta_col0 = (int64_t)blockIdx.x * GP * C;
+    for (int idx = t; idx < r * a.slab_ld; idx += blockDim.x) {
+      const int k = idx / a.slab_ld, c = idx % a.slab_ld;
+      bs[idx] = (cta_col0 + c < a.n) ? a.b[(int64_t)k * a.ld_b + cta_col0 + c] : T(0);
+    }
+    __syncthreads();
+  }
+
   unsigned epoch = 0;
   double eps0 = 0.0, eps = 1.0;
   int cnt = 1;
@@ -155,7 +168,18 @@ __global__ void __launch_bounds__(MAXT, 1) hals_sweep_kernel(SweepArgs<T> a) {
             const bool owner = (lane_l == lo);
             if (dk != T(0)) {
               T bk[C];
-              if (owner) {
+              if (owner && a.slab_ld > 0) {
+                const T* bp = bs + k * a.slab_ld + gid * C;
+                if (C * sizeof(T) == 16) {
+                  const V4 q = *reinterpret_cast<const V4*>(bp);
+                  const T* qq = reinterpret_cast<const T*>(&q);
+#pragma unroll
+                  for (int c = 0; c < C; ++c) bk[c] = qq[c];
+                } else {
+#pragma unroll
+                  for (int c = 0; c < C; ++c) bk[c] = bp[c];
+                }
+              } else if (owner) {
                 const T* bp = a.b + (int64_t)k * a.ld_b + col0;
                 if (vec_b && col0 + C <= a.n) {
                   const V4 q = *reinterpret_cast<const V4*>(bp);
@@ -266,13 +290,226 @@ __global__ void __launch_bounds__(MAXT, 1) hals_sweep_kernel(SweepArgs<T> a) {
   }
 }
 
+
+// --------------------------------------------------------------------------------------------
+// Chunk-blocked sweep (the production path when no per-row global operation is requested).
+//
+// Rows are processed VEC (= 16 bytes / sizeof(T)) at a time; the VEC rows of a chunk belong to
+// one lane.  Phase 1: every lane forms its partial dot products for the VEC rows against the
+// values V had when the chunk started (VEC * NR * C independent FMAs, one shuffle reduction).
+// Phase 2: the owning lane walks the VEC rows in order and adds the in-chunk corrections
+// G[k,k'] * dV[k'] for k' < k, which restores the exact Gauss-Seidel recurrence
+//   dV[k] = max((UtM[k] - UtU[k,:] V - sp) / UtU[k,k], -V[k])            (nnls.py:163/167)
+// while the sequential dependency chain is paid once per chunk instead of once per row.
+// The row loop is a run-time loop (the code stays inside the instruction cache); the owner
+// copies its chunk in and out of the register tile through a switch on the chunk slot.
+// --------------------------------------------------------------------------------------------
+#define NNFAC_SLOT_CASES(OP) \
+  switch (slot) {            \
+    case 0: OP(0) break;  case 1: OP(1) break;  case 2: OP(2) break;  case 3: OP(3) break;     \
+    case 4: OP(4) break;  case 5: OP(5) break;  case 6: OP(6) break;  case 7: OP(7) break;     \
+    case 8: OP(8) break;  case 9: OP(9) break;  case 10: OP(10) break; case 11: OP(11) break;  \
+    case 12: OP(12) break; case 13: OP(13) break; case 14: OP(14) break; default: OP(15) break; \
+  }
+
+template <typename T, int RP, int L, int C, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) hals_sweep_chunked_kernel(SweepArgs<T> a) {
+  constexpr int VEC = VecT<T>::N;
+  constexpr int NR = RP / L;
+  constexpr int NCH = NR / VEC;
+  static_assert(NCH >= 1 && NCH <= 16 && NCH * VEC * L == RP, "bad sweep tiling");
+  using V4 = typename VecT<T>::type;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* Gs = reinterpret_cast<T*>(smem_raw);
+  T* diag = Gs + RP * RP;
+  double* sh = reinterpret_cast<double*>(diag + RP);
+  T* bs = reinterpret_cast<T*>(sh + 40);
+
+  const int t = threadIdx.x;
+  const int lane_l = t % L;
+  const int gid = t / L;
+  const int GP = blockDim.x / L;
+  const int r = a.r;
+
+  for (int idx = t; idx < RP * RP; idx += blockDim.x) {
+    const int i = idx / RP, j = idx % RP;
+    Gs[idx] = (i < r && j < r) ? a.G[(int64_t)i * a.ld_g + j] : T(0);
+  }
+  for (int i = t; i < RP; i += blockDim.x) diag[i] = i < r ? a.G[(int64_t)i * a.ld_g + i] : T(0);
+  if (a.slab_ld > 0) {
+    const int64_t cta_col0 = (int64_t)blockIdx.x * GP * C;
+    for (int idx = t; idx < r * a.slab_ld; idx += blockDim.x) {
+      const int k = idx / a.slab_ld, c = idx % a.slab_ld;
+      bs[idx] = (cta_col0 + c < a.n) ? a.b[(int64_t)k * a.ld_b + cta_col0 + c] : T(0);
+    }
+  }
+  __syncthreads();
+
+  T v[NCH][VEC][C];
+  const bool single = (a.nbatch == 1);
+  auto col_of = [&](int64_t batch) -> int64_t {
+    return ((batch * gridDim.x + blockIdx.x) * (int64_t)GP + gid) * C;
+  };
+  auto load_v = [&](int64_t col0) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const int row = VEC * (lane_l + L * i) + e;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          v[i][e][c] = (row < r && col0 + c < a.n) ? a.V[(int64_t)row * a.ld_v + col0 + c] : T(0);
+      }
+  };
+  auto store_v = [&](int64_t col0) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const int row = VEC * (lane_l + L * i) + e;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          if (row < r && col0 + c < a.n) a.V[(int64_t)row * a.ld_v + col0 + c] = v[i][e][c];
+      }
+  };
+
+  unsigned epoch = 0;
+  double eps0 = 0.0, eps = 1.0;
+  int cnt = 1;
+  const int nchunks = (r + VEC - 1) / VEC;
+  if (single) load_v(col_of(0));
+
+  while (eps >= a.delta * eps0 && cnt <= a.maxiter) {
+    T nd = T(0);
+    for (int64_t batch = 0; batch < a.nbatch; ++batch) {
+      const int64_t col0 = col_of(batch);
+      if (!single) load_v(col0);
+#pragma unroll 1
+      for (int q = 0; q < nchunks; ++q) {
+        const int lo = q % L, slot = q / L, k0 = q * VEC;
+        // ---- phase 1: partial dots of the chunk's rows against V as it is now ----
+        T acc[VEC][C];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[e][c] = T(0);
+        const T* grow = Gs + k0 * RP + VEC * lane_l;
+#pragma unroll
+        for (int i2 = 0; i2 < NCH; ++i2) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            const V4 g4 = *reinterpret_cast<const V4*>(grow + e * RP + VEC * L * i2);
+            const T* gg = reinterpret_cast<const T*>(&g4);
+#pragma unroll
+            for (int e2 = 0; e2 < VEC; ++e2)
+#pragma unroll
+              for (int c = 0; c < C; ++c) acc[e][c] = fma(gg[e2], v[i2][e2][c], acc[e][c]);
+          }
+        }
+#pragma unroll
+        for (int off = L / 2; off > 0; off >>= 1)
+#pragma unroll
+          for (int e = 0; e < VEC; ++e)
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[e][c] += __shfl_xor_sync(0xffffffffu, acc[e][c], off);
+        // ---- phase 2: the owner applies the rows in order ----
+        if (lane_l == lo) {
+          T w[VEC][C], d[VEC][C];
+#define NNFAC_COPY_IN(S)                                        \
+  if (S < NCH) {                                                \
+    _Pragma("unroll") for (int e = 0; e < VEC; ++e)             \
+      _Pragma("unroll") for (int c = 0; c < C; ++c) w[e][c] = v[S < NCH ? S : 0][e][c]; \
+  }
+          NNFAC_SLOT_CASES(NNFAC_COPY_IN)
+#undef NNFAC_COPY_IN
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            const int k = k0 + e;
+            const T dk = diag[k];
+            if (k < r && dk != T(0)) {
+              T bk[C];
+              if (a.slab_ld > 0) {
+                const T* bp = bs + k * a.slab_ld + gid * C;
+                if (C * sizeof(T) == 16) {
+                  const V4 qv = *reinterpret_cast<const V4*>(bp);
+                  const T* qq = reinterpret_cast<const T*>(&qv);
+#pragma unroll
+                  for (int c = 0; c < C; ++c) bk[c] = qq[c];
+                } else {
+#pragma unroll
+                  for (int c = 0; c < C; ++c) bk[c] = bp[c];
+                }
+              } else {
+                const T* bp = a.b + (int64_t)k * a.ld_b + col0;
+#pragma unroll
+                for (int c = 0; c < C; ++c) bk[c] = (col0 + c < a.n) ? bp[c] : T(0);
+              }
+              // in-chunk corrections: rows k0 .. k-1 of this chunk have already moved by d
+              T gk[VEC];
+              {
+                const V4 g4 = *reinterpret_cast<const V4*>(Gs + k * RP + k0);
+                const T* gg = reinterpret_cast<const T*>(&g4);
+#pragma unroll
+                for (int e2 = 0; e2 < VEC; ++e2) gk[e2] = gg[e2];
+              }
+#pragma unroll
+              for (int c = 0; c < C; ++c) {
+                T s = acc[e][c];
+#pragma unroll
+                for (int e2 = 0; e2 < VEC; ++e2)
+                  if (e2 < e) s = fma(gk[e2], d[e2][c], s);
+                const T cur = w[e][c];
+                T dd = (bk[c] - s - a.sp) / dk;
+                dd = dd > -cur ? dd : -cur;
+                if (col0 + c >= a.n) dd = T(0);
+                w[e][c] = cur + dd;
+                d[e][c] = dd;
+                nd = fma(dd, dd, nd);
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < C; ++c) d[e][c] = T(0);
+            }
+          }
+#define NNFAC_COPY_OUT(S)                                       \
+  if (S < NCH) {                                                \
+    _Pragma("unroll") for (int e = 0; e < VEC; ++e)             \
+      _Pragma("unroll") for (int c = 0; c < C; ++c) v[S < NCH ? S : 0][e][c] = w[e][c]; \
+  }
+          NNFAC_SLOT_CASES(NNFAC_COPY_OUT)
+#undef NNFAC_COPY_OUT
+        }
+      }
+      if (!single) store_v(col0);
+    }
+    double tot = block_sum((double)nd, sh), dummy = 0.0;
+    grid_reduce(tot, dummy, a.part, a.counter, epoch, sh);
+    if (cnt == 1) eps0 = tot;
+    eps = tot;
+    ++cnt;
+    if (tot == 0.0) {
+      if (cnt < a.maxiter + 1) cnt = a.maxiter + 1;
+      break;
+    }
+  }
+  if (single) store_v(col_of(0));
+  if (blockIdx.x == 0 && t == 0) {
+    a.result[0] = eps;
+    a.result[1] = (double)cnt;
+    a.result[2] = -1.0;
+    a.result[3] = (double)(cnt - 1);
+  }
+}
+
 template <typename T, int RP, int L, int C, bool ROWOPS, int MAXT>
 int launch(nnfac_ctx* ctx, SweepArgs<T> a, cudaStream_t st) {
-  auto kern = hals_sweep_kernel<T, RP, L, C, ROWOPS, MAXT>;
-  const size_t smem = (size_t)(RP * RP + RP) * sizeof(T) + 40 * sizeof(double);
-  NNFAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void (*kern)(SweepArgs<T>) = hals_sweep_kernel<T, RP, L, C, true, MAXT>;
+  if (!ROWOPS) kern = hals_sweep_chunked_kernel<T, RP, L, C, MAXT>;
+  const size_t smem_base = (size_t)(RP * RP + RP) * sizeof(T) + 40 * sizeof(double);
   int per_sm = 0;
-  NNFAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MAXT, smem));
+  NNFAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_base));
+  NNFAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MAXT, smem_base));
   if (per_sm < 1) {
     nnfac_set_error("hals sweep kernel <RP=%d,L=%d,C=%d> does not fit on an SM", RP, L, C);
     return NNFAC_ERR_UNSUPPORTED;
@@ -295,6 +532,15 @@ int launch(nnfac_ctx* ctx, SweepArgs<T> a, cudaStream_t st) {
     return NNFAC_ERR_UNSUPPORTED;
   }
   a.nbatch = nbatch;
+  // UtM slice in shared memory when it fits next to the Gram (single batch only)
+  size_t smem = smem_base;
+  a.slab_ld = 0;
+  if (nbatch == 1) {
+    const int64_t slab_ld = (threads / L) * (int64_t)C;     // multiple of C, so 16-byte rows stay aligned
+    const size_t slab = (size_t)a.r * slab_ld * sizeof(T);
+    if (smem_base + slab <= (size_t)200 * 1024) { a.slab_ld = (int)slab_ld; smem += slab; }
+  }
+  NNFAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if ((size_t)(4 * grid) > ctx->red_count) {
     nnfac_set_error("hals_nnls: barrier scratch too small");
     return NNFAC_ERR_UNSUPPORTED;

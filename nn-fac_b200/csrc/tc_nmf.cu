@@ -1,0 +1,414 @@
+// fp32 headline path for NMF: X resident in HBM as bf16 hi/lo planes (4 bytes per element, the
+// same HBM bytes as fp32, ~17 mantissa bits) in BOTH orientations, so that each of the two
+// X passes of an outer iteration streams K-major tiles through TMA into tcgen05.mma.
+//
+//   cross(which=0):  VMt (r x m) = V  X^T   (nmf.py:408)   contraction over n, planes of X   [m x n]
+//   cross(which=1):  UtM (r x n) = U^T X    (nmf.py:433)   contraction over m, planes of X^T [n x m]
+//
+// Each product runs as 3 bf16 MMAs (hi*hi + lo*hi + hi*lo) with fp32 accumulation in TMEM; the
+// dropped lo*lo term is 2^-18 relative.  Work is cut into units of (128 rows of the X plane) x
+// (a fixed range of the contraction axis); every unit writes its own fp32 partial, and a
+// fixed-order reduction sums the partials, so results are deterministic.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+#include <stdlib.h>
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int TILE_ROWS = 128;   // UMMA M
+constexpr int BK = 64;           // bf16 elements per 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NTHREADS = 256;    // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows x cols] (leading dimension ld elements), box = box_rows x 64, 128B swizzle.
+int make_map(CUtensorMap* map, const bf16* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { nnfac_set_error("cuTensorMapEncodeTiled is not available from the driver"); return NNFAC_ERR_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(bf16)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) { nnfac_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)rc); return NNFAC_ERR_CUDA; }
+  return NNFAC_OK;
+}
+
+// ---- ingest: fp32 -> bf16 hi/lo planes ----------------------------------------------------------
+__global__ void split_planes_kernel(const float* __restrict__ in, int64_t ld_in, int64_t rows, int64_t cols,
+                                    bf16* __restrict__ hi, bf16* __restrict__ lo, int64_t ld_out) {
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, c = i % cols;
+    bf16 h, l;
+    tc::split_bf16(in[r * ld_in + c], h, l);
+    hi[r * ld_out + c] = h;
+    lo[r * ld_out + c] = l;
+  }
+}
+
+// out planes hold in^T: hiT/loT are [cols x rows] with leading dimension ld_out
+__global__ void split_planes_transposed_kernel(const float* __restrict__ in, int64_t ld_in, int64_t rows, int64_t cols,
+                                               bf16* __restrict__ hiT, bf16* __restrict__ loT, int64_t ld_out) {
+  __shared__ float tile[32][33];
+  const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? in[r * ld_in + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) {
+      bf16 h, l;
+      tc::split_bf16(tile[threadIdx.x][i], h, l);
+      hiT[c * ld_out + r] = h;
+      loT[c * ld_out + r] = l;
+    }
+  }
+}
+
+// ---- the cross-product kernel --------------------------------------------------------------------
+struct CrossParams {
+  int r_pad;            // UMMA N (multiple of 16)
+  int splits;           // S: contraction ranges per row tile
+  int stages_per_unit;  // 64-wide k-blocks per unit
+  int num_units;        // row_tiles * splits
+  int num_stages;       // smem ring depth
+  int drain;            // stages per TMEM accumulation chain (the tensor core accumulates with truncation)
+  int64_t ld_partial;   // row pitch of the partial buffer (multiple of 128)
+  float* partial;       // [splits][r_pad][ld_partial]
+};
+
+template <int MAX_RPAD>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_cross_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                const __grid_constant__ CUtensorMap map_fh, const __grid_constant__ CUtensorMap map_fl,
+                const CrossParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t x_bytes = TILE_ROWS * BK * sizeof(bf16);        // 16 KiB
+  const uint32_t f_bytes = (uint32_t)p.r_pad * BK * sizeof(bf16);
+  const uint32_t stage_bytes = 2 * x_bytes + 2 * f_bytes;
+  uint8_t* ring = smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.num_stages * stage_bytes);
+  uint64_t* empty = full + p.num_stages;
+  uint64_t* acc_full = empty + p.num_stages;   // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const uint32_t acc_cols = (uint32_t)p.r_pad;  // fp32 accumulator columns per buffer
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&map_xh); tc::prefetch_tmap(&map_xl); tc::prefetch_tmap(&map_fh); tc::prefetch_tmap(&map_fl);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.num_stages; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc(tmem_slot, tmem_cols);
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    int stage = 0; uint32_t phase = 0;
+    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      const int tile = u / p.splits, split = u % p.splits;
+      const int row0 = tile * TILE_ROWS;
+      const int k0 = split * p.stages_per_unit * BK;
+      for (int ks = 0; ks < p.stages_per_unit; ++ks) {
+        tc::mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* st = ring + (size_t)stage * stage_bytes;
+        tc::mbar_arrive_expect_tx(&full[stage], stage_bytes);
+        const int c = k0 + ks * BK;
+        tc::tma_load_2d_hint(st, &map_xh, &full[stage], c, row0, tc::kEvictFirst);
+        tc::tma_load_2d_hint(st + x_bytes, &map_xl, &full[stage], c, row0, tc::kEvictFirst);
+        tc::tma_load_2d_hint(st + 2 * x_bytes, &map_fh, &full[stage], c, 0, tc::kEvictLast);
+        tc::tma_load_2d_hint(st + 2 * x_bytes + f_bytes, &map_fl, &full[stage], c, 0, tc::kEvictLast);
+        if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    // The tensor core adds into the fp32 accumulator with truncation, so a long chain drifts low
+    // (measured: -1.9e-5 relative over 768 accumulations).  Chains are therefore cut every
+    // `drain` stages; the epilogue warps sum the chain results in registers (round-to-nearest).
+    const uint32_t idesc = tc::umma_idesc_bf16(TILE_ROWS, p.r_pad);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      for (int ks0 = 0; ks0 < p.stages_per_unit; ks0 += p.drain) {
+        tc::mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc::tcgen05_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)acc * acc_cols;
+        const int ks1 = ks0 + p.drain < p.stages_per_unit ? ks0 + p.drain : p.stages_per_unit;
+        for (int ks = ks0; ks < ks1; ++ks) {
+          tc::mbar_wait(&full[stage], phase);
+          tc::tcgen05_fence_after();
+          const uint32_t st = tc::smem_u32(ring + (size_t)stage * stage_bytes);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint32_t koff = k * UMMA_K * sizeof(bf16);   // 32 B inside the 128 B swizzle row
+            const uint64_t xh = tc::umma_desc_k_sw128(st + koff);
+            const uint64_t xl = tc::umma_desc_k_sw128(st + x_bytes + koff);
+            const uint64_t fh = tc::umma_desc_k_sw128(st + 2 * x_bytes + koff);
+            const uint64_t fl = tc::umma_desc_k_sw128(st + 2 * x_bytes + f_bytes + koff);
+            tc::umma_bf16(d, xh, fh, idesc, (ks != ks0) || (k != 0));
+            tc::umma_bf16(d, xl, fh, idesc, true);
+            tc::umma_bf16(d, xh, fl, idesc, true);
+          }
+          tc::umma_commit(&empty[stage]);                      // frees the smem slot when the MMAs retire
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+        tc::umma_commit(&acc_full[acc]);                       // chain result ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM chains -> register sums -> partial[split][k][row] (coalesced along rows) =====
+    const int q = warp & 3;                                  // TMEM lane quadrant of this warp
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      const int tile = u / p.splits, split = u % p.splits;
+      const int64_t row = (int64_t)tile * TILE_ROWS + q * 32 + lane;
+      float* out = p.partial + (int64_t)split * p.r_pad * p.ld_partial + row;
+      float sum[MAX_RPAD];
+#pragma unroll
+      for (int j = 0; j < MAX_RPAD; ++j) sum[j] = 0.f;
+      for (int ks0 = 0; ks0 < p.stages_per_unit; ks0 += p.drain) {
+        tc::mbar_wait(&acc_full[acc], acc_phase);
+        tc::tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+        for (int c0 = 0; c0 < MAX_RPAD; c0 += 16) {
+          if (c0 < p.r_pad) {
+            uint32_t v[16];
+            tc::tmem_ld16(taddr + c0, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sum[c0 + j] += __uint_as_float(v[j]);
+          }
+        }
+        tc::tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+#pragma unroll
+      for (int j = 0; j < MAX_RPAD; ++j)
+        if (j < p.r_pad) out[(int64_t)j * p.ld_partial] = sum[j];
+    }
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tmem_base, tmem_cols);
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int splits, int r, int r_pad, int64_t R,
+                                       int64_t ld_partial, float* __restrict__ out, int64_t ld_out) {
+  const int64_t total = (int64_t)r * R;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = i / R, row = i % R;
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += partial[((int64_t)sp * r_pad + k) * ld_partial + row];   // fixed order
+    out[k * ld_out + row] = s;
+  }
+}
+
+struct Side {           // one orientation of X
+  int64_t R, C, ld;     // plane is [R x C], leading dimension ld
+  bf16 *xh, *xl;        // X planes
+  bf16 *fh, *fl;        // factor planes [r_pad x ld]
+  CUtensorMap map_xh, map_xl, map_fh, map_fl;
+  CrossParams cp;
+  int grid;
+  size_t smem;
+};
+
+}  // namespace
+
+struct nnfac_nmf_plan {
+  nnfac_ctx* ctx;
+  int64_t m, n;
+  int r, r_pad;
+  Side side[2];         // [0]: planes of X (m x n), used for V X^T;  [1]: planes of X^T (n x m), used for U^T X
+  float* partial;
+  size_t partial_bytes;
+};
+
+namespace {
+
+int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+void choose_partition(int sm, int64_t R, int64_t C, int r_pad, Side* s) {
+  const int64_t tiles = ceil_div64(R, TILE_ROWS), kblocks = ceil_div64(C, BK);
+  int best_s = 1;
+  double best_eff = -1.0;
+  for (int S = 1; S <= 64; ++S) {
+    if (S > 1 && kblocks / S < 8) break;
+    const int64_t units = tiles * S;
+    const int64_t waves = ceil_div64(units, sm);
+    // efficiency of the last wave, discounted by the extra partial traffic of more splits
+    const double eff = (double)units / (double)(waves * sm) - 0.002 * S;
+    if (eff > best_eff + 1e-9) { best_eff = eff; best_s = S; }
+  }
+  s->cp.r_pad = r_pad;
+  s->cp.splits = best_s;
+  s->cp.stages_per_unit = (int)ceil_div64(kblocks, best_s);
+  s->cp.splits = (int)ceil_div64(kblocks, s->cp.stages_per_unit);
+  s->cp.num_units = (int)(tiles * s->cp.splits);
+  const size_t stage_bytes = 2 * (size_t)TILE_ROWS * BK * 2 + 2 * (size_t)r_pad * BK * 2;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 6) stages = 6;
+  if (stages < 2) stages = 2;
+  s->cp.num_stages = stages;
+  s->cp.drain = 2;
+  s->cp.ld_partial = round_up(R, TILE_ROWS);
+  s->smem = (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16;
+  s->grid = s->cp.num_units < sm ? s->cp.num_units : sm;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nnfac_nmf_plan_destroy(nnfac_nmf_plan* p) {
+  if (!p) return NNFAC_OK;
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(p->side[i].xh); cudaFree(p->side[i].xl); cudaFree(p->side[i].fh); cudaFree(p->side[i].fl);
+  }
+  cudaFree(p->partial);
+  free(p);
+  return NNFAC_OK;
+}
+
+int nnfac_nmf_plan_create(nnfac_ctx* ctx, int64_t m, int64_t n, int r, nnfac_nmf_plan** out) {
+  NNFAC_ARG(ctx && out && m > 0 && n > 0 && r > 0, "nnfac_nmf_plan_create: bad argument");
+  if (r > 128) { nnfac_set_error("nnfac_nmf_plan_create: rank %d > 128 is not covered by the tensor-core path", r); return NNFAC_ERR_UNSUPPORTED; }
+  if (m >= (1ll << 31) - 256 || n >= (1ll << 31) - 256) { nnfac_set_error("nnfac_nmf_plan_create: dimension too large"); return NNFAC_ERR_UNSUPPORTED; }
+  nnfac_nmf_plan* p = (nnfac_nmf_plan*)calloc(1, sizeof(nnfac_nmf_plan));
+  if (!p) return NNFAC_ERR_ALLOC;
+  p->ctx = ctx; p->m = m; p->n = n; p->r = r;
+  p->r_pad = (int)round_up(r, 16);
+  size_t partial_bytes = 0;
+  for (int i = 0; i < 2; ++i) {
+    Side* s = &p->side[i];
+    s->R = i == 0 ? m : n;
+    s->C = i == 0 ? n : m;
+    s->ld = round_up(s->C, 64);
+    const size_t xb = (size_t)s->R * s->ld * sizeof(bf16), fb = (size_t)p->r_pad * s->ld * sizeof(bf16);
+    if (cudaMalloc(&s->xh, xb) != cudaSuccess || cudaMalloc(&s->xl, xb) != cudaSuccess ||
+        cudaMalloc(&s->fh, fb) != cudaSuccess || cudaMalloc(&s->fl, fb) != cudaSuccess) {
+      cudaGetLastError();
+      nnfac_set_error("nnfac_nmf_plan_create: out of device memory (%zu bytes per X plane)", xb);
+      nnfac_nmf_plan_destroy(p);
+      return NNFAC_ERR_ALLOC;
+    }
+    cudaMemset(s->fh, 0, fb);
+    cudaMemset(s->fl, 0, fb);
+    choose_partition(ctx->sm_count, s->R, s->C, p->r_pad, s);
+    int rc = make_map(&s->map_xh, s->xh, s->R, s->C, s->ld, TILE_ROWS);
+    if (!rc) rc = make_map(&s->map_xl, s->xl, s->R, s->C, s->ld, TILE_ROWS);
+    if (!rc) rc = make_map(&s->map_fh, s->fh, p->r_pad, s->C, s->ld, p->r_pad);
+    if (!rc) rc = make_map(&s->map_fl, s->fl, p->r_pad, s->C, s->ld, p->r_pad);
+    if (rc) { nnfac_nmf_plan_destroy(p); return rc; }
+    const size_t pb = (size_t)s->cp.splits * p->r_pad * s->cp.ld_partial * sizeof(float);
+    if (pb > partial_bytes) partial_bytes = pb;
+    cudaError_t e = p->r_pad <= 64
+        ? cudaFuncSetAttribute(tc_cross_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem)
+        : cudaFuncSetAttribute(tc_cross_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem);
+    if (e != cudaSuccess) { nnfac_set_error("cudaFuncSetAttribute(smem=%zu): %s", s->smem, cudaGetErrorString(e)); nnfac_nmf_plan_destroy(p); return NNFAC_ERR_CUDA; }
+  }
+  if (cudaMalloc(&p->partial, partial_bytes) != cudaSuccess) {
+    cudaGetLastError();
+    nnfac_set_error("nnfac_nmf_plan_create: out of device memory (partials)");
+    nnfac_nmf_plan_destroy(p);
+    return NNFAC_ERR_ALLOC;
+  }
+  p->partial_bytes = partial_bytes;
+  *out = p;
+  return NNFAC_OK;
+}
+
+int nnfac_nmf_plan_load_x(nnfac_nmf_plan* p, const float* X, int64_t ldx, void* stream) {
+  NNFAC_ARG(p && X && ldx >= p->n, "nnfac_nmf_plan_load_x: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = p->m * p->n;
+  int grid = (int)(ceil_div64(total, 256) < (int64_t)p->ctx->sm_count * 32 ? ceil_div64(total, 256) : (int64_t)p->ctx->sm_count * 32);
+  split_planes_kernel<<<grid, 256, 0, st>>>(X, ldx, p->m, p->n, p->side[0].xh, p->side[0].xl, p->side[0].ld);
+  NNFAC_LAUNCH_CHECK(p->ctx);
+  NNFAC_ARG(ceil_div64(p->m, 32) <= 65535 * 32ll, "nnfac_nmf_plan_load_x: too many rows");
+  // grid.y is limited to 65535 blocks of 32 rows: walk the rows in slabs
+  const int64_t slab = 65535ll * 32;
+  for (int64_t r0 = 0; r0 < p->m; r0 += slab) {
+    const int64_t rows = p->m - r0 < slab ? p->m - r0 : slab;
+    dim3 g((unsigned)ceil_div64(p->n, 32), (unsigned)ceil_div64(rows, 32)), b(32, 8);
+    split_planes_transposed_kernel<<<g, b, 0, st>>>(X + r0 * ldx, ldx, rows, p->n, p->side[1].xh + r0, p->side[1].xl + r0,
+                                                    p->side[1].ld);
+    NNFAC_LAUNCH_CHECK(p->ctx);
+  }
+  return NNFAC_OK;
+}
+
+int nnfac_nmf_plan_cross(nnfac_nmf_plan* p, int which, const float* F, int64_t ldf, float* out, int64_t ld_out,
+                         void* stream) {
+  NNFAC_ARG(p && F && out && (which == 0 || which == 1), "nnfac_nmf_plan_cross: bad argument");
+  Side* s = &p->side[which];
+  NNFAC_ARG(ldf >= s->C && ld_out >= s->R, "nnfac_nmf_plan_cross: leading dimension too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = (int64_t)p->r * s->C;
+  int grid = (int)(ceil_div64(total, 256) < (int64_t)p->ctx->sm_count * 8 ? ceil_div64(total, 256) : (int64_t)p->ctx->sm_count * 8);
+  split_planes_kernel<<<grid, 256, 0, st>>>(F, ldf, p->r, s->C, s->fh, s->fl, s->ld);
+  NNFAC_LAUNCH_CHECK(p->ctx);
+  CrossParams cp = s->cp;
+  cp.partial = p->partial;
+  if (p->r_pad <= 64)
+    tc_cross_kernel<64><<<s->grid, NTHREADS, s->smem, st>>>(s->map_xh, s->map_xl, s->map_fh, s->map_fl, cp);
+  else
+    tc_cross_kernel<128><<<s->grid, NTHREADS, s->smem, st>>>(s->map_xh, s->map_xl, s->map_fh, s->map_fl, cp);
+  NNFAC_LAUNCH_CHECK(p->ctx);
+  const int64_t tot2 = (int64_t)p->r * s->R;
+  grid = (int)(ceil_div64(tot2, 256) < (int64_t)p->ctx->sm_count * 8 ? ceil_div64(tot2, 256) : (int64_t)p->ctx->sm_count * 8);
+  reduce_partials_kernel<<<grid, 256, 0, st>>>(p->partial, cp.splits, p->r, p->r_pad, s->R, cp.ld_partial, out, ld_out);
+  NNFAC_LAUNCH_CHECK(p->ctx);
+  return NNFAC_OK;
+}
+
+int nnfac_nmf_plan_info(const nnfac_nmf_plan* p, int which, int* splits, int* stages_per_unit, int* num_units,
+                        int* num_stages, int* grid) {
+  NNFAC_ARG(p && (which == 0 || which == 1), "nnfac_nmf_plan_info: bad argument");
+  const Side* s = &p->side[which];
+  if (splits) *splits = s->cp.splits;
+  if (stages_per_unit) *stages_per_unit = s->cp.stages_per_unit;
+  if (num_units) *num_units = s->cp.num_units;
+  if (num_stages) *num_stages = s->cp.num_stages;
+  if (grid) *grid = s->grid;
+  return NNFAC_OK;
+}
+
+}  // extern "C"

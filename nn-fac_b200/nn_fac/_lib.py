@@ -40,6 +40,12 @@ SIGNATURES = {
     "nnfac_khatri_rao": [_P, _INT, _P, _P, _I64, _P, _I64, _I64, _P],
     "nnfac_hadamard": [_P, _INT, _P, _P, _P, _I64, _P],
     "nnfac_normalize_rows": [_P, _INT, _P, _I64, _I64, _I64, _P],
+    "nnfac_nmf_plan_create": [_P, _I64, _I64, _INT, _c.POINTER(_P)],
+    "nnfac_nmf_plan_destroy": [_P],
+    "nnfac_nmf_plan_load_x": [_P, _P, _I64, _P],
+    "nnfac_nmf_plan_cross": [_P, _INT, _P, _I64, _P, _I64, _P],
+    "nnfac_nmf_plan_info": [_P, _INT, _c.POINTER(_INT), _c.POINTER(_INT), _c.POINTER(_INT), _c.POINTER(_INT),
+                            _c.POINTER(_INT)],
 }
 _RESTYPES = {"nnfac_last_error": _c.c_char_p, "nnfac_ctx_launch_count": _I64}
 

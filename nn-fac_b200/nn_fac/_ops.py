@@ -196,3 +196,48 @@ def unfold_times(P, B, mode):
     if right == 1:
         return gemm(P, (1, I, 0, 0), B, (R, 1, 0, 0), I, R, left)
     return gemm(P, (right, 1, I * right, 0), B, (1, right, R * right, 0), I, R, right, kb=left)
+
+
+class NMFPlan:
+    """Owner of an nnfac_nmf_plan (X resident as bf16 hi/lo planes in both orientations; tcgen05 path)."""
+
+    def __init__(self, X):
+        import ctypes
+        assert X.dtype == torch.float32 and X.dim() == 2
+        self.m, self.n = X.shape
+        self.device = X.device
+        self.handle = ctypes.c_void_p()
+        self.r = None
+        self._X = X
+
+    def bind_rank(self, r):
+        import ctypes
+        self.r = r
+        L.check(_lib().nnfac_nmf_plan_create(L.ctx(self.device), self.m, self.n, r, ctypes.byref(self.handle)))
+        L.check(_lib().nnfac_nmf_plan_load_x(self.handle, L.ptr(self._X), self._X.stride(0), L.stream_ptr()))
+        self._X = None
+        return self
+
+    def cross(self, which, F, out=None):
+        """which=0: F = V (r x n) -> V X^T (r x m); which=1: F = U^T (r x m) -> U^T X (r x n)."""
+        R = self.m if which == 0 else self.n
+        if out is None:
+            out = torch.empty((self.r, R), dtype=torch.float32, device=self.device)
+        L.check(_lib().nnfac_nmf_plan_cross(self.handle, which, L.ptr(F), F.stride(0), L.ptr(out), out.stride(0),
+                                            L.stream_ptr()))
+        return out
+
+    def info(self, which):
+        import ctypes
+        vals = [ctypes.c_int() for _ in range(5)]
+        L.check(_lib().nnfac_nmf_plan_info(self.handle, which, *[ctypes.byref(v) for v in vals]))
+        return dict(zip(("splits", "stages_per_unit", "num_units", "num_stages", "grid"), [v.value for v in vals]))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                torch.cuda.synchronize(self.device)
+                _lib().nnfac_nmf_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

@@ -93,6 +93,8 @@ class DeviceNMF:
         self.m, self.n = self.X.shape
         self.r = self.U.shape[1]
         self.scal = torch.zeros(8, dtype=torch.float64, device=self.X.device)
+        # fp32: X also lives as bf16 hi/lo planes in both orientations for the tcgen05 X passes
+        self.plan = ops.NMFPlan(self.X).bind_rank(self.r) if (dtype == torch.float32 and self.r <= 128) else None
         self.hals_stats = torch.zeros((2, 4), dtype=torch.float64, device=self.X.device)
 
     # -- HALS -----------------------------------------------------------------------------------
@@ -102,7 +104,10 @@ class DeviceNMF:
             V = self.V
             with _Phase(self, "cross_U"):
                 VVt = ops.gemm(V, (n, 1), V, (1, n), r, r, n)              # nmf.py:407
-                VMt = ops.gemm(V, (n, 1), X, (1, n), r, m, n)              # nmf.py:408 (V X^T, r x m)
+                if self.plan is not None:
+                    VMt = self.plan.cross(0, V)                            # nmf.py:408 on tcgen05
+                else:
+                    VMt = ops.gemm(V, (n, 1), X, (1, n), r, m, n)          # nmf.py:408 (V X^T, r x m)
             with _Phase(self, "sweep_U"):
                 Ut = ops.transpose(self.U)
                 nnls.hals_nnls_device(VMt, VVt, Ut, r, maxiter=100, delta=0.01, sparsity_coefficient=sparsity[0],
@@ -115,7 +120,10 @@ class DeviceNMF:
             Ut = self.Ut
             with _Phase(self, "cross_V"):
                 UtU = ops.gemm(Ut, (m, 1), Ut, (1, m), r, r, m)            # nmf.py:432
-                UtM = ops.gemm(Ut, (m, 1), X, (n, 1), r, n, m)             # nmf.py:433
+                if self.plan is not None:
+                    UtM = self.plan.cross(1, Ut)                           # nmf.py:433 on tcgen05
+                else:
+                    UtM = ops.gemm(Ut, (m, 1), X, (n, 1), r, n, m)         # nmf.py:433
             with _Phase(self, "sweep_V"):
                 nnls.hals_nnls_device(UtM, UtU, self.V, r, maxiter=100, delta=0.01, sparsity_coefficient=sparsity[1],
                                       normalize=normalize[1], nonzero=False, result=self.hals_stats[1])  # nmf.py:440
