@@ -1,10 +1,16 @@
 // C-ABI entry of the HALS NNLS solver; dispatches on dtype and padded rank.
 #include "hals_sweep.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 #define DECL(tag, T, rp) int nnfac_sweep_##tag##_##rp(nnfac_ctx*, hals::SweepArgs<T>, cudaStream_t);
 DECL(f32, float, 16) DECL(f32, float, 32) DECL(f32, float, 64) DECL(f32, float, 128)
 DECL(f64, double, 16) DECL(f64, double, 32) DECL(f64, double, 64) DECL(f64, double, 128)
 #undef DECL
+
+int nnfac_tc_sweep_try(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const float* UtU, int64_t ld_utu, float* V,
+                       int64_t ld_v, int r, int64_t n, int maxiter, double delta, double sparsity, double* result,
+                       cudaStream_t st);
 
 namespace {
 template <typename T>
@@ -33,6 +39,15 @@ extern "C" int nnfac_hals_nnls(nnfac_ctx* ctx, int dtype, const void* UtM, int64
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int rp = r <= 16 ? 16 : r <= 32 ? 32 : r <= 64 ? 64 : 128;
+  if (dtype == NNFAC_F32 && flags == 0) {
+    // tensor-core blocked sweep when the shape fits (rank <= 64, n <= 512 columns per SM); NNFAC_SWEEP=fma disables it
+    static const bool force_fma = getenv("NNFAC_SWEEP") && !strcmp(getenv("NNFAC_SWEEP"), "fma");
+    if (!force_fma) {
+      const int rc = nnfac_tc_sweep_try(ctx, (const float*)UtM, ld_utm, (const float*)UtU, ld_utu, (float*)V, ld_v, r, n,
+                                        maxiter, delta, sparsity, result, st);
+      if (rc != NNFAC_ERR_UNSUPPORTED) return rc;
+    }
+  }
   if (dtype == NNFAC_F32) {
     auto a = make_args<float>(UtM, ld_utm, UtU, ld_utu, V, ld_v, r, n, maxiter, delta, sparsity, flags, result);
     switch (rp) {

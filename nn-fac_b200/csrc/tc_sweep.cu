@@ -1,0 +1,356 @@
+// Tensor-core HALS sweep (fp32 path, rank <= 64): blocked Gauss-Seidel that reproduces the exact
+// row-by-row recurrence of nn_fac/update_rules/nnls.py:158-170.
+//
+// For a block of 16 rows the reference's dot products UtU[k,:] @ V split into
+//   (a) the part against V as it stood when the block started  -> one [128 cols x 64] x [64 x 16]
+//       product per column tile on tcgen05 (bf16 hi/lo split, 3 MMAs per k-step, fp32 in TMEM), and
+//   (b) the in-block corrections UtU[k,k'] * dV[k'] for k' < k   -> 120 FMAs per column whose Gram
+//       operands come from __constant__ memory (they are the same for every column).
+// That removes ~7/8 of the FP32-FMA work of the plain sweep and all of its shared-memory operand
+// traffic.  One thread owns one column of V: 64 fp32 master values in registers for the whole
+// call, UtM for that column parked in TMEM, the bf16 operand planes of V in shared memory
+// (rewritten 16 rows at a time after each block).  A CTA carries up to 4 column tiles whose
+// MMA / update phases interleave.  The per-sweep stop test is the same fixed-order grid reduction
+// as the FMA kernel (deterministic, identical on every CTA).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int RP = 64;            // padded rank (K extent of the MMA, rows of the register tile)
+constexpr int BLK = 16;           // rows per Gauss-Seidel block (UMMA N)
+constexpr int NBLK = RP / BLK;
+constexpr int TILE = 128;         // columns per tile (UMMA M)
+constexpr int MAX_TILES = 4;
+constexpr int UPD_THREADS = MAX_TILES * TILE;   // 512
+constexpr int NTHREADS = UPD_THREADS;
+constexpr int TMEM_PER_TILE = 128;              // 64 columns UtM + 4 x 16 columns of block dot products
+constexpr uint32_t PLANE_BYTES = TILE * RP * sizeof(bf16);   // 16 KiB
+constexpr uint32_t G_PLANE_BYTES = RP * RP * sizeof(bf16);   // 8 KiB
+constexpr uint32_t G_BLOCK_BYTES = 3 * BLK * 128;             // per block: 16 rows hi, 16 mid, 16 lo
+constexpr int NPLANES = 3;
+
+struct SweepConst {
+  float gblk[NBLK][BLK][BLK];   // diagonal blocks of UtU
+  float invd[RP];               // 1 / UtU[k][k], 0 when the diagonal entry is 0 or k >= r
+};
+__constant__ SweepConst c_sw;
+
+__global__ void sweep_prep_kernel(const float* __restrict__ G, int64_t ld_g, int r, SweepConst* out) {
+  for (int idx = threadIdx.x; idx < NBLK * BLK * BLK; idx += blockDim.x) {
+    const int B = idx / (BLK * BLK), e = (idx / BLK) % BLK, e2 = idx % BLK;
+    const int k = B * BLK + e, l = B * BLK + e2;
+    out->gblk[B][e][e2] = (k < r && l < r) ? G[(int64_t)k * ld_g + l] : 0.f;
+  }
+  for (int k = threadIdx.x; k < RP; k += blockDim.x) {
+    const float d = k < r ? G[(int64_t)k * ld_g + k] : 0.f;
+    out->invd[k] = d != 0.f ? 1.f / d : 0.f;
+  }
+}
+
+struct TcSweepArgs {
+  const float* b;   // UtM r x n
+  const float* G;   // UtU r x r
+  float* V;         // r x n, in place
+  int64_t ld_b, ld_g, ld_v, n;
+  int r, maxiter, cols_per_cta;
+  double delta;
+  float sp;
+  double* part;
+  unsigned* counter;
+  double* result;
+};
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);   // .x = a (low half), .y = b
+  return *reinterpret_cast<const uint32_t*>(&p);
+}
+
+// Write 8 consecutive K-elements (one 16-byte chunk) of row `row` into the three K-major SW128 planes
+// (hi, mid, lo: x = hi + mid + lo to ~2^-24, i.e. fp32 operands for the tensor core).
+__device__ __forceinline__ void store_chunk(uint8_t* plane_hi, int row, int chunk, const float* x, uint32_t plane_stride) {
+  uint32_t h[4], m[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = x[2 * i], b = x[2 * i + 1];
+    const float ah = __bfloat162float(__float2bfloat16_rn(a)), bh = __bfloat162float(__float2bfloat16_rn(b));
+    const float a1 = a - ah, b1 = b - bh;
+    const float am = __bfloat162float(__float2bfloat16_rn(a1)), bm = __bfloat162float(__float2bfloat16_rn(b1));
+    h[i] = pack_bf16(ah, bh);
+    m[i] = pack_bf16(am, bm);
+    l[i] = pack_bf16(a1 - am, b1 - bm);
+  }
+  uint8_t* p = plane_hi + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+  *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(p + plane_stride) = make_uint4(m[0], m[1], m[2], m[3]);
+  *reinterpret_cast<uint4*>(p + 2 * plane_stride) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Issue the tensor-core part of block B for one tile.  Operands are 3-term bf16 splits; six of the
+// nine partial products are kept (the dropped ones are below 2^-24):
+//   cols [0,48)  : V_hi  x [G_hi ; G_mid ; G_lo]   (N = 48)
+//   cols [0,32)  : V_mid x [G_hi ; G_mid]          (N = 32, accumulated on top)
+//   cols [48,64) : V_lo  x  G_hi                   (N = 16, independent chain)
+// The update threads add the four 16-column groups.
+__device__ __forceinline__ void issue_block_mma(uint64_t a_hi, uint64_t a_mid, uint64_t a_lo, uint64_t g_blk, uint32_t d,
+                                                int nks, uint32_t idesc48, uint32_t idesc32, uint32_t idesc16,
+                                                uint64_t* bar) {
+  for (int ks = 0; ks < nks; ++ks) {
+    const uint64_t koff = (uint64_t)(ks * 2);                 // 32 bytes >> 4 inside the 128-byte row
+    tc::umma_bf16(d, a_hi + koff, g_blk + koff, idesc48, ks != 0);
+    tc::umma_bf16(d + 48, a_lo + koff, g_blk + koff, idesc16, ks != 0);
+    tc::umma_bf16(d, a_mid + koff, g_blk + koff, idesc32, true);
+  }
+  tc::umma_commit(bar);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* g_planes = smem;                                            // per block: 16 rows hi, 16 mid, 16 lo (6 KiB)
+  uint8_t* v_planes = smem + NPLANES * G_PLANE_BYTES;                  // [tile][hi|mid|lo][16 KiB]
+  uint8_t* tail = v_planes + (size_t)MAX_TILES * NPLANES * PLANE_BYTES;
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(tail);                // [MAX_TILES]
+  double* red = reinterpret_cast<double*>(s_full + MAX_TILES);         // [24]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(red + 24);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = a.r;
+  const int nblk = (r + BLK - 1) / BLK;
+  const int64_t cta_col0 = (int64_t)blockIdx.x * a.cols_per_cta;
+  int64_t cta_cols = a.n - cta_col0;
+  if (cta_cols > a.cols_per_cta) cta_cols = a.cols_per_cta;
+  const int ntiles = (int)((cta_cols + TILE - 1) / TILE);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int t = 0; t < MAX_TILES; ++t) tc::mbar_init(&s_full[t], 1);
+      tc::fence_barrier_init();
+    }
+    __syncwarp();
+    tc::tmem_alloc(tmem_slot, 512);
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // one thread per column; 4 warps (= 128 TMEM lanes) per tile; the first lane of a tile issues its MMAs
+  const int tile = warp >> 2, q = warp & 3;
+  const bool active = tile < ntiles;
+  const bool issuer = active && q == 0 && lane == 0;
+  const int row = q * 32 + lane;                                       // row of the A tile == TMEM lane
+  const int64_t col = cta_col0 + (int64_t)tile * TILE + row;
+  const bool valid = active && (int64_t)tile * TILE + row < cta_cols;
+  uint8_t* vh = v_planes + (size_t)tile * NPLANES * PLANE_BYTES;
+  const uint32_t t_b = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile * TMEM_PER_TILE);
+  const uint32_t t_s = t_b + RP;
+  const uint32_t d_tile = tmem_base + (uint32_t)(tile * TMEM_PER_TILE + RP);
+  const uint32_t idesc48 = tc::umma_idesc_bf16(TILE, 3 * BLK), idesc32 = tc::umma_idesc_bf16(TILE, 2 * BLK),
+                 idesc16 = tc::umma_idesc_bf16(TILE, BLK);
+  const uint64_t a_hi = tc::umma_desc_k_sw128(tc::smem_u32(vh)), a_mid = tc::umma_desc_k_sw128(tc::smem_u32(vh) + PLANE_BYTES),
+                 a_lo = tc::umma_desc_k_sw128(tc::smem_u32(vh) + 2 * PLANE_BYTES);
+  const uint64_t g_desc = tc::umma_desc_k_sw128(tc::smem_u32(g_planes));
+
+  // Gram operand planes (K-major, 128B swizzle), block B at byte offset B * 4096: rows 0-15 hi, 16-31 lo
+  {
+    const int k = threadIdx.x >> 3, c = threadIdx.x & 7;
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int l = c * 8 + i;
+      x[i] = (k < r && l < r) ? a.G[(int64_t)k * a.ld_g + l] : 0.f;
+    }
+    uint8_t* blk = g_planes + (size_t)(k / BLK) * G_BLOCK_BYTES;
+    store_chunk(blk, k % BLK, c, x, BLK * 128);    // (k % 16) & 7 == k & 7: the swizzle phase is preserved
+  }
+
+  float v[RP];
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < RP; ++k) v[k] = (valid && k < r) ? a.V[(int64_t)k * a.ld_v + col] : 0.f;
+    // UtM of this column -> TMEM (stays there for the whole call)
+#pragma unroll
+    for (int c0 = 0; c0 < RP; c0 += 16) {
+      uint32_t w[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        w[j] = __float_as_uint((valid && c0 + j < r) ? a.b[(int64_t)(c0 + j) * a.ld_b + col] : 0.f);
+      tmem_st16(t_b + c0, w);
+    }
+    tmem_st_wait();
+#pragma unroll
+    for (int c = 0; c < RP / 8; ++c) store_chunk(vh, row, c, &v[c * 8], PLANE_BYTES);
+  }
+  tc::fence_proxy_async_smem();
+  tc::tcgen05_fence_before();
+  named_bar_sync(1, UPD_THREADS);                                      // Gram and V planes complete
+  if (issuer) {
+    tc::tcgen05_fence_after();
+    issue_block_mma(a_hi, a_mid, a_lo, g_desc, d_tile, nblk, idesc48, idesc32, idesc16, &s_full[tile]);
+  }
+
+  double eps0 = 0.0, eps = 1.0;
+  int cnt = 1;
+  unsigned epoch = 0;
+  uint32_t s_phase = 0;
+  while (eps >= a.delta * eps0 && cnt <= a.maxiter) {
+    float nd = 0.f;
+    if (active) {
+#pragma unroll
+      for (int B = 0; B < NBLK; ++B) {
+        if (B < nblk) {
+          tc::mbar_wait(&s_full[tile], s_phase);
+          s_phase ^= 1;
+          tc::tcgen05_fence_after();
+          uint32_t s0[16], s1[16], s2[16], s3[16], bu[16];
+          tc::tmem_ld16(t_s, s0);
+          tc::tmem_ld16(t_s + 16, s1);
+          tc::tmem_ld16(t_s + 32, s2);
+          tc::tmem_ld16(t_s + 48, s3);
+          tc::tmem_ld16(t_b + B * BLK, bu);
+          tc::tmem_ld_wait();
+          tc::tcgen05_fence_before();
+          float s[BLK];
+#pragma unroll
+          for (int e = 0; e < BLK; ++e)
+            s[e] = __uint_as_float(s0[e]) + ((__uint_as_float(s1[e]) + __uint_as_float(s3[e])) + __uint_as_float(s2[e]));
+#pragma unroll
+          for (int e = 0; e < BLK; ++e) {
+            const int k = B * BLK + e;
+            const float inv = c_sw.invd[k];
+            const float cur = v[k];
+            float dd = (__uint_as_float(bu[e]) - s[e] - a.sp) * inv;    // nnls.py:163/167 (reciprocal multiply)
+            dd = fmaxf(dd, -cur);
+            dd = (inv != 0.f && valid) ? dd : 0.f;                      // zero diagonal: row skipped (nnls.py:160)
+            v[k] = cur + dd;
+            nd = fmaf(dd, dd, nd);                                      // nnls.py:170
+#pragma unroll
+            for (int e2 = e + 1; e2 < BLK; ++e2) s[e2] = fmaf(c_sw.gblk[B][e2][e], dd, s[e2]);
+          }
+          store_chunk(vh, row, 2 * B, &v[B * BLK], PLANE_BYTES);
+          store_chunk(vh, row, 2 * B + 1, &v[B * BLK + 8], PLANE_BYTES);
+          tc::fence_proxy_async_smem();
+          tc::tcgen05_fence_before();
+          named_bar_sync(2 + tile, TILE);                               // this tile's planes are rewritten
+          if (issuer) {
+            // next block (speculatively block 0 of the next sweep after the last one: its result is
+            // simply dropped if the stop test ends the solve, and it overlaps the grid reduction)
+            const int nb = (B + 1 < nblk) ? B + 1 : 0;
+            tc::tcgen05_fence_after();
+            issue_block_mma(a_hi, a_mid, a_lo, g_desc + (uint64_t)(nb * (int)G_BLOCK_BYTES >> 4), d_tile, nblk, idesc48, idesc32,
+                            idesc16, &s_full[tile]);
+          }
+        }
+      }
+    }
+    // ---- sum of squared steps over the whole grid, fixed order ----
+    double t = warp_sum((double)nd);
+    if (lane == 0) red[warp] = t;
+    named_bar_sync(1, UPD_THREADS);
+    if (threadIdx.x == 0) {
+      double sum = 0.0;
+      for (int w = 0; w < 16; ++w) sum += red[w];
+      const unsigned nb = gridDim.x;
+      if (nb > 1) {
+        double* slot = a.part + (size_t)(epoch & 1u) * nb;
+        slot[blockIdx.x] = sum;
+        __threadfence();
+        atomicAdd(a.counter, 1u);
+        const unsigned target = (epoch + 1u) * nb;
+        while (ld_relaxed_u32(a.counter) < target) {}
+        __threadfence();
+      } else {
+        red[16] = sum;
+      }
+    }
+    named_bar_sync(1, UPD_THREADS);
+    if (gridDim.x > 1) {
+      if (warp == 0) {
+        const double* slot = a.part + (size_t)(epoch & 1u) * gridDim.x;
+        double sum = 0.0;
+        for (unsigned i = lane; i < gridDim.x; i += 32) sum += __ldcg(slot + i);
+        sum = warp_sum(sum);
+        if (lane == 0) red[16] = sum;
+      }
+      named_bar_sync(1, UPD_THREADS);
+    }
+    const double tot = red[16];
+    ++epoch;
+    if (cnt == 1) eps0 = tot;
+    eps = tot;
+    ++cnt;
+    if (tot == 0.0) {                                                   // further sweeps are no-ops (nnls.py:156)
+      if (cnt < a.maxiter + 1) cnt = a.maxiter + 1;
+      break;
+    }
+  }
+  if (active) {
+    tc::mbar_wait(&s_full[tile], s_phase);                              // drain the speculative block
+    tc::tcgen05_fence_after();
+  }
+  if (valid) {
+#pragma unroll
+    for (int k = 0; k < RP; ++k)
+      if (k < r) a.V[(int64_t)k * a.ld_v + col] = v[k];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.result[0] = eps;
+    a.result[1] = (double)cnt;
+    a.result[2] = -1.0;
+    a.result[3] = (double)(cnt - 1);
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+// Returns NNFAC_ERR_UNSUPPORTED (without setting an error) when the shape is outside this kernel's
+// envelope, so that the caller can use the FMA kernel instead.
+int nnfac_tc_sweep_try(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const float* UtU, int64_t ld_utu, float* V,
+                       int64_t ld_v, int r, int64_t n, int maxiter, double delta, double sparsity, double* result,
+                       cudaStream_t st) {
+  if (r > RP || maxiter < 1) return NNFAC_ERR_UNSUPPORTED;
+  int64_t cols = ceil_div64(n, ctx->sm_count);
+  cols = ceil_div64(cols, 32) * 32;
+  if (cols > MAX_TILES * TILE) return NNFAC_ERR_UNSUPPORTED;
+  const int64_t grid = ceil_div64(n, cols);
+  static SweepConst* staging = nullptr;   // one per process is enough: calls are stream-ordered per context
+  if (!staging) NNFAC_CUDA(cudaMalloc(&staging, sizeof(SweepConst)));
+  sweep_prep_kernel<<<1, 256, 0, st>>>(UtU, ld_utu, r, staging);
+  NNFAC_LAUNCH_CHECK(ctx);
+  NNFAC_CUDA(cudaMemcpyToSymbolAsync(c_sw, staging, sizeof(SweepConst), 0, cudaMemcpyDeviceToDevice, st));
+  TcSweepArgs a;
+  a.b = UtM; a.G = UtU; a.V = V; a.ld_b = ld_utm; a.ld_g = ld_utu; a.ld_v = ld_v; a.n = n;
+  a.r = r; a.maxiter = maxiter; a.cols_per_cta = (int)cols; a.delta = delta; a.sp = (float)sparsity;
+  a.part = ctx->red; a.counter = ctx->sync; a.result = result;
+  const size_t smem = NPLANES * G_PLANE_BYTES + (size_t)MAX_TILES * NPLANES * PLANE_BYTES + 512;
+  NNFAC_CUDA(cudaFuncSetAttribute(tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NNFAC_CUDA(cudaMemsetAsync(ctx->sync, 0, sizeof(unsigned), st));
+  void* params[] = {&a};
+  NNFAC_CUDA(cudaLaunchCooperativeKernel((const void*)tc_sweep_kernel, dim3((unsigned)grid), dim3(NTHREADS), params, smem, st));
+  ctx->launches++;
+  return NNFAC_OK;
+}
