@@ -140,6 +140,17 @@ int nnfac_nmf_plan_load_x(nnfac_nmf_plan* plan, const float* X, int64_t ldx, voi
  * F and out are device fp32, row-major.  Deterministic. */
 int nnfac_nmf_plan_cross(nnfac_nmf_plan* plan, int which, const float* F, int64_t ldf, float* out,
                          int64_t ld_out, void* stream);
+/* Install a factor into the plan (builds all of its bf16 operand planes):
+ * which = 0: U, passed as U^T (r x m, row-major); which = 1: V (r x n). */
+int nnfac_nmf_plan_set_factor(nnfac_nmf_plan* plan, int which, const float* Ft, int64_t ld, void* stream);
+/* One fused X pass (rank <= 64) over side 0 (rows of X) or side 1 (rows of X^T), using the installed
+ * factors: the model tile U V is formed and consumed on chip, never written to HBM.
+ *   mode 0: out (r x rows) = the HALS cross product of nmf.py:408 / :433, cost_out = ||X - U V||_F^2 (nmf.py:452)
+ *   mode 1: out (r x rows) = the beta=1 MU numerator ((X / UV) V^T)^T of mu.py:84-88 (side 0) or its
+ *           transposed twin for V (mu.py:27, side 1); cost_out = KL(X | U V) when want_cost != 0.
+ * cost_out is a device double and may be NULL. */
+int nnfac_nmf_plan_fused(nnfac_nmf_plan* plan, int side, int mode, int want_cost, float* out, int64_t ld_out,
+                         double* cost_out, void* stream);
 /* Work decomposition chosen for one side (for benchmarks / DESIGN.md); any pointer may be NULL. */
 int nnfac_nmf_plan_info(const nnfac_nmf_plan* plan, int which, int* splits, int* stages_per_unit,
                         int* num_units, int* num_stages, int* grid);

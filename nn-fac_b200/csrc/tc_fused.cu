@@ -1,0 +1,359 @@
+// Fused X pass (rank <= 64): the model tile K = W H is formed on tcgen05, consumed in registers,
+// and never reaches HBM.
+//
+// For one 128-row tile of an X plane and each 64-column stage:
+//   GEMM-1   D1[128 x 64] = A1[128 x 64] * Fk^T          A1 = rows of the factor aligned with X's rows,
+//                                                         Fk = 64 rows of the other factor (rank contiguous)
+//   transform (8 warps)    MODE_MU  : Q = X / K  (mu.py:84), written over the X tile in shared memory;
+//                                     cost += K * ((1+d) log1p(d) - d), d = (X-K)/K   (beta_divergence.py:45-48)
+//                          MODE_RES : cost += (X - K)^2                                (nmf.py:452)
+//   GEMM-2   D2[128 x r]  += A2[128 x 64] * Fn^T          A2 = Q (MU, mu.py:88) or X (HALS cross product, nmf.py:408)
+// so one pass over X yields the contraction the update needs AND the cost of the factors it started
+// from (the reference re-forms U V in a third pass for that).  All products are bf16 hi/lo splits
+// (3 MMAs each) with fp32 accumulation in TMEM; D2 chains are cut every `drain` stages and summed in
+// registers because the tensor core accumulates with truncation.
+#include "tc_plan.cuh"
+
+namespace {
+using namespace tcplan;
+
+constexpr int FUSED_THREADS = 384;   // warp0 TMA, warp1 MMA, warp2 TMEM, warps 4-11 transform/epilogue
+constexpr int FSTAGES = 3;
+constexpr uint32_t X_BYTES = TILE_ROWS * BK * sizeof(bf16);   // 16 KiB per plane tile
+constexpr uint32_t FK_BYTES = 64 * BK * sizeof(bf16);         // 8 KiB  (64 columns of X x rank 64)
+constexpr uint32_t FN_BYTES = 64 * BK * sizeof(bf16);         // 8 KiB  (rank rows, padded to 64, x 64 columns)
+constexpr uint32_t STAGE_BYTES = 2 * X_BYTES + 2 * FK_BYTES + 2 * FN_BYTES;   // 64 KiB
+constexpr uint32_t A1_BYTES = 2 * X_BYTES;                    // 32 KiB
+constexpr int MODE_RES = 0, MODE_MU = 1;
+
+struct FusedParams {
+  int r_pad, splits, stages_per_unit, num_units, drain, want_cost;
+  int64_t ld_partial;
+  float* partial;
+  double* cost_part;
+};
+
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+template <int MODE>
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
+tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                const __grid_constant__ CUtensorMap map_fnh, const __grid_constant__ CUtensorMap map_fnl,
+                const __grid_constant__ CUtensorMap map_fkh, const __grid_constant__ CUtensorMap map_fkl,
+                const __grid_constant__ CUtensorMap map_a1h, const __grid_constant__ CUtensorMap map_a1l,
+                const FusedParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* a1 = smem;                                   // [hi | lo]
+  uint8_t* ring = smem + A1_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)FSTAGES * STAGE_BYTES);
+  uint64_t* full = bars;                 // [3]
+  uint64_t* empty = bars + 3;            // [3]  count 9: GEMM-2 commit + 8 transform warps
+  uint64_t* a2_ready = bars + 6;         // [3]  count 8
+  uint64_t* a1_full = bars + 9;
+  uint64_t* a1_empty = bars + 10;
+  uint64_t* d1_full = bars + 11;         // [2]
+  uint64_t* d1_empty = bars + 13;        // [2] count 8
+  uint64_t* d2_full = bars + 15;         // [2]
+  uint64_t* d2_empty = bars + 17;        // [2] count 8
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  double* cost_sh = reinterpret_cast<double*>(bars + 20);   // [8]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t fn_bytes = (uint32_t)p.r_pad * BK * sizeof(bf16);
+  const uint32_t stage_tx = 2 * X_BYTES + 2 * FK_BYTES + 2 * fn_bytes;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&map_xh); tc::prefetch_tmap(&map_xl); tc::prefetch_tmap(&map_fnh); tc::prefetch_tmap(&map_fnl);
+    tc::prefetch_tmap(&map_fkh); tc::prefetch_tmap(&map_fkl); tc::prefetch_tmap(&map_a1h); tc::prefetch_tmap(&map_a1l);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < FSTAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 9); tc::mbar_init(&a2_ready[s], 8); }
+    tc::mbar_init(a1_full, 1); tc::mbar_init(a1_empty, 1);
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(&d1_full[b], 1); tc::mbar_init(&d1_empty[b], 8);
+      tc::mbar_init(&d2_full[b], 1); tc::mbar_init(&d2_empty[b], 8);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc(tmem_slot, 256);
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t D1 = tmem_base, D2 = tmem_base + 128;   // two 64-column buffers each
+  const int S = p.stages_per_unit;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0; uint32_t phase = 0, a1_phase = 0;
+    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      const int tile = u / p.splits, split = u % p.splits;
+      const int row0 = tile * TILE_ROWS, k0 = split * S * BK;
+      tc::mbar_wait(a1_empty, a1_phase ^ 1);
+      a1_phase ^= 1;
+      tc::mbar_arrive_expect_tx(a1_full, A1_BYTES);
+      tc::tma_load_2d_hint(a1, &map_a1h, a1_full, 0, row0, tc::kEvictLast);
+      tc::tma_load_2d_hint(a1 + X_BYTES, &map_a1l, a1_full, 0, row0, tc::kEvictLast);
+      for (int ks = 0; ks < S; ++ks) {
+        tc::mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* st = ring + (size_t)stage * STAGE_BYTES;
+        tc::mbar_arrive_expect_tx(&full[stage], stage_tx);
+        const int c = k0 + ks * BK;
+        tc::tma_load_2d_hint(st, &map_xh, &full[stage], c, row0, tc::kEvictFirst);
+        tc::tma_load_2d_hint(st + X_BYTES, &map_xl, &full[stage], c, row0, tc::kEvictFirst);
+        tc::tma_load_2d_hint(st + 2 * X_BYTES, &map_fkh, &full[stage], 0, c, tc::kEvictLast);
+        tc::tma_load_2d_hint(st + 2 * X_BYTES + FK_BYTES, &map_fkl, &full[stage], 0, c, tc::kEvictLast);
+        tc::tma_load_2d_hint(st + 2 * X_BYTES + 2 * FK_BYTES, &map_fnh, &full[stage], c, 0, tc::kEvictLast);
+        tc::tma_load_2d_hint(st + 2 * X_BYTES + 2 * FK_BYTES + FN_BYTES, &map_fnl, &full[stage], c, 0, tc::kEvictLast);
+        if (++stage == FSTAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc1 = tc::umma_idesc_bf16(TILE_ROWS, 64);
+    const uint32_t idesc2 = tc::umma_idesc_bf16(TILE_ROWS, p.r_pad);
+    const uint64_t a1h = tc::umma_desc_k_sw128(tc::smem_u32(a1)), a1l = tc::umma_desc_k_sw128(tc::smem_u32(a1) + X_BYTES);
+    int st1 = 0; uint32_t ph1 = 0;          // ring position of the next GEMM-1
+    int st2 = 0; uint32_t ph2 = 0;          // ring position of the next GEMM-2 (one stage behind)
+    int b1 = 0; uint32_t b1_phase = 0;      // D1 buffer
+    int b2 = 0; uint32_t b2_phase = 0;      // D2 buffer
+    uint32_t a1_phase = 0;
+    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      tc::mbar_wait(a1_full, a1_phase);
+      a1_phase ^= 1;
+      for (int i = 0; i <= S; ++i) {
+        if (i < S) {
+          tc::mbar_wait(&full[st1], ph1);
+          tc::mbar_wait(&d1_empty[b1], b1_phase ^ 1);
+          tc::tcgen05_fence_after();
+          const uint32_t sb = tc::smem_u32(ring + (size_t)st1 * STAGE_BYTES);
+          const uint64_t fkh = tc::umma_desc_k_sw128(sb + 2 * X_BYTES), fkl = tc::umma_desc_k_sw128(sb + 2 * X_BYTES + FK_BYTES);
+          const uint32_t d = D1 + (uint32_t)b1 * 64;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t ko = (uint64_t)(k * 2);
+            tc::umma_bf16(d, a1h + ko, fkh + ko, idesc1, k != 0);
+            tc::umma_bf16(d, a1l + ko, fkh + ko, idesc1, true);
+            tc::umma_bf16(d, a1h + ko, fkl + ko, idesc1, true);
+          }
+          tc::umma_commit(&d1_full[b1]);
+          if (i == S - 1) tc::umma_commit(a1_empty);
+          if (++b1 == 2) { b1 = 0; b1_phase ^= 1; }
+          if (++st1 == FSTAGES) { st1 = 0; ph1 ^= 1; }
+        }
+        if (i > 0) {
+          const int j = i - 1;
+          const bool chain_start = (j % p.drain) == 0;
+          const bool chain_end = ((j + 1) % p.drain) == 0 || j == S - 1;
+          if (MODE == MODE_MU) tc::mbar_wait(&a2_ready[st2], ph2);
+          if (chain_start) tc::mbar_wait(&d2_empty[b2], b2_phase ^ 1);
+          tc::tcgen05_fence_after();
+          const uint32_t sb = tc::smem_u32(ring + (size_t)st2 * STAGE_BYTES);
+          const uint64_t xh = tc::umma_desc_k_sw128(sb), xl = tc::umma_desc_k_sw128(sb + X_BYTES);
+          const uint64_t fnh = tc::umma_desc_k_sw128(sb + 2 * X_BYTES + 2 * FK_BYTES);
+          const uint64_t fnl = tc::umma_desc_k_sw128(sb + 2 * X_BYTES + 2 * FK_BYTES + FN_BYTES);
+          const uint32_t d = D2 + (uint32_t)b2 * 64;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t ko = (uint64_t)(k * 2);
+            tc::umma_bf16(d, xh + ko, fnh + ko, idesc2, !(chain_start && k == 0));
+            tc::umma_bf16(d, xl + ko, fnh + ko, idesc2, true);
+            tc::umma_bf16(d, xh + ko, fnl + ko, idesc2, true);
+          }
+          tc::umma_commit(&empty[st2]);
+          if (chain_end) {
+            tc::umma_commit(&d2_full[b2]);
+            if (++b2 == 2) { b2 = 0; b2_phase ^= 1; }
+          }
+          if (++st2 == FSTAGES) { st2 = 0; ph2 ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== transform + epilogue warps =====================
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int ncol2 = p.r_pad - 32 * half > 32 ? 32 : (p.r_pad - 32 * half > 0 ? p.r_pad - 32 * half : 0);   // D2 columns of this half
+    int st = 0; uint32_t ph = 0;
+    int b1 = 0; uint32_t b1_phase = 0;
+    int b2 = 0; uint32_t b2_phase = 0;
+    double cost = 0.0;
+    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      const int tile = u / p.splits, split = u % p.splits;
+      float sum[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sum[j] = 0.f;
+      auto drain_chain = [&]() {
+        tc::mbar_wait(&d2_full[b2], b2_phase);
+        tc::tcgen05_fence_after();
+        const uint32_t ta = D2 + (uint32_t)b2 * 64 + lane_base + 32 * half;
+#pragma unroll
+        for (int c0 = 0; c0 < 32; c0 += 16) {
+          if (c0 < ncol2) {
+            uint32_t v[16];
+            tc::tmem_ld16(ta + c0, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sum[c0 + j] += __uint_as_float(v[j]);
+          }
+        }
+        tc::tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&d2_empty[b2]);
+        if (++b2 == 2) { b2 = 0; b2_phase ^= 1; }
+      };
+      for (int i = 0; i < S; ++i) {
+        // ---- model tile for this stage ----
+        tc::mbar_wait(&d1_full[b1], b1_phase);
+        tc::tcgen05_fence_after();
+        uint32_t kk[32];
+        tc::tmem_ld32(D1 + (uint32_t)b1 * 64 + lane_base + 32 * half, kk);
+        tc::tmem_ld_wait();
+        tc::tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&d1_empty[b1]);
+        if (++b1 == 2) { b1 = 0; b1_phase ^= 1; }
+        // the stage's TMA data is visible: GEMM-1 of this stage already waited on full[st]; this
+        // thread must observe it too before reading X through the generic proxy
+        tc::mbar_wait(&full[st], ph);
+        uint8_t* xh = ring + (size_t)st * STAGE_BYTES;
+        uint8_t* xl = xh + X_BYTES;
+        float acc = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int chunk = 4 * half + cc;
+          const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+          const uint4 h4 = *reinterpret_cast<const uint4*>(xh + off);
+          const uint4 l4 = *reinterpret_cast<const uint4*>(xl + off);
+          const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+          uint32_t qh[4], ql[4];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const float x0 = bf_lo(hw[w]) + bf_lo(lw[w]), x1 = bf_hi(hw[w]) + bf_hi(lw[w]);
+            const float k0 = __uint_as_float(kk[cc * 8 + 2 * w]), k1 = __uint_as_float(kk[cc * 8 + 2 * w + 1]);
+            if (MODE == MODE_RES) {
+              const float r0 = x0 - k0, r1 = x1 - k1;
+              acc = fmaf(r0, r0, acc);
+              acc = fmaf(r1, r1, acc);
+            } else {
+              const float i0 = k0 > 0.f ? __frcp_rn(k0) : 0.f, i1 = k1 > 0.f ? __frcp_rn(k1) : 0.f;
+              const float q0 = x0 * i0, q1 = x1 * i1;
+              if (p.want_cost) {
+                const float d0 = (x0 - k0) * i0, d1 = (x1 - k1) * i1;
+                acc += k0 * fmaf(1.f + d0, log1pf(d0), -d0);
+                acc += k1 * fmaf(1.f + d1, log1pf(d1), -d1);
+              }
+              const __nv_bfloat162 hq = __floats2bfloat162_rn(q0, q1);
+              const uint32_t hqw = *reinterpret_cast<const uint32_t*>(&hq);
+              const __nv_bfloat162 lq = __floats2bfloat162_rn(q0 - bf_lo(hqw), q1 - bf_hi(hqw));
+              qh[w] = hqw;
+              ql[w] = *reinterpret_cast<const uint32_t*>(&lq);
+            }
+          }
+          if (MODE == MODE_MU) {
+            *reinterpret_cast<uint4*>(xh + off) = make_uint4(qh[0], qh[1], qh[2], qh[3]);
+            *reinterpret_cast<uint4*>(xl + off) = make_uint4(ql[0], ql[1], ql[2], ql[3]);
+          }
+        }
+        if (p.want_cost) cost += (double)acc;
+        if (MODE == MODE_MU) {
+          tc::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&a2_ready[st]);
+        } else {
+          __syncwarp();
+        }
+        if (lane == 0) tc::mbar_arrive(&empty[st]);
+        if (++st == FSTAGES) { st = 0; ph ^= 1; }
+        if (i >= 1 && (i % p.drain) == 0) drain_chain();      // the chain that ended with stage i-1
+      }
+      drain_chain();                                           // the chain that ended with stage S-1
+      float* out = p.partial + ((int64_t)split * p.r_pad + 32 * half) * p.ld_partial + (int64_t)tile * TILE_ROWS + row;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncol2) out[(int64_t)j * p.ld_partial] = sum[j];
+    }
+    // per-CTA cost partial (fixed order)
+    cost = warp_sum(cost);
+    if (lane == 0) cost_sh[warp - 4] = cost;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (warp == 4 && lane == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += cost_sh[w];
+      p.cost_part[blockIdx.x] = t;
+    }
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tmem_base, 256);
+}
+
+__global__ void sum_cost_parts_kernel(const double* part, int n, double* out) {
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += part[i];
+    out[0] = s;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// which = 0: U given as U^T (r x m); which = 1: V (r x n).  Builds every bf16 operand plane of that factor.
+int nnfac_nmf_plan_set_factor(nnfac_nmf_plan* p, int which, const float* Ft, int64_t ld, void* stream) {
+  NNFAC_ARG(p && Ft && (which == 0 || which == 1), "nnfac_nmf_plan_set_factor: bad argument");
+  const int64_t len = which == 0 ? p->m : p->n;
+  NNFAC_ARG(ld >= len, "nnfac_nmf_plan_set_factor: leading dimension too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Side* cs = &p->side[which == 0 ? 1 : 0];        // U^T planes are the Fn operand of side 1, V planes of side 0
+  const int64_t total = (int64_t)p->r * len;
+  int grid = (int)(ceil_div64(total, 256) < (int64_t)p->ctx->sm_count * 8 ? ceil_div64(total, 256) : (int64_t)p->ctx->sm_count * 8);
+  nnfac_split_planes(Ft, ld, p->r, len, cs->fh, cs->fl, cs->ld, grid, st);
+  NNFAC_LAUNCH_CHECK(p->ctx);
+  if (p->fused_ok) {
+    nnfac_split_planes_transposed(Ft, ld, p->r, len, p->rowp_h[which], p->rowp_l[which], 64, st);
+    NNFAC_LAUNCH_CHECK(p->ctx);
+  }
+  return NNFAC_OK;
+}
+
+// One fused pass over side `side` (0: planes of X, rows = m; 1: planes of X^T, rows = n).
+//   mode 0: out (r x R) = Fn X-plane^T (the HALS cross product), cost = ||X - U V||_F^2
+//   mode 1: out (r x R) = Fn (X / (U V))^T (the beta=1 MU numerator), cost = KL(X | U V) when want_cost
+// Uses the factor planes installed by nnfac_nmf_plan_set_factor for BOTH factors.
+int nnfac_nmf_plan_fused(nnfac_nmf_plan* p, int side, int mode, int want_cost, float* out, int64_t ld_out, double* cost_out,
+                         void* stream) {
+  NNFAC_ARG(p && out && (side == 0 || side == 1) && (mode == 0 || mode == 1), "nnfac_nmf_plan_fused: bad argument");
+  if (!p->fused_ok) { nnfac_set_error("nnfac_nmf_plan_fused: rank %d > 64 is not covered by the fused pass", p->r); return NNFAC_ERR_UNSUPPORTED; }
+  Side* s = &p->side[side];
+  NNFAC_ARG(ld_out >= s->R, "nnfac_nmf_plan_fused: leading dimension too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  FusedParams fp;
+  fp.r_pad = p->r_pad; fp.splits = s->cp.splits; fp.stages_per_unit = s->cp.stages_per_unit; fp.num_units = s->cp.num_units;
+  fp.drain = 2; fp.want_cost = (mode == 0 || want_cost) ? 1 : 0;
+  fp.ld_partial = s->cp.ld_partial; fp.partial = p->partial; fp.cost_part = p->cost_part;
+  const size_t smem = A1_BYTES + (size_t)FSTAGES * STAGE_BYTES + 256;
+  const int other = 1 - side;
+  if (mode == 0) {
+    NNFAC_CUDA(cudaFuncSetAttribute(tc_fused_kernel<MODE_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_fused_kernel<MODE_RES><<<s->grid, FUSED_THREADS, smem, st>>>(s->map_xh, s->map_xl, s->map_fh, s->map_fl,
+        p->map_row_b_h[other], p->map_row_b_l[other], p->map_row_a_h[side], p->map_row_a_l[side], fp);
+  } else {
+    NNFAC_CUDA(cudaFuncSetAttribute(tc_fused_kernel<MODE_MU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_fused_kernel<MODE_MU><<<s->grid, FUSED_THREADS, smem, st>>>(s->map_xh, s->map_xl, s->map_fh, s->map_fl,
+        p->map_row_b_h[other], p->map_row_b_l[other], p->map_row_a_h[side], p->map_row_a_l[side], fp);
+  }
+  NNFAC_LAUNCH_CHECK(p->ctx);
+  nnfac_reduce_partials(p->partial, fp.splits, p->r, p->r_pad, s->R, fp.ld_partial, out, ld_out, p->ctx->sm_count, st);
+  NNFAC_LAUNCH_CHECK(p->ctx);
+  if (cost_out && fp.want_cost) {
+    sum_cost_parts_kernel<<<1, 32, 0, st>>>(p->cost_part, s->grid, cost_out);
+    NNFAC_LAUNCH_CHECK(p->ctx);
+  }
+  return NNFAC_OK;
+}
+
+}  // extern "C"

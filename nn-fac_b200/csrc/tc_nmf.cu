@@ -9,50 +9,12 @@
 // dropped lo*lo term is 2^-18 relative.  Work is cut into units of (128 rows of the X plane) x
 // (a fixed range of the contraction axis); every unit writes its own fp32 partial, and a
 // fixed-order reduction sums the partials, so results are deterministic.
-#include "common.cuh"
-#include "tc_common.cuh"
+#include "tc_plan.cuh"
 
 #include <stdlib.h>
 
 namespace {
-
-using bf16 = __nv_bfloat16;
-
-constexpr int TILE_ROWS = 128;   // UMMA M
-constexpr int BK = 64;           // bf16 elements per 128-byte swizzle row
-constexpr int UMMA_K = 16;
-constexpr int NTHREADS = 256;    // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
-// 2-D bf16 row-major [rows x cols] (leading dimension ld elements), box = box_rows x 64, 128B swizzle.
-int make_map(CUtensorMap* map, const bf16* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) { nnfac_set_error("cuTensorMapEncodeTiled is not available from the driver"); return NNFAC_ERR_CUDA; }
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(bf16)};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, gdim, gstr, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (rc != CUDA_SUCCESS) { nnfac_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)rc); return NNFAC_ERR_CUDA; }
-  return NNFAC_OK;
-}
+using namespace tcplan;
 
 // ---- ingest: fp32 -> bf16 hi/lo planes ----------------------------------------------------------
 __global__ void split_planes_kernel(const float* __restrict__ in, int64_t ld_in, int64_t rows, int64_t cols,
@@ -87,18 +49,6 @@ __global__ void split_planes_transposed_kernel(const float* __restrict__ in, int
     }
   }
 }
-
-// ---- the cross-product kernel --------------------------------------------------------------------
-struct CrossParams {
-  int r_pad;            // UMMA N (multiple of 16)
-  int splits;           // S: contraction ranges per row tile
-  int stages_per_unit;  // 64-wide k-blocks per unit
-  int num_units;        // row_tiles * splits
-  int num_stages;       // smem ring depth
-  int drain;            // stages per TMEM accumulation chain (the tensor core accumulates with truncation)
-  int64_t ld_partial;   // row pitch of the partial buffer (multiple of 128)
-  float* partial;       // [splits][r_pad][ld_partial]
-};
 
 template <int MAX_RPAD>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -240,26 +190,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int sp
   }
 }
 
-struct Side {           // one orientation of X
-  int64_t R, C, ld;     // plane is [R x C], leading dimension ld
-  bf16 *xh, *xl;        // X planes
-  bf16 *fh, *fl;        // factor planes [r_pad x ld]
-  CUtensorMap map_xh, map_xl, map_fh, map_fl;
-  CrossParams cp;
-  int grid;
-  size_t smem;
-};
-
 }  // namespace
-
-struct nnfac_nmf_plan {
-  nnfac_ctx* ctx;
-  int64_t m, n;
-  int r, r_pad;
-  Side side[2];         // [0]: planes of X (m x n), used for V X^T;  [1]: planes of X^T (n x m), used for U^T X
-  float* partial;
-  size_t partial_bytes;
-};
 
 namespace {
 
@@ -295,6 +226,24 @@ void choose_partition(int sm, int64_t R, int64_t C, int r_pad, Side* s) {
 
 }  // namespace
 
+void nnfac_split_planes(const float* in, int64_t ld_in, int64_t rows, int64_t cols, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                        int64_t ld_out, int grid, cudaStream_t st) {
+  split_planes_kernel<<<grid, 256, 0, st>>>(in, ld_in, rows, cols, hi, lo, ld_out);
+}
+
+void nnfac_split_planes_transposed(const float* in, int64_t ld_in, int64_t rows, int64_t cols, __nv_bfloat16* hiT,
+                                   __nv_bfloat16* loT, int64_t ld_out, cudaStream_t st) {
+  dim3 g((unsigned)ceil_div64(cols, 32), (unsigned)ceil_div64(rows, 32)), b(32, 8);
+  split_planes_transposed_kernel<<<g, b, 0, st>>>(in, ld_in, rows, cols, hiT, loT, ld_out);
+}
+
+void nnfac_reduce_partials(const float* partial, int splits, int r, int r_pad, int64_t R, int64_t ld_partial, float* out,
+                           int64_t ld_out, int sm_count, cudaStream_t st) {
+  const int64_t total = (int64_t)r * R;
+  const int grid = (int)(ceil_div64(total, 256) < (int64_t)sm_count * 8 ? ceil_div64(total, 256) : (int64_t)sm_count * 8);
+  reduce_partials_kernel<<<grid, 256, 0, st>>>(partial, splits, r, r_pad, R, ld_partial, out, ld_out);
+}
+
 extern "C" {
 
 int nnfac_nmf_plan_destroy(nnfac_nmf_plan* p) {
@@ -303,6 +252,8 @@ int nnfac_nmf_plan_destroy(nnfac_nmf_plan* p) {
     cudaFree(p->side[i].xh); cudaFree(p->side[i].xl); cudaFree(p->side[i].fh); cudaFree(p->side[i].fl);
   }
   cudaFree(p->partial);
+  for (int i = 0; i < 2; ++i) { cudaFree(p->rowp_h[i]); cudaFree(p->rowp_l[i]); }
+  cudaFree(p->cost_part);
   free(p);
   return NNFAC_OK;
 }
@@ -351,6 +302,32 @@ int nnfac_nmf_plan_create(nnfac_ctx* ctx, int64_t m, int64_t n, int r, nnfac_nmf
     return NNFAC_ERR_ALLOC;
   }
   p->partial_bytes = partial_bytes;
+  // fused passes: row planes of both factors (rank axis contiguous, padded to 64) and per-CTA cost partials
+  p->fused_ok = p->r_pad <= 64;
+  if (p->fused_ok) {
+    for (int i = 0; i < 2; ++i) {
+      const int64_t len = i == 0 ? m : n;
+      const size_t rb = (size_t)len * 64 * sizeof(bf16);
+      if (cudaMalloc(&p->rowp_h[i], rb) != cudaSuccess || cudaMalloc(&p->rowp_l[i], rb) != cudaSuccess) {
+        cudaGetLastError();
+        nnfac_set_error("nnfac_nmf_plan_create: out of device memory (factor planes)");
+        nnfac_nmf_plan_destroy(p);
+        return NNFAC_ERR_ALLOC;
+      }
+      cudaMemset(p->rowp_h[i], 0, rb);
+      cudaMemset(p->rowp_l[i], 0, rb);
+      int rc = make_map(&p->map_row_a_h[i], p->rowp_h[i], len, 64, 64, TILE_ROWS);
+      if (!rc) rc = make_map(&p->map_row_a_l[i], p->rowp_l[i], len, 64, 64, TILE_ROWS);
+      if (!rc) rc = make_map(&p->map_row_b_h[i], p->rowp_h[i], len, 64, 64, 64);
+      if (!rc) rc = make_map(&p->map_row_b_l[i], p->rowp_l[i], len, 64, 64, 64);
+      if (rc) { nnfac_nmf_plan_destroy(p); return rc; }
+    }
+    if (cudaMalloc(&p->cost_part, sizeof(double) * 1024) != cudaSuccess) {
+      cudaGetLastError();
+      nnfac_nmf_plan_destroy(p);
+      return NNFAC_ERR_ALLOC;
+    }
+  }
   *out = p;
   return NNFAC_OK;
 }

@@ -1,0 +1,93 @@
+// Shared declarations of the NMF plan (tensor-core path): X planes, factor planes, TMA maps, work partition.
+#pragma once
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace tcplan {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int TILE_ROWS = 128;   // UMMA M
+constexpr int BK = 64;           // bf16 elements per 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NTHREADS = 256;    // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows x cols] (leading dimension ld elements), box = box_rows x 64, 128B swizzle.
+inline int make_map(CUtensorMap* map, const bf16* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { nnfac_set_error("cuTensorMapEncodeTiled is not available from the driver"); return NNFAC_ERR_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(bf16)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) { nnfac_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)rc); return NNFAC_ERR_CUDA; }
+  return NNFAC_OK;
+}
+
+// ---- the cross-product kernel --------------------------------------------------------------------
+struct CrossParams {
+  int r_pad;            // UMMA N (multiple of 16)
+  int splits;           // S: contraction ranges per row tile
+  int stages_per_unit;  // 64-wide k-blocks per unit
+  int num_units;        // row_tiles * splits
+  int num_stages;       // smem ring depth
+  int drain;            // stages per TMEM accumulation chain (the tensor core accumulates with truncation)
+  int64_t ld_partial;   // row pitch of the partial buffer (multiple of 128)
+  float* partial;       // [splits][r_pad][ld_partial]
+};
+
+struct Side {           // one orientation of X
+  int64_t R, C, ld;     // plane is [R x C], leading dimension ld
+  bf16 *xh, *xl;        // X planes
+  bf16 *fh, *fl;        // factor planes [r_pad x ld]
+  CUtensorMap map_xh, map_xl, map_fh, map_fl;
+  CrossParams cp;
+  int grid;
+  size_t smem;
+};
+
+}  // namespace tcplan
+
+struct nnfac_nmf_plan {
+  nnfac_ctx* ctx;
+  int64_t m, n;
+  int r, r_pad;
+  tcplan::Side side[2];         // [0]: planes of X (m x n), used for V X^T;  [1]: planes of X^T (n x m), used for U^T X
+  float* partial;
+  size_t partial_bytes;
+  // fused passes (rank <= 64): factor "row planes" with the rank axis contiguous, padded to 64:
+  //   rowp[0] = U [m x 64], rowp[1] = V^T [n x 64]; map_row_a: 128-row boxes (A operand of the model GEMM),
+  //   map_row_b: 64-row boxes (B operand of the model GEMM)
+  __nv_bfloat16 *rowp_h[2], *rowp_l[2];
+  CUtensorMap map_row_a_h[2], map_row_a_l[2], map_row_b_h[2], map_row_b_l[2];
+  double* cost_part;    // [sm_count] per-CTA cost partials of a fused pass
+  int fused_ok;
+};
+
+
+// helpers shared between tc_nmf.cu and tc_fused.cu (defined in tc_nmf.cu)
+void nnfac_split_planes(const float* in, int64_t ld_in, int64_t rows, int64_t cols, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                        int64_t ld_out, int grid, cudaStream_t st);
+void nnfac_split_planes_transposed(const float* in, int64_t ld_in, int64_t rows, int64_t cols, __nv_bfloat16* hiT,
+                                   __nv_bfloat16* loT, int64_t ld_out, cudaStream_t st);
+void nnfac_reduce_partials(const float* partial, int splits, int r, int r_pad, int64_t R, int64_t ld_partial, float* out,
+                           int64_t ld_out, int sm_count, cudaStream_t st);

@@ -44,6 +44,8 @@ SIGNATURES = {
     "nnfac_nmf_plan_destroy": [_P],
     "nnfac_nmf_plan_load_x": [_P, _P, _I64, _P],
     "nnfac_nmf_plan_cross": [_P, _INT, _P, _I64, _P, _I64, _P],
+    "nnfac_nmf_plan_set_factor": [_P, _INT, _P, _I64, _P],
+    "nnfac_nmf_plan_fused": [_P, _INT, _INT, _INT, _P, _I64, _P, _P],
     "nnfac_nmf_plan_info": [_P, _INT, _c.POINTER(_INT), _c.POINTER(_INT), _c.POINTER(_INT), _c.POINTER(_INT),
                             _c.POINTER(_INT)],
 }

@@ -227,6 +227,26 @@ class NMFPlan:
                                             L.stream_ptr()))
         return out
 
+    def set_factor(self, which, Ft):
+        """which=0: U given as U^T (r x m); which=1: V (r x n).  Rebuilds that factor's bf16 operand planes."""
+        L.check(_lib().nnfac_nmf_plan_set_factor(self.handle, which, L.ptr(Ft), Ft.stride(0), L.stream_ptr()))
+
+    def fused(self, side, mode, want_cost=True, out=None, cost_out=None):
+        """One fused X pass with the installed factors (rank <= 64).  mode 0: HALS cross product + ||X-UV||^2;
+        mode 1: beta=1 MU numerator + KL(X|UV).  Returns (out r x rows, cost device scalar or None)."""
+        R = self.m if side == 0 else self.n
+        if out is None:
+            out = torch.empty((self.r, R), dtype=torch.float32, device=self.device)
+        if cost_out is None and (want_cost or mode == 0):
+            cost_out = torch.empty(1, dtype=torch.float64, device=self.device)
+        L.check(_lib().nnfac_nmf_plan_fused(self.handle, side, mode, 1 if want_cost else 0, L.ptr(out), out.stride(0),
+                                            L.ptr(cost_out), L.stream_ptr()))
+        return out, cost_out
+
+    @property
+    def fused_ok(self):
+        return self.r is not None and self.r <= 64
+
     def info(self, which):
         import ctypes
         vals = [ctypes.c_int() for _ in range(5)]

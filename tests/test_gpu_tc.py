@@ -39,3 +39,34 @@ def test_plan_cross_is_deterministic_and_linear():
     assert torch.equal(a, b)
     c = plan.cross(0, 2.0 * V)
     torch.testing.assert_close(c, 2.0 * a, rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("m,n,r", [(128, 64, 16), (384, 320, 64), (1000, 500, 10), (777, 1300, 33), (2048, 4096, 64)])
+def test_fused_pass_matches_float64(m, n, r):
+    """Fused X pass (model tile formed and consumed on chip) against float64 numpy, both sides, both modes."""
+    import torch
+    from nn_fac import _ops as ops
+    rng = np.random.RandomState(m * 7 + n + r)
+    U = rng.rand(m, r).astype(np.float32) + 0.05
+    V = rng.rand(r, n).astype(np.float32) + 0.05
+    X = ((rng.rand(m, r) @ rng.rand(r, n)) * (1 + 0.2 * rng.rand(m, n)) + 1e-3).astype(np.float32)
+    plan = ops.NMFPlan(torch.from_numpy(X).cuda()).bind_rank(r)
+    plan.set_factor(0, torch.from_numpy(np.ascontiguousarray(U.T)).cuda())
+    plan.set_factor(1, torch.from_numpy(V).cuda())
+    X64, U64, V64 = X.astype(np.float64), U.astype(np.float64), V.astype(np.float64)
+    K = U64 @ V64
+    # mode 0: cross products + squared residual
+    out, cost = plan.fused(0, 0)
+    np.testing.assert_allclose(out.cpu().numpy(), V64 @ X64.T, rtol=2e-5)
+    np.testing.assert_allclose(cost.item(), np.sum((X64 - K) ** 2), rtol=2e-5)
+    out, cost = plan.fused(1, 0)
+    np.testing.assert_allclose(out.cpu().numpy(), U64.T @ X64, rtol=2e-5)
+    np.testing.assert_allclose(cost.item(), np.sum((X64 - K) ** 2), rtol=2e-5)
+    # mode 1: beta = 1 numerators + KL divergence
+    kl = np.sum(X64 * np.log(X64 / K) - X64 + K)
+    out, cost = plan.fused(0, 1)
+    np.testing.assert_allclose(out.cpu().numpy(), V64 @ (X64 / K).T, rtol=3e-5)
+    np.testing.assert_allclose(cost.item(), kl, rtol=2e-5)
+    out, cost = plan.fused(1, 1)
+    np.testing.assert_allclose(out.cpu().numpy(), U64.T @ (X64 / K), rtol=3e-5)
+    np.testing.assert_allclose(cost.item(), kl, rtol=2e-5)
