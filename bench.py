@@ -189,46 +189,46 @@ def main():
     del W0, H0
     sp, fixed, norm = [None, None], [], [False, False]
 
-    states = {"hals": nmf.DeviceNMF(X, U0, V0, torch.float32), "mu": nmf.DeviceNMF(X, U0, V0, torch.float32)}
+    from nn_fac import _fast
+    fused = args.rank <= 64
+    if fused:
+        states = {"hals": _fast.FusedNMF(X, U0, V0), "mu": _fast.FusedNMF(X, U0, V0)}
+    else:
+        states = {"hals": nmf.DeviceNMF(X, U0, V0, torch.float32), "mu": nmf.DeviceNMF(X, U0, V0, torch.float32)}
 
-    def one_step():
-        c1 = states["hals"].step("hals", 2, sp, fixed, norm)
-        c2 = states["mu"].step("mu", 1, sp, fixed, norm)
-        return c1, c2
+    def run_rule(rule, iters):
+        """`iters` outer iterations of one rule on its resident state; returns the list of costs."""
+        st = states[rule]
+        if fused:
+            return st.run(iters, 0.0, rule, sp, fixed, norm)[0]
+        return [st.step(rule, 2 if rule == "hals" else 1, sp, fixed, norm) for _ in range(iters)]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        one_step()
+    if args.warmup > 0:
+        run_rule("hals", args.warmup)
+        run_rule("mu", args.warmup)
     # phase timers (CUDA events on the launching stream) are collected during the timed region
     for s in states.values():
         s.events = []
+        if fused:
+            s.sweep_log = []
     launches0 = _lib.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    evm = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     barrier()
     with ClockSampler(local_rank) as clocks:
-        ev0.record()
-        t_rule = {"hals": 0.0, "mu": 0.0}
-        costs = None
-        for i in range(args.steps):
-            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True); c = torch.cuda.Event(enable_timing=True)
-            a.record()
-            c1 = states["hals"].step("hals", 2, sp, fixed, norm)
-            b.record()
-            c2 = states["mu"].step("mu", 1, sp, fixed, norm)
-            c.record()
-            evm[i] = (a, b, c)
-            costs = (c1, c2)
-        ev1.record()
+        ev[0].record()
+        c1 = run_rule("hals", args.steps)
+        ev[1].record()
+        c2 = run_rule("mu", args.steps)
+        ev[2].record()
         barrier()
-    total_ms = ev0.elapsed_time(ev1)
-    for a, b, c in evm[:args.steps]:
-        t_rule["hals"] += a.elapsed_time(b)
-        t_rule["mu"] += b.elapsed_time(c)
+    costs = (c1[-1], c2[-1])
+    total_ms = ev[0].elapsed_time(ev[2])
+    t_rule = {"hals": ev[0].elapsed_time(ev[1]), "mu": ev[1].elapsed_time(ev[2])}
     launches = _lib.launch_count() - launches0
     if world > 1:
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
@@ -244,7 +244,7 @@ def main():
     phase_ms = {k: sum(v) / len(v) for k, v in phases.items()}
     peak, peak_src = measured_peaks()
     x_bytes = m * n * 4
-    dom = max((k for k in phase_ms if "cross" in k or "update" in k), key=lambda k: phase_ms[k], default=None)
+    dom = max((k for k in phase_ms if "cross" in k or "update" in k or "pass" in k), key=lambda k: phase_ms[k], default=None)
     roofline = None
     if dom is not None:
         fac_bytes = 2 * (m + n) * r * 4
@@ -265,7 +265,8 @@ def main():
             "hals_its_per_s": per_rule["hals"], "mu_its_per_s": per_rule["mu"],
             "frac_of_hbm_roofline_per_iteration": iter_roofline,
             "phase_ms": phase_ms, "final_costs": {"hals": costs[0], "mu": costs[1]},
-            "hals_sweeps_last": [float(x) for x in states["hals"].hals_stats[:, 3].cpu().tolist()],
+            "hals_sweeps_per_call": ([[float(v) for v in t.cpu().tolist()] for t in states["hals"].sweep_log[-3:]] if fused
+                                     else [float(x) for x in states["hals"].hals_stats[:, 3].cpu().tolist()]),
             "gpu_launches": int(launches), "roofline": roofline}
 
     if rank == 0:

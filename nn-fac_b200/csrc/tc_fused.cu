@@ -18,11 +18,10 @@ namespace {
 using namespace tcplan;
 
 constexpr int FUSED_THREADS = 384;   // warp0 TMA, warp1 MMA, warp2 TMEM, warps 4-11 transform/epilogue
-constexpr int FSTAGES = 3;
+constexpr int FSTAGES = 4;
 constexpr uint32_t X_BYTES = TILE_ROWS * BK * sizeof(bf16);   // 16 KiB per plane tile
 constexpr uint32_t FK_BYTES = 64 * BK * sizeof(bf16);         // 8 KiB  (64 columns of X x rank 64)
-constexpr uint32_t FN_BYTES = 64 * BK * sizeof(bf16);         // 8 KiB  (rank rows, padded to 64, x 64 columns)
-constexpr uint32_t STAGE_BYTES = 2 * X_BYTES + 2 * FK_BYTES + 2 * FN_BYTES;   // 64 KiB
+constexpr uint32_t STAGE_BYTES = 2 * X_BYTES + 2 * FK_BYTES;  // 48 KiB
 constexpr uint32_t A1_BYTES = 2 * X_BYTES;                    // 32 KiB
 constexpr int MODE_RES = 0, MODE_MU = 1;
 
@@ -33,13 +32,31 @@ struct FusedParams {
   double* cost_part;
 };
 
+__device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, <= 1 ulp: no IEEE fix-up branch
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// q ln q - q + 1 with q = 1 + d (one KL term divided by the model value, beta_divergence.py:45-48).
+// Near q = 1 the closed form cancels, so |d| < 1/8 uses the alternating series d^2 (1/2 - d/6 + d^2/12 - ...)
+// (truncation < 2e-8 relative); elsewhere MUFU.LG2 is accurate enough (< 3e-5 relative on the term).
+__device__ __forceinline__ float kl_term(float q, float d) {
+  float s = fmaf(d, 1.f / 56.f, -1.f / 42.f);
+  s = fmaf(d, s, 1.f / 30.f);
+  s = fmaf(d, s, -1.f / 20.f);
+  s = fmaf(d, s, 1.f / 12.f);
+  s = fmaf(d, s, -1.f / 6.f);
+  s = fmaf(d, s, 0.5f);
+  const float series = d * d * s;
+  const float closed = fmaf(q, __logf(fmaxf(q, 1e-30f)), -d);
+  return fabsf(d) < 0.125f ? series : closed;
+}
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
 template <int MODE>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
-                const __grid_constant__ CUtensorMap map_fnh, const __grid_constant__ CUtensorMap map_fnl,
                 const __grid_constant__ CUtensorMap map_fkh, const __grid_constant__ CUtensorMap map_fkl,
                 const __grid_constant__ CUtensorMap map_a1h, const __grid_constant__ CUtensorMap map_a1l,
                 const FusedParams p) {
@@ -47,41 +64,46 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
   uint8_t* a1 = smem;                                   // [hi | lo]
   uint8_t* ring = smem + A1_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)FSTAGES * STAGE_BYTES);
-  uint64_t* full = bars;                 // [3]
-  uint64_t* empty = bars + 3;            // [3]  count 9: GEMM-2 commit + 8 transform warps
-  uint64_t* a2_ready = bars + 6;         // [3]  count 8
+  uint64_t* full = bars;                 // [4]
+  uint64_t* empty = bars + 4;            // [4]  count 9: GEMM-2 commit + 8 transform warps
   uint64_t* a1_full = bars + 9;
   uint64_t* a1_empty = bars + 10;
   uint64_t* d1_full = bars + 11;         // [2]
   uint64_t* d1_empty = bars + 13;        // [2] count 8
   uint64_t* d2_full = bars + 15;         // [2]
   uint64_t* d2_empty = bars + 17;        // [2] count 8
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
-  double* cost_sh = reinterpret_cast<double*>(bars + 20);   // [8]
+  uint64_t* a1t_ready = bars + 19;       // A1 copied into tensor memory (count 8)
+  uint64_t* a1t_free = bars + 20;        // every model GEMM of the unit has retired
+  uint64_t* q_ready = bars + 21;         // [2] count 8: ratio tile written to tensor memory
+  uint64_t* q_free = bars + 23;          // [2] contraction GEMM that read it has retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+  double* cost_sh = reinterpret_cast<double*>(bars + 26);   // [8]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t fn_bytes = (uint32_t)p.r_pad * BK * sizeof(bf16);
-  const uint32_t stage_tx = 2 * X_BYTES + 2 * FK_BYTES + 2 * fn_bytes;
+  const uint32_t stage_tx = STAGE_BYTES;
 
   if (warp == 0 && lane == 0) {
-    tc::prefetch_tmap(&map_xh); tc::prefetch_tmap(&map_xl); tc::prefetch_tmap(&map_fnh); tc::prefetch_tmap(&map_fnl);
+    tc::prefetch_tmap(&map_xh); tc::prefetch_tmap(&map_xl); 
     tc::prefetch_tmap(&map_fkh); tc::prefetch_tmap(&map_fkl); tc::prefetch_tmap(&map_a1h); tc::prefetch_tmap(&map_a1l);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < FSTAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 9); tc::mbar_init(&a2_ready[s], 8); }
-    tc::mbar_init(a1_full, 1); tc::mbar_init(a1_empty, 1);
+    for (int s = 0; s < FSTAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 9); }
+    tc::mbar_init(a1_full, 1); tc::mbar_init(a1_empty, 8);
+    tc::mbar_init(a1t_ready, 8); tc::mbar_init(a1t_free, 1);
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(&q_ready[b], 8); tc::mbar_init(&q_free[b], 1); }
     for (int b = 0; b < 2; ++b) {
       tc::mbar_init(&d1_full[b], 1); tc::mbar_init(&d1_empty[b], 8);
       tc::mbar_init(&d2_full[b], 1); tc::mbar_init(&d2_empty[b], 8);
     }
     tc::fence_barrier_init();
   }
-  if (warp == 2) tc::tmem_alloc(tmem_slot, 256);
+  if (warp == 2) tc::tmem_alloc(tmem_slot, 512);
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t D1 = tmem_base, D2 = tmem_base + 128;   // two 64-column buffers each
+  // tensor-memory map (columns): D1 2x64 | D2 2x64 | A1 hi 32 + lo 32 | Q 2 x (hi 32 + lo 32)
+  const uint32_t D1 = tmem_base, D2 = tmem_base + 128, A1T = tmem_base + 256, QT = tmem_base + 320;
   const int S = p.stages_per_unit;
 
   if (warp == 0 && lane == 0) {
@@ -104,70 +126,86 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         tc::tma_load_2d_hint(st + X_BYTES, &map_xl, &full[stage], c, row0, tc::kEvictFirst);
         tc::tma_load_2d_hint(st + 2 * X_BYTES, &map_fkh, &full[stage], 0, c, tc::kEvictLast);
         tc::tma_load_2d_hint(st + 2 * X_BYTES + FK_BYTES, &map_fkl, &full[stage], 0, c, tc::kEvictLast);
-        tc::tma_load_2d_hint(st + 2 * X_BYTES + 2 * FK_BYTES, &map_fnh, &full[stage], c, 0, tc::kEvictLast);
-        tc::tma_load_2d_hint(st + 2 * X_BYTES + 2 * FK_BYTES + FN_BYTES, &map_fnl, &full[stage], c, 0, tc::kEvictLast);
         if (++stage == FSTAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer 1: model GEMM  D1 = A1 * Fk^T =====================
+    // (two issuing threads: a single thread needs ~100 cycles per tcgen05.mma for descriptor set-up,
+    //  which alone would cap a 24-MMA stage below the HBM rate)
     const uint32_t idesc1 = tc::umma_idesc_bf16(TILE_ROWS, 64);
-    const uint32_t idesc2 = tc::umma_idesc_bf16(TILE_ROWS, p.r_pad);
-    const uint64_t a1h = tc::umma_desc_k_sw128(tc::smem_u32(a1)), a1l = tc::umma_desc_k_sw128(tc::smem_u32(a1) + X_BYTES);
-    int st1 = 0; uint32_t ph1 = 0;          // ring position of the next GEMM-1
-    int st2 = 0; uint32_t ph2 = 0;          // ring position of the next GEMM-2 (one stage behind)
-    int b1 = 0; uint32_t b1_phase = 0;      // D1 buffer
-    int b2 = 0; uint32_t b2_phase = 0;      // D2 buffer
+    int st1 = 0; uint32_t ph1 = 0;
+    int b1 = 0; uint32_t b1_phase = 0;
     uint32_t a1_phase = 0;
     for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-      tc::mbar_wait(a1_full, a1_phase);
+      tc::mbar_wait(a1t_ready, a1_phase);
       a1_phase ^= 1;
-      for (int i = 0; i <= S; ++i) {
-        if (i < S) {
-          tc::mbar_wait(&full[st1], ph1);
-          tc::mbar_wait(&d1_empty[b1], b1_phase ^ 1);
-          tc::tcgen05_fence_after();
-          const uint32_t sb = tc::smem_u32(ring + (size_t)st1 * STAGE_BYTES);
-          const uint64_t fkh = tc::umma_desc_k_sw128(sb + 2 * X_BYTES), fkl = tc::umma_desc_k_sw128(sb + 2 * X_BYTES + FK_BYTES);
-          const uint32_t d = D1 + (uint32_t)b1 * 64;
+      for (int i = 0; i < S; ++i) {
+        tc::mbar_wait(&full[st1], ph1);
+        tc::mbar_wait(&d1_empty[b1], b1_phase ^ 1);
+        tc::tcgen05_fence_after();
+        const uint32_t sb = tc::smem_u32(ring + (size_t)st1 * STAGE_BYTES);
+        const uint64_t fkh = tc::umma_desc_k_sw128(sb + 2 * X_BYTES), fkl = tc::umma_desc_k_sw128(sb + 2 * X_BYTES + FK_BYTES);
+        const uint32_t d = D1 + (uint32_t)b1 * 64;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t ko = (uint64_t)(k * 2);
-            tc::umma_bf16(d, a1h + ko, fkh + ko, idesc1, k != 0);
-            tc::umma_bf16(d, a1l + ko, fkh + ko, idesc1, true);
-            tc::umma_bf16(d, a1h + ko, fkl + ko, idesc1, true);
-          }
-          tc::umma_commit(&d1_full[b1]);
-          if (i == S - 1) tc::umma_commit(a1_empty);
-          if (++b1 == 2) { b1 = 0; b1_phase ^= 1; }
-          if (++st1 == FSTAGES) { st1 = 0; ph1 ^= 1; }
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t ko = (uint64_t)(k * 2);
+          tc::umma_bf16_ts(d, A1T + 8 * k, fkh + ko, idesc1, k != 0);
+          tc::umma_bf16_ts(d, A1T + 32 + 8 * k, fkh + ko, idesc1, true);
+          tc::umma_bf16_ts(d, A1T + 8 * k, fkl + ko, idesc1, true);
         }
-        if (i > 0) {
-          const int j = i - 1;
-          const bool chain_start = (j % p.drain) == 0;
-          const bool chain_end = ((j + 1) % p.drain) == 0 || j == S - 1;
-          if (MODE == MODE_MU) tc::mbar_wait(&a2_ready[st2], ph2);
-          if (chain_start) tc::mbar_wait(&d2_empty[b2], b2_phase ^ 1);
-          tc::tcgen05_fence_after();
-          const uint32_t sb = tc::smem_u32(ring + (size_t)st2 * STAGE_BYTES);
-          const uint64_t xh = tc::umma_desc_k_sw128(sb), xl = tc::umma_desc_k_sw128(sb + X_BYTES);
-          const uint64_t fnh = tc::umma_desc_k_sw128(sb + 2 * X_BYTES + 2 * FK_BYTES);
-          const uint64_t fnl = tc::umma_desc_k_sw128(sb + 2 * X_BYTES + 2 * FK_BYTES + FN_BYTES);
-          const uint32_t d = D2 + (uint32_t)b2 * 64;
+        tc::umma_commit(&d1_full[b1]);
+        if (i == S - 1) tc::umma_commit(a1t_free);
+        if (++b1 == 2) { b1 = 0; b1_phase ^= 1; }
+        if (++st1 == FSTAGES) { st1 = 0; ph1 ^= 1; }
+      }
+    }
+  } else if (warp == 3 && lane == 0) {
+    // ===================== MMA issuer 2: contraction GEMM  D2 += A2 * Fn^T =====================
+    const uint32_t idesc2 = tc::umma_idesc_bf16(TILE_ROWS, p.r_pad) | (1u << 16);   // B operand MN-major
+    int qb = 0; uint32_t qb_phase = 0;      // Q buffer (MU)
+    int st2 = 0; uint32_t ph2 = 0;
+    int b2 = 0; uint32_t b2_phase = 0;      // D2 buffer
+    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      for (int j = 0; j < S; ++j) {
+        const bool chain_start = (j % p.drain) == 0;
+        const bool chain_end = ((j + 1) % p.drain) == 0 || j == S - 1;
+        tc::mbar_wait(&full[st2], ph2);
+        if (MODE == MODE_MU) tc::mbar_wait(&q_ready[qb], qb_phase);
+        if (chain_start) tc::mbar_wait(&d2_empty[b2], b2_phase ^ 1);
+        tc::tcgen05_fence_after();
+        const uint32_t sb = tc::smem_u32(ring + (size_t)st2 * STAGE_BYTES);
+        const uint64_t xh = tc::umma_desc_k_sw128(sb), xl = tc::umma_desc_k_sw128(sb + X_BYTES);
+        // B operand = the SAME 64-column slab of the other factor that the model GEMM reads K-major, addressed
+        // MN-major here (rank contiguous = N, columns = K): no second copy of the factor travels through L2
+        const uint64_t fnh = tc::umma_desc_mn_sw128(sb + 2 * X_BYTES);
+        const uint64_t fnl = tc::umma_desc_mn_sw128(sb + 2 * X_BYTES + FK_BYTES);
+        const uint32_t d = D2 + (uint32_t)b2 * 64;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t ko = (uint64_t)(k * 2);
-            tc::umma_bf16(d, xh + ko, fnh + ko, idesc2, !(chain_start && k == 0));
-            tc::umma_bf16(d, xl + ko, fnh + ko, idesc2, true);
-            tc::umma_bf16(d, xh + ko, fnl + ko, idesc2, true);
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t ko = (uint64_t)(k * 2);            // A (K-major): 16 bf16 = 32 B inside the 128 B row
+          const uint64_t kb = (uint64_t)(k * 128);          // B (MN-major): 16 rows of 128 B = 2048 B
+          if (MODE == MODE_MU) {
+            const uint32_t qa = QT + (uint32_t)qb * 64 + 8 * k;
+            tc::umma_bf16_ts(d, qa, fnh + kb, idesc2, !(chain_start && k == 0));
+            tc::umma_bf16_ts(d, qa + 32, fnh + kb, idesc2, true);
+            tc::umma_bf16_ts(d, qa, fnl + kb, idesc2, true);
+          } else {
+            tc::umma_bf16(d, xh + ko, fnh + kb, idesc2, !(chain_start && k == 0));
+            tc::umma_bf16(d, xl + ko, fnh + kb, idesc2, true);
+            tc::umma_bf16(d, xh + ko, fnl + kb, idesc2, true);
           }
-          tc::umma_commit(&empty[st2]);
-          if (chain_end) {
-            tc::umma_commit(&d2_full[b2]);
-            if (++b2 == 2) { b2 = 0; b2_phase ^= 1; }
-          }
-          if (++st2 == FSTAGES) { st2 = 0; ph2 ^= 1; }
         }
+        tc::umma_commit(&empty[st2]);
+        if (MODE == MODE_MU) {
+          tc::umma_commit(&q_free[qb]);
+          if (++qb == 2) { qb = 0; qb_phase ^= 1; }
+        }
+        if (chain_end) {
+          tc::umma_commit(&d2_full[b2]);
+          if (++b2 == 2) { b2 = 0; b2_phase ^= 1; }
+        }
+        if (++st2 == FSTAGES) { st2 = 0; ph2 ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -179,12 +217,36 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     int st = 0; uint32_t ph = 0;
     int b1 = 0; uint32_t b1_phase = 0;
     int b2 = 0; uint32_t b2_phase = 0;
+    int qb = 0; uint32_t qb_phase = 0;
+    uint32_t a1_phase = 0;
     double cost = 0.0;
     for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
       const int tile = u / p.splits, split = u % p.splits;
       float sum[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) sum[j] = 0.f;
+      {
+        // A1 (this unit's rows of the aligned factor): shared memory -> tensor memory, this thread's row and K half
+        tc::mbar_wait(a1_full, a1_phase);
+        tc::mbar_wait(a1t_free, a1_phase ^ 1);
+        a1_phase ^= 1;
+        tc::tcgen05_fence_after();
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+          uint32_t w[16];
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const int chunk = 4 * half + cc;
+            const uint4 v4 = *reinterpret_cast<const uint4*>(a1 + pl * X_BYTES + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4));
+            w[4 * cc] = v4.x; w[4 * cc + 1] = v4.y; w[4 * cc + 2] = v4.z; w[4 * cc + 3] = v4.w;
+          }
+          tc::tmem_st16(A1T + lane_base + 32 * pl + 16 * half, w);
+        }
+        tc::tmem_st_wait();
+        tc::tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) { tc::mbar_arrive(a1t_ready); tc::mbar_arrive(a1_empty); }
+      }
       auto drain_chain = [&]() {
         tc::mbar_wait(&d2_full[b2], b2_phase);
         tc::tcgen05_fence_after();
@@ -221,6 +283,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         uint8_t* xh = ring + (size_t)st * STAGE_BYTES;
         uint8_t* xl = xh + X_BYTES;
         float acc = 0.f;
+        uint32_t qhw[16], qlw[16];
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           const int chunk = 4 * half + cc;
@@ -238,12 +301,13 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
               acc = fmaf(r0, r0, acc);
               acc = fmaf(r1, r1, acc);
             } else {
-              const float i0 = k0 > 0.f ? __frcp_rn(k0) : 0.f, i1 = k1 > 0.f ? __frcp_rn(k1) : 0.f;
+              // padded rows / columns have x = 0 and k = 0: the floor keeps 0 * (1/k) = 0 there
+              const float i0 = rcp_approx(fmaxf(k0, 1e-30f)), i1 = rcp_approx(fmaxf(k1, 1e-30f));
               const float q0 = x0 * i0, q1 = x1 * i1;
               if (p.want_cost) {
                 const float d0 = (x0 - k0) * i0, d1 = (x1 - k1) * i1;
-                acc += k0 * fmaf(1.f + d0, log1pf(d0), -d0);
-                acc += k1 * fmaf(1.f + d1, log1pf(d1), -d1);
+                acc += k0 * kl_term(q0, d0);
+                acc += k1 * kl_term(q1, d1);
               }
               const __nv_bfloat162 hq = __floats2bfloat162_rn(q0, q1);
               const uint32_t hqw = *reinterpret_cast<const uint32_t*>(&hq);
@@ -253,20 +317,27 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
             }
           }
           if (MODE == MODE_MU) {
-            *reinterpret_cast<uint4*>(xh + off) = make_uint4(qh[0], qh[1], qh[2], qh[3]);
-            *reinterpret_cast<uint4*>(xl + off) = make_uint4(ql[0], ql[1], ql[2], ql[3]);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) { qhw[4 * cc + w] = qh[w]; qlw[4 * cc + w] = ql[w]; }
           }
         }
         if (p.want_cost) cost += (double)acc;
-        if (MODE == MODE_MU) {
-          tc::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&a2_ready[st]);
-        } else {
-          __syncwarp();
-        }
-        if (lane == 0) tc::mbar_arrive(&empty[st]);
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&empty[st]);          // done with the stage's X tile
         if (++st == FSTAGES) { st = 0; ph ^= 1; }
+        if (MODE == MODE_MU) {
+          // ratio tile -> tensor memory (A operand of the contraction GEMM): hi 32 columns, lo 32 columns
+          tc::mbar_wait(&q_free[qb], qb_phase ^ 1);
+          tc::tcgen05_fence_after();
+          const uint32_t qa = QT + (uint32_t)qb * 64 + lane_base + 16 * half;
+          tc::tmem_st16(qa, qhw);
+          tc::tmem_st16(qa + 32, qlw);
+          tc::tmem_st_wait();
+          tc::tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&q_ready[qb]);
+          if (++qb == 2) { qb = 0; qb_phase ^= 1; }
+        }
         if (i >= 1 && (i % p.drain) == 0) drain_chain();      // the chain that ended with stage i-1
       }
       drain_chain();                                           // the chain that ended with stage S-1
@@ -287,7 +358,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
   }
   tc::tcgen05_fence_before();
   __syncthreads();
-  if (warp == 2) tc::tmem_dealloc(tmem_base, 256);
+  if (warp == 2) tc::tmem_dealloc(tmem_base, 512);
 }
 
 __global__ void sum_cost_parts_kernel(const double* part, int n, double* out) {
@@ -335,15 +406,15 @@ int nnfac_nmf_plan_fused(nnfac_nmf_plan* p, int side, int mode, int want_cost, f
   fp.r_pad = p->r_pad; fp.splits = s->cp.splits; fp.stages_per_unit = s->cp.stages_per_unit; fp.num_units = s->cp.num_units;
   fp.drain = 2; fp.want_cost = (mode == 0 || want_cost) ? 1 : 0;
   fp.ld_partial = s->cp.ld_partial; fp.partial = p->partial; fp.cost_part = p->cost_part;
-  const size_t smem = A1_BYTES + (size_t)FSTAGES * STAGE_BYTES + 256;
+  const size_t smem = A1_BYTES + (size_t)FSTAGES * STAGE_BYTES + 512;
   const int other = 1 - side;
   if (mode == 0) {
     NNFAC_CUDA(cudaFuncSetAttribute(tc_fused_kernel<MODE_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_fused_kernel<MODE_RES><<<s->grid, FUSED_THREADS, smem, st>>>(s->map_xh, s->map_xl, s->map_fh, s->map_fl,
+    tc_fused_kernel<MODE_RES><<<s->grid, FUSED_THREADS, smem, st>>>(s->map_xh, s->map_xl,
         p->map_row_b_h[other], p->map_row_b_l[other], p->map_row_a_h[side], p->map_row_a_l[side], fp);
   } else {
     NNFAC_CUDA(cudaFuncSetAttribute(tc_fused_kernel<MODE_MU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_fused_kernel<MODE_MU><<<s->grid, FUSED_THREADS, smem, st>>>(s->map_xh, s->map_xl, s->map_fh, s->map_fl,
+    tc_fused_kernel<MODE_MU><<<s->grid, FUSED_THREADS, smem, st>>>(s->map_xh, s->map_xl,
         p->map_row_b_h[other], p->map_row_b_l[other], p->map_row_a_h[side], p->map_row_a_l[side], fp);
   }
   NNFAC_LAUNCH_CHECK(p->ctx);

@@ -19,6 +19,7 @@ import nn_fac.update_rules.mu as mu
 import nn_fac.update_rules.nnls as nnls
 import nn_fac.utils.errors as err
 import nn_fac.utils.initialize_factors as init_factors
+from nn_fac import _fast
 from nn_fac import _lib as L
 from nn_fac import _ops as ops
 
@@ -174,6 +175,16 @@ def compute_nmf(data, rank, U_in, V_in, n_iter_max=100, tol=1e-8,
     if normalize is None or normalize is False:
         normalize = [False, False]
     dt = L.resolve_dtype(data, U_in, V_in)
+    if n_iter_max > 0 and _fast.eligible(dt, int(np.shape(U_in)[1]), update_rule, beta):
+        # fp32, rank <= 64: two X passes per iteration on tcgen05, cost fused with a lag of one pass
+        _check_step_arguments(update_rule, beta, sparsity_coefficients)
+        fast = _fast.FusedNMF(data, U_in, V_in)
+        cost_fct_vals, toc = fast.run(n_iter_max, tol, update_rule, sparsity_coefficients, fixed_modes, normalize, verbose)
+        U_dev, V_dev = fast.factors()
+        U_out, V_out = _to_output(U_dev, data), _to_output(V_dev, data)
+        if return_costs:
+            return U_out, V_out, cost_fct_vals, toc
+        return U_out, V_out
     state = None
     cost_fct_vals, toc = [], []
     tic = time.time()
