@@ -17,7 +17,12 @@
 namespace {
 using namespace tcplan;
 
-constexpr int FUSED_THREADS = 384;   // warp0 TMA, warp1 MMA, warp2 TMEM, warps 4-11 transform/epilogue
+constexpr int NSP = 4;               // column splits of a stage among the transform warps
+constexpr int CW = 64 / NSP;         // X columns (and D2 columns) per transform thread and stage
+constexpr int NCHK = CW / 8;         // 16-byte chunks per thread, plane and stage
+constexpr int NWT = 4 * NSP;         // transform warps: 4 TMEM lane quadrants x NSP column parts
+constexpr int FUSED_THREADS = 128 + 32 * NWT;   // warp0 TMA, warps 1/3 MMA issuers, warp2 TMEM, then transform warps
+static_assert(CW == 16, "the transform below moves 16 columns per tcgen05.ld / 8 words per tcgen05.st");
 constexpr int FSTAGES = 4;
 constexpr uint32_t X_BYTES = TILE_ROWS * BK * sizeof(bf16);   // 16 KiB per plane tile
 constexpr uint32_t FK_BYTES = 64 * BK * sizeof(bf16);         // 8 KiB  (64 columns of X x rank 64)
@@ -87,13 +92,13 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     tc::prefetch_tmap(&map_fkh); tc::prefetch_tmap(&map_fkl); tc::prefetch_tmap(&map_a1h); tc::prefetch_tmap(&map_a1l);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < FSTAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 9); }
-    tc::mbar_init(a1_full, 1); tc::mbar_init(a1_empty, 8);
-    tc::mbar_init(a1t_ready, 8); tc::mbar_init(a1t_free, 1);
-    for (int b = 0; b < 2; ++b) { tc::mbar_init(&q_ready[b], 8); tc::mbar_init(&q_free[b], 1); }
+    for (int s = 0; s < FSTAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], NWT + 1); }
+    tc::mbar_init(a1_full, 1); tc::mbar_init(a1_empty, NWT);
+    tc::mbar_init(a1t_ready, NWT); tc::mbar_init(a1t_free, 1);
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(&q_ready[b], NWT); tc::mbar_init(&q_free[b], 1); }
     for (int b = 0; b < 2; ++b) {
-      tc::mbar_init(&d1_full[b], 1); tc::mbar_init(&d1_empty[b], 8);
-      tc::mbar_init(&d2_full[b], 1); tc::mbar_init(&d2_empty[b], 8);
+      tc::mbar_init(&d1_full[b], 1); tc::mbar_init(&d1_empty[b], NWT);
+      tc::mbar_init(&d2_full[b], 1); tc::mbar_init(&d2_empty[b], NWT);
     }
     tc::fence_barrier_init();
   }
@@ -210,10 +215,10 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     }
   } else if (warp >= 4) {
     // ===================== transform + epilogue warps =====================
-    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int q = warp & 3, part = (warp - 4) >> 2;           // TMEM lane quadrant, column part (0..NSP-1)
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const int ncol2 = p.r_pad - 32 * half > 32 ? 32 : (p.r_pad - 32 * half > 0 ? p.r_pad - 32 * half : 0);   // D2 columns of this half
+    const bool has_d2 = CW * part < p.r_pad;                   // r_pad is a multiple of 16 = CW
     int st = 0; uint32_t ph = 0;
     int b1 = 0; uint32_t b1_phase = 0;
     int b2 = 0; uint32_t b2_phase = 0;
@@ -222,25 +227,25 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     double cost = 0.0;
     for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
       const int tile = u / p.splits, split = u % p.splits;
-      float sum[32];
+      float sum[CW];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) sum[j] = 0.f;
+      for (int j = 0; j < CW; ++j) sum[j] = 0.f;
       {
-        // A1 (this unit's rows of the aligned factor): shared memory -> tensor memory, this thread's row and K half
+        // A1 (this unit's rows of the aligned factor): shared memory -> tensor memory, this thread's row and K part
         tc::mbar_wait(a1_full, a1_phase);
         tc::mbar_wait(a1t_free, a1_phase ^ 1);
         a1_phase ^= 1;
         tc::tcgen05_fence_after();
 #pragma unroll
         for (int pl = 0; pl < 2; ++pl) {
-          uint32_t w[16];
+          uint32_t w[4 * NCHK];
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            const int chunk = 4 * half + cc;
+          for (int cc = 0; cc < NCHK; ++cc) {
+            const int chunk = NCHK * part + cc;
             const uint4 v4 = *reinterpret_cast<const uint4*>(a1 + pl * X_BYTES + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4));
             w[4 * cc] = v4.x; w[4 * cc + 1] = v4.y; w[4 * cc + 2] = v4.z; w[4 * cc + 3] = v4.w;
           }
-          tc::tmem_st16(A1T + lane_base + 32 * pl + 16 * half, w);
+          tc::tmem_st8(A1T + lane_base + 32 * pl + (CW / 2) * part, w);
         }
         tc::tmem_st_wait();
         tc::tcgen05_fence_before();
@@ -250,16 +255,12 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
       auto drain_chain = [&]() {
         tc::mbar_wait(&d2_full[b2], b2_phase);
         tc::tcgen05_fence_after();
-        const uint32_t ta = D2 + (uint32_t)b2 * 64 + lane_base + 32 * half;
+        if (has_d2) {
+          uint32_t v[16];
+          tc::tmem_ld16(D2 + (uint32_t)b2 * 64 + lane_base + CW * part, v);
+          tc::tmem_ld_wait();
 #pragma unroll
-        for (int c0 = 0; c0 < 32; c0 += 16) {
-          if (c0 < ncol2) {
-            uint32_t v[16];
-            tc::tmem_ld16(ta + c0, v);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) sum[c0 + j] += __uint_as_float(v[j]);
-          }
+          for (int j = 0; j < 16; ++j) sum[j] += __uint_as_float(v[j]);
         }
         tc::tcgen05_fence_before();
         __syncwarp();
@@ -270,28 +271,27 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         // ---- model tile for this stage ----
         tc::mbar_wait(&d1_full[b1], b1_phase);
         tc::tcgen05_fence_after();
-        uint32_t kk[32];
-        tc::tmem_ld32(D1 + (uint32_t)b1 * 64 + lane_base + 32 * half, kk);
+        uint32_t kk[CW];
+        tc::tmem_ld16(D1 + (uint32_t)b1 * 64 + lane_base + CW * part, kk);
         tc::tmem_ld_wait();
         tc::tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&d1_empty[b1]);
         if (++b1 == 2) { b1 = 0; b1_phase ^= 1; }
-        // the stage's TMA data is visible: GEMM-1 of this stage already waited on full[st]; this
-        // thread must observe it too before reading X through the generic proxy
+        // the stage's TMA data is visible to the MMA issuers; this thread must observe the barrier too
+        // before reading X through the generic proxy
         tc::mbar_wait(&full[st], ph);
         uint8_t* xh = ring + (size_t)st * STAGE_BYTES;
         uint8_t* xl = xh + X_BYTES;
         float acc = 0.f;
-        uint32_t qhw[16], qlw[16];
+        uint32_t qhw[4 * NCHK], qlw[4 * NCHK];
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const int chunk = 4 * half + cc;
+        for (int cc = 0; cc < NCHK; ++cc) {
+          const int chunk = NCHK * part + cc;
           const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
           const uint4 h4 = *reinterpret_cast<const uint4*>(xh + off);
           const uint4 l4 = *reinterpret_cast<const uint4*>(xl + off);
           const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
-          uint32_t qh[4], ql[4];
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
             const float x0 = bf_lo(hw[w]) + bf_lo(lw[w]), x1 = bf_hi(hw[w]) + bf_hi(lw[w]);
@@ -312,13 +312,9 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
               const __nv_bfloat162 hq = __floats2bfloat162_rn(q0, q1);
               const uint32_t hqw = *reinterpret_cast<const uint32_t*>(&hq);
               const __nv_bfloat162 lq = __floats2bfloat162_rn(q0 - bf_lo(hqw), q1 - bf_hi(hqw));
-              qh[w] = hqw;
-              ql[w] = *reinterpret_cast<const uint32_t*>(&lq);
+              qhw[4 * cc + w] = hqw;
+              qlw[4 * cc + w] = *reinterpret_cast<const uint32_t*>(&lq);
             }
-          }
-          if (MODE == MODE_MU) {
-#pragma unroll
-            for (int w = 0; w < 4; ++w) { qhw[4 * cc + w] = qh[w]; qlw[4 * cc + w] = ql[w]; }
           }
         }
         if (p.want_cost) cost += (double)acc;
@@ -329,9 +325,9 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
           // ratio tile -> tensor memory (A operand of the contraction GEMM): hi 32 columns, lo 32 columns
           tc::mbar_wait(&q_free[qb], qb_phase ^ 1);
           tc::tcgen05_fence_after();
-          const uint32_t qa = QT + (uint32_t)qb * 64 + lane_base + 16 * half;
-          tc::tmem_st16(qa, qhw);
-          tc::tmem_st16(qa + 32, qlw);
+          const uint32_t qa = QT + (uint32_t)qb * 64 + lane_base + (CW / 2) * part;
+          tc::tmem_st8(qa, qhw);
+          tc::tmem_st8(qa + 32, qlw);
           tc::tmem_st_wait();
           tc::tcgen05_fence_before();
           __syncwarp();
@@ -341,18 +337,19 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         if (i >= 1 && (i % p.drain) == 0) drain_chain();      // the chain that ended with stage i-1
       }
       drain_chain();                                           // the chain that ended with stage S-1
-      float* out = p.partial + ((int64_t)split * p.r_pad + 32 * half) * p.ld_partial + (int64_t)tile * TILE_ROWS + row;
+      if (has_d2) {
+        float* out = p.partial + ((int64_t)split * p.r_pad + CW * part) * p.ld_partial + (int64_t)tile * TILE_ROWS + row;
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncol2) out[(int64_t)j * p.ld_partial] = sum[j];
+        for (int j = 0; j < CW; ++j) out[(int64_t)j * p.ld_partial] = sum[j];
+      }
     }
     // per-CTA cost partial (fixed order)
     cost = warp_sum(cost);
     if (lane == 0) cost_sh[warp - 4] = cost;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * NWT) : "memory");
     if (warp == 4 && lane == 0) {
       double t = 0.0;
-      for (int w = 0; w < 8; ++w) t += cost_sh[w];
+      for (int w = 0; w < NWT; ++w) t += cost_sh[w];
       p.cost_part[blockIdx.x] = t;
     }
   }
