@@ -9,13 +9,22 @@ the first pass of iteration t+1 forms (nmf.py:452/455 re-form it in a third pass
 therefore learns cost[t] while iteration t+1 is already in flight; if the reference's stop test
 (|cost[t-1] - cost[t]| < tol, nmf.py:320) fires, the speculative iteration is discarded.  A final
 cost-only pass closes the last iteration.
+
+Several GPUs (one process each): X is sharded by COLUMNS.  Rank p holds X_p (m x n_p) and V_p (r x n_p);
+U is replicated.  Per outer iteration there is one exchange step on each side of the U update:
+  * the partial cross products of the first pass (V_p X_p^T, r x m) and the partial Gram V_p V_p^T are
+    summed with one all-reduce (HALS), or the partial MU numerator and the partial row sums of V (MU);
+  * for HALS the U solve is split by rows of U (columns of U^T): every rank sweeps its own m/P slice and
+    the slices are all-gathered, so the solve shrinks with P instead of being repeated on every rank.
+The V side needs no exchange.  The HALS stop test (nnls.py:156) is evaluated PER SLICE in this mode
+(each rank stops on the squared-step ratio of the columns it owns): a grid-wide scalar per sweep
+across GPUs would cost more than the sweep itself.  Costs are summed with a scalar all-reduce.
 """
 import time
 
 import torch
 
 import nn_fac.update_rules.mu as mu
-import nn_fac.update_rules.nnls as nnls
 from nn_fac import _lib as L
 from nn_fac import _ops as ops
 
@@ -26,26 +35,127 @@ def eligible(dtype, rank, update_rule, beta):
     return dtype == torch.float32 and rank <= 64 and (update_rule == "hals" or (update_rule == "mu" and beta == 1))
 
 
+class Comm:
+    """The exchange steps of the column-sharded path over a torch.distributed group (NCCL on GPUs).
+    With a single rank every call returns its argument untouched and no collective is issued."""
+
+    def __init__(self, group=None, align=128):
+        self.group = group
+        self.align = align      # slices of the U solve start on multiples of this many rows of U
+        if group is None:
+            self.world, self.rank = 1, 0
+        else:
+            import torch.distributed as dist
+            self.dist = dist
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+
+    def sum_(self, t):
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def max_(self, t):
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def slice_of(self, length):
+        """Equal aligned chunks of range(length): returns (chunk, lo, hi) of this rank."""
+        chunk = -(-length // self.world)
+        chunk = -(-chunk // self.align) * self.align
+        lo = min(self.rank * chunk, length)
+        return chunk, lo, min(lo + chunk, length)
+
+    def gather_columns_(self, Ft, chunk, lo, hi):
+        """Every rank owns columns [lo, hi) of Ft (r x length); afterwards every rank holds all of them."""
+        if self.world == 1:
+            return Ft
+        r, length = Ft.shape
+        send = torch.zeros((r, chunk), dtype=Ft.dtype, device=Ft.device)
+        send[:, :hi - lo].copy_(Ft[:, lo:hi])
+        recv = torch.empty((self.world * r, chunk), dtype=Ft.dtype, device=Ft.device)
+        self.dist.all_gather_into_tensor(recv, send, group=self.group)
+        Ft.copy_(recv.view(self.world, r, chunk).permute(1, 0, 2).reshape(r, self.world * chunk)[:, :length])
+        return Ft
+
+
+class CudaEngine:
+    """The device operators one outer iteration is made of, all in libnnfac_b200 (no torch arithmetic)."""
+
+    def __init__(self, X, r):
+        self.plan = ops.NMFPlan(X).bind_rank(r)
+
+    def set_factor(self, which, Ft):
+        self.plan.set_factor(which, Ft)
+
+    def fused(self, side, mode, want_cost):
+        return self.plan.fused(side, mode, want_cost=want_cost)
+
+    def cross(self, which, F):
+        return self.plan.cross(which, F)
+
+    @staticmethod
+    def gram(F, out=None):
+        """F (r x len, row-major) -> F F^T (nmf.py:407 / :432)."""
+        r, length = F.shape
+        if out is None:
+            return ops.gemm(F, (F.stride(0), 1), F, (1, F.stride(0)), r, r, length)
+        return ops.gemm(F, (F.stride(0), 1), F, (1, F.stride(0)), r, r, length, out=out, ldc=out.stride(0), sc_b=0)
+
+    @staticmethod
+    def sweep(UtM, UtU, V, r, sparsity, normalize, result):
+        sp = 0.0 if sparsity is None else float(sparsity)
+        ops.hals_nnls(UtM, UtU, V, r, 100, 0.01, sp, bool(normalize), False, result)   # nmf.py:415 / :440
+
+    @staticmethod
+    def mu_apply(F, num, den_vec):
+        return ops.mu_apply(F, num, den_vec=den_vec, vec_per_row=True, gamma=1.0, floor=mu.epsilon)   # mu.py:88
+
+    row_sums = staticmethod(ops.row_sums)
+
+    @staticmethod
+    def max_col_abs_sum(F):
+        """numpy's matrix 1-norm of F (nmf.py:452)."""
+        return ops.norm1(F)
+
+    transpose = staticmethod(ops.transpose)
+
+
 class FusedNMF:
     events = None   # set to [] to collect (name, start_event, end_event) per phase
 
-    def __init__(self, data, U, V, device=None):
-        X = L.to_device(data, torch.float32, device)
-        self.m, self.n = X.shape
-        self.device = X.device
+    def __init__(self, data, U, V, device=None, group=None, engine=None):
+        """data: X (m x n), or this rank's column block X_p when `group` spans several ranks;
+        U: m x r (replicated); V: r x n, or this rank's block V_p."""
+        self.comm = group if isinstance(group, Comm) else Comm(group)
         self.r = int(U.shape[1])
-        self.plan = ops.NMFPlan(X).bind_rank(self.r)
-        del X
-        U_dev = L.to_device(U, torch.float32, device)
-        self.Ut = ops.transpose(U_dev)
-        V_dev = L.to_device(V, torch.float32, device)
+        if engine is None:
+            X = L.to_device(data, torch.float32, device)
+            self.eng = CudaEngine(X, self.r)
+            self.m, self.n = X.shape
+            self.device = X.device
+            del X
+            U_dev = L.to_device(U, torch.float32, device)
+            V_dev = L.to_device(V, torch.float32, device)
+            self._on_gpu = True
+        else:
+            self.eng = engine
+            self.m, self.n = data.shape
+            U_dev, V_dev = torch.as_tensor(U), torch.as_tensor(V)
+            self.device = U_dev.device
+            self._on_gpu = self.device.type == "cuda"
+        self.Ut = self.eng.transpose(U_dev)
         self.V = V_dev.clone() if isinstance(V, torch.Tensor) else V_dev
-        self.plan.set_factor(0, self.Ut)
-        self.plan.set_factor(1, self.V)
+        self.eng.set_factor(0, self.Ut)
+        self.eng.set_factor(1, self.V)
         self.hals_stats = torch.zeros((2, 4), dtype=torch.float64, device=self.device)
         self.sweep_log = []
-        self._host = torch.zeros(4, dtype=torch.float64).pin_memory()
+        self._host = torch.zeros(4, dtype=torch.float64)
+        if self._on_gpu:
+            self._host = self._host.pin_memory()
         self._dev_scal = torch.zeros(4, dtype=torch.float64, device=self.device)
+        # exchange buffer of the U side: [cross product or numerator (r x m) | Gram (r x r) or row sums (r)]
+        self._xbuf = torch.empty(self.r * self.m + self.r * self.r, dtype=self.Ut.dtype, device=self.device)
 
     def _phase(self, name):
         from nn_fac.nmf import _Phase
@@ -53,39 +163,59 @@ class FusedNMF:
 
     # one outer iteration, given the result of its first pass
     def _apply_hals(self, VMt, sparsity, fixed_modes, normalize):
-        r, m, n = self.r, self.m, self.n
-        Ut, V = self.Ut, self.V
+        r, m = self.r, self.m
+        Ut, V, comm, eng = self.Ut, self.V, self.comm, self.eng
         if 0 not in fixed_modes:
             with self._phase("gram_U"):
-                VVt = ops.gemm(V, (n, 1), V, (1, n), r, r, n)                      # nmf.py:407
+                if comm.world == 1:
+                    VVt = eng.gram(V)                                              # nmf.py:407
+                else:
+                    # partial V_p X_p^T and V_p V_p^T of this column block, summed over the blocks
+                    xb = self._xbuf
+                    xb[:r * m].view(r, m).copy_(VMt)
+                    eng.gram(V, out=xb[r * m:].view(r, r))
+                    comm.sum_(xb)
+                    VMt, VVt = xb[:r * m].view(r, m), xb[r * m:].view(r, r)
             with self._phase("sweep_U"):
                 Ut = Ut.clone()
-                nnls.hals_nnls_device(VMt, VVt, Ut, r, maxiter=100, delta=0.01, sparsity_coefficient=sparsity[0],
-                                      normalize=normalize[0], nonzero=False, result=self.hals_stats[0])   # nmf.py:415
-                self.plan.set_factor(0, Ut)
+                if comm.world == 1 or normalize[0]:
+                    eng.sweep(VMt, VVt, Ut, r, sparsity[0], normalize[0], self.hals_stats[0])   # nmf.py:415
+                else:
+                    chunk, lo, hi = comm.slice_of(m)
+                    if hi > lo:
+                        eng.sweep(VMt[:, lo:hi], VVt, Ut[:, lo:hi], r, sparsity[0], False, self.hals_stats[0])
+                    comm.gather_columns_(Ut, chunk, lo, hi)
+                eng.set_factor(0, Ut)
         if 1 not in fixed_modes:
             with self._phase("cross_V"):
-                UtM = self.plan.cross(1, Ut)                                       # nmf.py:433
-                UtU = ops.gemm(Ut, (m, 1), Ut, (1, m), r, r, m)                    # nmf.py:432
+                UtM = eng.cross(1, Ut)                                             # nmf.py:433
+                UtU = eng.gram(Ut)                                                 # nmf.py:432
             with self._phase("sweep_V"):
                 V = V.clone()
-                nnls.hals_nnls_device(UtM, UtU, V, r, maxiter=100, delta=0.01, sparsity_coefficient=sparsity[1],
-                                      normalize=normalize[1], nonzero=False, result=self.hals_stats[1])   # nmf.py:440
-                self.plan.set_factor(1, V)
+                eng.sweep(UtM, UtU, V, r, sparsity[1], normalize[1], self.hals_stats[1])        # nmf.py:440
+                eng.set_factor(1, V)
         return Ut, V
 
     def _apply_mu(self, numU, fixed_modes):
-        Ut, V = self.Ut, self.V
+        r, m = self.r, self.m
+        Ut, V, comm, eng = self.Ut, self.V, self.comm, self.eng
         if 0 not in fixed_modes:
             with self._phase("apply_U"):
-                Ut = ops.mu_apply(Ut, numU, den_vec=ops.row_sums(V), vec_per_row=True, gamma=1.0, floor=mu.epsilon)
-                self.plan.set_factor(0, Ut)                                        # mu.py:84-88
+                den = eng.row_sums(V)                                              # mu.py:85-87
+                if comm.world > 1:
+                    xb = self._xbuf[:r * m + r]
+                    xb[:r * m].view(r, m).copy_(numU)
+                    xb[r * m:].copy_(den)
+                    comm.sum_(xb)
+                    numU, den = xb[:r * m].view(r, m), xb[r * m:]
+                Ut = eng.mu_apply(Ut, numU, den)                                   # mu.py:84-88
+                eng.set_factor(0, Ut)
         if 1 not in fixed_modes:
             with self._phase("pass_V"):
-                numV, _ = self.plan.fused(1, MODE_MU, want_cost=False)
+                numV, _ = eng.fused(1, MODE_MU, False)
             with self._phase("apply_V"):
-                V = ops.mu_apply(V, numV, den_vec=ops.row_sums(Ut), vec_per_row=True, gamma=1.0, floor=mu.epsilon)
-                self.plan.set_factor(1, V)                                         # mu.py:27
+                V = eng.mu_apply(V, numV, eng.row_sums(Ut))                        # mu.py:27
+                eng.set_factor(1, V)
         return Ut, V
 
     def run(self, n_iter_max, tol, update_rule, sparsity=(None, None), fixed_modes=(), normalize=(False, False),
@@ -94,19 +224,25 @@ class FusedNMF:
         mode = MODE_RES if update_rule == "hals" else MODE_MU
         sp = [0.0 if s is None else float(s) for s in sparsity]
         with_sparsity = update_rule == "hals" and (sp[0] != 0.0 or sp[1] != 0.0)
+        if self.comm.world > 1 and update_rule == "hals" and normalize[1]:
+            raise NotImplementedError("column-sharded HALS cannot normalise the rows of V: a row spans every rank")
         costs, toc = [], []
         tic = time.time()
-        done = torch.cuda.Event()
+        done = torch.cuda.Event() if self._on_gpu else None
         for it in range(n_iter_max + 1):
             with self._phase("pass_U"):
-                outA, cost_dev = self.plan.fused(0, mode, want_cost=True)
+                outA, cost_dev = self.eng.fused(0, mode, True)
             if it > 0:
                 self._dev_scal[0:1].copy_(cost_dev)
+                self._dev_scal[1:3].zero_()
+                self.comm.sum_(self._dev_scal[0:1])
                 if with_sparsity:       # nmf.py:449-452: matrix 1-norms of the factors the cost refers to
-                    self._dev_scal[1:2].copy_(ops.norm1(ops.transpose(self.Ut)))
-                    self._dev_scal[2:3].copy_(ops.norm1(self.V))
+                    self._dev_scal[1:2].copy_(self.eng.max_col_abs_sum(self.eng.transpose(self.Ut)))
+                    self._dev_scal[2:3].copy_(self.eng.max_col_abs_sum(self.V))
+                    self.comm.max_(self._dev_scal[2:3])
                 self._host.copy_(self._dev_scal, non_blocking=True)
-                done.record()
+                if done is not None:
+                    done.record()
             # launch iteration `it` before looking at the cost of iteration it-1
             if it < n_iter_max:
                 if mode == MODE_RES:
@@ -114,7 +250,8 @@ class FusedNMF:
                 else:
                     new_Ut, new_V = self._apply_mu(outA, fixed_modes)
             if it > 0:
-                done.synchronize()
+                if done is not None:
+                    done.synchronize()
                 cost = float(self._host[0])
                 if with_sparsity:
                     cost += 2 * (sp[0] * float(self._host[1]) + sp[1] * float(self._host[2]))
@@ -132,8 +269,8 @@ class FusedNMF:
                         print('Converged in {} iterations.'.format(len(costs) - 1))
                     # the speculative iteration is dropped: self.Ut / self.V are untouched; put their planes back
                     if it < n_iter_max:
-                        self.plan.set_factor(0, self.Ut)
-                        self.plan.set_factor(1, self.V)
+                        self.eng.set_factor(0, self.Ut)
+                        self.eng.set_factor(1, self.V)
                     break
             if it == n_iter_max:
                 break
@@ -143,4 +280,4 @@ class FusedNMF:
         return costs, toc
 
     def factors(self):
-        return ops.transpose(self.Ut), self.V
+        return self.eng.transpose(self.Ut), self.V
