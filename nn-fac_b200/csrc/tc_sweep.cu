@@ -12,6 +12,8 @@
 // (rewritten 16 rows at a time after each block).  A CTA carries up to 4 column tiles whose
 // MMA / update phases interleave.  The per-sweep stop test is the same fixed-order grid reduction
 // as the FMA kernel (deterministic, identical on every CTA).
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -33,7 +35,7 @@ constexpr uint32_t G_BLOCK_BYTES = 3 * BLK * 128;             // per block: 16 r
 constexpr int NPLANES = 3;
 
 struct SweepConst {
-  float gblk[NBLK][BLK][BLK];   // diagonal blocks of UtU
+  float nh[NBLK][BLK][BLK];     // -UtU[k][l] / UtU[k][k] inside the diagonal blocks (row k, column l)
   float invd[RP];               // 1 / UtU[k][k], 0 when the diagonal entry is 0 or k >= r
 };
 __constant__ SweepConst c_sw;
@@ -42,7 +44,8 @@ __global__ void sweep_prep_kernel(const float* __restrict__ G, int64_t ld_g, int
   for (int idx = threadIdx.x; idx < NBLK * BLK * BLK; idx += blockDim.x) {
     const int B = idx / (BLK * BLK), e = (idx / BLK) % BLK, e2 = idx % BLK;
     const int k = B * BLK + e, l = B * BLK + e2;
-    out->gblk[B][e][e2] = (k < r && l < r) ? G[(int64_t)k * ld_g + l] : 0.f;
+    const float dk = k < r ? G[(int64_t)k * ld_g + k] : 0.f;
+    out->nh[B][e][e2] = (k < r && l < r && dk != 0.f) ? -G[(int64_t)k * ld_g + l] * (1.f / dk) : 0.f;
   }
   for (int k = threadIdx.x; k < RP; k += blockDim.x) {
     const float d = k < r ? G[(int64_t)k * ld_g + k] : 0.f;
@@ -76,18 +79,18 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 // Write 8 consecutive K-elements (one 16-byte chunk) of row `row` into the three K-major SW128 planes
-// (hi, mid, lo: x = hi + mid + lo to ~2^-24, i.e. fp32 operands for the tensor core).
+// (hi, mid, lo: x = hi + mid + lo exactly for normal fp32 values, i.e. fp32 operands for the tensor core).
+// Two values per conversion (cvt.rn.bf16x2.f32); the halves are widened back with a shift / a mask.
 __device__ __forceinline__ void store_chunk(uint8_t* plane_hi, int row, int chunk, const float* x, uint32_t plane_stride) {
   uint32_t h[4], m[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float a = x[2 * i], b = x[2 * i + 1];
-    const float ah = __bfloat162float(__float2bfloat16_rn(a)), bh = __bfloat162float(__float2bfloat16_rn(b));
-    const float a1 = a - ah, b1 = b - bh;
-    const float am = __bfloat162float(__float2bfloat16_rn(a1)), bm = __bfloat162float(__float2bfloat16_rn(b1));
-    h[i] = pack_bf16(ah, bh);
-    m[i] = pack_bf16(am, bm);
-    l[i] = pack_bf16(a1 - am, b1 - bm);
+    h[i] = pack_bf16(a, b);
+    const float a1 = a - __uint_as_float(h[i] << 16), b1 = b - __uint_as_float(h[i] & 0xffff0000u);
+    m[i] = pack_bf16(a1, b1);
+    const float a2 = a1 - __uint_as_float(m[i] << 16), b2 = b1 - __uint_as_float(m[i] & 0xffff0000u);
+    l[i] = pack_bf16(a2, b2);
   }
   uint8_t* p = plane_hi + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
   *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
@@ -110,11 +113,14 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
 __device__ __forceinline__ void issue_block_mma(uint64_t a_hi, uint64_t a_mid, uint64_t a_lo, uint64_t g_blk, uint32_t d,
                                                 int nks, uint32_t idesc48, uint32_t idesc32, uint32_t idesc16,
                                                 uint64_t* bar) {
-  for (int ks = 0; ks < nks; ++ks) {
-    const uint64_t koff = (uint64_t)(ks * 2);                 // 32 bytes >> 4 inside the 128-byte row
-    tc::umma_bf16(d, a_hi + koff, g_blk + koff, idesc48, ks != 0);
-    tc::umma_bf16(d + 48, a_lo + koff, g_blk + koff, idesc16, ks != 0);
-    tc::umma_bf16(d, a_mid + koff, g_blk + koff, idesc32, true);
+#pragma unroll
+  for (int ks = 0; ks < NBLK; ++ks) {
+    if (ks < nks) {
+      const uint64_t koff = (uint64_t)(ks * 2);               // 32 bytes >> 4 inside the 128-byte row
+      tc::umma_bf16(d, a_hi + koff, g_blk + koff, idesc48, ks != 0);
+      tc::umma_bf16(d + 48, a_lo + koff, g_blk + koff, idesc16, ks != 0);
+      tc::umma_bf16(d, a_mid + koff, g_blk + koff, idesc32, true);
+    }
   }
   tc::umma_commit(bar);
 }
@@ -204,98 +210,165 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
     issue_block_mma(a_hi, a_mid, a_lo, g_desc, d_tile, nblk, idesc48, idesc32, idesc16, &s_full[tile]);
   }
 
+  // One Gauss-Seidel block (16 rows) of this thread's column: wait for the tensor-core part, run the
+  // in-block recurrence, rewrite the operand planes of the 16 rows and hand the next block to the tensor
+  // core.  Returns the squared step of the block (nnls.py:170).
+  uint32_t s_phase = 0;
+  const float sp_t = valid ? a.sp : 0.f;
+#ifdef SWEEP_PROF
+  long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PROF_T(i) { const long long t__ = clock64(); prof[i] += t__ - tp; tp = t__; }
+#define PROF_START long long tp = clock64();
+#else
+#define PROF_T(i)
+#define PROF_START
+#endif
+  auto block_update = [&](auto Bc) -> float {
+    constexpr int B = decltype(Bc)::value;
+    float nd = 0.f;
+    PROF_START
+    uint32_t bu[16];
+    tc::tmem_ld16(t_b + B * BLK, bu);                               // UtM of the block: does not wait for the MMA
+    tc::mbar_wait(&s_full[tile], s_phase);
+    s_phase ^= 1;
+    tc::tcgen05_fence_after();
+    PROF_T(0)
+    // u[e] = (UtM[k] - UtU[k,:] V - sp) / UtU[k,k] with V as it stood when the block started (tensor-core part)
+    float u[BLK];
+    {
+      uint32_t s0[16], s1[16];
+      tc::tmem_ld16(t_s + 16, s0);
+      tc::tmem_ld16(t_s + 48, s1);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < BLK; ++e) u[e] = __uint_as_float(s0[e]) + __uint_as_float(s1[e]);
+      tc::tmem_ld16(t_s + 32, s0);
+      tc::tmem_ld16(t_s, s1);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < BLK; ++e) u[e] = __uint_as_float(s1[e]) + (u[e] + __uint_as_float(s0[e]));
+#pragma unroll
+      for (int e = 0; e < BLK; ++e) u[e] = (__uint_as_float(bu[e]) - u[e] - sp_t) * c_sw.invd[B * BLK + e];
+    }
+    tc::tcgen05_fence_before();
+    PROF_T(1)
+    // In-block Gauss-Seidel recurrence (nnls.py:158-170) on the scaled residuals: the step of row k is
+    // max(u, -V[k]) and every later row of the block sees it through -UtU[k2][k] / UtU[k2][k2].
+    // Two dependent instructions per row (FMNMX, FFMA) instead of the six of the literal formula.
+#pragma unroll
+    for (int e = 0; e < BLK; ++e) {
+      const int k = B * BLK + e;
+      const float cur = v[k];
+      const float lb = c_sw.invd[k] != 0.f ? -cur : 0.f;            // zero diagonal: row skipped (nnls.py:160), u = 0
+      const float dd = fmaxf(u[e], lb);                             // nnls.py:163/167
+      if (e + 1 < BLK) u[e + 1] = fmaf(c_sw.nh[B][e + 1][e], dd, u[e + 1]);
+      v[k] = cur + dd;
+      nd = fmaf(dd, dd, nd);                                        // nnls.py:170
+#pragma unroll
+      for (int e2 = e + 2; e2 < BLK; ++e2) u[e2] = fmaf(c_sw.nh[B][e2][e], dd, u[e2]);
+    }
+    PROF_T(2)
+    store_chunk(vh, row, 2 * B, &v[B * BLK], PLANE_BYTES);
+    store_chunk(vh, row, 2 * B + 1, &v[B * BLK + 8], PLANE_BYTES);
+    PROF_T(3)
+    tc::fence_proxy_async_smem();
+    tc::tcgen05_fence_before();
+    named_bar_sync(2 + tile, TILE);                                 // this tile's planes are rewritten
+    PROF_T(4)
+    if (issuer) {
+      // next block (block 0 of the next sweep after the last one: if the stop test ends the solve its
+      // result is simply dropped)
+      const int nb = (B + 1 < nblk) ? B + 1 : 0;
+      tc::tcgen05_fence_after();
+      issue_block_mma(a_hi, a_mid, a_lo, g_desc + (uint64_t)(nb * (int)G_BLOCK_BYTES >> 4), d_tile, nblk, idesc48, idesc32,
+                      idesc16, &s_full[tile]);
+    }
+    PROF_T(5)
+    return nd;
+  };
+
   double eps0 = 0.0, eps = 1.0;
   int cnt = 1;
   unsigned epoch = 0;
-  uint32_t s_phase = 0;
-  while (eps >= a.delta * eps0 && cnt <= a.maxiter) {
-    float nd = 0.f;
+  // Block 0 of the coming sweep is run SPECULATIVELY while the grid-wide sum of the finished sweep is in
+  // flight (the stop test of nnls.py:156 needs that sum): `bk` keeps the 16 values it overwrites.
+  bool have_spec = false;
+  float nd_spec = 0.f;
+  float bk[BLK];
+  while (true) {
+    float nd = have_spec ? nd_spec : 0.f;
     if (active) {
-#pragma unroll
-      for (int B = 0; B < NBLK; ++B) {
-        if (B < nblk) {
-          tc::mbar_wait(&s_full[tile], s_phase);
-          s_phase ^= 1;
-          tc::tcgen05_fence_after();
-          uint32_t s0[16], s1[16], s2[16], s3[16], bu[16];
-          tc::tmem_ld16(t_s, s0);
-          tc::tmem_ld16(t_s + 16, s1);
-          tc::tmem_ld16(t_s + 32, s2);
-          tc::tmem_ld16(t_s + 48, s3);
-          tc::tmem_ld16(t_b + B * BLK, bu);
-          tc::tmem_ld_wait();
-          tc::tcgen05_fence_before();
-          float s[BLK];
-#pragma unroll
-          for (int e = 0; e < BLK; ++e)
-            s[e] = __uint_as_float(s0[e]) + ((__uint_as_float(s1[e]) + __uint_as_float(s3[e])) + __uint_as_float(s2[e]));
-#pragma unroll
-          for (int e = 0; e < BLK; ++e) {
-            const int k = B * BLK + e;
-            const float inv = c_sw.invd[k];
-            const float cur = v[k];
-            float dd = (__uint_as_float(bu[e]) - s[e] - a.sp) * inv;    // nnls.py:163/167 (reciprocal multiply)
-            dd = fmaxf(dd, -cur);
-            dd = (inv != 0.f && valid) ? dd : 0.f;                      // zero diagonal: row skipped (nnls.py:160)
-            v[k] = cur + dd;
-            nd = fmaf(dd, dd, nd);                                      // nnls.py:170
-#pragma unroll
-            for (int e2 = e + 1; e2 < BLK; ++e2) s[e2] = fmaf(c_sw.gblk[B][e2][e], dd, s[e2]);
-          }
-          store_chunk(vh, row, 2 * B, &v[B * BLK], PLANE_BYTES);
-          store_chunk(vh, row, 2 * B + 1, &v[B * BLK + 8], PLANE_BYTES);
-          tc::fence_proxy_async_smem();
-          tc::tcgen05_fence_before();
-          named_bar_sync(2 + tile, TILE);                               // this tile's planes are rewritten
-          if (issuer) {
-            // next block (speculatively block 0 of the next sweep after the last one: its result is
-            // simply dropped if the stop test ends the solve, and it overlaps the grid reduction)
-            const int nb = (B + 1 < nblk) ? B + 1 : 0;
-            tc::tcgen05_fence_after();
-            issue_block_mma(a_hi, a_mid, a_lo, g_desc + (uint64_t)(nb * (int)G_BLOCK_BYTES >> 4), d_tile, nblk, idesc48, idesc32,
-                            idesc16, &s_full[tile]);
-          }
-        }
-      }
+      if (!have_spec) nd += block_update(std::integral_constant<int, 0>{});
+      if (nblk > 1) nd += block_update(std::integral_constant<int, 1>{});
+      if (nblk > 2) nd += block_update(std::integral_constant<int, 2>{});
+      if (nblk > 3) nd += block_update(std::integral_constant<int, 3>{});
     }
-    // ---- sum of squared steps over the whole grid, fixed order ----
+    // ---- sum of squared steps over the whole grid, fixed order: post this CTA's partial ... ----
     double t = warp_sum((double)nd);
     if (lane == 0) red[warp] = t;
     named_bar_sync(1, UPD_THREADS);
+    const unsigned nb = gridDim.x;
     if (threadIdx.x == 0) {
       double sum = 0.0;
       for (int w = 0; w < 16; ++w) sum += red[w];
-      const unsigned nb = gridDim.x;
       if (nb > 1) {
         double* slot = a.part + (size_t)(epoch & 1u) * nb;
         slot[blockIdx.x] = sum;
         __threadfence();
         atomicAdd(a.counter, 1u);
-        const unsigned target = (epoch + 1u) * nb;
-        while (ld_relaxed_u32(a.counter) < target) {}
-        __threadfence();
       } else {
         red[16] = sum;
       }
     }
-    named_bar_sync(1, UPD_THREADS);
-    if (gridDim.x > 1) {
+    // ---- ... run block 0 of the next sweep while the other CTAs arrive ... ----
+    have_spec = false;
+    if (cnt + 1 <= a.maxiter) {
+      have_spec = true;
+      nd_spec = 0.f;
+      if (active) {
+#pragma unroll
+        for (int e = 0; e < BLK; ++e) bk[e] = v[e];
+        nd_spec = block_update(std::integral_constant<int, 0>{});
+      }
+    }
+    // ---- ... then collect the total ----
+#ifdef SWEEP_PROF
+    const long long tg0 = clock64();
+#endif
+    if (nb > 1) {
       if (warp == 0) {
-        const double* slot = a.part + (size_t)(epoch & 1u) * gridDim.x;
+        const unsigned target = (epoch + 1u) * nb;
+        if (lane == 0) {
+          while (ld_relaxed_u32(a.counter) < target) {}
+          __threadfence();
+        }
+        __syncwarp();
+        const double* slot = a.part + (size_t)(epoch & 1u) * nb;
         double sum = 0.0;
-        for (unsigned i = lane; i < gridDim.x; i += 32) sum += __ldcg(slot + i);
+        for (unsigned i = lane; i < nb; i += 32) sum += __ldcg(slot + i);
         sum = warp_sum(sum);
         if (lane == 0) red[16] = sum;
       }
-      named_bar_sync(1, UPD_THREADS);
     }
+    named_bar_sync(1, UPD_THREADS);
+#ifdef SWEEP_PROF
+    prof[6] += clock64() - tg0;
+#endif
     const double tot = red[16];
     ++epoch;
     if (cnt == 1) eps0 = tot;
     eps = tot;
     ++cnt;
+    bool stop = !(eps >= a.delta * eps0 && cnt <= a.maxiter);
     if (tot == 0.0) {                                                   // further sweeps are no-ops (nnls.py:156)
       if (cnt < a.maxiter + 1) cnt = a.maxiter + 1;
+      stop = true;
+    }
+    if (stop) {
+      if (have_spec && active) {
+#pragma unroll
+        for (int e = 0; e < BLK; ++e) v[e] = bk[e];                     // undo the speculative block
+      }
       break;
     }
   }
@@ -308,6 +381,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
     for (int k = 0; k < RP; ++k)
       if (k < r) a.V[(int64_t)k * a.ld_v + col] = v[k];
   }
+#ifdef SWEEP_PROF
+  if (blockIdx.x == 1 && (threadIdx.x == 0 || threadIdx.x == 32)) {
+    printf("sweep prof (cycles/sweep) thr %d: mma_wait %lld tmem_ld %lld chain %lld split_store %lld fence_bar %lld issue %lld grid %lld\n",
+           threadIdx.x, prof[0] / (cnt - 1), prof[1] / (cnt - 1), prof[2] / (cnt - 1), prof[3] / (cnt - 1), prof[4] / (cnt - 1),
+           prof[5] / (cnt - 1), prof[6] / (cnt - 1));
+  }
+#endif
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.result[0] = eps;
     a.result[1] = (double)cnt;

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libnnfac_b200.so")
+LIB_PATH = os.environ.get("NNFAC_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libnnfac_b200.so")
 
 F32, F64 = 0, 1
 HALS_NORMALIZE, HALS_NONZERO = 1, 2
