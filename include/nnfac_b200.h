@@ -75,6 +75,11 @@ int nnfac_gemm_strided(nnfac_ctx* ctx, int dtype, void* C, int64_t ldc, int64_t 
                        int64_t sb_k, int64_t sb_j, int64_t sb_q, int64_t sb_b, int64_t M, int64_t N,
                        int64_t K, int64_t kb, int64_t batch, void* stream);
 
+/* Gram of a rank-major factor: out (r x r) = F F^T with F (r x len) row-major -- V V^T (nmf.py:407) and U^T U
+ * (nmf.py:432) when the factors are kept as V (r x n) and U^T (r x m).  Deterministic. */
+int nnfac_gram(nnfac_ctx* ctx, int dtype, void* out, int64_t ld_out, const void* F, int64_t ld_f, int r,
+               int64_t len, void* stream);
+
 /* Multiplicative-update element-wise terms, mu.py:84-97 / mu.py:143-155:
  *   P = K^(beta-2) * X   and   Q = K^(beta-1)   (either output may be NULL; in-place on K allowed) */
 int nnfac_mu_terms(nnfac_ctx* ctx, int dtype, double beta, const void* K, const void* X, void* P,
@@ -148,9 +153,15 @@ int nnfac_nmf_plan_set_factor(nnfac_nmf_plan* plan, int which, const float* Ft, 
  *   mode 0: out (r x rows) = the HALS cross product of nmf.py:408 / :433, cost_out = ||X - U V||_F^2 (nmf.py:452)
  *   mode 1: out (r x rows) = the beta=1 MU numerator ((X / UV) V^T)^T of mu.py:84-88 (side 0) or its
  *           transposed twin for V (mu.py:27, side 1); cost_out = KL(X | U V) when want_cost != 0.
- * cost_out is a device double and may be NULL. */
+ * cost_out is a device double and may be NULL.  out may be NULL in mode 1 (see nnfac_nmf_plan_mu_finish). */
 int nnfac_nmf_plan_fused(nnfac_nmf_plan* plan, int side, int mode, int want_cost, float* out, int64_t ld_out,
                          double* cost_out, void* stream);
+/* beta = 1 multiplicative update of factor `which` (0: U as U^T, 1: V), mu.py:84-88, straight from the numerator
+ * partials that the last mode-1 nnfac_nmf_plan_fused call over side `which` left in the plan when it was given
+ * out = NULL:  F_out = max(F_in * num / den[k], floor_value), den = r row sums of the other factor (mu.py:85-87).
+ * F_out is installed in the plan as nnfac_nmf_plan_set_factor would do.  One kernel. */
+int nnfac_nmf_plan_mu_finish(nnfac_nmf_plan* plan, int which, const float* F_in, int64_t ld_in, const float* den,
+                             double floor_value, float* F_out, int64_t ld_out, void* stream);
 /* Work decomposition chosen for one side (for benchmarks / DESIGN.md); any pointer may be NULL. */
 int nnfac_nmf_plan_info(const nnfac_nmf_plan* plan, int which, int* splits, int* stages_per_unit,
                         int* num_units, int* num_stages, int* grid);

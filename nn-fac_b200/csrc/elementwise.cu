@@ -109,6 +109,17 @@ __global__ void row_sums_kernel(const T* __restrict__ A, int64_t lda, int64_t ro
   if ((threadIdx.x & 31) == 0) out[row] = (T)s;
 }
 
+// long rows: one CTA per row, fixed-order block reduction
+template <typename T>
+__global__ void __launch_bounds__(256) row_sums_wide_kernel(const T* __restrict__ A, int64_t lda, int64_t cols, T* out) {
+  __shared__ double sh[33];
+  const T* row = A + (int64_t)blockIdx.x * lda;
+  double s = 0.0;
+  for (int64_t j = threadIdx.x; j < cols; j += 256) s += (double)row[j];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) out[blockIdx.x] = (T)s;
+}
+
 // column abs sums -> per-block maxima (matrix 1-norm)
 template <typename T>
 __global__ void __launch_bounds__(RB) norm1_stage1(const T* __restrict__ A, int64_t lda, int64_t rows,
@@ -243,9 +254,14 @@ int nnfac_row_sums(nnfac_ctx* ctx, int dtype, const void* A, int64_t lda, int64_
                    int64_t cols, void* out, void* stream) {
   NNFAC_ARG(ctx && A && out && rows > 0 && cols > 0, "nnfac_row_sums: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = (int)ceil_div64(rows, 8);
-  DISPATCH_T(dtype, (row_sums_kernel<float><<<grid, 256, 0, st>>>((const float*)A, lda, rows, cols, (float*)out)),
-             (row_sums_kernel<double><<<grid, 256, 0, st>>>((const double*)A, lda, rows, cols, (double*)out)));
+  if (cols >= 2048 && rows <= 65535) {
+    DISPATCH_T(dtype, (row_sums_wide_kernel<float><<<(unsigned)rows, 256, 0, st>>>((const float*)A, lda, cols, (float*)out)),
+               (row_sums_wide_kernel<double><<<(unsigned)rows, 256, 0, st>>>((const double*)A, lda, cols, (double*)out)));
+  } else {
+    const int grid = (int)ceil_div64(rows, 8);
+    DISPATCH_T(dtype, (row_sums_kernel<float><<<grid, 256, 0, st>>>((const float*)A, lda, rows, cols, (float*)out)),
+               (row_sums_kernel<double><<<grid, 256, 0, st>>>((const double*)A, lda, rows, cols, (double*)out)));
+  }
   NNFAC_LAUNCH_CHECK(ctx);
   return NNFAC_OK;
 }

@@ -164,7 +164,92 @@ int run_gemm(nnfac_ctx* ctx, T* C, int64_t ldc, int64_t sc_b, const T* A, int64_
   return NNFAC_OK;
 }
 
+// ---- Gram of a rank-major factor: out (r x r) = F F^T, F (r x len), r <= 64 -------------------------------
+// nmf.py:407 (V V^T) and nmf.py:432 (U^T U): a short-and-wide product (K = len up to 10^5..10^6, M = N = r).
+// Every CTA owns a contiguous range of columns, stages 64-column slabs of F in shared memory (transposed, so
+// that a thread reads its 4 + 4 operands with two 16-byte loads) and keeps a 4 x 4 block of the Gram in
+// registers; the per-CTA partials are added in fixed order by a second kernel (fp64 adder).
+constexpr int GR = 64, GC = 64, GPADF = 68;
+
+template <typename T>
+__global__ void __launch_bounds__(256) gram_partial_kernel(const T* __restrict__ F, int64_t ld_f, int r, int64_t len,
+                                                           int64_t cols_per_cta, T* __restrict__ part) {
+  __shared__ __align__(16) T tile[GC][GPADF];
+  const int t = threadIdx.x, ti = t >> 4, tj = t & 15;
+  const int64_t c_begin = (int64_t)blockIdx.x * cols_per_cta;
+  int64_t c_end = c_begin + cols_per_cta;
+  if (c_end > len) c_end = len;
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+  for (int64_t c0 = c_begin; c0 < c_end; c0 += GC) {
+    __syncthreads();
+    for (int idx = t; idx < GR * GC; idx += 256) {
+      const int k = idx >> 6, cx = idx & 63;
+      const int64_t c = c0 + cx;
+      tile[cx][k] = (k < r && c < c_end) ? F[(int64_t)k * ld_f + c] : T(0);
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int cx = 0; cx < GC; ++cx) {
+      T a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = tile[cx][4 * ti + i]; b[i] = tile[cx][4 * tj + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+  }
+  T* out = part + (size_t)blockIdx.x * GR * GR;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[(4 * ti + i) * GR + 4 * tj + j] = acc[i][j];
+}
+
+template <typename T>
+__global__ void gram_reduce_kernel(const T* __restrict__ part, int nparts, int r, T* __restrict__ out, int64_t ld_out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= r * r) return;
+  const int i = idx / r, j = idx % r;
+  double s = 0.0;
+  for (int p = 0; p < nparts; ++p) s += (double)part[(size_t)p * GR * GR + i * GR + j];   // fixed order
+  out[(int64_t)i * ld_out + j] = (T)s;
+}
+
+template <typename T>
+int run_gram(nnfac_ctx* ctx, T* out, int64_t ld_out, const T* F, int64_t ld_f, int r, int64_t len, cudaStream_t st) {
+  int64_t cols = ceil_div64(len, ctx->sm_count);
+  cols = ceil_div64(cols, GC) * GC;
+  const int grid = (int)ceil_div64(len, cols);
+  const size_t need = (size_t)grid * GR * GR * sizeof(T);
+  const int rc = nnfac_ws_reserve(ctx, need, st);
+  if (rc != NNFAC_OK) return rc;
+  gram_partial_kernel<T><<<grid, 256, 0, st>>>(F, ld_f, r, len, cols, (T*)ctx->ws);
+  NNFAC_LAUNCH_CHECK(ctx);
+  gram_reduce_kernel<T><<<(r * r + 255) / 256, 256, 0, st>>>((const T*)ctx->ws, grid, r, out, ld_out);
+  NNFAC_LAUNCH_CHECK(ctx);
+  return NNFAC_OK;
+}
+
 }  // namespace
+
+extern "C" int nnfac_gram(nnfac_ctx* ctx, int dtype, void* out, int64_t ld_out, const void* F, int64_t ld_f, int r,
+                          int64_t len, void* stream) {
+  NNFAC_ARG(ctx && out && F && r > 0 && len > 0 && ld_out >= r && ld_f >= len, "nnfac_gram: bad argument");
+  NNFAC_ARG(dtype == NNFAC_F32 || dtype == NNFAC_F64, "nnfac_gram: bad dtype %d", dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (r > GR) {   // wider factors go through the general kernel
+    if (dtype == NNFAC_F32)
+      return run_gemm<float>(ctx, (float*)out, ld_out, 0, (const float*)F, ld_f, 1, 0, 0, (const float*)F, 1, ld_f, 0, 0, r, r, len, 1, 1, st);
+    return run_gemm<double>(ctx, (double*)out, ld_out, 0, (const double*)F, ld_f, 1, 0, 0, (const double*)F, 1, ld_f, 0, 0, r, r, len, 1, 1, st);
+  }
+  if (dtype == NNFAC_F32) return run_gram<float>(ctx, (float*)out, ld_out, (const float*)F, ld_f, r, len, st);
+  return run_gram<double>(ctx, (double*)out, ld_out, (const double*)F, ld_f, r, len, st);
+}
 
 extern "C" int nnfac_gemm_strided(nnfac_ctx* ctx, int dtype, void* C, int64_t ldc, int64_t sc_b,
                                   const void* A, int64_t sa_i, int64_t sa_k, int64_t sa_q,

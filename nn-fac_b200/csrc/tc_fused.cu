@@ -358,6 +358,56 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
   if (warp == 2) tc::tmem_dealloc(tmem_base, 512);
 }
 
+// One pass that finishes a factor update and installs the factor in the plan:
+//   APPLY: F = max(F_in * (sum of the split partials of the last fused pass) / den[k], floor)      (mu.py:84-88)
+//   else : F = F_in                                                                                 (after a HALS solve)
+// and writes F (fp32, rank-major), its K-major bf16 hi/lo planes [r_pad x ld_plane] (operand of the cross product)
+// and its rank-contiguous planes [R x 64] (operands of the fused pass).  Block = 32 columns x all ranks.
+template <bool APPLY>
+__global__ void __launch_bounds__(256) factor_finish_kernel(const float* __restrict__ partial, int splits, int r, int r_pad, int64_t R,
+                                                            int64_t ldp, const float* __restrict__ F_in, int64_t ld_in,
+                                                            const float* __restrict__ den, float floor_value, float* __restrict__ F_out,
+                                                            int64_t ld_out, bf16* __restrict__ fh, bf16* __restrict__ fl, int64_t ld_plane,
+                                                            bf16* __restrict__ rowh, bf16* __restrict__ rowl) {
+  __shared__ float tile[64][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c0 = (int64_t)blockIdx.x * 32, c = c0 + tx;
+  for (int k = ty; k < 64; k += 8) {
+    float f = 0.f;
+    if (k < r && c < R) {
+      f = F_in[(int64_t)k * ld_in + c];
+      if (APPLY) {
+        float num = 0.f;
+        for (int sp = 0; sp < splits; ++sp) num += partial[((int64_t)sp * r_pad + k) * ldp + c];   // fixed order
+        const float v = f * (num / den[k]);
+        f = v > floor_value ? v : floor_value;      // np.maximum(., epsilon); NaN propagates like numpy
+        if (v != v) f = v;
+      }
+      if (F_out) F_out[(int64_t)k * ld_out + c] = f;
+      bf16 h, l;
+      tc::split_bf16(f, h, l);
+      fh[(int64_t)k * ld_plane + c] = h;
+      fl[(int64_t)k * ld_plane + c] = l;
+    }
+    tile[k][tx] = f;
+  }
+  if (rowh == nullptr) return;
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t cc = c0 + i;
+    if (cc < R) {
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int k = tx + 32 * h2;
+        bf16 h, l;
+        tc::split_bf16(tile[k][i], h, l);
+        rowh[cc * 64 + k] = h;
+        rowl[cc * 64 + k] = l;
+      }
+    }
+  }
+}
+
 __global__ void sum_cost_parts_kernel(const double* part, int n, double* out) {
   if (threadIdx.x == 0) {
     double s = 0.0;
@@ -368,6 +418,24 @@ __global__ void sum_cost_parts_kernel(const double* part, int n, double* out) {
 
 }  // namespace
 
+static int finish_factor(nnfac_nmf_plan* p, int which, bool apply, const float* F_in, int64_t ld_in, const float* den,
+                         float floor_value, float* F_out, int64_t ld_out, cudaStream_t st) {
+  const int64_t len = which == 0 ? p->m : p->n;
+  Side* cs = &p->side[which == 0 ? 1 : 0];        // U^T planes are the Fn operand of side 1, V planes of side 0
+  Side* ps = &p->side[which];                     // the pass whose partials feed this factor
+  const unsigned grid = (unsigned)ceil_div64(len, 32);
+  bf16* rh = p->fused_ok ? p->rowp_h[which] : nullptr;
+  bf16* rl = p->fused_ok ? p->rowp_l[which] : nullptr;
+  if (apply)
+    factor_finish_kernel<true><<<grid, 256, 0, st>>>(p->partial, ps->cp.splits, p->r, p->r_pad, len, ps->cp.ld_partial, F_in, ld_in, den,
+                                                     floor_value, F_out, ld_out, cs->fh, cs->fl, cs->ld, rh, rl);
+  else
+    factor_finish_kernel<false><<<grid, 256, 0, st>>>(nullptr, 0, p->r, p->r_pad, len, 0, F_in, ld_in, nullptr, 0.f, F_out, ld_out,
+                                                      cs->fh, cs->fl, cs->ld, rh, rl);
+  NNFAC_LAUNCH_CHECK(p->ctx);
+  return NNFAC_OK;
+}
+
 extern "C" {
 
 // which = 0: U given as U^T (r x m); which = 1: V (r x n).  Builds every bf16 operand plane of that factor.
@@ -375,17 +443,19 @@ int nnfac_nmf_plan_set_factor(nnfac_nmf_plan* p, int which, const float* Ft, int
   NNFAC_ARG(p && Ft && (which == 0 || which == 1), "nnfac_nmf_plan_set_factor: bad argument");
   const int64_t len = which == 0 ? p->m : p->n;
   NNFAC_ARG(ld >= len, "nnfac_nmf_plan_set_factor: leading dimension too small");
-  cudaStream_t st = (cudaStream_t)stream;
-  Side* cs = &p->side[which == 0 ? 1 : 0];        // U^T planes are the Fn operand of side 1, V planes of side 0
-  const int64_t total = (int64_t)p->r * len;
-  int grid = (int)(ceil_div64(total, 256) < (int64_t)p->ctx->sm_count * 8 ? ceil_div64(total, 256) : (int64_t)p->ctx->sm_count * 8);
-  nnfac_split_planes(Ft, ld, p->r, len, cs->fh, cs->fl, cs->ld, grid, st);
-  NNFAC_LAUNCH_CHECK(p->ctx);
-  if (p->fused_ok) {
-    nnfac_split_planes_transposed(Ft, ld, p->r, len, p->rowp_h[which], p->rowp_l[which], 64, st);
-    NNFAC_LAUNCH_CHECK(p->ctx);
-  }
-  return NNFAC_OK;
+  return finish_factor(p, which, false, Ft, ld, nullptr, 0.f, nullptr, 0, (cudaStream_t)stream);
+}
+
+// beta = 1 multiplicative update of factor `which` from the numerator partials the last fused pass over side `which`
+// left in the plan (call nnfac_nmf_plan_fused with out = NULL): F_out = max(F_in * num / den[k], floor), mu.py:84-88,
+// and F_out is installed in the plan (as nnfac_nmf_plan_set_factor would).  den: r row sums of the other factor.
+int nnfac_nmf_plan_mu_finish(nnfac_nmf_plan* p, int which, const float* F_in, int64_t ld_in, const float* den, double floor_value,
+                             float* F_out, int64_t ld_out, void* stream) {
+  NNFAC_ARG(p && F_in && den && F_out && (which == 0 || which == 1), "nnfac_nmf_plan_mu_finish: bad argument");
+  const int64_t len = which == 0 ? p->m : p->n;
+  NNFAC_ARG(ld_in >= len && ld_out >= len, "nnfac_nmf_plan_mu_finish: leading dimension too small");
+  if (!p->fused_ok) { nnfac_set_error("nnfac_nmf_plan_mu_finish: rank %d > 64 is not covered by the fused pass", p->r); return NNFAC_ERR_UNSUPPORTED; }
+  return finish_factor(p, which, true, F_in, ld_in, den, (float)floor_value, F_out, ld_out, (cudaStream_t)stream);
 }
 
 // One fused pass over side `side` (0: planes of X, rows = m; 1: planes of X^T, rows = n).
@@ -394,10 +464,10 @@ int nnfac_nmf_plan_set_factor(nnfac_nmf_plan* p, int which, const float* Ft, int
 // Uses the factor planes installed by nnfac_nmf_plan_set_factor for BOTH factors.
 int nnfac_nmf_plan_fused(nnfac_nmf_plan* p, int side, int mode, int want_cost, float* out, int64_t ld_out, double* cost_out,
                          void* stream) {
-  NNFAC_ARG(p && out && (side == 0 || side == 1) && (mode == 0 || mode == 1), "nnfac_nmf_plan_fused: bad argument");
+  NNFAC_ARG(p && (side == 0 || side == 1) && (mode == 0 || mode == 1), "nnfac_nmf_plan_fused: bad argument");
   if (!p->fused_ok) { nnfac_set_error("nnfac_nmf_plan_fused: rank %d > 64 is not covered by the fused pass", p->r); return NNFAC_ERR_UNSUPPORTED; }
   Side* s = &p->side[side];
-  NNFAC_ARG(ld_out >= s->R, "nnfac_nmf_plan_fused: leading dimension too small");
+  NNFAC_ARG(!out || ld_out >= s->R, "nnfac_nmf_plan_fused: leading dimension too small");
   cudaStream_t st = (cudaStream_t)stream;
   FusedParams fp;
   fp.r_pad = p->r_pad; fp.splits = s->cp.splits; fp.stages_per_unit = s->cp.stages_per_unit; fp.num_units = s->cp.num_units;
@@ -415,8 +485,10 @@ int nnfac_nmf_plan_fused(nnfac_nmf_plan* p, int side, int mode, int want_cost, f
         p->map_row_b_h[other], p->map_row_b_l[other], p->map_row_a_h[side], p->map_row_a_l[side], fp);
   }
   NNFAC_LAUNCH_CHECK(p->ctx);
-  nnfac_reduce_partials(p->partial, fp.splits, p->r, p->r_pad, s->R, fp.ld_partial, out, ld_out, p->ctx->sm_count, st);
-  NNFAC_LAUNCH_CHECK(p->ctx);
+  if (out) {      // out == NULL: the split partials stay in the plan for nnfac_nmf_plan_mu_finish
+    nnfac_reduce_partials(p->partial, fp.splits, p->r, p->r_pad, s->R, fp.ld_partial, out, ld_out, p->ctx->sm_count, st);
+    NNFAC_LAUNCH_CHECK(p->ctx);
+  }
   if (cost_out && fp.want_cost) {
     sum_cost_parts_kernel<<<1, 32, 0, st>>>(p->cost_part, s->grid, cost_out);
     NNFAC_LAUNCH_CHECK(p->ctx);

@@ -88,19 +88,18 @@ class CudaEngine:
     def set_factor(self, which, Ft):
         self.plan.set_factor(which, Ft)
 
-    def fused(self, side, mode, want_cost):
-        return self.plan.fused(side, mode, want_cost=want_cost)
+    def fused(self, side, mode, want_cost, keep_partials=False):
+        return self.plan.fused(side, mode, want_cost=want_cost, keep_partials=keep_partials)
+
+    def mu_finish(self, which, F, den_vec):
+        """mu.py:84-88 on the numerator the last fused(which, MODE_MU, keep_partials=True) left in the plan,
+        plus the installation of the new factor: one kernel."""
+        return self.plan.mu_finish(which, F, den_vec, mu.epsilon)
 
     def cross(self, which, F):
         return self.plan.cross(which, F)
 
-    @staticmethod
-    def gram(F, out=None):
-        """F (r x len, row-major) -> F F^T (nmf.py:407 / :432)."""
-        r, length = F.shape
-        if out is None:
-            return ops.gemm(F, (F.stride(0), 1), F, (1, F.stride(0)), r, r, length)
-        return ops.gemm(F, (F.stride(0), 1), F, (1, F.stride(0)), r, r, length, out=out, ldc=out.stride(0), sc_b=0)
+    gram = staticmethod(ops.gram)                      # F (r x len) -> F F^T (nmf.py:407 / :432)
 
     @staticmethod
     def sweep(UtM, UtU, V, r, sparsity, normalize, result):
@@ -208,14 +207,15 @@ class FusedNMF:
                     xb[r * m:].copy_(den)
                     comm.sum_(xb)
                     numU, den = xb[:r * m].view(r, m), xb[r * m:]
-                Ut = eng.mu_apply(Ut, numU, den)                                   # mu.py:84-88
-                eng.set_factor(0, Ut)
+                    Ut = eng.mu_apply(Ut, numU, den)                               # mu.py:84-88
+                    eng.set_factor(0, Ut)
+                else:
+                    Ut = eng.mu_finish(0, Ut, den)                                 # mu.py:84-88 + planes, one kernel
         if 1 not in fixed_modes:
             with self._phase("pass_V"):
-                numV, _ = eng.fused(1, MODE_MU, False)
+                eng.fused(1, MODE_MU, False, keep_partials=True)
             with self._phase("apply_V"):
-                V = eng.mu_apply(V, numV, eng.row_sums(Ut))                        # mu.py:27
-                eng.set_factor(1, V)
+                V = eng.mu_finish(1, V, eng.row_sums(Ut))                          # mu.py:27
         return Ut, V
 
     def run(self, n_iter_max, tol, update_rule, sparsity=(None, None), fixed_modes=(), normalize=(False, False),
@@ -231,7 +231,9 @@ class FusedNMF:
         done = torch.cuda.Event() if self._on_gpu else None
         for it in range(n_iter_max + 1):
             with self._phase("pass_U"):
-                outA, cost_dev = self.eng.fused(0, mode, True)
+                # single GPU, MU: the numerator stays in the plan as split partials and is consumed by mu_finish
+                keep = mode == MODE_MU and self.comm.world == 1 and it < n_iter_max and 0 not in fixed_modes
+                outA, cost_dev = self.eng.fused(0, mode, True, keep_partials=keep)
             if it > 0:
                 self._dev_scal[0:1].copy_(cost_dev)
                 self._dev_scal[1:3].zero_()

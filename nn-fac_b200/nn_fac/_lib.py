@@ -29,6 +29,7 @@ SIGNATURES = {
     "nnfac_hals_nnls": [_P, _INT, _P, _I64, _P, _I64, _P, _I64, _INT, _I64, _INT, _DBL, _DBL, _U32, _P, _P],
     "nnfac_gemm_strided": [_P, _INT, _P, _I64, _I64, _P, _I64, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I64,
                            _I64, _I64, _I64, _I64, _I64, _P],
+    "nnfac_gram": [_P, _INT, _P, _I64, _P, _I64, _INT, _I64, _P],
     "nnfac_mu_terms": [_P, _INT, _DBL, _P, _P, _P, _P, _I64, _P],
     "nnfac_mu_apply": [_P, _INT, _P, _P, _P, _P, _P, _INT, _I64, _I64, _DBL, _DBL, _P],
     "nnfac_beta_divergence": [_P, _INT, _DBL, _P, _P, _I64, _P, _P],
@@ -46,6 +47,7 @@ SIGNATURES = {
     "nnfac_nmf_plan_cross": [_P, _INT, _P, _I64, _P, _I64, _P],
     "nnfac_nmf_plan_set_factor": [_P, _INT, _P, _I64, _P],
     "nnfac_nmf_plan_fused": [_P, _INT, _INT, _INT, _P, _I64, _P, _P],
+    "nnfac_nmf_plan_mu_finish": [_P, _INT, _P, _I64, _P, _DBL, _P, _I64, _P],
     "nnfac_nmf_plan_info": [_P, _INT, _c.POINTER(_INT), _c.POINTER(_INT), _c.POINTER(_INT), _c.POINTER(_INT),
                             _c.POINTER(_INT)],
 }

@@ -27,6 +27,16 @@ def gemm(A, a_str, B, b_str, M, N, K, kb=1, batch=1, out=None, ldc=None, sc_b=0)
     return out
 
 
+def gram(F, out=None):
+    """F (r x len, row-major) -> F F^T (r x r): V V^T (nmf.py:407) / U^T U (nmf.py:432) for rank-major factors."""
+    r, length = F.shape
+    if out is None:
+        out = torch.empty((r, r), dtype=F.dtype, device=F.device)
+    L.check(_lib().nnfac_gram(L.ctx(F.device), L.code_of(F.dtype), L.ptr(out), out.stride(0), L.ptr(F), F.stride(0), r,
+                              length, L.stream_ptr()))
+    return out
+
+
 def matmul(A, B):
     """Row-major A (M x K) @ B (K x N)."""
     M, K = A.shape
@@ -231,16 +241,25 @@ class NMFPlan:
         """which=0: U given as U^T (r x m); which=1: V (r x n).  Rebuilds that factor's bf16 operand planes."""
         L.check(_lib().nnfac_nmf_plan_set_factor(self.handle, which, L.ptr(Ft), Ft.stride(0), L.stream_ptr()))
 
-    def fused(self, side, mode, want_cost=True, out=None, cost_out=None):
+    def mu_finish(self, which, F, den, floor):
+        """max(F * num / den[:, None], floor) from the numerator partials of the last fused(which, 1, keep_partials=True);
+        the result is installed as factor `which` (mu.py:84-88 + set_factor in one kernel)."""
+        out = torch.empty_like(F)
+        L.check(_lib().nnfac_nmf_plan_mu_finish(self.handle, which, L.ptr(F), F.stride(0), L.ptr(den), float(floor),
+                                                L.ptr(out), out.stride(0), L.stream_ptr()))
+        return out
+
+    def fused(self, side, mode, want_cost=True, out=None, cost_out=None, keep_partials=False):
         """One fused X pass with the installed factors (rank <= 64).  mode 0: HALS cross product + ||X-UV||^2;
-        mode 1: beta=1 MU numerator + KL(X|UV).  Returns (out r x rows, cost device scalar or None)."""
+        mode 1: beta=1 MU numerator + KL(X|UV).  Returns (out r x rows, cost device scalar or None).
+        keep_partials: leave the split partials in the plan for mu_finish instead of reducing them into `out`."""
         R = self.m if side == 0 else self.n
-        if out is None:
+        if out is None and not keep_partials:
             out = torch.empty((self.r, R), dtype=torch.float32, device=self.device)
         if cost_out is None and (want_cost or mode == 0):
             cost_out = torch.empty(1, dtype=torch.float64, device=self.device)
-        L.check(_lib().nnfac_nmf_plan_fused(self.handle, side, mode, 1 if want_cost else 0, L.ptr(out), out.stride(0),
-                                            L.ptr(cost_out), L.stream_ptr()))
+        L.check(_lib().nnfac_nmf_plan_fused(self.handle, side, mode, 1 if want_cost else 0, L.ptr(out),
+                                            out.stride(0) if out is not None else 0, L.ptr(cost_out), L.stream_ptr()))
         return out, cost_out
 
     @property

@@ -36,11 +36,14 @@ class OracleEngine:
     def set_factor(self, which, Ft):
         self.F[which] = Ft.clone()
 
-    def fused(self, side, mode, want_cost):
+    def fused(self, side, mode, want_cost, keep_partials=False):
         Ut, V, X = self.F[0], self.F[1], self.X
         K = Ut.T @ V
         A = X if mode == 0 else X / K
         out = V @ A.T if side == 0 else Ut @ A
+        if keep_partials:
+            self.kept = (side, out.contiguous())
+            out = torch.empty(0)
         if mode == 0:
             cost = ((X - K) ** 2).sum()
         else:
@@ -70,6 +73,13 @@ class OracleEngine:
     @staticmethod
     def mu_apply(F, num, den_vec):
         return torch.clamp(F * (num / den_vec[:, None]), min=EPS)
+
+    def mu_finish(self, which, F, den_vec):
+        side, num = self.kept
+        assert side == which
+        new = self.mu_apply(F, num, den_vec)
+        self.set_factor(which, new)
+        return new
 
     @staticmethod
     def row_sums(F):
