@@ -39,11 +39,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (the launch fails with an error) after ~4 s instead of hanging the GPU.
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if ((++spins & 1023u) == 0 && global_ns() - t0 > 4000000000ull) __trap();
   }
 }
 
