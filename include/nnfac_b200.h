@@ -137,12 +137,23 @@ int nnfac_normalize_rows(nnfac_ctx* ctx, int dtype, void* A, int64_t lda, int64_
  * -------------------------------------------------------------------------------------------*/
 typedef struct nnfac_nmf_plan nnfac_nmf_plan;
 int nnfac_nmf_plan_create(nnfac_ctx* ctx, int64_t m, int64_t n, int r, nnfac_nmf_plan** out);
+/* Same plan inside a caller-owned device workspace (256-byte aligned, >= nnfac_nmf_plan_bytes() bytes, e.g. a block of a
+ * caching allocator): repeated factorisations of same-shaped data then never call cudaMalloc / cudaFree.  The workspace is
+ * cleared on `stream` and must outlive the plan. */
+int nnfac_nmf_plan_bytes(nnfac_ctx* ctx, int64_t m, int64_t n, int r, size_t* bytes);
+int nnfac_nmf_plan_create_in(nnfac_ctx* ctx, int64_t m, int64_t n, int r, void* workspace, size_t workspace_bytes,
+                             void* stream, nnfac_nmf_plan** out);
 int nnfac_nmf_plan_destroy(nnfac_nmf_plan* plan);
 /* Ingest X (device fp32, row-major, leading dimension ldx >= n): one read of X, two plane writes. */
 int nnfac_nmf_plan_load_x(nnfac_nmf_plan* plan, const float* X, int64_t ldx, void* stream);
+/* The same ingest slab by slab (rows [row0, row0+rows) of X; Xrows points at row row0), so that a host can overlap the
+ * upload of X with its ingest; call nnfac_nmf_plan_load_x_done once after the last slab. */
+int nnfac_nmf_plan_load_x_rows(nnfac_nmf_plan* plan, const float* Xrows, int64_t ldx, int64_t row0, int64_t rows, void* stream);
+int nnfac_nmf_plan_load_x_done(nnfac_nmf_plan* plan, void* stream);
 /* which = 0: out (r x m) = F X^T with F = V (r x n)      -- VMt, nmf.py:408
  * which = 1: out (r x n) = F X   with F = U^T (r x m)    -- UtM, nmf.py:433
- * F and out are device fp32, row-major.  Deterministic. */
+ * F and out are device fp32, row-major.  Deterministic.  F == NULL: use the factor installed in the plan
+ * (nnfac_nmf_plan_set_factor / nnfac_nmf_plan_mu_finish), whose operand planes already exist. */
 int nnfac_nmf_plan_cross(nnfac_nmf_plan* plan, int which, const float* F, int64_t ldf, float* out,
                          int64_t ld_out, void* stream);
 /* Install a factor into the plan (builds all of its bf16 operand planes):

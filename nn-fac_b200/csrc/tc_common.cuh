@@ -45,12 +45,20 @@ __device__ __forceinline__ uint64_t global_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+static __device__ __noinline__ void mbar_wait_timeout_check(uint64_t& t0) {
+  const uint64_t now = global_ns();
+  if (t0 == 0) t0 = now;
+  else if (now - t0 > 4000000000ull) __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = global_ns();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 1023u) == 0 && global_ns() - t0 > 4000000000ull) __trap();
+  uint64_t t0 = 0;
+  for (;;) {
+    // the hot spin is try_wait + counter only; the clock is read once every 4096 failed attempts
+#pragma unroll 1
+    for (uint32_t spins = 0; spins < 4096u; ++spins)
+      if (mbar_try_wait(bar, parity)) return;
+    mbar_wait_timeout_check(t0);
   }
 }
 

@@ -4,8 +4,9 @@
 // For one 128-row tile of an X plane and each 64-column stage:
 //   GEMM-1   D1[128 x 64] = A1[128 x 64] * Fk^T          A1 = rows of the factor aligned with X's rows,
 //                                                         Fk = 64 rows of the other factor (rank contiguous)
-//   transform (8 warps)    MODE_MU  : Q = X / K  (mu.py:84), written over the X tile in shared memory;
-//                                     cost += K * ((1+d) log1p(d) - d), d = (X-K)/K   (beta_divergence.py:45-48)
+//   transform (16 warps)   MODE_MU  : Q = X / K  (mu.py:84), written to tensor memory as the A operand of GEMM-2;
+//                                     cost partial += X log2(X / K); KL(X | K) = ln2 * that - sum(X) + sum(K)
+//                                     with sum(K) = <column sums of U, row sums of V>     (beta_divergence.py:45-48)
 //                          MODE_RES : cost += (X - K)^2                                (nmf.py:452)
 //   GEMM-2   D2[128 x r]  += A2[128 x 64] * Fn^T          A2 = Q (MU, mu.py:88) or X (HALS cross product, nmf.py:408)
 // so one pass over X yields the contraction the update needs AND the cost of the factors it started
@@ -29,6 +30,7 @@ constexpr uint32_t FK_BYTES = 64 * BK * sizeof(bf16);         // 8 KiB  (64 colu
 constexpr uint32_t STAGE_BYTES = 2 * X_BYTES + 2 * FK_BYTES;  // 48 KiB
 constexpr uint32_t A1_BYTES = 2 * X_BYTES;                    // 32 KiB
 constexpr int MODE_RES = 0, MODE_MU = 1;
+constexpr int DRAIN = 2;             // stages per TMEM accumulation chain of the contraction GEMM (the tensor core accumulates with truncation)
 
 struct FusedParams {
   int r_pad, splits, stages_per_unit, num_units, drain, want_cost;
@@ -42,24 +44,15 @@ __device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, <= 1 ulp: 
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// q ln q - q + 1 with q = 1 + d (one KL term divided by the model value, beta_divergence.py:45-48).
-// Near q = 1 the closed form cancels, so |d| < 1/8 uses the alternating series d^2 (1/2 - d/6 + d^2/12 - ...)
-// (truncation < 2e-8 relative); elsewhere MUFU.LG2 is accurate enough (< 3e-5 relative on the term).
-__device__ __forceinline__ float kl_term(float q, float d) {
-  float s = fmaf(d, 1.f / 56.f, -1.f / 42.f);
-  s = fmaf(d, s, 1.f / 30.f);
-  s = fmaf(d, s, -1.f / 20.f);
-  s = fmaf(d, s, 1.f / 12.f);
-  s = fmaf(d, s, -1.f / 6.f);
-  s = fmaf(d, s, 0.5f);
-  const float series = d * d * s;
-  const float closed = fmaf(q, __logf(fmaxf(q, 1e-30f)), -d);
-  return fabsf(d) < 0.125f ? series : closed;
+__device__ __forceinline__ float lg2_approx(float x) {   // MUFU.LG2 without the denormal pre-scaling (arguments are >= 1e-30)
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
-template <int MODE>
+template <int MODE, bool COST>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                 const __grid_constant__ CUtensorMap map_fkh, const __grid_constant__ CUtensorMap map_fkl,
@@ -82,7 +75,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
   uint64_t* q_ready = bars + 21;         // [2] count 8: ratio tile written to tensor memory
   uint64_t* q_free = bars + 23;          // [2] contraction GEMM that read it has retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
-  double* cost_sh = reinterpret_cast<double*>(bars + 26);   // [8]
+  double* cost_sh = reinterpret_cast<double*>(bars + 26);   // [2 * NWT]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t stage_tx = STAGE_BYTES;
@@ -173,8 +166,8 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     int b2 = 0; uint32_t b2_phase = 0;      // D2 buffer
     for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
       for (int j = 0; j < S; ++j) {
-        const bool chain_start = (j % p.drain) == 0;
-        const bool chain_end = ((j + 1) % p.drain) == 0 || j == S - 1;
+        const bool chain_start = (j % DRAIN) == 0;
+        const bool chain_end = ((j + 1) % DRAIN) == 0 || j == S - 1;
         tc::mbar_wait(&full[st2], ph2);
         if (MODE == MODE_MU) tc::mbar_wait(&q_ready[qb], qb_phase);
         if (chain_start) tc::mbar_wait(&d2_empty[b2], b2_phase ^ 1);
@@ -224,7 +217,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     int b2 = 0; uint32_t b2_phase = 0;
     int qb = 0; uint32_t qb_phase = 0;
     uint32_t a1_phase = 0;
-    double cost = 0.0;
+    double cost = 0.0, costk = 0.0;
     for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
       const int tile = u / p.splits, split = u % p.splits;
       float sum[CW];
@@ -267,6 +260,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         if (lane == 0) tc::mbar_arrive(&d2_empty[b2]);
         if (++b2 == 2) { b2 = 0; b2_phase ^= 1; }
       };
+      int drained = 0;
       for (int i = 0; i < S; ++i) {
         // ---- model tile for this stage ----
         tc::mbar_wait(&d1_full[b1], b1_phase);
@@ -283,7 +277,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         tc::mbar_wait(&full[st], ph);
         uint8_t* xh = ring + (size_t)st * STAGE_BYTES;
         uint8_t* xl = xh + X_BYTES;
-        float acc = 0.f;
+        float acc = 0.f, acck = 0.f;
         uint32_t qhw[4 * NCHK], qlw[4 * NCHK];
 #pragma unroll
         for (int cc = 0; cc < NCHK; ++cc) {
@@ -304,10 +298,12 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
               // padded rows / columns have x = 0 and k = 0: the floor keeps 0 * (1/k) = 0 there
               const float i0 = rcp_approx(fmaxf(k0, 1e-30f)), i1 = rcp_approx(fmaxf(k1, 1e-30f));
               const float q0 = x0 * i0, q1 = x1 * i1;
-              if (p.want_cost) {
-                const float d0 = (x0 - k0) * i0, d1 = (x1 - k1) * i1;
-                acc += k0 * kl_term(q0, d0);
-                acc += k1 * kl_term(q1, d1);
+              if (COST) {
+                // sum of x log2(x / k) and sum of k (the model tile as the tensor core produced it, so that the two terms
+                // stay consistent); the sum of x is a constant of the plan (see kl_cost_finish_kernel)
+                acc = fmaf(x0, lg2_approx(fmaxf(q0, 1e-30f)), acc);
+                acc = fmaf(x1, lg2_approx(fmaxf(q1, 1e-30f)), acc);
+                acck += k0 + k1;
               }
               const __nv_bfloat162 hq = __floats2bfloat162_rn(q0, q1);
               const uint32_t hqw = *reinterpret_cast<const uint32_t*>(&hq);
@@ -317,7 +313,10 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
             }
           }
         }
-        if (p.want_cost) cost += (double)acc;
+        if (COST) {
+          cost += (double)acc;
+          if (MODE == MODE_MU) costk += (double)acck;
+        }
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&empty[st]);          // done with the stage's X tile
         if (++st == FSTAGES) { st = 0; ph ^= 1; }
@@ -334,23 +333,29 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
           if (lane == 0) tc::mbar_arrive(&q_ready[qb]);
           if (++qb == 2) { qb = 0; qb_phase ^= 1; }
         }
-        if (i >= 1 && (i % p.drain) == 0) drain_chain();      // the chain that ended with stage i-1
+        // drain with a lag of one more stage: chain (i-3)/2 ended with stage i-2, its GEMMs have retired by now, and
+        // its TMEM buffer is only needed again by the chain that starts with stage i+1
+        if (i >= 3 && (i & 1)) { drain_chain(); ++drained; }
       }
-      drain_chain();                                           // the chain that ended with stage S-1
+      for (; drained < (S + DRAIN - 1) / DRAIN; ++drained) drain_chain();
       if (has_d2) {
         float* out = p.partial + ((int64_t)split * p.r_pad + CW * part) * p.ld_partial + (int64_t)tile * TILE_ROWS + row;
 #pragma unroll
         for (int j = 0; j < CW; ++j) out[(int64_t)j * p.ld_partial] = sum[j];
       }
     }
-    // per-CTA cost partial (fixed order)
-    cost = warp_sum(cost);
-    if (lane == 0) cost_sh[warp - 4] = cost;
-    asm volatile("bar.sync 1, %0;" ::"n"(32 * NWT) : "memory");
-    if (warp == 4 && lane == 0) {
-      double t = 0.0;
-      for (int w = 0; w < NWT; ++w) t += cost_sh[w];
-      p.cost_part[blockIdx.x] = t;
+    // per-CTA cost partials (fixed order): [blockIdx] = sum of squares or sum of x log2(x/k); [512 + blockIdx] = sum of k
+    if (COST) {
+      cost = warp_sum(cost);
+      if (MODE == MODE_MU) costk = warp_sum(costk);
+      if (lane == 0) { cost_sh[warp - 4] = cost; cost_sh[NWT + warp - 4] = costk; }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * NWT) : "memory");
+      if (warp == 4 && lane == 0) {
+        double t = 0.0, tk = 0.0;
+        for (int w = 0; w < NWT; ++w) { t += cost_sh[w]; tk += cost_sh[NWT + w]; }
+        p.cost_part[blockIdx.x] = t;
+        p.cost_part[512 + blockIdx.x] = tk;
+      }
     }
   }
   tc::tcgen05_fence_before();
@@ -416,6 +421,16 @@ __global__ void sum_cost_parts_kernel(const double* part, int n, double* out) {
   }
 }
 
+// KL(X | U V) = sum x ln(x / k) - sum x + sum k   (beta_divergence.py:45-48; terms with x = 0 contribute k).
+// part[0..n): per-CTA sums of x log2(x / k); part[512..512+n): per-CTA sums of k; sums[0] = sum of X (constant of the plan).
+__global__ void kl_cost_finish_kernel(const double* part, int n, const double* sums, double* out) {
+  if (threadIdx.x == 0) {
+    double s = 0.0, sk = 0.0;
+    for (int i = 0; i < n; ++i) { s += part[i]; sk += part[512 + i]; }
+    out[0] = 0.6931471805599453 * s - sums[0] + sk;
+  }
+}
+
 }  // namespace
 
 static int finish_factor(nnfac_nmf_plan* p, int which, bool apply, const float* F_in, int64_t ld_in, const float* den,
@@ -471,26 +486,30 @@ int nnfac_nmf_plan_fused(nnfac_nmf_plan* p, int side, int mode, int want_cost, f
   cudaStream_t st = (cudaStream_t)stream;
   FusedParams fp;
   fp.r_pad = p->r_pad; fp.splits = s->cp.splits; fp.stages_per_unit = s->cp.stages_per_unit; fp.num_units = s->cp.num_units;
-  fp.drain = 2; fp.want_cost = (mode == 0 || want_cost) ? 1 : 0;
+  fp.drain = DRAIN; fp.want_cost = (mode == 0 || want_cost) ? 1 : 0;
   fp.ld_partial = s->cp.ld_partial; fp.partial = p->partial; fp.cost_part = p->cost_part;
   const size_t smem = A1_BYTES + (size_t)FSTAGES * STAGE_BYTES + 512;
   const int other = 1 - side;
-  if (mode == 0) {
-    NNFAC_CUDA(cudaFuncSetAttribute(tc_fused_kernel<MODE_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_fused_kernel<MODE_RES><<<s->grid, FUSED_THREADS, smem, st>>>(s->map_xh, s->map_xl,
-        p->map_row_b_h[other], p->map_row_b_l[other], p->map_row_a_h[side], p->map_row_a_l[side], fp);
-  } else {
-    NNFAC_CUDA(cudaFuncSetAttribute(tc_fused_kernel<MODE_MU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_fused_kernel<MODE_MU><<<s->grid, FUSED_THREADS, smem, st>>>(s->map_xh, s->map_xl,
-        p->map_row_b_h[other], p->map_row_b_l[other], p->map_row_a_h[side], p->map_row_a_l[side], fp);
-  }
+#define NNFAC_LAUNCH_FUSED(M, C)                                                                                         \
+  do {                                                                                                                   \
+    NNFAC_CUDA(cudaFuncSetAttribute(tc_fused_kernel<M, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    tc_fused_kernel<M, C><<<s->grid, FUSED_THREADS, smem, st>>>(s->map_xh, s->map_xl, p->map_row_b_h[other],            \
+        p->map_row_b_l[other], p->map_row_a_h[side], p->map_row_a_l[side], fp);                                          \
+  } while (0)
+  if (mode == 0) NNFAC_LAUNCH_FUSED(MODE_RES, true);
+  else if (fp.want_cost) NNFAC_LAUNCH_FUSED(MODE_MU, true);
+  else NNFAC_LAUNCH_FUSED(MODE_MU, false);
+#undef NNFAC_LAUNCH_FUSED
   NNFAC_LAUNCH_CHECK(p->ctx);
   if (out) {      // out == NULL: the split partials stay in the plan for nnfac_nmf_plan_mu_finish
     nnfac_reduce_partials(p->partial, fp.splits, p->r, p->r_pad, s->R, fp.ld_partial, out, ld_out, p->ctx->sm_count, st);
     NNFAC_LAUNCH_CHECK(p->ctx);
   }
   if (cost_out && fp.want_cost) {
-    sum_cost_parts_kernel<<<1, 32, 0, st>>>(p->cost_part, s->grid, cost_out);
+    if (mode == 0)
+      sum_cost_parts_kernel<<<1, 32, 0, st>>>(p->cost_part, s->grid, cost_out);
+    else
+      kl_cost_finish_kernel<<<1, 32, 0, st>>>(p->cost_part, s->grid, p->sums, cost_out);
     NNFAC_LAUNCH_CHECK(p->ctx);
   }
   return NNFAC_OK;

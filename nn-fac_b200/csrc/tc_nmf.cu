@@ -224,6 +224,33 @@ void choose_partition(int sm, int64_t R, int64_t C, int r_pad, Side* s) {
   s->grid = s->cp.num_units < sm ? s->cp.num_units : sm;
 }
 
+// Sum of hi + lo over an [rows x cols] plane pair: per-block fp64 partials (rows are dealt round-robin to the blocks).
+__global__ void __launch_bounds__(256) plane_total_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, int64_t ld,
+                                                          int64_t rows, int64_t cols, double* part) {
+  __shared__ double sh[33];
+  double s = 0.0;
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const bf16* h = hi + r * ld;
+    const bf16* l = lo + r * ld;
+    float t = 0.f;
+    int cnt = 0;
+    for (int64_t c = threadIdx.x; c < cols; c += 256) {
+      t += __bfloat162float(h[c]) + __bfloat162float(l[c]);
+      if (++cnt == 16) { s += (double)t; t = 0.f; cnt = 0; }
+    }
+    s += (double)t;
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+__global__ void plane_total_finish_kernel(const double* part, int n, double* out) {
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += part[i];
+    out[0] = s;
+  }
+}
+
 }  // namespace
 
 void nnfac_split_planes(const float* in, int64_t ld_in, int64_t rows, int64_t cols, __nv_bfloat16* hi, __nv_bfloat16* lo,
@@ -248,120 +275,181 @@ extern "C" {
 
 int nnfac_nmf_plan_destroy(nnfac_nmf_plan* p) {
   if (!p) return NNFAC_OK;
-  for (int i = 0; i < 2; ++i) {
-    cudaFree(p->side[i].xh); cudaFree(p->side[i].xl); cudaFree(p->side[i].fh); cudaFree(p->side[i].fl);
-  }
-  cudaFree(p->partial);
-  for (int i = 0; i < 2; ++i) { cudaFree(p->rowp_h[i]); cudaFree(p->rowp_l[i]); }
-  cudaFree(p->cost_part);
+  if (p->owns_buffer) cudaFree(p->buffer);
   free(p);
   return NNFAC_OK;
 }
 
-int nnfac_nmf_plan_create(nnfac_ctx* ctx, int64_t m, int64_t n, int r, nnfac_nmf_plan** out) {
-  NNFAC_ARG(ctx && out && m > 0 && n > 0 && r > 0, "nnfac_nmf_plan_create: bad argument");
+// Every device buffer of a plan is carved out of ONE allocation (256-byte aligned pieces): either the caller's
+// workspace (`buffer`, at least nnfac_nmf_plan_bytes() bytes -- e.g. a block of a caching allocator, so that repeated
+// factorisations of same-shaped data never reach cudaMalloc / cudaFree) or one cudaMalloc owned by the plan.
+static int plan_build(nnfac_ctx* ctx, int64_t m, int64_t n, int r, void* buffer, size_t buffer_bytes, cudaStream_t st,
+                      nnfac_nmf_plan** out, size_t* bytes_out) {
+  NNFAC_ARG(ctx && m > 0 && n > 0 && r > 0, "nnfac_nmf_plan_create: bad argument");
   if (r > 128) { nnfac_set_error("nnfac_nmf_plan_create: rank %d > 128 is not covered by the tensor-core path", r); return NNFAC_ERR_UNSUPPORTED; }
   if (m >= (1ll << 31) - 256 || n >= (1ll << 31) - 256) { nnfac_set_error("nnfac_nmf_plan_create: dimension too large"); return NNFAC_ERR_UNSUPPORTED; }
   nnfac_nmf_plan* p = (nnfac_nmf_plan*)calloc(1, sizeof(nnfac_nmf_plan));
   if (!p) return NNFAC_ERR_ALLOC;
   p->ctx = ctx; p->m = m; p->n = n; p->r = r;
   p->r_pad = (int)round_up(r, 16);
+  p->fused_ok = p->r_pad <= 64;
+  // ---- sizes ----
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  size_t o_xh[2], o_xl[2], o_fh[2], o_fl[2], o_rh[2] = {0, 0}, o_rl[2] = {0, 0}, xb[2], fb[2], rb[2] = {0, 0};
   size_t partial_bytes = 0;
   for (int i = 0; i < 2; ++i) {
     Side* s = &p->side[i];
     s->R = i == 0 ? m : n;
     s->C = i == 0 ? n : m;
     s->ld = round_up(s->C, 64);
-    const size_t xb = (size_t)s->R * s->ld * sizeof(bf16), fb = (size_t)p->r_pad * s->ld * sizeof(bf16);
-    if (cudaMalloc(&s->xh, xb) != cudaSuccess || cudaMalloc(&s->xl, xb) != cudaSuccess ||
-        cudaMalloc(&s->fh, fb) != cudaSuccess || cudaMalloc(&s->fl, fb) != cudaSuccess) {
+    xb[i] = (size_t)s->R * s->ld * sizeof(bf16);
+    fb[i] = (size_t)p->r_pad * s->ld * sizeof(bf16);
+    o_xh[i] = take(xb[i]); o_xl[i] = take(xb[i]); o_fh[i] = take(fb[i]); o_fl[i] = take(fb[i]);
+    choose_partition(ctx->sm_count, s->R, s->C, p->r_pad, s);
+    const size_t pb = (size_t)s->cp.splits * p->r_pad * s->cp.ld_partial * sizeof(float);
+    if (pb > partial_bytes) partial_bytes = pb;
+  }
+  const size_t o_partial = take(partial_bytes);
+  if (p->fused_ok)
+    for (int i = 0; i < 2; ++i) {
+      rb[i] = (size_t)(i == 0 ? m : n) * 64 * sizeof(bf16);
+      o_rh[i] = take(rb[i]); o_rl[i] = take(rb[i]);
+    }
+  const size_t o_cost = take(sizeof(double) * 2048);
+  if (bytes_out) *bytes_out = off;
+  if (!out) { free(p); return NNFAC_OK; }      // size query only
+  // ---- memory ----
+  if (buffer) {
+    if (buffer_bytes < off || ((uintptr_t)buffer & 255)) {
+      nnfac_set_error("nnfac_nmf_plan_create_in: workspace of %zu bytes (256-byte aligned) needed, got %zu", off, buffer_bytes);
+      free(p);
+      return NNFAC_ERR_ARG;
+    }
+    p->buffer = buffer;
+  } else {
+    if (cudaMalloc(&p->buffer, off) != cudaSuccess) {
       cudaGetLastError();
-      nnfac_set_error("nnfac_nmf_plan_create: out of device memory (%zu bytes per X plane)", xb);
-      nnfac_nmf_plan_destroy(p);
+      nnfac_set_error("nnfac_nmf_plan_create: out of device memory (%zu bytes)", off);
+      free(p);
       return NNFAC_ERR_ALLOC;
     }
-    cudaMemset(s->fh, 0, fb);
-    cudaMemset(s->fl, 0, fb);
-    choose_partition(ctx->sm_count, s->R, s->C, p->r_pad, s);
+    p->owns_buffer = 1;
+  }
+  p->buffer_bytes = off;
+  uint8_t* base = (uint8_t*)p->buffer;
+  for (int i = 0; i < 2; ++i) {
+    Side* s = &p->side[i];
+    s->xh = (bf16*)(base + o_xh[i]); s->xl = (bf16*)(base + o_xl[i]);
+    s->fh = (bf16*)(base + o_fh[i]); s->fl = (bf16*)(base + o_fl[i]);
+    cudaMemsetAsync(s->fh, 0, fb[i], st);
+    cudaMemsetAsync(s->fl, 0, fb[i], st);
     int rc = make_map(&s->map_xh, s->xh, s->R, s->C, s->ld, TILE_ROWS);
     if (!rc) rc = make_map(&s->map_xl, s->xl, s->R, s->C, s->ld, TILE_ROWS);
     if (!rc) rc = make_map(&s->map_fh, s->fh, p->r_pad, s->C, s->ld, p->r_pad);
     if (!rc) rc = make_map(&s->map_fl, s->fl, p->r_pad, s->C, s->ld, p->r_pad);
     if (rc) { nnfac_nmf_plan_destroy(p); return rc; }
-    const size_t pb = (size_t)s->cp.splits * p->r_pad * s->cp.ld_partial * sizeof(float);
-    if (pb > partial_bytes) partial_bytes = pb;
     cudaError_t e = p->r_pad <= 64
         ? cudaFuncSetAttribute(tc_cross_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem)
         : cudaFuncSetAttribute(tc_cross_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem);
     if (e != cudaSuccess) { nnfac_set_error("cudaFuncSetAttribute(smem=%zu): %s", s->smem, cudaGetErrorString(e)); nnfac_nmf_plan_destroy(p); return NNFAC_ERR_CUDA; }
   }
-  if (cudaMalloc(&p->partial, partial_bytes) != cudaSuccess) {
-    cudaGetLastError();
-    nnfac_set_error("nnfac_nmf_plan_create: out of device memory (partials)");
-    nnfac_nmf_plan_destroy(p);
-    return NNFAC_ERR_ALLOC;
-  }
+  p->partial = (float*)(base + o_partial);
   p->partial_bytes = partial_bytes;
   // fused passes: row planes of both factors (rank axis contiguous, padded to 64) and per-CTA cost partials
-  p->fused_ok = p->r_pad <= 64;
   if (p->fused_ok) {
     for (int i = 0; i < 2; ++i) {
       const int64_t len = i == 0 ? m : n;
-      const size_t rb = (size_t)len * 64 * sizeof(bf16);
-      if (cudaMalloc(&p->rowp_h[i], rb) != cudaSuccess || cudaMalloc(&p->rowp_l[i], rb) != cudaSuccess) {
-        cudaGetLastError();
-        nnfac_set_error("nnfac_nmf_plan_create: out of device memory (factor planes)");
-        nnfac_nmf_plan_destroy(p);
-        return NNFAC_ERR_ALLOC;
-      }
-      cudaMemset(p->rowp_h[i], 0, rb);
-      cudaMemset(p->rowp_l[i], 0, rb);
+      p->rowp_h[i] = (bf16*)(base + o_rh[i]); p->rowp_l[i] = (bf16*)(base + o_rl[i]);
+      cudaMemsetAsync(p->rowp_h[i], 0, rb[i], st);
+      cudaMemsetAsync(p->rowp_l[i], 0, rb[i], st);
       int rc = make_map(&p->map_row_a_h[i], p->rowp_h[i], len, 64, 64, TILE_ROWS);
       if (!rc) rc = make_map(&p->map_row_a_l[i], p->rowp_l[i], len, 64, 64, TILE_ROWS);
       if (!rc) rc = make_map(&p->map_row_b_h[i], p->rowp_h[i], len, 64, 64, 64);
       if (!rc) rc = make_map(&p->map_row_b_l[i], p->rowp_l[i], len, 64, 64, 64);
       if (rc) { nnfac_nmf_plan_destroy(p); return rc; }
     }
-    if (cudaMalloc(&p->cost_part, sizeof(double) * 1024) != cudaSuccess) {
-      cudaGetLastError();
-      nnfac_nmf_plan_destroy(p);
-      return NNFAC_ERR_ALLOC;
-    }
   }
+  p->cost_part = (double*)(base + o_cost);
+  cudaMemsetAsync(p->cost_part, 0, sizeof(double) * 2048, st);
+  p->sums = p->cost_part + 1024;
+  if (cudaGetLastError() != cudaSuccess) { nnfac_set_error("nnfac_nmf_plan_create: clearing the workspace failed"); nnfac_nmf_plan_destroy(p); return NNFAC_ERR_CUDA; }
   *out = p;
   return NNFAC_OK;
 }
 
-int nnfac_nmf_plan_load_x(nnfac_nmf_plan* p, const float* X, int64_t ldx, void* stream) {
-  NNFAC_ARG(p && X && ldx >= p->n, "nnfac_nmf_plan_load_x: bad argument");
+int nnfac_nmf_plan_create(nnfac_ctx* ctx, int64_t m, int64_t n, int r, nnfac_nmf_plan** out) {
+  NNFAC_ARG(out != nullptr, "nnfac_nmf_plan_create: out is NULL");
+  return plan_build(ctx, m, n, r, nullptr, 0, (cudaStream_t)0, out, nullptr);
+}
+
+int nnfac_nmf_plan_bytes(nnfac_ctx* ctx, int64_t m, int64_t n, int r, size_t* bytes) {
+  NNFAC_ARG(bytes != nullptr, "nnfac_nmf_plan_bytes: bytes is NULL");
+  return plan_build(ctx, m, n, r, nullptr, 0, (cudaStream_t)0, nullptr, bytes);
+}
+
+int nnfac_nmf_plan_create_in(nnfac_ctx* ctx, int64_t m, int64_t n, int r, void* workspace, size_t workspace_bytes,
+                             void* stream, nnfac_nmf_plan** out) {
+  NNFAC_ARG(out != nullptr && workspace != nullptr, "nnfac_nmf_plan_create_in: NULL argument");
+  return plan_build(ctx, m, n, r, workspace, workspace_bytes, (cudaStream_t)stream, out, nullptr);
+}
+
+// Rows [row0, row0 + rows) of X (device fp32, `Xrows` points at row row0): both plane orientations of that slab.
+// Lets the host pipeline the upload of X with its ingest (see NMFPlan.load_host in nn_fac/_ops.py).
+int nnfac_nmf_plan_load_x_rows(nnfac_nmf_plan* p, const float* Xrows, int64_t ldx, int64_t row0, int64_t rows, void* stream) {
+  NNFAC_ARG(p && Xrows && ldx >= p->n && row0 >= 0 && rows > 0 && row0 + rows <= p->m, "nnfac_nmf_plan_load_x_rows: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t total = p->m * p->n;
+  const int64_t total = rows * p->n;
   int grid = (int)(ceil_div64(total, 256) < (int64_t)p->ctx->sm_count * 32 ? ceil_div64(total, 256) : (int64_t)p->ctx->sm_count * 32);
-  split_planes_kernel<<<grid, 256, 0, st>>>(X, ldx, p->m, p->n, p->side[0].xh, p->side[0].xl, p->side[0].ld);
+  split_planes_kernel<<<grid, 256, 0, st>>>(Xrows, ldx, rows, p->n, p->side[0].xh + row0 * p->side[0].ld,
+                                            p->side[0].xl + row0 * p->side[0].ld, p->side[0].ld);
   NNFAC_LAUNCH_CHECK(p->ctx);
-  NNFAC_ARG(ceil_div64(p->m, 32) <= 65535 * 32ll, "nnfac_nmf_plan_load_x: too many rows");
   // grid.y is limited to 65535 blocks of 32 rows: walk the rows in slabs
   const int64_t slab = 65535ll * 32;
-  for (int64_t r0 = 0; r0 < p->m; r0 += slab) {
-    const int64_t rows = p->m - r0 < slab ? p->m - r0 : slab;
-    dim3 g((unsigned)ceil_div64(p->n, 32), (unsigned)ceil_div64(rows, 32)), b(32, 8);
-    split_planes_transposed_kernel<<<g, b, 0, st>>>(X + r0 * ldx, ldx, rows, p->n, p->side[1].xh + r0, p->side[1].xl + r0,
-                                                    p->side[1].ld);
+  for (int64_t r0 = 0; r0 < rows; r0 += slab) {
+    const int64_t nr = rows - r0 < slab ? rows - r0 : slab;
+    dim3 g((unsigned)ceil_div64(p->n, 32), (unsigned)ceil_div64(nr, 32)), b(32, 8);
+    split_planes_transposed_kernel<<<g, b, 0, st>>>(Xrows + r0 * ldx, ldx, nr, p->n, p->side[1].xh + row0 + r0,
+                                                    p->side[1].xl + row0 + r0, p->side[1].ld);
     NNFAC_LAUNCH_CHECK(p->ctx);
   }
   return NNFAC_OK;
 }
 
+// After the last slab: constants of the data that the passes need (sum of X for the KL cost).
+int nnfac_nmf_plan_load_x_done(nnfac_nmf_plan* p, void* stream) {
+  NNFAC_ARG(p != nullptr, "nnfac_nmf_plan_load_x_done: plan is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->fused_ok) {
+    // sum of X as the passes see it (hi + lo planes), fp64, fixed order: the constant term of the KL cost
+    const int blocks = p->ctx->sm_count * 4;
+    plane_total_kernel<<<blocks, 256, 0, st>>>(p->side[0].xh, p->side[0].xl, p->side[0].ld, p->m, p->n, p->ctx->red);
+    NNFAC_LAUNCH_CHECK(p->ctx);
+    plane_total_finish_kernel<<<1, 32, 0, st>>>(p->ctx->red, blocks, p->sums);
+    NNFAC_LAUNCH_CHECK(p->ctx);
+  }
+  return NNFAC_OK;
+}
+
+int nnfac_nmf_plan_load_x(nnfac_nmf_plan* p, const float* X, int64_t ldx, void* stream) {
+  NNFAC_ARG(p && X && ldx >= p->n, "nnfac_nmf_plan_load_x: bad argument");
+  const int rc = nnfac_nmf_plan_load_x_rows(p, X, ldx, 0, p->m, stream);
+  return rc ? rc : nnfac_nmf_plan_load_x_done(p, stream);
+}
+
 int nnfac_nmf_plan_cross(nnfac_nmf_plan* p, int which, const float* F, int64_t ldf, float* out, int64_t ld_out,
                          void* stream) {
-  NNFAC_ARG(p && F && out && (which == 0 || which == 1), "nnfac_nmf_plan_cross: bad argument");
+  NNFAC_ARG(p && out && (which == 0 || which == 1), "nnfac_nmf_plan_cross: bad argument");
   Side* s = &p->side[which];
-  NNFAC_ARG(ldf >= s->C && ld_out >= s->R, "nnfac_nmf_plan_cross: leading dimension too small");
+  NNFAC_ARG((!F || ldf >= s->C) && ld_out >= s->R, "nnfac_nmf_plan_cross: leading dimension too small");
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t total = (int64_t)p->r * s->C;
-  int grid = (int)(ceil_div64(total, 256) < (int64_t)p->ctx->sm_count * 8 ? ceil_div64(total, 256) : (int64_t)p->ctx->sm_count * 8);
-  split_planes_kernel<<<grid, 256, 0, st>>>(F, ldf, p->r, s->C, s->fh, s->fl, s->ld);
-  NNFAC_LAUNCH_CHECK(p->ctx);
+  int grid;
+  if (F) {   // F == NULL: the operand planes of the factor installed by nnfac_nmf_plan_set_factor / _mu_finish are current
+    const int64_t total = (int64_t)p->r * s->C;
+    grid = (int)(ceil_div64(total, 256) < (int64_t)p->ctx->sm_count * 8 ? ceil_div64(total, 256) : (int64_t)p->ctx->sm_count * 8);
+    split_planes_kernel<<<grid, 256, 0, st>>>(F, ldf, p->r, s->C, s->fh, s->fl, s->ld);
+    NNFAC_LAUNCH_CHECK(p->ctx);
+  }
   CrossParams cp = s->cp;
   cp.partial = p->partial;
   if (p->r_pad <= 64)

@@ -79,8 +79,12 @@ struct nnfac_nmf_plan {
   //   map_row_b: 64-row boxes (B operand of the model GEMM)
   __nv_bfloat16 *rowp_h[2], *rowp_l[2];
   CUtensorMap map_row_a_h[2], map_row_a_l[2], map_row_b_h[2], map_row_b_l[2];
-  double* cost_part;    // [sm_count] per-CTA cost partials of a fused pass
+  double* cost_part;    // [1024] per-CTA cost partials of a fused pass ([512 + i]: second partial of CTA i)
+  double* sums;         // cost_part + 1024: [0] sum of X (as stored in the planes)
   int fused_ok;
+  void* buffer;         // the one device allocation every pointer above points into
+  size_t buffer_bytes;
+  int owns_buffer;      // 0: caller's workspace (nnfac_nmf_plan_create_in)
 };
 
 

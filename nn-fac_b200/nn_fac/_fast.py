@@ -82,8 +82,8 @@ class Comm:
 class CudaEngine:
     """The device operators one outer iteration is made of, all in libnnfac_b200 (no torch arithmetic)."""
 
-    def __init__(self, X, r):
-        self.plan = ops.NMFPlan(X).bind_rank(r)
+    def __init__(self, X, r, device=None):
+        self.plan = ops.NMFPlan(X, device).bind_rank(r)
 
     def set_factor(self, which, Ft):
         self.plan.set_factor(which, Ft)
@@ -129,11 +129,12 @@ class FusedNMF:
         self.comm = group if isinstance(group, Comm) else Comm(group)
         self.r = int(U.shape[1])
         if engine is None:
-            X = L.to_device(data, torch.float32, device)
-            self.eng = CudaEngine(X, self.r)
-            self.m, self.n = X.shape
-            self.device = X.device
-            del X
+            # a host-resident X goes straight into the plan (upload pipelined with the ingest)
+            if isinstance(data, torch.Tensor) and data.is_cuda:
+                data = data.to(dtype=torch.float32).contiguous()
+            self.eng = CudaEngine(data, self.r, device)
+            self.m, self.n = self.eng.plan.m, self.eng.plan.n
+            self.device = self.eng.plan.device
             U_dev = L.to_device(U, torch.float32, device)
             V_dev = L.to_device(V, torch.float32, device)
             self._on_gpu = True
@@ -187,7 +188,7 @@ class FusedNMF:
                 eng.set_factor(0, Ut)
         if 1 not in fixed_modes:
             with self._phase("cross_V"):
-                UtM = eng.cross(1, Ut)                                             # nmf.py:433
+                UtM = eng.cross(1, None)                                           # nmf.py:433 (planes of the U just installed)
                 UtU = eng.gram(Ut)                                                 # nmf.py:432
             with self._phase("sweep_V"):
                 V = V.clone()

@@ -42,8 +42,12 @@ SIGNATURES = {
     "nnfac_hadamard": [_P, _INT, _P, _P, _P, _I64, _P],
     "nnfac_normalize_rows": [_P, _INT, _P, _I64, _I64, _I64, _P],
     "nnfac_nmf_plan_create": [_P, _I64, _I64, _INT, _c.POINTER(_P)],
+    "nnfac_nmf_plan_bytes": [_P, _I64, _I64, _INT, _c.POINTER(_c.c_size_t)],
+    "nnfac_nmf_plan_create_in": [_P, _I64, _I64, _INT, _P, _c.c_size_t, _P, _c.POINTER(_P)],
     "nnfac_nmf_plan_destroy": [_P],
     "nnfac_nmf_plan_load_x": [_P, _P, _I64, _P],
+    "nnfac_nmf_plan_load_x_rows": [_P, _P, _I64, _I64, _I64, _P],
+    "nnfac_nmf_plan_load_x_done": [_P, _P],
     "nnfac_nmf_plan_cross": [_P, _INT, _P, _I64, _P, _I64, _P],
     "nnfac_nmf_plan_set_factor": [_P, _INT, _P, _I64, _P],
     "nnfac_nmf_plan_fused": [_P, _INT, _INT, _INT, _P, _I64, _P, _P],

@@ -3,6 +3,7 @@
 These are the building blocks the drop-in modules (nmf, ntf, ntd, update_rules.*) are written
 with.  torch allocates the buffers; it never computes.
 """
+import numpy as np
 import torch
 
 from . import _lib as L
@@ -211,11 +212,22 @@ def unfold_times(P, B, mode):
 class NMFPlan:
     """Owner of an nnfac_nmf_plan (X resident as bf16 hi/lo planes in both orientations; tcgen05 path)."""
 
-    def __init__(self, X):
+    SLAB_BYTES = 64 << 20     # upload granularity of a host-resident X
+
+    def __init__(self, X, device=None):
+        """X: float32 CUDA tensor (m x n), or a host array / CPU tensor, which is uploaded slab by slab with the
+        upload of slab i+1 overlapping the ingest of slab i (the fp32 X never exists on the device as a whole)."""
         import ctypes
-        assert X.dtype == torch.float32 and X.dim() == 2
+        if isinstance(X, torch.Tensor) and X.is_cuda:
+            assert X.dtype == torch.float32 and X.dim() == 2
+            self.device = X.device
+        else:
+            if not isinstance(X, torch.Tensor):
+                X = torch.from_numpy(np.ascontiguousarray(np.asarray(X)))
+            assert X.dim() == 2
+            X = X.contiguous()
+            self.device = torch.device("cuda", L.device_index(device))
         self.m, self.n = X.shape
-        self.device = X.device
         self.handle = ctypes.c_void_p()
         self.r = None
         self._X = X
@@ -223,17 +235,53 @@ class NMFPlan:
     def bind_rank(self, r):
         import ctypes
         self.r = r
-        L.check(_lib().nnfac_nmf_plan_create(L.ctx(self.device), self.m, self.n, r, ctypes.byref(self.handle)))
-        L.check(_lib().nnfac_nmf_plan_load_x(self.handle, L.ptr(self._X), self._X.stride(0), L.stream_ptr()))
+        # the plan lives in one block of torch's caching allocator: a second factorisation of same-shaped data
+        # reuses it without any cudaMalloc / cudaFree
+        nbytes = ctypes.c_size_t()
+        L.check(_lib().nnfac_nmf_plan_bytes(L.ctx(self.device), self.m, self.n, r, ctypes.byref(nbytes)))
+        self._workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        L.check(_lib().nnfac_nmf_plan_create_in(L.ctx(self.device), self.m, self.n, r, L.ptr(self._workspace), nbytes.value,
+                                                L.stream_ptr(), ctypes.byref(self.handle)))
+        if self._X.is_cuda:
+            L.check(_lib().nnfac_nmf_plan_load_x(self.handle, L.ptr(self._X), self._X.stride(0), L.stream_ptr()))
+        else:
+            self._load_host(self._X)
         self._X = None
         return self
 
+    def _load_host(self, host):
+        """Double-buffered upload + ingest: copy stream fills slab b while the main stream splits slab 1-b into planes."""
+        m, n = self.m, self.n
+        rows_per = max(32, (self.SLAB_BYTES // max(1, n * host.element_size())) // 32 * 32)
+        rows_per = min(rows_per, m)
+        main = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(main)
+        bufs = [torch.empty((rows_per, n), dtype=host.dtype, device=self.device) for _ in range(2)]
+        copied = [torch.cuda.Event() for _ in range(2)]
+        ingested = [torch.cuda.Event() for _ in range(2)]
+        for i, r0 in enumerate(range(0, m, rows_per)):
+            b, rows = i & 1, min(rows_per, m - r0)
+            with torch.cuda.stream(side):
+                if i >= 2:
+                    side.wait_event(ingested[b])
+                bufs[b][:rows].copy_(host[r0:r0 + rows], non_blocking=True)
+                copied[b].record(side)
+            main.wait_event(copied[b])
+            slab = bufs[b][:rows]
+            if slab.dtype != torch.float32:
+                slab = slab.float()
+            L.check(_lib().nnfac_nmf_plan_load_x_rows(self.handle, L.ptr(slab), slab.stride(0), r0, rows, L.stream_ptr()))
+            ingested[b].record(main)
+        L.check(_lib().nnfac_nmf_plan_load_x_done(self.handle, L.stream_ptr()))
+
     def cross(self, which, F, out=None):
-        """which=0: F = V (r x n) -> V X^T (r x m); which=1: F = U^T (r x m) -> U^T X (r x n)."""
+        """which=0: F = V (r x n) -> V X^T (r x m); which=1: F = U^T (r x m) -> U^T X (r x n).
+        F=None: the factor installed with set_factor / mu_finish (its operand planes are reused)."""
         R = self.m if which == 0 else self.n
         if out is None:
             out = torch.empty((self.r, R), dtype=torch.float32, device=self.device)
-        L.check(_lib().nnfac_nmf_plan_cross(self.handle, which, L.ptr(F), F.stride(0), L.ptr(out), out.stride(0),
+        L.check(_lib().nnfac_nmf_plan_cross(self.handle, which, L.ptr(F), F.stride(0) if F is not None else 0, L.ptr(out), out.stride(0),
                                             L.stream_ptr()))
         return out
 
@@ -275,8 +323,7 @@ class NMFPlan:
     def __del__(self):
         try:
             if self.handle:
-                torch.cuda.synchronize(self.device)
-                _lib().nnfac_nmf_plan_destroy(self.handle)
-                self.handle = None
+                _lib().nnfac_nmf_plan_destroy(self.handle)      # host bookkeeping only: the workspace is a torch tensor,
+                self.handle = None                              # released stream-ordered by the caching allocator
         except Exception:
             pass

@@ -51,6 +51,8 @@ class OracleEngine:
         return out.contiguous(), cost.reshape(1).to(torch.float64)
 
     def cross(self, which, F):
+        if F is None:                      # the installed factor: V for which=0, U^T for which=1
+            F = self.F[1 - which]
         return (F @ self.X.T if which == 0 else F @ self.X).contiguous()
 
     @staticmethod

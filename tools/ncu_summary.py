@@ -76,7 +76,8 @@ def launches(path):
     for r in rows[1:]:
         if len(r) != len(hdr):
             continue
-        name = r[ki].split("(")[0].split("<")[0].replace("void ", "").strip()[:60]
+        name = r[ki].replace("<unnamed>::", "").replace("void ", "").split("(")[0]
+        name = (name.split("<")[0] + ("<" + name.split("<", 1)[1][:12] if "<" in name and name.split("<")[0].startswith("tc_") else "")).strip()[:60]
         v = float(r[vi].replace(",", ""))
         v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(r[ui], 1.0)
         a = agg.setdefault(name, [0, 0.0])
