@@ -43,6 +43,7 @@ struct alignas(16) SweepConst {
   float nh[NBLK][BLK][BLK];     // [B][e][e2] = -UtU[k2][k] / UtU[k2][k2] (source row k = 16B+e, target row k2 = 16B+e2)
   float invd[RP];               // 1 / UtU[k][k], 0 when the diagonal entry is 0 or k >= r
   float lbs[RP];                // -1 when the row is updated, 0 when it is skipped (nnls.py:160)
+  int has_zero_diag;            // some row k < r has UtU[k][k] == 0
 };
 __constant__ SweepConst c_sw;
 
@@ -58,6 +59,11 @@ __global__ void sweep_prep_kernel(const float* __restrict__ G, int64_t ld_g, int
     out->invd[k] = d != 0.f ? 1.f / d : 0.f;
     out->lbs[k] = d != 0.f ? -1.f : 0.f;
   }
+  if (threadIdx.x == 0) {
+    int z = 0;
+    for (int k = 0; k < r; ++k) z |= (G[(int64_t)k * ld_g + k] == 0.f);
+    out->has_zero_diag = z;
+  }
 }
 
 struct TcSweepArgs {
@@ -68,7 +74,8 @@ struct TcSweepArgs {
   int r, maxiter, cols_per_cta;
   double delta;
   float sp;
-  unsigned long long* mail;   // [2][grid][grid] tagged partial sums
+  unsigned long long* mail;   // [2][grid][grid] tagged partial sums (tag = generation << 16 | sweep)
+  unsigned gen;               // call generation: stale mailbox contents of earlier calls never match
   double* result;
 };
 
@@ -198,14 +205,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
     __syncwarp();
     tc::tmem_alloc(tmem_slot, 512);
   }
-  // -UtU operand planes (K-major, 128B swizzle): row j = output row of the rank update, K = source row
+  // Operand planes of -UtU[j][:] / UtU[j][j] (K-major, 128B swizzle): row j = output row of the rank update, K = source
+  // row.  With the rows scaled by the diagonal the accumulator holds the SCALED residual, i.e. the unclamped step.
   if (threadIdx.x < UPD_THREADS) {
     const int j = threadIdx.x >> 3, c = threadIdx.x & 7;
+    const float dj = j < r ? a.G[(int64_t)j * a.ld_g + j] : 0.f;
+    const float sj = dj != 0.f ? -1.f / dj : 0.f;
     float x[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int l = c * 8 + i;
-      x[i] = (j < r && l < r) ? -a.G[(int64_t)j * a.ld_g + l] : 0.f;
+      x[i] = (j < r && l < r) ? a.G[(int64_t)j * a.ld_g + l] * sj : 0.f;
     }
     store_chunk(g_planes, j, c, x, G_PLANE_BYTES);
   }
@@ -270,13 +280,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
 #pragma unroll
         for (int j = 0; j < 16; ++j) x[j] = (valid && c0 + j < r) ? a.V[(int64_t)(c0 + j) * a.ld_v + col] : 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) w[j] = __float_as_uint(x[j]);
+        for (int j = 0; j < 16; ++j) w[j] = __float_as_uint(c_sw.invd[c0 + j] != 0.f ? x[j] : 0.f);   // skipped rows: master 0
         tmem_st16(t_v + c0, w);
         store_chunk(vh, row, c0 / 8, &x[0], PLANE_BYTES);
         store_chunk(vh, row, c0 / 8 + 1, &x[8], PLANE_BYTES);
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          w[j] = __float_as_uint((valid && c0 + j < r) ? a.b[(int64_t)(c0 + j) * a.ld_b + col] - a.sp : 0.f);
+          w[j] = __float_as_uint((valid && c0 + j < r) ? (a.b[(int64_t)(c0 + j) * a.ld_b + col] - a.sp) * c_sw.invd[c0 + j] : 0.f);
         tmem_st16(t_w + c0, w);
       }
       tmem_st_wait();
@@ -286,6 +296,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
     }
 
     uint32_t s_phase = 0;
+    uint8_t* bkrow = vh + 2 * PLANE_BYTES + (uint32_t)row * 128u;       // 128 B: masters of up to 2 speculative blocks
 #ifdef SWEEP_PROF
     long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define PROF_T(i) { const long long t__ = clock64(); prof[i] += t__ - tp; tp = t__; }
@@ -298,11 +309,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
     // run the in-block recurrence, write the new masters and the operand planes of the 16 steps and hand
     // them to the issuing warp.  Returns the squared step of the block (nnls.py:170).  `keep` receives the
     // masters the block overwrote (needed to undo a speculative block).
-    auto block_update = [&](auto Bc, uint32_t (&keep)[BLK]) -> float {
+    uint32_t bk2[BLK];                                                  // masters a speculative block 2 overwrote
+    auto block_update = [&](auto Bc, auto Backup) -> float {
       constexpr int B = decltype(Bc)::value;
+      constexpr bool BACKUP = decltype(Backup)::value;
       float nd = 0.f;
       PROF_START
-      uint32_t wb[BLK];
+      uint32_t wb[BLK], keep[BLK];
       tc::tmem_ld16(t_v + B * BLK, keep);                              // masters: do not wait for the MMA
       tc::mbar_wait(&s_full[tile], s_phase);
       s_phase ^= 1;
@@ -310,9 +323,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
       PROF_T(0)
       tc::tmem_ld16(t_w + B * BLK, wb);
       tc::tmem_ld_wait();
+      if (BACKUP && B < 2) {
+        // speculative block: the masters it overwrites go to this thread's row of the (now unused) third operand plane
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(bkrow + (((B * 4 + c) ^ (row & 7)) << 4)) = make_uint4(keep[4 * c], keep[4 * c + 1], keep[4 * c + 2], keep[4 * c + 3]);
+      }
+      if (BACKUP && B == 2) {                                          // ... the third one's stay in registers
+#pragma unroll
+        for (int e = 0; e < BLK; ++e) bk2[e] = keep[e];
+      }
       float u[BLK];
 #pragma unroll
-      for (int e = 0; e < BLK; ++e) u[e] = __uint_as_float(wb[e]) * c_sw.invd[B * BLK + e];
+      for (int e = 0; e < BLK; ++e) u[e] = __uint_as_float(wb[e]);
       PROF_T(1)
       // In-block Gauss-Seidel recurrence (nnls.py:158-170) on the scaled residuals: the step of row k is
       // max(u, -V[k]) and every later row of the block sees it through -UtU[k2][k] / UtU[k2][k2].
@@ -320,9 +343,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
       uint32_t vn[BLK];
 #pragma unroll
       for (int e = 0; e < BLK; ++e) {
-        const int k = B * BLK + e;
         const float cur = __uint_as_float(keep[e]);
-        const float d = fmaxf(u[e], cur * c_sw.lbs[k]);                // nnls.py:163/167; skipped row: u = 0, bound = 0
+        // nnls.py:163/167.  A skipped row (zero diagonal, nnls.py:160) has u = 0 and a master of 0 (its true value only
+        // enters the initial residual and is left untouched in memory), so its step is max(0, -0) = 0.
+        const float d = fmaxf(u[e], -cur);
         if (e + 1 < BLK) u[e + 1] = fmaf(c_sw.nh[B][e][e + 1], d, u[e + 1]);
         dd[e] = d;
         vn[e] = __float_as_uint(cur + d);
@@ -347,52 +371,68 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
     int cnt = 1;
     unsigned epoch = 0;
     const unsigned nb = gridDim.x;
-    // Block 0 of the coming sweep is run SPECULATIVELY while the grid-wide sum of the finished sweep is in
-    // flight (the stop test of nnls.py:156 needs that sum): `bk` keeps the 16 masters it overwrites.
-    bool have_spec = false;
+    // Stop test of nnls.py:156: it needs the sum of squared steps over ALL columns after every sweep.  Every CTA posts
+    // its partial into the mailbox of every CTA (one 64-bit store each, tag | value) and adds the partials it receives
+    // in a fixed order, so that all CTAs obtain the same bits and take the same decision.  While the partials travel,
+    // the first blocks of the coming sweep are run SPECULATIVELY (the masters they overwrite are kept aside), which
+    // hides the L2 round trip; if the test ends the solve they are undone.
+    constexpr int NSPEC = 3;
+    int nspec = 0;                                                        // speculative blocks of the current sweep already done
     float nd_spec = 0.f;
-    uint32_t bk[BLK], scratch[BLK];
+    std::integral_constant<bool, false> plain;
+    std::integral_constant<bool, true> backup;
     while (true) {
-      float nd = have_spec ? nd_spec : 0.f;
+      float nd = nd_spec;
       if (active) {
-        if (!have_spec) nd += block_update(std::integral_constant<int, 0>{}, scratch);
-        if (nblk > 1) nd += block_update(std::integral_constant<int, 1>{}, scratch);
-        if (nblk > 2) nd += block_update(std::integral_constant<int, 2>{}, scratch);
-        if (nblk > 3) nd += block_update(std::integral_constant<int, 3>{}, scratch);
+        if (nspec < 1) nd += block_update(std::integral_constant<int, 0>{}, plain);
+        if (nblk > 1 && nspec < 2) nd += block_update(std::integral_constant<int, 1>{}, plain);
+        if (nblk > 2 && nspec < 3) nd += block_update(std::integral_constant<int, 2>{}, plain);
+        if (nblk > 3) nd += block_update(std::integral_constant<int, 3>{}, plain);
       }
-      // ---- sum of squared steps over the whole grid, fixed order: post this CTA's partial to every CTA ... ----
-      // (fp32 trees: every CTA adds the same numbers in the same order, so all take the same decision)
+      // (fp32 trees: every CTA adds the same numbers in the same order)
       const float t = warp_sum_f(nd);
       if (lane == 0) redf[warp] = t;
       named_bar_sync(1, UPD_THREADS);
-      const unsigned tag = epoch + 1u;
-      if (nb > 1) {
-        if (threadIdx.x < nb) {
-          float sum = 0.f;
+      const unsigned tag = (a.gen << 16) | (epoch + 1u);
+      if (nb > 1 && threadIdx.x < nb) {
+        float sum = 0.f;
 #pragma unroll
-          for (int w = 0; w < UPD_THREADS / 32; ++w) sum += redf[w];
-          const unsigned long long bits = ((unsigned long long)tag << 32) | __float_as_uint(sum);
-          st_relaxed_u64(a.mail + ((size_t)(epoch & 1u) * nb + threadIdx.x) * nb + blockIdx.x, bits);
+        for (int w = 0; w < UPD_THREADS / 32; ++w) sum += redf[w];
+        const unsigned long long bits = ((unsigned long long)tag << 32) | __float_as_uint(sum);
+        st_relaxed_u64(a.mail + ((size_t)(epoch & 1u) * nb + threadIdx.x) * nb + blockIdx.x, bits);
+      }
+      // ---- speculative blocks of the next sweep; the first look into the mailbox is issued before the last of them,
+      //      so that its L2 round trip runs under that block ----
+      const unsigned long long* slot = a.mail + ((size_t)(epoch & 1u) * nb + blockIdx.x) * nb + threadIdx.x;
+      const bool poller = nb > 1 && threadIdx.x < nb;
+      unsigned long long early = 0ull;
+      nspec = 0;
+      nd_spec = 0.f;
+      if (cnt + 1 <= a.maxiter) {
+        nspec = nblk < NSPEC ? nblk : NSPEC;
+        if (nspec == 1 && poller) early = ld_relaxed_u64(slot);
+        if (active) nd_spec = block_update(std::integral_constant<int, 0>{}, backup);
+        if (nspec > 1) {
+          if (nspec == 2 && poller) early = ld_relaxed_u64(slot);
+          if (active) nd_spec += block_update(std::integral_constant<int, 1>{}, backup);
+        }
+        if (nspec > 2) {
+          if (poller) early = ld_relaxed_u64(slot);
+          if (active) nd_spec += block_update(std::integral_constant<int, 2>{}, backup);
         }
       }
-      // ---- ... run block 0 of the next sweep while the other CTAs' partials arrive ... ----
-      have_spec = false;
-      if (cnt + 1 <= a.maxiter) {
-        have_spec = true;
-        nd_spec = active ? block_update(std::integral_constant<int, 0>{}, bk) : 0.f;
-      }
-      // ---- ... then collect the total ----
+      // ---- collect the total ----
 #ifdef SWEEP_PROF
       const long long tg0 = clock64();
 #endif
       float totf = 0.f;
       if (nb > 1) {
         float got = 0.f;
-        if (threadIdx.x < nb) {
-          const unsigned long long* slot = a.mail + ((size_t)(epoch & 1u) * nb + blockIdx.x) * nb + threadIdx.x;
-          unsigned long long bits;
+        if (poller) {
+          unsigned long long bits = early;
           uint32_t spins = 0;
-          while ((unsigned)((bits = ld_relaxed_u64(slot)) >> 32) != tag) {
+          while ((unsigned)(bits >> 32) != tag) {
+            bits = ld_relaxed_u64(slot);
             if (++spins > (1u << 24)) __trap();
           }
           got = __uint_as_float((unsigned)bits);
@@ -435,11 +475,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
         uint32_t w[16];
         tc::tmem_ld16(t_v + c0, w);
         tc::tmem_ld_wait();
+        if (c0 / BLK == 2 && nspec > 2) {                                   // undo the speculative blocks
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const uint32_t val = (c0 == 0 && have_spec) ? bk[j] : w[j];       // undo the speculative block
-          if (valid && c0 + j < r) a.V[(int64_t)(c0 + j) * a.ld_v + col] = __uint_as_float(val);
+          for (int e = 0; e < BLK; ++e) w[e] = bk2[e];
+        } else if (c0 / BLK < nspec) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 b4 = *reinterpret_cast<const uint4*>(bkrow + ((((c0 / BLK) * 4 + c) ^ (row & 7)) << 4));
+            w[4 * c] = b4.x; w[4 * c + 1] = b4.y; w[4 * c + 2] = b4.z; w[4 * c + 3] = b4.w;
+          }
         }
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (valid && c0 + j < r && c_sw.invd[c0 + j] != 0.f) a.V[(int64_t)(c0 + j) * a.ld_v + col] = __uint_as_float(w[j]);
       }
     }
 #ifdef SWEEP_PROF
@@ -473,7 +521,7 @@ int nnfac_tc_sweep_try(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const f
   cols = ceil_div64(cols, 32) * 32;
   if (cols > MAX_TILES * TILE) return NNFAC_ERR_UNSUPPORTED;
   const int64_t grid = ceil_div64(n, cols);
-  if ((size_t)(2 * grid * grid) > ctx->red_count) return NNFAC_ERR_UNSUPPORTED;
+  if ((size_t)(2 * grid * grid) > ctx->mail_count || maxiter > 65000) return NNFAC_ERR_UNSUPPORTED;
   static SweepConst* staging = nullptr;   // one per process is enough: calls are stream-ordered per context
   if (!staging) NNFAC_CUDA(cudaMalloc(&staging, sizeof(SweepConst)));
   sweep_prep_kernel<<<1, 256, 0, st>>>(UtU, ld_utu, r, staging);
@@ -482,10 +530,15 @@ int nnfac_tc_sweep_try(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const f
   TcSweepArgs a;
   a.b = UtM; a.G = UtU; a.V = V; a.ld_b = ld_utm; a.ld_g = ld_utu; a.ld_v = ld_v; a.n = n;
   a.r = r; a.maxiter = maxiter; a.cols_per_cta = (int)cols; a.delta = delta; a.sp = (float)sparsity;
-  a.mail = reinterpret_cast<unsigned long long*>(ctx->red); a.result = result;
+  // mailbox tags carry a call generation, so that the slots never need clearing between calls
+  ctx->sweep_gen = (ctx->sweep_gen + 1) & 0xffffu;
+  if (ctx->sweep_gen == 0) {
+    NNFAC_CUDA(cudaMemsetAsync(ctx->mail, 0, ctx->mail_count * sizeof(unsigned long long), st));
+    ctx->sweep_gen = 1;
+  }
+  a.mail = ctx->mail; a.gen = ctx->sweep_gen; a.result = result;
   const size_t smem = NPLANES * G_PLANE_BYTES + (size_t)MAX_TILES * NPLANES * PLANE_BYTES + 512;
   NNFAC_CUDA(cudaFuncSetAttribute(tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (grid > 1) NNFAC_CUDA(cudaMemsetAsync(ctx->red, 0, (size_t)(2 * grid * grid) * sizeof(double), st));   // tag 0 = empty
   void* params[] = {&a};
   NNFAC_CUDA(cudaLaunchCooperativeKernel((const void*)tc_sweep_kernel, dim3((unsigned)grid), dim3(NTHREADS), params, smem, st));
   ctx->launches++;
