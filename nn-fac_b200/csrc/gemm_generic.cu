@@ -172,7 +172,7 @@ int run_gemm(nnfac_ctx* ctx, T* C, int64_t ldc, int64_t sc_b, const T* A, int64_
 constexpr int GR = 64, GC = 64, GPADF = 68;
 
 template <typename T>
-__global__ void __launch_bounds__(256) gram_partial_kernel(const T* __restrict__ F, int64_t ld_f, int r, int64_t len,
+__global__ void __launch_bounds__(256, 4) gram_partial_kernel(const T* __restrict__ F, int64_t ld_f, int r, int64_t len,
                                                            int64_t cols_per_cta, T* __restrict__ part) {
   __shared__ __align__(16) T tile[GC][GPADF];
   const int t = threadIdx.x, ti = t >> 4, tj = t & 15;
@@ -222,7 +222,8 @@ __global__ void gram_reduce_kernel(const T* __restrict__ part, int nparts, int r
 
 template <typename T>
 int run_gram(nnfac_ctx* ctx, T* out, int64_t ld_out, const T* F, int64_t ld_f, int r, int64_t len, cudaStream_t st) {
-  int64_t cols = ceil_div64(len, ctx->sm_count);
+  // four CTAs per SM hide the latency of the slab loads; at most 4 * sm_count partials for the fixed-order adder
+  int64_t cols = ceil_div64(len, (int64_t)ctx->sm_count * 4);
   cols = ceil_div64(cols, GC) * GC;
   const int grid = (int)ceil_div64(len, cols);
   const size_t need = (size_t)grid * GR * GR * sizeof(T);

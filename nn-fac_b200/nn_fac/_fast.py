@@ -154,6 +154,9 @@ class FusedNMF:
         if self._on_gpu:
             self._host = self._host.pin_memory()
         self._dev_scal = torch.zeros(4, dtype=torch.float64, device=self.device)
+        # Grams of the single-GPU HALS path are computed on a side stream, under the X pass that precedes their use
+        self._side = torch.cuda.Stream(self.device) if self._on_gpu else None
+        self._gram = [torch.empty((self.r, self.r), dtype=self.Ut.dtype, device=self.device) for _ in range(2)]
         # exchange buffer of the U side: [cross product or numerator (r x m) | Gram (r x r) or row sums (r)]
         self._xbuf = torch.empty(self.r * self.m + self.r * self.r, dtype=self.Ut.dtype, device=self.device)
 
@@ -161,14 +164,30 @@ class FusedNMF:
         from nn_fac.nmf import _Phase
         return _Phase(self, name)
 
+    def _gram_async(self, which, F):
+        """F F^T into self._gram[which] on the side stream (it only reads F, which is final by now); returns a
+        function that makes the current stream wait for it."""
+        if self._side is None:
+            self.eng.gram(F, out=self._gram[which])
+            return lambda: self._gram[which]
+        main = torch.cuda.current_stream(self.device)
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            self.eng.gram(F, out=self._gram[which])
+
+        def join():
+            main.wait_stream(self._side)
+            return self._gram[which]
+        return join
+
     # one outer iteration, given the result of its first pass
-    def _apply_hals(self, VMt, sparsity, fixed_modes, normalize):
+    def _apply_hals(self, VMt, sparsity, fixed_modes, normalize, VVt_join=None):
         r, m = self.r, self.m
         Ut, V, comm, eng = self.Ut, self.V, self.comm, self.eng
         if 0 not in fixed_modes:
             with self._phase("gram_U"):
                 if comm.world == 1:
-                    VVt = eng.gram(V)                                              # nmf.py:407
+                    VVt = VVt_join() if VVt_join is not None else eng.gram(V)      # nmf.py:407
                 else:
                     # partial V_p X_p^T and V_p V_p^T of this column block, summed over the blocks
                     xb = self._xbuf
@@ -188,8 +207,9 @@ class FusedNMF:
                 eng.set_factor(0, Ut)
         if 1 not in fixed_modes:
             with self._phase("cross_V"):
+                join = self._gram_async(1, Ut) if comm.world == 1 else None        # nmf.py:432, under the X pass
                 UtM = eng.cross(1, None)                                           # nmf.py:433 (planes of the U just installed)
-                UtU = eng.gram(Ut)                                                 # nmf.py:432
+                UtU = join() if join is not None else eng.gram(Ut)
             with self._phase("sweep_V"):
                 V = V.clone()
                 eng.sweep(UtM, UtU, V, r, sparsity[1], normalize[1], self.hals_stats[1])        # nmf.py:440
@@ -231,6 +251,9 @@ class FusedNMF:
         tic = time.time()
         done = torch.cuda.Event() if self._on_gpu else None
         for it in range(n_iter_max + 1):
+            VVt_join = None
+            if mode == MODE_RES and self.comm.world == 1 and it < n_iter_max and 0 not in fixed_modes:
+                VVt_join = self._gram_async(0, self.V)                             # V V^T under the first pass
             with self._phase("pass_U"):
                 # single GPU, MU: the numerator stays in the plan as split partials and is consumed by mu_finish
                 keep = mode == MODE_MU and self.comm.world == 1 and it < n_iter_max and 0 not in fixed_modes
@@ -249,7 +272,7 @@ class FusedNMF:
             # launch iteration `it` before looking at the cost of iteration it-1
             if it < n_iter_max:
                 if mode == MODE_RES:
-                    new_Ut, new_V = self._apply_hals(outA, sparsity, fixed_modes, normalize)
+                    new_Ut, new_V = self._apply_hals(outA, sparsity, fixed_modes, normalize, VVt_join)
                 else:
                     new_Ut, new_V = self._apply_mu(outA, fixed_modes)
             if it > 0:
