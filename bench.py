@@ -45,6 +45,27 @@ def parse_args():
     return p.parse_args()
 
 
+def ncu_traffic(phase):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind `phase`, from the committed
+    `ncu --set full` capture (profiles/r1_ncu_full_summaries.json); None when there is no capture of it."""
+    report = {"hals.pass_U": "r1c_fused_res_s0", "mu.pass_U": "r1c_fused_mu_s0_cost", "mu.pass_V": "r1c_fused_mu_s1_nocost",
+              "hals.cross_V": "r1c_cross_s1"}.get(phase)
+    path = os.path.join(ROOT, "profiles", "r1_ncu_full_summaries.json")
+    if report is None or not os.path.exists(path):
+        return None
+    import re
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for blk in re.findall(r"\{.*?\n\}", open(path).read(), re.S):
+        d = json.loads(blk)
+        if d.get("report", "").startswith(report):
+            tot = 0.0
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                val, u = d[key].split()
+                tot += float(val) * unit[u]
+            return tot
+    return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -149,8 +170,9 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 2000.0 / base["value"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"NMF {args.m}x{args.n} r={args.rank}: HALS + MU beta=1 outer iterations",
-                       "note": "reference algorithm (numpy float64 port in oracle/) on the host cores"},
+            "config": {"workload": f"NMF {args.m}x{args.n} r={args.rank}: 1 HALS + 1 MU(beta=1) outer iteration per step",
+                       "noise": NOISE, "note": "reference algorithm (numpy float64 port in oracle/) on the host cores, "
+                                               "bounded row-subsample scaled to the full shape"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t0}
@@ -261,7 +283,9 @@ def main():
         algo = x_bytes + fac_bytes                      # one pass over X + both factor-sized operands in/out
         ach = algo / (phase_ms[dom] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
+                    "traffic": ncu_traffic(dom) if (m, n, r, world) == (65536, 8192, 64, 1) else None,
+                    "traffic_source": "ncu --set full capture of this kernel at this shape (profiles/r1_ncu_full_summaries.json)",
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
                     "ms_per_launch": phase_ms[dom]}
     algo_iter = 2 * m * n * 4 + 4 * (m + n) * r * 4     # bytes per outer iteration (whole job)
     per_rule = {k: args.steps / (t_rule[k] / 1e3) for k in t_rule}
