@@ -261,6 +261,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         if (++b2 == 2) { b2 = 0; b2_phase ^= 1; }
       };
       int drained = 0;
+      float acc = 0.f, acck = 0.f;      // fp32 partial sums of up to 8 stages (128 elements); FP64 adds are scarce on this part
       for (int i = 0; i < S; ++i) {
         // ---- model tile for this stage ----
         tc::mbar_wait(&d1_full[b1], b1_phase);
@@ -277,7 +278,6 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         tc::mbar_wait(&full[st], ph);
         uint8_t* xh = ring + (size_t)st * STAGE_BYTES;
         uint8_t* xl = xh + X_BYTES;
-        float acc = 0.f, acck = 0.f;
         uint32_t qhw[4 * NCHK], qlw[4 * NCHK];
 #pragma unroll
         for (int cc = 0; cc < NCHK; ++cc) {
@@ -313,9 +313,10 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
             }
           }
         }
-        if (COST) {
+        if (COST && ((i & 7) == 7 || i == S - 1)) {
           cost += (double)acc;
-          if (MODE == MODE_MU) costk += (double)acck;
+          acc = 0.f;
+          if (MODE == MODE_MU) { costk += (double)acck; acck = 0.f; }
         }
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&empty[st]);          // done with the stage's X tile

@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
       return nd;
     };
 
-    double eps0 = 0.0, eps = 1.0;
+    float thr = 0.f, epsf = 1.f;
     int cnt = 1;
     unsigned epoch = 0;
     const unsigned nb = gridDim.x;
@@ -447,16 +447,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
         for (int w = 0; w < UPD_THREADS / 32; ++w) totf += redf[w];
         named_bar_sync(1, UPD_THREADS);                                 // redf[] is rewritten by the next sweep
       }
-      const double tot = (double)totf;
 #ifdef SWEEP_PROF
       prof[6] += clock64() - tg0;
 #endif
       ++epoch;
-      if (cnt == 1) eps0 = tot;
-      eps = tot;
+      if (cnt == 1) {
+        // eps >= delta * eps0 (nnls.py:156, evaluated in double) <=> totf >= thr with thr = delta * eps0 rounded UP to
+        // fp32: the per-sweep test then needs no FP64 instruction (scarce on this part)
+        const double thr_d = a.delta * (double)totf;
+        thr = (float)thr_d;
+        if ((double)thr < thr_d) thr = __uint_as_float(__float_as_uint(thr) + 1u);   // thr_d >= 0: next float up
+      }
+      epsf = totf;
       ++cnt;
-      bool stop = !(eps >= a.delta * eps0 && cnt <= a.maxiter);
-      if (tot == 0.0) {                                                   // further sweeps are no-ops (nnls.py:156)
+      bool stop = !(epsf >= thr && cnt <= a.maxiter);
+      if (totf == 0.f) {                                                  // further sweeps are no-ops (nnls.py:156)
         if (cnt < a.maxiter + 1) cnt = a.maxiter + 1;
         stop = true;
       }
@@ -498,7 +503,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
     }
 #endif
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-      a.result[0] = eps;
+      a.result[0] = (double)epsf;
       a.result[1] = (double)cnt;
       a.result[2] = -1.0;
       a.result[3] = (double)(cnt - 1);
