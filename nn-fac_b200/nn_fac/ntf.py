@@ -7,6 +7,7 @@ tensor per mode, ntf.py:309-311).  HALS uses the deterministic inner stopping ru
 Reference quirk kept: ``ntf`` returns ``np.array(factors)`` (ntf.py:342-344), which numpy >= 1.24
 rejects for non-cubic tensors; here a non-cubic result is returned as an object array of factors.
 """
+import os
 import time
 
 import numpy as np
@@ -60,6 +61,17 @@ class DeviceNTF:
         self.factors = [L.to_device(f, dtype, device) for f in factors]
         self.norm_sq = None
         self.stats = torch.zeros(4, dtype=torch.float64, device=self.T.device)
+        # fp32, rank <= 128: the MTTKRP of every mode runs on tcgen05.  One plan per mode holds unfold(T, mode)
+        # (I_mode x rest, C order) as K-major bf16 hi/lo planes -- the same bytes as the fp32 unfolded copies the
+        # reference keeps (ntf.py:309-311) -- and the MTTKRP is the plan's cross product F X^T with F = krao^T.
+        self.plans = None
+        rank = int(self.factors[0].shape[1])
+        if dtype == torch.float32 and rank <= 128 and self.T.dim() >= 2 and os.environ.get("NNFAC_NTF_TC", "1") != "0":
+            self.plans = []
+            for mode in range(self.T.dim()):
+                Xm = self.T.movedim(mode, 0).reshape(self.shape[mode], -1).contiguous()
+                self.plans.append(ops.NMFPlan(Xm).bind_rank(rank))
+                del Xm
 
     def khatri_rao(self, skip):
         kept = [f for i, f in enumerate(self.factors) if i != skip]
@@ -106,8 +118,12 @@ class DeviceNTF:
                     if i != mode:
                         gram = ops.gemm(f, (1, f.shape[1]), f, (f.shape[1], 1), rank, rank, f.shape[0])  # ntf.py:445
                         cross = gram if cross is None else ops.hadamard_(cross, gram)
-                rhs = self.mttkrp(mode, krao)
-                rhs_t = ops.transpose(rhs)
+                if self.plans is not None:
+                    rhs_t = self.plans[mode].cross(0, ops.transpose(krao))   # (unfold(T, mode) @ krao)^T, ntf.py:449
+                    rhs = None
+                else:
+                    rhs = self.mttkrp(mode, krao)
+                    rhs_t = ops.transpose(rhs)
                 Ft = ops.transpose(self.factors[mode])
                 nnls.hals_nnls_device(rhs_t, cross, Ft, rank, maxiter=100, delta=0.01,
                                       sparsity_coefficient=sparsity[mode], normalize=normalize[mode],
@@ -125,7 +141,8 @@ class DeviceNTF:
         if update_rule == "hals":
             # ntf.py:470; ||F krao^T||^2 = <F^T F, krao^T krao> and krao^T krao = cross (Hadamard of Grams)
             ftf = ops.gemm(F, (1, rank), F, (rank, 1), rank, rank, F.shape[0])
-            parts = torch.cat([ops.dot(F, rhs), ops.dot(ftf, cross)]).cpu().numpy()
+            inner = ops.dot(F, rhs) if rhs is not None else ops.dot(Ft, rhs_t)     # <F, rhs>, either layout
+            parts = torch.cat([inner, ops.dot(ftf, cross)]).cpu().numpy()
             rec_error = norm_tensor ** 2 - 2 * parts[0] + parts[1]
         else:
             K = self.reconstruct_unfolded(mode, krao)
