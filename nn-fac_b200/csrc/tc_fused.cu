@@ -52,7 +52,7 @@ __device__ __forceinline__ float lg2_approx(float x) {   // MUFU.LG2 without the
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
-template <int MODE, bool COST>
+template <int MODE, bool COST, bool XF32>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                 const __grid_constant__ CUtensorMap map_fkh, const __grid_constant__ CUtensorMap map_fkl,
@@ -120,8 +120,9 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         uint8_t* st = ring + (size_t)stage * STAGE_BYTES;
         tc::mbar_arrive_expect_tx(&full[stage], stage_tx);
         const int c = k0 + ks * BK;
+        // XF32: map_xh is the fp32 copy of X; the two 16 KiB halves of the tile are its columns [c, c+32) and [c+32, c+64)
         tc::tma_load_2d_hint(st, &map_xh, &full[stage], c, row0, tc::kEvictFirst);
-        tc::tma_load_2d_hint(st + X_BYTES, &map_xl, &full[stage], c, row0, tc::kEvictFirst);
+        tc::tma_load_2d_hint(st + X_BYTES, XF32 ? &map_xh : &map_xl, &full[stage], XF32 ? c + 32 : c, row0, tc::kEvictFirst);
         tc::tma_load_2d_hint(st + 2 * X_BYTES, &map_fkh, &full[stage], 0, c, tc::kEvictLast);
         tc::tma_load_2d_hint(st + 2 * X_BYTES + FK_BYTES, &map_fkl, &full[stage], 0, c, tc::kEvictLast);
         if (++stage == FSTAGES) { stage = 0; phase ^= 1; }
@@ -281,14 +282,29 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         uint32_t qhw[4 * NCHK], qlw[4 * NCHK];
 #pragma unroll
         for (int cc = 0; cc < NCHK; ++cc) {
-          const int chunk = NCHK * part + cc;
-          const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
-          const uint4 h4 = *reinterpret_cast<const uint4*>(xh + off);
-          const uint4 l4 = *reinterpret_cast<const uint4*>(xl + off);
-          const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+          float xv[8];
+          if (XF32) {
+            // fp32 tile: half (part >> 1) holds 32 columns = 8 chunks of 4 floats per row; this thread's 16 columns are
+            // chunks 4 (part & 1) .. +3, two of them per iteration
+            const uint8_t* xb = xh + (size_t)(part >> 1) * X_BYTES + (uint32_t)row * 128u;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int chunk = 4 * (part & 1) + 2 * cc + h;
+              const float4 v4 = *reinterpret_cast<const float4*>(xb + ((chunk ^ (row & 7)) << 4));
+              xv[4 * h] = v4.x; xv[4 * h + 1] = v4.y; xv[4 * h + 2] = v4.z; xv[4 * h + 3] = v4.w;
+            }
+          } else {
+            const int chunk = NCHK * part + cc;
+            const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+            const uint4 h4 = *reinterpret_cast<const uint4*>(xh + off);
+            const uint4 l4 = *reinterpret_cast<const uint4*>(xl + off);
+            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+            for (int w = 0; w < 4; ++w) { xv[2 * w] = bf_lo(hw[w]) + bf_lo(lw[w]); xv[2 * w + 1] = bf_hi(hw[w]) + bf_hi(lw[w]); }
+          }
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
-            const float x0 = bf_lo(hw[w]) + bf_lo(lw[w]), x1 = bf_hi(hw[w]) + bf_hi(lw[w]);
+            const float x0 = xv[2 * w], x1 = xv[2 * w + 1];
             const float k0 = __uint_as_float(kk[cc * 8 + 2 * w]), k1 = __uint_as_float(kk[cc * 8 + 2 * w + 1]);
             if (MODE == MODE_RES) {
               const float r0 = x0 - k0, r1 = x1 - k1;
@@ -432,6 +448,16 @@ __global__ void kl_cost_finish_kernel(const double* part, int n, const double* s
   }
 }
 
+// fp32 copy of a plane pair: out = hi + lo (exact: 16 significant bits), [rows x ld].
+__global__ void __launch_bounds__(256) planes_to_f32_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, int64_t count,
+                                                            float* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 2;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < count; i += stride) {
+    const uint32_t h = *reinterpret_cast<const uint32_t*>(hi + i), l = *reinterpret_cast<const uint32_t*>(lo + i);
+    *reinterpret_cast<float2*>(out + i) = make_float2(bf_lo(h) + bf_lo(l), bf_hi(h) + bf_hi(l));
+  }
+}
+
 }  // namespace
 
 static int finish_factor(nnfac_nmf_plan* p, int which, bool apply, const float* F_in, int64_t ld_in, const float* den,
@@ -453,6 +479,39 @@ static int finish_factor(nnfac_nmf_plan* p, int which, bool apply, const float* 
 }
 
 extern "C" {
+
+// fp32 copies of X for the beta = 1 fused pass (see nnfac_nmf_plan::xf): `workspace` (256-byte aligned, caller-owned,
+// >= nnfac_nmf_plan_f32_bytes) receives X and X^T as fp32; call after the ingest.  Optional: without it the pass
+// reconstructs x = hi + lo from the bf16 planes.
+int nnfac_nmf_plan_f32_bytes(const nnfac_nmf_plan* p, size_t* bytes) {
+  NNFAC_ARG(p && bytes, "nnfac_nmf_plan_f32_bytes: NULL argument");
+  size_t tot = 0;
+  for (int i = 0; i < 2; ++i) tot += (((size_t)p->side[i].R * p->side[i].ld * sizeof(float)) + 255) & ~(size_t)255;
+  *bytes = tot;
+  return NNFAC_OK;
+}
+
+int nnfac_nmf_plan_enable_f32(nnfac_nmf_plan* p, void* workspace, size_t workspace_bytes, void* stream) {
+  NNFAC_ARG(p && workspace && (((uintptr_t)workspace) & 255) == 0, "nnfac_nmf_plan_enable_f32: bad argument");
+  size_t need = 0;
+  nnfac_nmf_plan_f32_bytes(p, &need);
+  NNFAC_ARG(workspace_bytes >= need, "nnfac_nmf_plan_enable_f32: workspace of %zu bytes needed, got %zu", need, workspace_bytes);
+  if (!p->fused_ok) { nnfac_set_error("nnfac_nmf_plan_enable_f32: rank %d > 64 is not covered by the fused pass", p->r); return NNFAC_ERR_UNSUPPORTED; }
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* base = (uint8_t*)workspace;
+  for (int i = 0; i < 2; ++i) {
+    Side* s = &p->side[i];
+    p->xf[i] = (float*)base;
+    const int64_t count = s->R * s->ld;                       // ld is a multiple of 64: pairs never straddle rows
+    base += (((size_t)count * sizeof(float)) + 255) & ~(size_t)255;
+    planes_to_f32_kernel<<<p->ctx->sm_count * 16, 256, 0, st>>>(s->xh, s->xl, count, p->xf[i]);
+    NNFAC_LAUNCH_CHECK(p->ctx);
+    const int rc = make_map_f32(&p->map_xf[i], p->xf[i], s->R, s->C, s->ld);
+    if (rc) return rc;
+  }
+  p->xf_ready = 1;
+  return NNFAC_OK;
+}
 
 // which = 0: U given as U^T (r x m); which = 1: V (r x n).  Builds every bf16 operand plane of that factor.
 int nnfac_nmf_plan_set_factor(nnfac_nmf_plan* p, int which, const float* Ft, int64_t ld, void* stream) {
@@ -491,15 +550,20 @@ int nnfac_nmf_plan_fused(nnfac_nmf_plan* p, int side, int mode, int want_cost, f
   fp.ld_partial = s->cp.ld_partial; fp.partial = p->partial; fp.cost_part = p->cost_part;
   const size_t smem = A1_BYTES + (size_t)FSTAGES * STAGE_BYTES + 512;
   const int other = 1 - side;
-#define NNFAC_LAUNCH_FUSED(M, C)                                                                                         \
+#define NNFAC_LAUNCH_FUSED(M, C, XF, MAPH, MAPL)                                                                             \
   do {                                                                                                                   \
-    NNFAC_CUDA(cudaFuncSetAttribute(tc_fused_kernel<M, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    tc_fused_kernel<M, C><<<s->grid, FUSED_THREADS, smem, st>>>(s->map_xh, s->map_xl, p->map_row_b_h[other],            \
+    NNFAC_CUDA(cudaFuncSetAttribute(tc_fused_kernel<M, C, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    tc_fused_kernel<M, C, XF><<<s->grid, FUSED_THREADS, smem, st>>>(MAPH, MAPL, p->map_row_b_h[other],                  \
         p->map_row_b_l[other], p->map_row_a_h[side], p->map_row_a_l[side], fp);                                          \
   } while (0)
-  if (mode == 0) NNFAC_LAUNCH_FUSED(MODE_RES, true);
-  else if (fp.want_cost) NNFAC_LAUNCH_FUSED(MODE_MU, true);
-  else NNFAC_LAUNCH_FUSED(MODE_MU, false);
+  if (mode == 0) NNFAC_LAUNCH_FUSED(MODE_RES, true, false, s->map_xh, s->map_xl);
+  else if (p->xf_ready) {   // beta = 1: X only travels through registers -> read its fp32 copy
+    if (fp.want_cost) NNFAC_LAUNCH_FUSED(MODE_MU, true, true, p->map_xf[side], p->map_xf[side]);
+    else NNFAC_LAUNCH_FUSED(MODE_MU, false, true, p->map_xf[side], p->map_xf[side]);
+  } else {
+    if (fp.want_cost) NNFAC_LAUNCH_FUSED(MODE_MU, true, false, s->map_xh, s->map_xl);
+    else NNFAC_LAUNCH_FUSED(MODE_MU, false, false, s->map_xh, s->map_xl);
+  }
 #undef NNFAC_LAUNCH_FUSED
   NNFAC_LAUNCH_CHECK(p->ctx);
   if (out) {      // out == NULL: the split partials stay in the plan for nnfac_nmf_plan_mu_finish

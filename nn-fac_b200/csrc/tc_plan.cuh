@@ -43,6 +43,21 @@ inline int make_map(CUtensorMap* map, const bf16* base, int64_t rows, int64_t co
   return NNFAC_OK;
 }
 
+// 2-D fp32 row-major [rows x cols], box = 128 rows x 32 columns (128 bytes), 128B swizzle.
+inline int make_map_f32(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { nnfac_set_error("cuTensorMapEncodeTiled is not available from the driver"); return NNFAC_ERR_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)TILE_ROWS};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) { nnfac_set_error("cuTensorMapEncodeTiled(f32) failed with CUresult %d", (int)rc); return NNFAC_ERR_CUDA; }
+  return NNFAC_OK;
+}
+
 // ---- the cross-product kernel --------------------------------------------------------------------
 struct CrossParams {
   int r_pad;            // UMMA N (multiple of 16)
@@ -85,6 +100,11 @@ struct nnfac_nmf_plan {
   void* buffer;         // the one device allocation every pointer above points into
   size_t buffer_bytes;
   int owns_buffer;      // 0: caller's workspace (nnfac_nmf_plan_create_in)
+  // optional fp32 copies of X (= hi + lo) in both orientations: the beta = 1 fused pass never needs X as a tensor-core
+  // operand, only in registers, and reads it 3 instructions per element cheaper from fp32 (nnfac_nmf_plan_enable_f32)
+  float* xf[2];
+  CUtensorMap map_xf[2];
+  int xf_ready;
 };
 
 

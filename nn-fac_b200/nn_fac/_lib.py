@@ -48,6 +48,8 @@ SIGNATURES = {
     "nnfac_nmf_plan_load_x": [_P, _P, _I64, _P],
     "nnfac_nmf_plan_load_x_rows": [_P, _P, _I64, _I64, _I64, _P],
     "nnfac_nmf_plan_load_x_done": [_P, _P],
+    "nnfac_nmf_plan_f32_bytes": [_P, _c.POINTER(_c.c_size_t)],
+    "nnfac_nmf_plan_enable_f32": [_P, _P, _c.c_size_t, _P],
     "nnfac_nmf_plan_cross": [_P, _INT, _P, _I64, _P, _I64, _P],
     "nnfac_nmf_plan_set_factor": [_P, _INT, _P, _I64, _P],
     "nnfac_nmf_plan_fused": [_P, _INT, _INT, _INT, _P, _I64, _P, _P],
