@@ -118,3 +118,130 @@ def test_mu_finish_equals_reduce_apply_install(m, n, r):
         a, ca = plans[0].fused(1 - which, 1)
         b, cb = plans[1].fused(1 - which, 1)
         assert torch.equal(a, b) and torch.equal(ca, cb)
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core HALS sweep (tc_sweep_kernel): shapes, edge cases and full parity of the stop rule
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("r,n,maxiter", [(64, 130, 100), (64, 20000, 100), (40, 777, 100), (17, 4096, 100), (1, 300, 50),
+                                         (64, 1, 30), (33, 5000, 1), (64, 3000, 2), (48, 70000, 7)])
+def test_tc_sweep_matches_oracle(r, n, maxiter):
+    """fp32 tcgen05 solve vs the float64 oracle on identical inputs: same sweep count (one flip near the threshold is
+    allowed), solution to fp32 accuracy, ragged tiles / partial warps / partial rank blocks."""
+    import nn_fac.update_rules.nnls as nnls
+    from oracle import nnfac_oracle as orc
+    rng = np.random.RandomState(7 * r + n)
+    m = 2 * r + 3
+    U = rng.rand(m, r)
+    M = U @ rng.rand(r, n) + 0.1 * rng.rand(m, n)
+    UtM, UtU, V0 = (U.T @ M).astype(np.float32), (U.T @ U).astype(np.float32), rng.rand(r, n).astype(np.float32)
+    V, eps, cnt, _ = nnls.hals_nnls_acc(UtM, UtU, V0, maxiter=maxiter, delta=0.01)
+    Vo, eps_o, cnt_o, _ = orc.hals_nnls_acc(UtM.astype(np.float64), UtU.astype(np.float64), V0.astype(np.float64),
+                                            maxiter=maxiter, delta=0.01)
+    assert V.dtype == np.float32 and V.shape == V0.shape
+    assert abs(cnt - cnt_o) <= 1
+    if cnt == cnt_o:
+        assert np.linalg.norm(V - Vo) <= 5e-4 * np.linalg.norm(Vo)
+        if eps_o > 1e-8 * np.sum(Vo ** 2):           # a fully converged solve ends on rounding noise (e.g. r = 1)
+            assert abs(eps - eps_o) <= 2e-3 * abs(eps_o)
+    assert (V >= 0).all()
+
+
+def test_tc_sweep_zero_diagonal_row_is_left_alone():
+    """nnls.py:160: a row whose diagonal entry of UtU is zero is skipped -- even when its initial value is negative."""
+    import nn_fac.update_rules.nnls as nnls
+    from oracle import nnfac_oracle as orc
+    rng = np.random.RandomState(3)
+    r, n = 20, 500
+    U = rng.rand(50, r)
+    U[:, 5] = 0.0                                     # column 5 of U is zero -> row/column 5 of UtU is zero
+    UtU = (U.T @ U).astype(np.float32)
+    UtM = (U.T @ (U @ rng.rand(r, n) + 0.05 * rng.rand(50, n))).astype(np.float32)
+    V0 = rng.rand(r, n).astype(np.float32)
+    V0[5, ::2] *= -1.0
+    V, _, cnt, _ = nnls.hals_nnls_acc(UtM, UtU, V0, maxiter=40, delta=0.01)
+    Vo, _, cnt_o, _ = orc.hals_nnls_acc(UtM.astype(np.float64), UtU.astype(np.float64), V0.astype(np.float64), maxiter=40,
+                                        delta=0.01)
+    np.testing.assert_array_equal(V[5], V0[5])
+    assert abs(cnt - cnt_o) <= 1
+    if cnt == cnt_o:
+        assert np.linalg.norm(V - Vo) <= 5e-4 * np.linalg.norm(Vo)
+
+
+def test_tc_sweep_is_deterministic_and_pure():
+    import torch
+    from nn_fac import _ops as ops
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    r, n = 64, 40000
+    U = torch.rand((150, r), generator=g, device="cuda")
+    G = (U.T @ U).contiguous()
+    b = (G @ torch.rand((r, n), generator=g, device="cuda")).contiguous()
+    V0 = torch.rand((r, n), generator=g, device="cuda")
+    outs = []
+    for _ in range(3):
+        V = V0.clone()
+        st = ops.hals_nnls(b, G, V, r, 100, 0.01, 0.0, False, False).clone()
+        outs.append((V, st))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][0], outs[2][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+
+
+# ---------------------------------------------------------------------------------------------
+# plan plumbing: caller workspace, slab-wise ingest of a host array, reuse of installed planes, fp32 copies
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_plan_from_host_equals_plan_from_device(dtype):
+    import torch
+    from nn_fac import _ops as ops
+    rng = np.random.RandomState(11)
+    m, n, r = 3001, 1700, 24
+    X = rng.rand(m, n).astype(dtype)
+    V = torch.from_numpy(rng.rand(r, n).astype(np.float32)).cuda()
+    dev_plan = ops.NMFPlan(torch.from_numpy(X.astype(np.float32)).cuda()).bind_rank(r)
+    old = ops.NMFPlan.SLAB_BYTES
+    ops.NMFPlan.SLAB_BYTES = 1 << 20                # many slabs, ragged last one
+    try:
+        host_plan = ops.NMFPlan(X).bind_rank(r)
+    finally:
+        ops.NMFPlan.SLAB_BYTES = old
+    for which, F in ((0, V), (1, torch.from_numpy(rng.rand(r, m).astype(np.float32)).cuda())):
+        assert torch.equal(dev_plan.cross(which, F), host_plan.cross(which, F))
+
+
+def test_cross_reuses_installed_planes_and_f32_copies_change_nothing():
+    import torch
+    from nn_fac import _ops as ops
+    rng = np.random.RandomState(12)
+    m, n, r = 1024, 2304, 48
+    X = torch.from_numpy((rng.rand(m, r) @ rng.rand(r, n) + 0.3 * rng.rand(m, n)).astype(np.float32)).cuda()
+    Ut = torch.from_numpy(rng.rand(r, m).astype(np.float32)).cuda()
+    V = torch.from_numpy(rng.rand(r, n).astype(np.float32)).cuda()
+    plan = ops.NMFPlan(X).bind_rank(r)
+    plan.set_factor(0, Ut)
+    plan.set_factor(1, V)
+    assert torch.equal(plan.cross(1, None), plan.cross(1, Ut))
+    assert torch.equal(plan.cross(0, None), plan.cross(0, V))
+    ref = [(o.clone(), c.clone()) for o, c in (plan.fused(0, 1), plan.fused(1, 1))]
+    plan.enable_f32()
+    for side in (0, 1):
+        out, cost = plan.fused(side, 1)
+        assert torch.equal(out, ref[side][0]) and torch.equal(cost, ref[side][1])
+
+
+def test_ntf_tensor_core_mttkrp_matches_generic_path(monkeypatch):
+    import torch
+    import nn_fac.ntf as ntf
+    rng = np.random.RandomState(13)
+    shape, r = (60, 45, 70), 12
+    fs = [rng.rand(s, r) for s in shape]
+    T = (np.einsum("ir,jr,kr->ijk", *fs) + 0.05 * rng.rand(*shape)).astype(np.float32)
+    F0 = [rng.rand(s, r).astype(np.float32) for s in shape]
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("NNFAC_NTF_TC", flag)
+        _, costs, _ = ntf.ntf(T, r, init="custom", factors_0=[f.copy() for f in F0], n_iter_max=6, tol=0, return_costs=True)
+        out[flag] = costs
+    # the reference's cost formula (ntf.py:470) subtracts numbers of the size of ||T||^2: in fp32 both paths carry an
+    # absolute noise of ~1e-6 ||T||^2 on a normalised cost of ~1e-3
+    np.testing.assert_allclose(out["1"], out["0"], rtol=5e-3)
+    assert out["1"][-1] < out["1"][0]
