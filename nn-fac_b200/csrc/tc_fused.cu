@@ -440,10 +440,17 @@ __global__ void sum_cost_parts_kernel(const double* part, int n, double* out) {
 
 // KL(X | U V) = sum x ln(x / k) - sum x + sum k   (beta_divergence.py:45-48; terms with x = 0 contribute k).
 // part[0..n): per-CTA sums of x log2(x / k); part[512..512+n): per-CTA sums of k; sums[0] = sum of X (constant of the plan).
+//
+// MUFU.LG2 (lg2.approx.ftz.f32) is not centred: on sm_100 its mean error is +6.05e-8 - 4.0e-8 * log2(q) for q in
+// [0.5, 2] (tools/micro/lg2_bias.cu; residual of that fit 1.4e-8 rms).  Weighted by x and summed over 10^8..10^9
+// elements this bias -- not the rounding noise -- is what limits the cost when the fit is good (cost << sum of X), so
+// it is taken out of the SUM here (no per-element work):  sum x (y - a0 - a1 y) = (1 - a1) S - a0 sum(x).
 __global__ void kl_cost_finish_kernel(const double* part, int n, const double* sums, double* out) {
   if (threadIdx.x == 0) {
     double s = 0.0, sk = 0.0;
     for (int i = 0; i < n; ++i) { s += part[i]; sk += part[512 + i]; }
+    constexpr double a0 = 6.05e-8, a1 = -4.0e-8;
+    s = (1.0 - a1) * s - a0 * sums[0];
     out[0] = 0.6931471805599453 * s - sums[0] + sk;
   }
 }

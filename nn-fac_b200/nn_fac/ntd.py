@@ -6,6 +6,7 @@ Covered: the multiplicative-update algorithm (``update_rule="mu"``, any beta >= 
 Not covered yet: ``update_rule="hals"`` (the projected-gradient core update of ntd.py:436-645 is
 row N2 of SURVEY.md section 8(f)); it raises NotImplementedError rather than falling back to a CPU.
 """
+import os
 import time
 import warnings
 
@@ -70,11 +71,30 @@ class DeviceNTD:
         self.T = L.to_device(tensor, dtype, device)
         self.core = L.to_device(core, dtype, device)
         self.factors = [L.to_device(f, dtype, device) for f in factors]
+        # fp32, every rank <= 64: the beta = 1 factor update of a mode is the NMF update of U for X = unfold(T, mode),
+        # V = unfold(G x_{j != mode} F_j, mode), i.e. one fused tcgen05 pass over the planes of that unfolding
+        # (model tile, ratio and contraction on chip; nothing of the size of the tensor is written).
+        self.plans = None
+        if (dtype == torch.float32 and max(int(f.shape[1]) for f in self.factors) <= 64
+                and os.environ.get("NNFAC_NTD_TC", "1") != "0"):
+            self.plans = []
+            for mode in range(self.T.dim()):
+                Xm = self.T.movedim(mode, 0).reshape(self.T.shape[mode], -1).contiguous()
+                self.plans.append(ops.NMFPlan(Xm).bind_rank(int(self.factors[mode].shape[1])))
+                del Xm
 
     def factor_update(self, mode, beta):
         """mu_betadivmin(F, unfold(G x_{j != mode} F_j, mode), unfold(T, mode), beta), ntd.py:672."""
         F = self.factors[mode]
         B = ops.multi_mode_dot(self.core, self.factors, skip=mode)          # shape of T except R_mode along `mode`
+        if self.plans is not None and beta == 1:
+            plan = self.plans[mode]
+            Vm = B.movedim(mode, 0).reshape(B.shape[mode], -1).contiguous()  # unfold(B, mode): r_mode x rest
+            Ft = ops.transpose(F)
+            plan.set_factor(0, Ft)
+            plan.set_factor(1, Vm)
+            plan.fused(0, 1, want_cost=False, keep_partials=True)           # (X / (F Vm)) Vm^T, mu.py:82-85
+            return ops.transpose(plan.mu_finish(0, Ft, ops.row_sums(Vm), mu.epsilon))   # mu.py:86-88
         K = ops.mode_dot(B, F, mode)                                        # = F @ unfold(B, mode), folded (mu.py:82)
         g = gamma_beta(beta)
         if beta == 2:
@@ -99,6 +119,16 @@ class DeviceNTD:
             flat = moved.reshape(moved.shape[0], -1)
             ops.normalize_rows_(flat)
             self.core = moved.movedim(0, mode_core_norm).contiguous()
+        if self.plans is not None and beta == 1:
+            # beta_divergence(T, G x_n F_n, 1) without forming the reconstruction: it is the cost output of a fused pass
+            # over unfold(T, last) with U = F_last, V = unfold(G x_{j != last} F_j, last)
+            last = self.T.dim() - 1
+            plan = self.plans[last]
+            B = ops.multi_mode_dot(self.core, self.factors, skip=last)
+            plan.set_factor(0, ops.transpose(self.factors[last]))
+            plan.set_factor(1, B.movedim(last, 0).reshape(B.shape[last], -1).contiguous())
+            _, cost = plan.fused(0, 1, want_cost=True)
+            return float(cost.item())                                       # ntd.py:694-696 (not normalised)
         K = ops.multi_mode_dot(self.core, self.factors)
         return float(ops.beta_divergence(self.T, K, beta).item())           # ntd.py:694-696 (not normalised)
 

@@ -245,3 +245,28 @@ def test_ntf_tensor_core_mttkrp_matches_generic_path(monkeypatch):
     # absolute noise of ~1e-6 ||T||^2 on a normalised cost of ~1e-3
     np.testing.assert_allclose(out["1"], out["0"], rtol=5e-3)
     assert out["1"][-1] < out["1"][0]
+
+
+@pytest.mark.parametrize("beta", [1, 2])
+def test_ntd_mu_fp32_objective(beta, monkeypatch):
+    """fp32 NTD (beta = 1: factor updates through the fused tcgen05 pass) against the float64 oracle, and against the
+    generic fp32 path: objective within 1e-4 relative after 8 iterations."""
+    import nn_fac.ntd as ntd
+    from oracle import nnfac_oracle as orc
+    rng = np.random.RandomState(21)
+    shape, ranks = (40, 36, 50), [6, 5, 7]
+    G = rng.rand(*ranks)
+    Fs = [rng.rand(s, r) for s, r in zip(shape, ranks)]
+    T = np.einsum("abc,ia,jb,kc->ijk", G, *Fs) + 0.05 * rng.rand(*shape) + 1e-3
+    G0, F0 = rng.rand(*ranks), [rng.rand(s, r) for s, r in zip(shape, ranks)]
+    _, _, ref = orc.compute_ntd_mu(T, G0, F0, n_iter_max=8, tol=0, beta=beta)
+    f32 = lambda x: x.astype(np.float32)  # noqa: E731
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("NNFAC_NTD_TC", flag)
+        _, _, costs, _ = ntd.ntd(f32(T), list(ranks), init="custom", core_0=f32(G0), factors_0=[f32(f) for f in F0], n_iter_max=8,
+                                 tol=0, update_rule="mu", beta=beta, sparsity_coefficients=[None] * 4, fixed_modes=[],
+                                 normalize=[False] * 4, return_costs=True, deterministic=True)
+        res[flag] = costs
+        assert abs(costs[-1] - ref[-1]) <= 1e-4 * abs(ref[-1])
+    np.testing.assert_allclose(res["1"], res["0"], rtol=1e-4)
