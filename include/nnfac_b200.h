@@ -164,6 +164,14 @@ int nnfac_nmf_plan_cross(nnfac_nmf_plan* plan, int which, const float* F, int64_
 /* Install a factor into the plan (builds all of its bf16 operand planes):
  * which = 0: U, passed as U^T (r x m, row-major); which = 1: V (r x n). */
 int nnfac_nmf_plan_set_factor(nnfac_nmf_plan* plan, int which, const float* Ft, int64_t ld, void* stream);
+/* HALS solve of factor `which` (nn_fac/update_rules/nnls.py:24-198, deterministic rule, no normalize / nonzero) whose
+ * result F_out (r x len, may not alias F_in) is installed in the plan by the sweep kernel itself (no separate pass over
+ * the factor).  result: double[4] = {eps, cnt, -1, sweeps}.  Returns NNFAC_ERR_UNSUPPORTED without an error text when
+ * the shape is outside the tensor-core sweep (rank > 64 or more than 512 columns per SM): use nnfac_hals_nnls +
+ * nnfac_nmf_plan_set_factor then. */
+int nnfac_nmf_plan_hals_solve(nnfac_nmf_plan* plan, int which, const float* UtM, int64_t ld_utm, const float* UtU,
+                              int64_t ld_utu, const float* F_in, int64_t ld_in, float* F_out, int64_t ld_out, int maxiter,
+                              double delta, double sparsity, double* result, void* stream);
 /* One fused X pass (rank <= 64) over side 0 (rows of X) or side 1 (rows of X^T), using the installed
  * factors: the model tile U V is formed and consumed on chip, never written to HBM.
  *   mode 0: out (r x rows) = the HALS cross product of nmf.py:408 / :433, cost_out = ||X - U V||_F^2 (nmf.py:452)

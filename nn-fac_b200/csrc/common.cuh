@@ -22,6 +22,17 @@ struct nnfac_ctx {
 };
 
 void nnfac_set_error(const char* fmt, ...);
+
+// operand planes the tensor-core HALS sweep can write for the NMF plan (all bf16; see csrc/tc_sweep.cu)
+struct nnfac_sweep_planes {
+  void *fh, *fl;      // [r_pad x ld_plane] K-major hi / lo
+  void *rowh, *rowl;  // [n x 64] rank-contiguous hi / lo (NULL: not wanted)
+  int64_t ld_plane;
+  int r_pad;
+};
+int nnfac_tc_sweep_run(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const float* UtU, int64_t ld_utu, const float* Vin,
+                       int64_t ld_vin, float* V, int64_t ld_v, int r, int64_t n, int maxiter, double delta, double sparsity,
+                       double* result, const nnfac_sweep_planes* planes, cudaStream_t st);
 int nnfac_ws_reserve(nnfac_ctx* ctx, size_t bytes, cudaStream_t st);
 
 #define NNFAC_CUDA(call)                                                                   \

@@ -528,6 +528,25 @@ int nnfac_nmf_plan_set_factor(nnfac_nmf_plan* p, int which, const float* Ft, int
   return finish_factor(p, which, false, Ft, ld, nullptr, 0.f, nullptr, 0, (cudaStream_t)stream);
 }
 
+// HALS solve of factor `which` (nnls.py:24-198, deterministic rule) that also installs the result in the plan:
+// F_out = hals_nnls_acc(UtM, UtU, F_in) and every operand plane of F_out, written by the sweep kernel itself.
+// Returns NNFAC_ERR_UNSUPPORTED (no error text) when the shape is outside the tensor-core sweep's envelope; the caller
+// then runs nnfac_hals_nnls + nnfac_nmf_plan_set_factor.
+int nnfac_nmf_plan_hals_solve(nnfac_nmf_plan* p, int which, const float* UtM, int64_t ld_utm, const float* UtU, int64_t ld_utu,
+                              const float* F_in, int64_t ld_in, float* F_out, int64_t ld_out, int maxiter, double delta,
+                              double sparsity, double* result, void* stream) {
+  NNFAC_ARG(p && UtM && UtU && F_in && F_out && result && (which == 0 || which == 1), "nnfac_nmf_plan_hals_solve: bad argument");
+  const int64_t len = which == 0 ? p->m : p->n;
+  NNFAC_ARG(ld_utm >= len && ld_in >= len && ld_out >= len && ld_utu >= p->r, "nnfac_nmf_plan_hals_solve: leading dimension too small");
+  Side* cs = &p->side[which == 0 ? 1 : 0];
+  nnfac_sweep_planes pl;
+  pl.fh = cs->fh; pl.fl = cs->fl; pl.ld_plane = cs->ld; pl.r_pad = p->r_pad;
+  pl.rowh = p->fused_ok ? p->rowp_h[which] : nullptr;
+  pl.rowl = p->fused_ok ? p->rowp_l[which] : nullptr;
+  return nnfac_tc_sweep_run(p->ctx, UtM, ld_utm, UtU, ld_utu, F_in, ld_in, F_out, ld_out, p->r, len, maxiter, delta, sparsity,
+                            result, &pl, (cudaStream_t)stream);
+}
+
 // beta = 1 multiplicative update of factor `which` from the numerator partials the last fused pass over side `which`
 // left in the plan (call nnfac_nmf_plan_fused with out = NULL): F_out = max(F_in * num / den[k], floor), mu.py:84-88,
 // and F_out is installed in the plan (as nnfac_nmf_plan_set_factor would).  den: r row sums of the other factor.

@@ -69,8 +69,14 @@ __global__ void sweep_prep_kernel(const float* __restrict__ G, int64_t ld_g, int
 struct TcSweepArgs {
   const float* b;   // UtM r x n
   const float* G;   // UtU r x r
-  float* V;         // r x n, in place
-  int64_t ld_b, ld_g, ld_v, n;
+  const float* Vin; // r x n start values (may alias V)
+  float* V;         // r x n result
+  int64_t ld_b, ld_g, ld_v, ld_vin, n;
+  // optional: bf16 hi/lo operand planes of the result for the NMF plan (nnfac_nmf_plan_hals_solve)
+  bf16 *fh, *fl;    // [r_pad x ld_plane], K-major (rank rows)
+  bf16 *rowh, *rowl;// [n x 64], rank contiguous (may be NULL)
+  int64_t ld_plane;
+  int r_pad;
   int r, maxiter, cols_per_cta;
   double delta;
   float sp;
@@ -278,7 +284,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
         float x[16];
         uint32_t w[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = (valid && c0 + j < r) ? a.V[(int64_t)(c0 + j) * a.ld_v + col] : 0.f;
+        for (int j = 0; j < 16; ++j) x[j] = (valid && c0 + j < r) ? a.Vin[(int64_t)(c0 + j) * a.ld_vin + col] : 0.f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) w[j] = __float_as_uint(c_sw.invd[c0 + j] != 0.f ? x[j] : 0.f);   // skipped rows: master 0
         tmem_st16(t_v + c0, w);
@@ -490,9 +496,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
             w[4 * c] = b4.x; w[4 * c + 1] = b4.y; w[4 * c + 2] = b4.z; w[4 * c + 3] = b4.w;
           }
         }
+        float x[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (valid && c0 + j < r && c_sw.invd[c0 + j] != 0.f) a.V[(int64_t)(c0 + j) * a.ld_v + col] = __uint_as_float(w[j]);
+        for (int j = 0; j < 16; ++j) {
+          x[j] = __uint_as_float(w[j]);
+          // a skipped row (zero diagonal) keeps its start value (its master was a placeholder 0)
+          if (c_sw.has_zero_diag && valid && c0 + j < r && c_sw.invd[c0 + j] == 0.f) x[j] = a.Vin[(int64_t)(c0 + j) * a.ld_vin + col];
+          if (valid && c0 + j < r) a.V[(int64_t)(c0 + j) * a.ld_v + col] = x[j];
+        }
+        if (a.fh != nullptr) {
+          // operand planes of the new factor, straight from the registers (replaces a separate pass over the factor)
+          uint32_t hw[8], lw[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float p0 = (valid && c0 + 2 * j < r) ? x[2 * j] : 0.f, p1 = (valid && c0 + 2 * j + 1 < r) ? x[2 * j + 1] : 0.f;
+            hw[j] = pack_bf16(p0, p1);
+            lw[j] = pack_bf16(p0 - __uint_as_float(hw[j] << 16), p1 - __uint_as_float(hw[j] & 0xffff0000u));
+          }
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (c0 + j < a.r_pad) {
+                const uint32_t h = (j & 1) ? (hw[j >> 1] >> 16) : (hw[j >> 1] & 0xffffu), l = (j & 1) ? (lw[j >> 1] >> 16) : (lw[j >> 1] & 0xffffu);
+                reinterpret_cast<unsigned short*>(a.fh)[(int64_t)(c0 + j) * a.ld_plane + col] = (unsigned short)h;
+                reinterpret_cast<unsigned short*>(a.fl)[(int64_t)(c0 + j) * a.ld_plane + col] = (unsigned short)l;
+              }
+            }
+            if (a.rowh != nullptr) {
+              uint4* rh = reinterpret_cast<uint4*>(a.rowh + col * 64 + c0);
+              uint4* rl = reinterpret_cast<uint4*>(a.rowl + col * 64 + c0);
+              rh[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]); rh[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+              rl[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]); rl[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+            }
+          }
+        }
       }
     }
 #ifdef SWEEP_PROF
@@ -517,24 +554,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
 }  // namespace
 
 // Returns NNFAC_ERR_UNSUPPORTED (without setting an error) when the shape is outside this kernel's
-// envelope, so that the caller can use the FMA kernel instead.
-int nnfac_tc_sweep_try(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const float* UtU, int64_t ld_utu, float* V,
-                       int64_t ld_v, int r, int64_t n, int maxiter, double delta, double sparsity, double* result,
-                       cudaStream_t st) {
+// envelope, so that the caller can use the FMA kernel instead.  `planes` (optional) receives the bf16 operand planes
+// of the result (see TcSweepArgs); Vin may alias V.
+int nnfac_tc_sweep_run(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const float* UtU, int64_t ld_utu, const float* Vin,
+                       int64_t ld_vin, float* V, int64_t ld_v, int r, int64_t n, int maxiter, double delta, double sparsity,
+                       double* result, const nnfac_sweep_planes* planes, cudaStream_t st) {
   if (r > RP || maxiter < 1) return NNFAC_ERR_UNSUPPORTED;
   int64_t cols = ceil_div64(n, ctx->sm_count);
   cols = ceil_div64(cols, 32) * 32;
   if (cols > MAX_TILES * TILE) return NNFAC_ERR_UNSUPPORTED;
   const int64_t grid = ceil_div64(n, cols);
   if ((size_t)(2 * grid * grid) > ctx->mail_count || maxiter > 65000) return NNFAC_ERR_UNSUPPORTED;
-  static SweepConst* staging = nullptr;   // one per process is enough: calls are stream-ordered per context
-  if (!staging) NNFAC_CUDA(cudaMalloc(&staging, sizeof(SweepConst)));
-  sweep_prep_kernel<<<1, 256, 0, st>>>(UtU, ld_utu, r, staging);
+  // the per-call constants are written straight into the __constant__ bank by a one-block kernel (constant caches are
+  // invalidated at kernel boundaries, and the stream orders it before the sweep)
+  static SweepConst* c_sw_dev = nullptr;
+  if (!c_sw_dev) NNFAC_CUDA(cudaGetSymbolAddress((void**)&c_sw_dev, c_sw));
+  sweep_prep_kernel<<<1, 256, 0, st>>>(UtU, ld_utu, r, c_sw_dev);
   NNFAC_LAUNCH_CHECK(ctx);
-  NNFAC_CUDA(cudaMemcpyToSymbolAsync(c_sw, staging, sizeof(SweepConst), 0, cudaMemcpyDeviceToDevice, st));
   TcSweepArgs a;
-  a.b = UtM; a.G = UtU; a.V = V; a.ld_b = ld_utm; a.ld_g = ld_utu; a.ld_v = ld_v; a.n = n;
+  a.b = UtM; a.G = UtU; a.Vin = Vin; a.V = V; a.ld_b = ld_utm; a.ld_g = ld_utu; a.ld_v = ld_v; a.ld_vin = ld_vin; a.n = n;
   a.r = r; a.maxiter = maxiter; a.cols_per_cta = (int)cols; a.delta = delta; a.sp = (float)sparsity;
+  a.fh = a.fl = a.rowh = a.rowl = nullptr; a.ld_plane = 0; a.r_pad = 0;
+  if (planes) {
+    a.fh = (bf16*)planes->fh; a.fl = (bf16*)planes->fl; a.rowh = (bf16*)planes->rowh; a.rowl = (bf16*)planes->rowl;
+    a.ld_plane = planes->ld_plane; a.r_pad = planes->r_pad;
+  }
   // mailbox tags carry a call generation, so that the slots never need clearing between calls
   ctx->sweep_gen = (ctx->sweep_gen + 1) & 0xffffu;
   if (ctx->sweep_gen == 0) {
@@ -548,4 +592,10 @@ int nnfac_tc_sweep_try(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const f
   NNFAC_CUDA(cudaLaunchCooperativeKernel((const void*)tc_sweep_kernel, dim3((unsigned)grid), dim3(NTHREADS), params, smem, st));
   ctx->launches++;
   return NNFAC_OK;
+}
+
+int nnfac_tc_sweep_try(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const float* UtU, int64_t ld_utu, float* V,
+                       int64_t ld_v, int r, int64_t n, int maxiter, double delta, double sparsity, double* result,
+                       cudaStream_t st) {
+  return nnfac_tc_sweep_run(ctx, UtM, ld_utm, UtU, ld_utu, V, ld_v, V, ld_v, r, n, maxiter, delta, sparsity, result, nullptr, st);
 }

@@ -101,6 +101,19 @@ class CudaEngine:
 
     gram = staticmethod(ops.gram)                      # F (r x len) -> F F^T (nmf.py:407 / :432)
 
+    def solve_install(self, which, UtM, UtU, F, r, sparsity, normalize, result):
+        """F <- hals_nnls_acc(UtM, UtU, F) (nmf.py:415 / :440) and F becomes factor `which` of the plan.  One kernel when the
+        tensor-core sweep covers the case (it writes the operand planes itself), else solve on a copy + set_factor."""
+        sp = 0.0 if sparsity is None else float(sparsity)
+        if not normalize and type(self).sweep is CudaEngine.sweep:
+            new = self.plan.hals_solve(which, UtM, UtU, F, 100, 0.01, sp, result)
+            if new is not None:
+                return new
+        new = F.clone()
+        self.sweep(UtM, UtU, new, r, sparsity, normalize, result)
+        self.set_factor(which, new)
+        return new
+
     @staticmethod
     def sweep(UtM, UtU, V, r, sparsity, normalize, result):
         sp = 0.0 if sparsity is None else float(sparsity)
@@ -196,24 +209,31 @@ class FusedNMF:
                     comm.sum_(xb)
                     VMt, VVt = xb[:r * m].view(r, m), xb[r * m:].view(r, r)
             with self._phase("sweep_U"):
-                Ut = Ut.clone()
-                if comm.world == 1 or normalize[0]:
-                    eng.sweep(VMt, VVt, Ut, r, sparsity[0], normalize[0], self.hals_stats[0])   # nmf.py:415
+                if (comm.world == 1 or normalize[0]) and hasattr(eng, "solve_install"):
+                    Ut = eng.solve_install(0, VMt, VVt, Ut, r, sparsity[0], normalize[0], self.hals_stats[0])   # nmf.py:415
+                elif comm.world == 1 or normalize[0]:
+                    Ut = Ut.clone()
+                    eng.sweep(VMt, VVt, Ut, r, sparsity[0], normalize[0], self.hals_stats[0])
+                    eng.set_factor(0, Ut)
                 else:
+                    Ut = Ut.clone()
                     chunk, lo, hi = comm.slice_of(m)
                     if hi > lo:
                         eng.sweep(VMt[:, lo:hi], VVt, Ut[:, lo:hi], r, sparsity[0], False, self.hals_stats[0])
                     comm.gather_columns_(Ut, chunk, lo, hi)
-                eng.set_factor(0, Ut)
+                    eng.set_factor(0, Ut)
         if 1 not in fixed_modes:
             with self._phase("cross_V"):
                 join = self._gram_async(1, Ut) if comm.world == 1 else None        # nmf.py:432, under the X pass
                 UtM = eng.cross(1, None)                                           # nmf.py:433 (planes of the U just installed)
                 UtU = join() if join is not None else eng.gram(Ut)
             with self._phase("sweep_V"):
-                V = V.clone()
-                eng.sweep(UtM, UtU, V, r, sparsity[1], normalize[1], self.hals_stats[1])        # nmf.py:440
-                eng.set_factor(1, V)
+                if hasattr(eng, "solve_install"):
+                    V = eng.solve_install(1, UtM, UtU, V, r, sparsity[1], normalize[1], self.hals_stats[1])   # nmf.py:440
+                else:
+                    V = V.clone()
+                    eng.sweep(UtM, UtU, V, r, sparsity[1], normalize[1], self.hals_stats[1])
+                    eng.set_factor(1, V)
         return Ut, V
 
     def _apply_mu(self, numU, fixed_modes):

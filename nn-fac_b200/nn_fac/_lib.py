@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NNFAC_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libnnfac_b200.so")
 
 F32, F64 = 0, 1
+ERR_UNSUPPORTED = -3
 HALS_NORMALIZE, HALS_NONZERO = 1, 2
 
 _c = ctypes
@@ -52,6 +53,7 @@ SIGNATURES = {
     "nnfac_nmf_plan_enable_f32": [_P, _P, _c.c_size_t, _P],
     "nnfac_nmf_plan_cross": [_P, _INT, _P, _I64, _P, _I64, _P],
     "nnfac_nmf_plan_set_factor": [_P, _INT, _P, _I64, _P],
+    "nnfac_nmf_plan_hals_solve": [_P, _INT, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _INT, _DBL, _DBL, _P, _P],
     "nnfac_nmf_plan_fused": [_P, _INT, _INT, _INT, _P, _I64, _P, _P],
     "nnfac_nmf_plan_mu_finish": [_P, _INT, _P, _I64, _P, _DBL, _P, _I64, _P],
     "nnfac_nmf_plan_info": [_P, _INT, _c.POINTER(_INT), _c.POINTER(_INT), _c.POINTER(_INT), _c.POINTER(_INT),

@@ -292,6 +292,18 @@ class NMFPlan:
         """which=0: U given as U^T (r x m); which=1: V (r x n).  Rebuilds that factor's bf16 operand planes."""
         L.check(_lib().nnfac_nmf_plan_set_factor(self.handle, which, L.ptr(Ft), Ft.stride(0), L.stream_ptr()))
 
+    def hals_solve(self, which, UtM, UtU, F, maxiter, delta, sparsity, result):
+        """hals_nnls_acc(UtM, UtU, F) on the tensor-core sweep with the result installed in the plan by the same kernel.
+        Returns the new factor (r x len), or None when the shape is outside that kernel (caller: hals_nnls + set_factor)."""
+        out = torch.empty_like(F)
+        rc = _lib().nnfac_nmf_plan_hals_solve(self.handle, which, L.ptr(UtM), UtM.stride(0), L.ptr(UtU), UtU.stride(0), L.ptr(F),
+                                              F.stride(0), L.ptr(out), out.stride(0), int(maxiter), float(delta), float(sparsity),
+                                              L.ptr(result), L.stream_ptr())
+        if rc == L.ERR_UNSUPPORTED:
+            return None
+        L.check(rc)
+        return out
+
     def mu_finish(self, which, F, den, floor):
         """max(F * num / den[:, None], floor) from the numerator partials of the last fused(which, 1, keep_partials=True);
         the result is installed as factor `which` (mu.py:84-88 + set_factor in one kernel)."""

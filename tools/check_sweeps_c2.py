@@ -15,18 +15,19 @@ X.add_(torch.rand((m, n), generator=gen, device=dev), alpha=1.0 * float(X.mean()
 U0 = torch.rand((m, r), generator=gen, device=dev); V0 = torch.rand((r, n), generator=gen, device=dev)
 
 log = []
-orig = _fast.CudaEngine.sweep
+orig = _fast.CudaEngine.solve_install
 
 
-def sweep(UtM, UtU, V, r_, sparsity, normalize, result):
-    V64 = V.double()
+def solve_install(self, which, UtM, UtU, F, r_, sparsity, normalize, result):
+    V64 = F.double()
     res64 = ops.hals_nnls(UtM.double().contiguous(), UtU.double().contiguous(), V64, r_, 100, 0.01, 0.0, False, False)
-    orig(UtM, UtU, V, r_, sparsity, normalize, result)
-    rel = float((V.double() - V64).norm() / V64.norm())
+    new = orig(self, which, UtM, UtU, F, r_, sparsity, normalize, result)
+    rel = float((new.double() - V64).norm() / V64.norm())
     log.append((int(result[3].item()), int(res64[3].item()), float(result[0].item()), float(res64[0].item()), rel))
+    return new
 
 
-_fast.CudaEngine.sweep = staticmethod(sweep)
+_fast.CudaEngine.solve_install = solve_install
 st = _fast.FusedNMF(X, U0, V0)
 costs, _ = st.run(iters, 0.0, "hals", [None, None], [], [False, False])
 for i in range(0, len(log), 2):
