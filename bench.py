@@ -48,7 +48,7 @@ def parse_args():
 def ncu_traffic(phase):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind `phase`, from the committed
     `ncu --set full` capture (profiles/r1_ncu_full_summaries.json); None when there is no capture of it."""
-    report = {"hals.pass_U": "r1c_fused_res_s0", "mu.pass_U": "r1c_fused_mu_s0_cost", "mu.pass_V": "r1c_fused_mu_s1_nocost",
+    report = {"hals.pass_U": "r1d_fused_res_s0", "mu.pass_U": "r1d_fused_mu_s0_cost", "mu.pass_V": "r1d_fused_mu_s1_nocost",
               "hals.cross_V": "r1c_cross_s1"}.get(phase)
     path = os.path.join(ROOT, "profiles", "r1_ncu_full_summaries.json")
     if report is None or not os.path.exists(path):
