@@ -111,6 +111,10 @@ class DeviceNTD:
         return ops.mu_apply(F, num, den_mat=ops.unfold_times(Q, B, mode), gamma=g, floor=mu.epsilon)
 
     def step_mu(self, beta, fixed_modes, normalize, mode_core_norm):
+        return float(self.step_mu_async(beta, fixed_modes, normalize, mode_core_norm).item())
+
+    def step_mu_async(self, beta, fixed_modes, normalize, mode_core_norm):
+        """One outer iteration; returns the cost as a device scalar (no synchronisation)."""
         for mode in [m for m in range(self.T.dim()) if m not in fixed_modes]:
             self.factors[mode] = self.factor_update(mode, beta)
         self.core = mu.mu_tensorial_device(self.core, self.factors, self.T, beta)   # ntd.py:674
@@ -128,9 +132,9 @@ class DeviceNTD:
             plan.set_factor(0, ops.transpose(self.factors[last]))
             plan.set_factor(1, B.movedim(last, 0).reshape(B.shape[last], -1).contiguous())
             _, cost = plan.fused(0, 1, want_cost=True)
-            return float(cost.item())                                       # ntd.py:694-696 (not normalised)
+            return cost                                                     # ntd.py:694-696 (not normalised)
         K = ops.multi_mode_dot(self.core, self.factors)
-        return float(ops.beta_divergence(self.T, K, beta).item())           # ntd.py:694-696 (not normalised)
+        return ops.beta_divergence(self.T, K, beta)                         # ntd.py:694-696 (not normalised)
 
 
 def compute_ntd(tensor_in, ranks, core_in, factors_in, n_iter_max=100, tol=1e-6,
@@ -164,21 +168,37 @@ def compute_ntd(tensor_in, ranks, core_in, factors_in, n_iter_max=100, tol=1e-6,
     state = DeviceNTD(tensor_in, core_in, factors_in, dt)
     cost_fct_vals, toc = [], []
     tic = time.time()
-    for iteration in range(n_iter_max):
-        cost = state.step_mu(beta, fixed_modes, normalize, mode_core_norm)
-        toc.append(time.time() - tic)
-        cost_fct_vals.append(cost)
-        if verbose:
-            if iteration == 0:
-                print('Normalized cost function value={}'.format(cost))
-            else:
-                gain = cost_fct_vals[-2] - cost_fct_vals[-1]
-                line = 'Normalized cost function value={}, variation={}.'.format(cost_fct_vals[-1], gain)
-                print(line if gain > 0 else '\033[91m' + line + '\033[0m')
-        if iteration > 0 and abs(cost_fct_vals[-2] - cost_fct_vals[-1]) < tol:
+    # The cost of iteration t is read while iteration t+1 is already queued; if the stop test (ntd.py:421) fires on it,
+    # the speculative iteration is dropped (core and factors are replaced, never modified in place).
+    host = torch.zeros(1, dtype=torch.float64).pin_memory()
+    pending = None
+    for iteration in range(n_iter_max + 1):
+        if iteration < n_iter_max:
+            before = (state.core, list(state.factors))
+            cost_dev = state.step_mu_async(beta, fixed_modes, normalize, mode_core_norm)
+        if pending is not None:
+            pending.synchronize()
+            cost = float(host[0])
+            toc.append(time.time() - tic)
+            cost_fct_vals.append(cost)
             if verbose:
-                print('Converged in {} iterations.'.format(iteration))
+                if len(cost_fct_vals) == 1:
+                    print('Normalized cost function value={}'.format(cost))
+                else:
+                    gain = cost_fct_vals[-2] - cost_fct_vals[-1]
+                    line = 'Normalized cost function value={}, variation={}.'.format(cost_fct_vals[-1], gain)
+                    print(line if gain > 0 else '\033[91m' + line + '\033[0m')
+            if len(cost_fct_vals) >= 2 and abs(cost_fct_vals[-2] - cost_fct_vals[-1]) < tol:
+                if verbose:
+                    print('Converged in {} iterations.'.format(len(cost_fct_vals) - 1))
+                if iteration < n_iter_max:
+                    state.core, state.factors = before
+                break
+        if iteration == n_iter_max:
             break
+        host.copy_(cost_dev.reshape(1).to(torch.float64), non_blocking=True)
+        pending = torch.cuda.Event()
+        pending.record()
     if isinstance(tensor_in, torch.Tensor):
         core, factors = state.core, state.factors
     else:

@@ -106,7 +106,8 @@ class DeviceNTF:
                          batch=nb, out=K.reshape(-1)[l0 * I * right:], ldc=right, sc_b=I * right)
         return K
 
-    def step(self, rank, norm_tensor, update_rule, beta, sparsity, fixed_modes, normalize):
+    def step_async(self, rank, norm_tensor, update_rule, beta, sparsity, fixed_modes, normalize):
+        """One pass over the modes; returns the device vector of cost terms (no synchronisation)."""
         modes = [m for m in range(len(self.shape)) if m not in fixed_modes]
         rhs = krao = cross = None
         mode = None
@@ -133,21 +134,39 @@ class DeviceNTF:
                 F = self.factors[mode]
                 K = self.reconstruct_unfolded(mode, krao)
                 self.factors[mode] = self._mu_factor(F, krao, K, mode, beta)   # ntf.py:459-460
-        sparsity_error = 0.0
-        for idx, s in enumerate(sparsity):
-            if s:
-                sparsity_error += 2 * (s * float(ops.norm1(self.factors[idx]).item()))   # ntf.py:463-466
+        # the cost terms stay on the device: [rec part a, rec part b, sparsity l1 norms...] (see finish_cost)
+        terms = []
         F = self.factors[mode]
         if update_rule == "hals":
             # ntf.py:470; ||F krao^T||^2 = <F^T F, krao^T krao> and krao^T krao = cross (Hadamard of Grams)
             ftf = ops.gemm(F, (1, rank), F, (rank, 1), rank, rank, F.shape[0])
             inner = ops.dot(F, rhs) if rhs is not None else ops.dot(Ft, rhs_t)     # <F, rhs>, either layout
-            parts = torch.cat([inner, ops.dot(ftf, cross)]).cpu().numpy()
-            rec_error = norm_tensor ** 2 - 2 * parts[0] + parts[1]
+            terms += [inner, ops.dot(ftf, cross)]
         else:
             K = self.reconstruct_unfolded(mode, krao)
-            rec_error = float(ops.beta_divergence(self.T, K, beta).item())  # ntf.py:473
-        return float((rec_error + sparsity_error) / (norm_tensor ** 2))     # ntf.py:475
+            terms += [ops.beta_divergence(self.T, K, beta)]                 # ntf.py:473
+        for idx, s in enumerate(sparsity):
+            if s:
+                terms.append(ops.norm1(self.factors[idx]))                  # ntf.py:463-466
+        return torch.cat([t.reshape(1).to(torch.float64) for t in terms])
+
+    @staticmethod
+    def finish_cost(terms_host, norm_tensor, update_rule, sparsity):
+        """ntf.py:463-475 from the device terms of step_async (host float64 arithmetic, as in the reference)."""
+        if update_rule == "hals":
+            rec_error = norm_tensor ** 2 - 2 * terms_host[0] + terms_host[1]
+            rest = terms_host[2:]
+        else:
+            rec_error = terms_host[0]
+            rest = terms_host[1:]
+        sparsity_error = 0.0
+        for s, l1 in zip([s for s in sparsity if s], rest):
+            sparsity_error += 2 * (s * float(l1))
+        return float((rec_error + sparsity_error) / (norm_tensor ** 2))
+
+    def step(self, rank, norm_tensor, update_rule, beta, sparsity, fixed_modes, normalize):
+        terms = self.step_async(rank, norm_tensor, update_rule, beta, sparsity, fixed_modes, normalize)
+        return self.finish_cost(terms.cpu().numpy(), norm_tensor, update_rule, sparsity)
 
     def _mu_factor(self, F, krao, K, mode, beta):
         """mu_betadivmin(F, krao.T, unfold(T, mode), beta) with the unfolding kept implicit."""
@@ -208,21 +227,40 @@ def compute_ntf(tensor_in, rank, factors_in, n_iter_max=100, tol=1e-8,
     norm_tensor = float(np.sqrt(ops.sq_diff(state.T).item()))              # ntf.py:290
     cost_fct_vals, toc = [], []
     tic = time.time()
-    for iteration in range(n_iter_max):
-        cost = state.step(rank, norm_tensor, update_rule, beta, sparsity_coefficients, fixed_modes, normalize)
-        toc.append(time.time() - tic)
-        cost_fct_vals.append(cost)
-        if verbose:
-            if iteration == 0:
-                print('Normalized cost function value={}'.format(cost))
-            else:
-                gain = cost_fct_vals[-2] - cost_fct_vals[-1]
-                line = 'Normalized cost function value={}, variation={}.'.format(cost_fct_vals[-1], gain)
-                print(line if gain > 0 else '\033[91m' + line + '\033[0m')
-        if iteration > 0 and abs(cost_fct_vals[-2] - cost_fct_vals[-1]) < tol:
+    # The cost of iteration t is read while iteration t+1 is already queued (no idle device between iterations); if the
+    # reference's stop test (ntf.py:337) fires on it, the speculative iteration is dropped (factors are replaced, not
+    # modified in place, so the previous list is simply kept).
+    host = torch.zeros(8, dtype=torch.float64).pin_memory()
+    pending = None                                     # (terms on host buffer, event, factors after that iteration)
+    for iteration in range(n_iter_max + 1):
+        if iteration < n_iter_max:
+            before = list(state.factors)
+            terms = state.step_async(rank, norm_tensor, update_rule, beta, sparsity_coefficients, fixed_modes, normalize)
+        if pending is not None:
+            ev, nterms, kept = pending
+            ev.synchronize()
+            cost = state.finish_cost(host[:nterms].numpy().copy(), norm_tensor, update_rule, sparsity_coefficients)
+            toc.append(time.time() - tic)
+            cost_fct_vals.append(cost)
             if verbose:
-                print('Converged in {} iterations.'.format(iteration))
+                if len(cost_fct_vals) == 1:
+                    print('Normalized cost function value={}'.format(cost))
+                else:
+                    gain = cost_fct_vals[-2] - cost_fct_vals[-1]
+                    line = 'Normalized cost function value={}, variation={}.'.format(cost_fct_vals[-1], gain)
+                    print(line if gain > 0 else '\033[91m' + line + '\033[0m')
+            if len(cost_fct_vals) >= 2 and abs(cost_fct_vals[-2] - cost_fct_vals[-1]) < tol:
+                if verbose:
+                    print('Converged in {} iterations.'.format(len(cost_fct_vals) - 1))
+                if iteration < n_iter_max:
+                    state.factors = before             # drop the speculative iteration
+                break
+        if iteration == n_iter_max:
             break
+        host[:terms.numel()].copy_(terms, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        pending = (ev, terms.numel(), None)
     out = _pack(state.factors, tensor_in)
     if return_costs:
         return out, cost_fct_vals, toc

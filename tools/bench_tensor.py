@@ -21,7 +21,7 @@ def timed(fn, iters):
     fn(3)                                            # warm-up (3 iterations)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); out = fn(iters); e1.record(); torch.cuda.synchronize()
+    e0.record(); out = fn(iters); e1.record(); torch.cuda.synchronize()   # fn syncs once, at its end
     return e0.elapsed_time(e1) / iters, out
 
 
@@ -37,10 +37,10 @@ if args.which in ("ntf", "both"):
     st = ntf.DeviceNTF(T, F0, torch.float32)
     norm = float(torch.linalg.vector_norm(T.double()).item())
     def run(k):
-        c = None
-        for _ in range(k):
-            c = st.step(r, norm, "hals", 2, [None] * 3, [], [False] * 3)
-        return c
+        terms = None
+        for _ in range(k):                           # no host synchronisation between iterations (as compute_ntf does)
+            terms = st.step_async(r, norm, "hals", 2, [None] * 3, [], [False] * 3)
+        return st.finish_cost(terms.cpu().numpy(), norm, "hals", [None] * 3)
     ms, cost = timed(run, args.iters)
     bytes_iter = 3 * I ** 3 * 4
     line = {"config": f"C4: NTF HALS {I}^3 rank {r} (fp32)", "outer_iters_per_s": 1e3 / ms, "ms_per_iter": ms,
@@ -73,8 +73,8 @@ if args.which in ("ntd", "both"):
     def run(k):
         c = None
         for _ in range(k):
-            c = st.step_mu(1, [], [False] * 4, None)
-        return c
+            c = st.step_mu_async(1, [], [False] * 4, None)
+        return float(c.item())
     ms, cost = timed(run, args.iters)
     flop = 3 * 2 * (2 * I ** 3 * rc) + 2 * 2 * I ** 3 * rc       # per mode: model + contraction over the tensor; core: up + down (leading terms)
     line = {"config": f"C5: NTD MU beta=1 {I}^3 core {rc}^3 (fp32)", "outer_iters_per_s": 1e3 / ms, "ms_per_iter": ms,
