@@ -161,6 +161,10 @@ int nnfac_nmf_plan_enable_f32(nnfac_nmf_plan* plan, void* workspace, size_t work
  * (nnfac_nmf_plan_set_factor / nnfac_nmf_plan_mu_finish), whose operand planes already exist. */
 int nnfac_nmf_plan_cross(nnfac_nmf_plan* plan, int which, const float* F, int64_t ldf, float* out,
                          int64_t ld_out, void* stream);
+/* MTTKRP operand (ntf.py:448-449): the Khatri-Rao product of two rank-major factors At (r x I), Bt (r x J), I*J == n,
+ * written straight into the operand planes that nnfac_nmf_plan_cross(which = 0, F = NULL) reads. */
+int nnfac_nmf_plan_set_krao(nnfac_nmf_plan* plan, const float* At, int64_t lda, int64_t I, const float* Bt, int64_t ldb,
+                            int64_t J, void* stream);
 /* Install a factor into the plan (builds all of its bf16 operand planes):
  * which = 0: U, passed as U^T (r x m, row-major); which = 1: V (r x n). */
 int nnfac_nmf_plan_set_factor(nnfac_nmf_plan* plan, int which, const float* Ft, int64_t ld, void* stream);

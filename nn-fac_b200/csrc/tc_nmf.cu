@@ -251,6 +251,24 @@ __global__ void plane_total_finish_kernel(const double* part, int n, double* out
   }
 }
 
+// K-major bf16 hi/lo planes of a Khatri-Rao product, never materialised in fp32: plane[q][a * J + b] = At[q][a] * Bt[q][b]
+// (ntf.py:448: the first kept factor's row index is the slow one).  One thread per column, rank loop inside.
+__global__ void __launch_bounds__(256) krao_planes_kernel(const float* __restrict__ At, int64_t lda, int64_t I, const float* __restrict__ Bt,
+                                                          int64_t ldb, int64_t J, int r, bf16* __restrict__ hi, bf16* __restrict__ lo,
+                                                          int64_t ld_out) {
+  const int64_t total = I * J;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t a = c / J, b = c - a * J;
+    for (int q = 0; q < r; ++q) {
+      const float v = At[(int64_t)q * lda + a] * Bt[(int64_t)q * ldb + b];
+      bf16 h, l;
+      tc::split_bf16(v, h, l);
+      hi[(int64_t)q * ld_out + c] = h;
+      lo[(int64_t)q * ld_out + c] = l;
+    }
+  }
+}
+
 }  // namespace
 
 void nnfac_split_planes(const float* in, int64_t ld_in, int64_t rows, int64_t cols, __nv_bfloat16* hi, __nv_bfloat16* lo,
@@ -460,6 +478,20 @@ int nnfac_nmf_plan_cross(nnfac_nmf_plan* p, int which, const float* F, int64_t l
   const int64_t tot2 = (int64_t)p->r * s->R;
   grid = (int)(ceil_div64(tot2, 256) < (int64_t)p->ctx->sm_count * 8 ? ceil_div64(tot2, 256) : (int64_t)p->ctx->sm_count * 8);
   reduce_partials_kernel<<<grid, 256, 0, st>>>(p->partial, cp.splits, p->r, p->r_pad, s->R, cp.ld_partial, out, ld_out);
+  NNFAC_LAUNCH_CHECK(p->ctx);
+  return NNFAC_OK;
+}
+
+// Install the Khatri-Rao product of two rank-major factors At (r x I) and Bt (r x J) as the r x (I*J) factor of
+// nnfac_nmf_plan_cross(which = 0, F = NULL): the MTTKRP operand of ntf.py:448-449, written straight into its bf16 operand
+// planes (no fp32 Khatri-Rao matrix, no transpose, no separate split pass).  Requires I * J == n of the plan.
+int nnfac_nmf_plan_set_krao(nnfac_nmf_plan* p, const float* At, int64_t lda, int64_t I, const float* Bt, int64_t ldb, int64_t J,
+                            void* stream) {
+  NNFAC_ARG(p && At && Bt && I > 0 && J > 0 && I * J == p->n && lda >= I && ldb >= J, "nnfac_nmf_plan_set_krao: bad argument");
+  Side* s = &p->side[0];
+  const int64_t total = I * J;
+  const int grid = (int)(ceil_div64(total, 256) < (int64_t)p->ctx->sm_count * 16 ? ceil_div64(total, 256) : (int64_t)p->ctx->sm_count * 16);
+  krao_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(At, lda, I, Bt, ldb, J, p->r, s->fh, s->fl, s->ld);
   NNFAC_LAUNCH_CHECK(p->ctx);
   return NNFAC_OK;
 }

@@ -292,6 +292,11 @@ class NMFPlan:
         """which=0: U given as U^T (r x m); which=1: V (r x n).  Rebuilds that factor's bf16 operand planes."""
         L.check(_lib().nnfac_nmf_plan_set_factor(self.handle, which, L.ptr(Ft), Ft.stride(0), L.stream_ptr()))
 
+    def set_krao(self, At, Bt):
+        """The r x (I*J) Khatri-Rao factor of two rank-major factors (r x I, r x J) as the operand of cross(0, None)."""
+        L.check(_lib().nnfac_nmf_plan_set_krao(self.handle, L.ptr(At), At.stride(0), At.shape[1], L.ptr(Bt), Bt.stride(0),
+                                               Bt.shape[1], L.stream_ptr()))
+
     def hals_solve(self, which, UtM, UtU, F, maxiter, delta, sparsity, result):
         """hals_nnls_acc(UtM, UtU, F) on the tensor-core sweep with the result installed in the plan by the same kernel.
         Returns the new factor (r x len), or None when the shape is outside that kernel (caller: hals_nnls + set_factor)."""

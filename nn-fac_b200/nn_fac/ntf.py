@@ -59,6 +59,7 @@ class DeviceNTF:
         self.T = L.to_device(tensor, dtype, device)
         self.shape = tuple(self.T.shape)
         self.factors = [L.to_device(f, dtype, device) for f in factors]
+        self.factors_t = [ops.transpose(f) for f in self.factors]           # rank-major copies (r x I): sweep / Gram / MTTKRP layout
         self.norm_sq = None
         self.stats = torch.zeros(4, dtype=torch.float64, device=self.T.device)
         # fp32, rank <= 128: the MTTKRP of every mode runs on tcgen05.  One plan per mode holds unfold(T, mode)
@@ -112,38 +113,46 @@ class DeviceNTF:
         rhs = krao = cross = None
         mode = None
         for mode in modes:
-            krao = self.khatri_rao(mode)
+            others = [i for i in range(len(self.factors)) if i != mode]
+            fused_krao = update_rule == "hals" and self.plans is not None and len(others) == 2
+            krao = None if fused_krao else self.khatri_rao(mode)
             if update_rule == "hals":
                 cross = None
-                for i, f in enumerate(self.factors):
-                    if i != mode:
-                        gram = ops.gemm(f, (1, f.shape[1]), f, (f.shape[1], 1), rank, rank, f.shape[0])  # ntf.py:445
-                        cross = gram if cross is None else ops.hadamard_(cross, gram)
-                if self.plans is not None:
-                    rhs_t = self.plans[mode].cross(0, ops.transpose(krao))   # (unfold(T, mode) @ krao)^T, ntf.py:449
+                for i in others:
+                    gram = ops.gram(self.factors_t[i])                       # F_i^T F_i, ntf.py:445
+                    cross = gram if cross is None else ops.hadamard_(cross, gram)
+                if fused_krao:
+                    # MTTKRP (ntf.py:448-449) on tcgen05: the Khatri-Rao operand goes straight into its bf16 planes
+                    self.plans[mode].set_krao(self.factors_t[others[0]], self.factors_t[others[1]])
+                    rhs_t = self.plans[mode].cross(0, None)                  # (unfold(T, mode) @ krao)^T
+                    rhs = None
+                elif self.plans is not None:
+                    rhs_t = self.plans[mode].cross(0, ops.transpose(krao))
                     rhs = None
                 else:
                     rhs = self.mttkrp(mode, krao)
                     rhs_t = ops.transpose(rhs)
-                Ft = ops.transpose(self.factors[mode])
+                Ft = self.factors_t[mode].clone()
                 nnls.hals_nnls_device(rhs_t, cross, Ft, rank, maxiter=100, delta=0.01,
                                       sparsity_coefficient=sparsity[mode], normalize=normalize[mode],
                                       nonzero=False, result=self.stats)    # ntf.py:454-456
+                self.factors_t[mode] = Ft
                 self.factors[mode] = ops.transpose(Ft)
             else:
                 F = self.factors[mode]
                 K = self.reconstruct_unfolded(mode, krao)
                 self.factors[mode] = self._mu_factor(F, krao, K, mode, beta)   # ntf.py:459-460
+                self.factors_t[mode] = ops.transpose(self.factors[mode])
         # the cost terms stay on the device: [rec part a, rec part b, sparsity l1 norms...] (see finish_cost)
         terms = []
         F = self.factors[mode]
         if update_rule == "hals":
             # ntf.py:470; ||F krao^T||^2 = <F^T F, krao^T krao> and krao^T krao = cross (Hadamard of Grams)
-            ftf = ops.gemm(F, (1, rank), F, (rank, 1), rank, rank, F.shape[0])
+            ftf = ops.gram(self.factors_t[mode])
             inner = ops.dot(F, rhs) if rhs is not None else ops.dot(Ft, rhs_t)     # <F, rhs>, either layout
             terms += [inner, ops.dot(ftf, cross)]
         else:
-            K = self.reconstruct_unfolded(mode, krao)
+            K = self.reconstruct_unfolded(mode, self.khatri_rao(mode) if krao is None else krao)
             terms += [ops.beta_divergence(self.T, K, beta)]                 # ntf.py:473
         for idx, s in enumerate(sparsity):
             if s:
@@ -254,6 +263,7 @@ def compute_ntf(tensor_in, rank, factors_in, n_iter_max=100, tol=1e-8,
                     print('Converged in {} iterations.'.format(len(cost_fct_vals) - 1))
                 if iteration < n_iter_max:
                     state.factors = before             # drop the speculative iteration
+                    state.factors_t = [ops.transpose(f) for f in before]
                 break
         if iteration == n_iter_max:
             break
