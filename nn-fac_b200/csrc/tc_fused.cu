@@ -25,6 +25,7 @@ constexpr int NWT = 4 * NSP;         // transform warps: 4 TMEM lane quadrants x
 constexpr int FUSED_THREADS = 128 + 32 * NWT;   // warp0 TMA, warps 1/3 MMA issuers, warp2 TMEM, then transform warps
 static_assert(CW == 16, "the transform below moves 16 columns per tcgen05.ld / 8 words per tcgen05.st");
 constexpr int FSTAGES = 4;
+constexpr int ND1 = 3;               // model-tile buffers in tensor memory: the model GEMM runs up to two stages ahead of the transform
 constexpr uint32_t X_BYTES = TILE_ROWS * BK * sizeof(bf16);   // 16 KiB per plane tile
 constexpr uint32_t FK_BYTES = 64 * BK * sizeof(bf16);         // 8 KiB  (64 columns of X x rank 64)
 constexpr uint32_t STAGE_BYTES = 2 * X_BYTES + 2 * FK_BYTES;  // 48 KiB
@@ -66,16 +67,16 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
   uint64_t* empty = bars + 4;            // [4]  count 9: GEMM-2 commit + 8 transform warps
   uint64_t* a1_full = bars + 9;
   uint64_t* a1_empty = bars + 10;
-  uint64_t* d1_full = bars + 11;         // [2]
-  uint64_t* d1_empty = bars + 13;        // [2] count 8
-  uint64_t* d2_full = bars + 15;         // [2]
-  uint64_t* d2_empty = bars + 17;        // [2] count 8
-  uint64_t* a1t_ready = bars + 19;       // A1 copied into tensor memory (count 8)
-  uint64_t* a1t_free = bars + 20;        // every model GEMM of the unit has retired
-  uint64_t* q_ready = bars + 21;         // [2] count 8: ratio tile written to tensor memory
-  uint64_t* q_free = bars + 23;          // [2] contraction GEMM that read it has retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
-  double* cost_sh = reinterpret_cast<double*>(bars + 26);   // [2 * NWT]
+  uint64_t* d1_full = bars + 11;         // [ND1]
+  uint64_t* d1_empty = bars + 14;        // [ND1] count NWT
+  uint64_t* d2_full = bars + 17;         // [2]
+  uint64_t* d2_empty = bars + 19;        // [2] count NWT
+  uint64_t* a1t_ready = bars + 21;       // A1 copied into tensor memory (count NWT)
+  uint64_t* a1t_free = bars + 22;        // every model GEMM of the unit has retired
+  uint64_t* q_ready = bars + 23;         // [2] count NWT: ratio tile written to tensor memory
+  uint64_t* q_free = bars + 25;          // [2] contraction GEMM that read it has retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
+  double* cost_sh = reinterpret_cast<double*>(bars + 28);   // [2 * NWT]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t stage_tx = STAGE_BYTES;
@@ -89,10 +90,8 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     tc::mbar_init(a1_full, 1); tc::mbar_init(a1_empty, NWT);
     tc::mbar_init(a1t_ready, NWT); tc::mbar_init(a1t_free, 1);
     for (int b = 0; b < 2; ++b) { tc::mbar_init(&q_ready[b], NWT); tc::mbar_init(&q_free[b], 1); }
-    for (int b = 0; b < 2; ++b) {
-      tc::mbar_init(&d1_full[b], 1); tc::mbar_init(&d1_empty[b], NWT);
-      tc::mbar_init(&d2_full[b], 1); tc::mbar_init(&d2_empty[b], NWT);
-    }
+    for (int b = 0; b < ND1; ++b) { tc::mbar_init(&d1_full[b], 1); tc::mbar_init(&d1_empty[b], NWT); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(&d2_full[b], 1); tc::mbar_init(&d2_empty[b], NWT); }
     tc::fence_barrier_init();
   }
   if (warp == 2) tc::tmem_alloc(tmem_slot, 512);
@@ -100,8 +99,8 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // tensor-memory map (columns): D1 2x64 | D2 2x64 | A1 hi 32 + lo 32 | Q 2 x (hi 32 + lo 32)
-  const uint32_t D1 = tmem_base, D2 = tmem_base + 128, A1T = tmem_base + 256, QT = tmem_base + 320;
+  // tensor-memory map (columns): D1 ND1 x 64 | D2 2x64 | A1 hi 32 + lo 32 | Q 2 x (hi 32 + lo 32)  (512 in all)
+  const uint32_t D1 = tmem_base, D2 = tmem_base + 64 * ND1, A1T = D2 + 128, QT = A1T + 64;
   const int S = p.stages_per_unit;
 
   if (warp == 0 && lane == 0) {
@@ -155,7 +154,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         }
         tc::umma_commit(&d1_full[b1]);
         if (i == S - 1) tc::umma_commit(a1t_free);
-        if (++b1 == 2) { b1 = 0; b1_phase ^= 1; }
+        if (++b1 == ND1) { b1 = 0; b1_phase ^= 1; }
         if (++st1 == FSTAGES) { st1 = 0; ph1 ^= 1; }
       }
     }
@@ -273,7 +272,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         tc::tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&d1_empty[b1]);
-        if (++b1 == 2) { b1 = 0; b1_phase ^= 1; }
+        if (++b1 == ND1) { b1 = 0; b1_phase ^= 1; }
         // the stage's TMA data is visible to the MMA issuers; this thread must observe the barrier too
         // before reading X through the generic proxy
         tc::mbar_wait(&full[st], ph);
