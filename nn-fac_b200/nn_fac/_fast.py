@@ -88,8 +88,8 @@ class CudaEngine:
     def set_factor(self, which, Ft):
         self.plan.set_factor(which, Ft)
 
-    def fused(self, side, mode, want_cost, keep_partials=False):
-        return self.plan.fused(side, mode, want_cost=want_cost, keep_partials=keep_partials)
+    def fused(self, side, mode, want_cost, keep_partials=False, cost_out=None):
+        return self.plan.fused(side, mode, want_cost=want_cost, keep_partials=keep_partials, cost_out=cost_out)
 
     def mu_finish(self, which, F, den_vec):
         """mu.py:84-88 on the numerator the last fused(which, MODE_MU, keep_partials=True) left in the plan,
@@ -277,10 +277,9 @@ class FusedNMF:
             with self._phase("pass_U"):
                 # single GPU, MU: the numerator stays in the plan as split partials and is consumed by mu_finish
                 keep = mode == MODE_MU and self.comm.world == 1 and it < n_iter_max and 0 not in fixed_modes
-                outA, cost_dev = self.eng.fused(0, mode, True, keep_partials=keep)
+                # the cost lands directly in the scalar block that travels to the host
+                outA, _ = self.eng.fused(0, mode, True, keep_partials=keep, cost_out=self._dev_scal[0:1])
             if it > 0:
-                self._dev_scal[0:1].copy_(cost_dev)
-                self._dev_scal[1:3].zero_()
                 self.comm.sum_(self._dev_scal[0:1])
                 if with_sparsity:       # nmf.py:449-452: matrix 1-norms of the factors the cost refers to
                     self._dev_scal[1:2].copy_(self.eng.max_col_abs_sum(self.eng.transpose(self.Ut)))

@@ -36,7 +36,7 @@ class OracleEngine:
     def set_factor(self, which, Ft):
         self.F[which] = Ft.clone()
 
-    def fused(self, side, mode, want_cost, keep_partials=False):
+    def fused(self, side, mode, want_cost, keep_partials=False, cost_out=None):
         Ut, V, X = self.F[0], self.F[1], self.X
         K = Ut.T @ V
         A = X if mode == 0 else X / K
@@ -48,7 +48,10 @@ class OracleEngine:
             cost = ((X - K) ** 2).sum()
         else:
             cost = torch.tensor(orc.beta_divergence(X.numpy(), K.numpy(), 1), dtype=torch.float64)
-        return out.contiguous(), cost.reshape(1).to(torch.float64)
+        cost = cost.reshape(1).to(torch.float64)
+        if cost_out is not None:
+            cost_out.copy_(cost)
+        return out.contiguous(), cost
 
     def cross(self, which, F):
         if F is None:                      # the installed factor: V for which=0, U^T for which=1
