@@ -126,6 +126,11 @@ int nnfac_hadamard(nnfac_ctx* ctx, int dtype, void* out, const void* A, const vo
                    int64_t count, void* stream);
 
 /* Row-wise L2 normalisation of the Tucker core unfolding (ntd.py:676-681), in place. */
+/* One projected-gradient step on the Tucker core, ntd.py:607-617:  delta = min(step * (-MtX + P + sparse), core);
+ * core -= delta; upd = ||delta||_2, with the loop state {upd_0, upd, cnt, done} kept on the device (double[4], start
+ * {0, 1, 1, 0}): the step is a no-op once `done` is set (cnt > 300 or upd < delta * upd_0).  P = core x_n (F_n^T F_n). */
+int nnfac_core_pg_step(nnfac_ctx* ctx, int dtype, void* core, const void* MtX, const void* P, int64_t count, double step,
+                       double sparse, double delta, double* state, void* stream);
 int nnfac_normalize_rows(nnfac_ctx* ctx, int dtype, void* A, int64_t lda, int64_t rows,
                          int64_t cols, void* stream);
 

@@ -188,6 +188,37 @@ inline int grid_for(int64_t count, int sm) {
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// ---- projected-gradient step on the Tucker core (ntd.py:607-617) -------------------------------------------
+// state = {upd_0, upd, cnt, done}: the loop `while cnt <= 300 and upd >= delta * upd_0` runs on the device; once
+// `done` is set the remaining launches of a batch return at once (the host looks at the flag only every few steps).
+template <typename T>
+__global__ void __launch_bounds__(RB) core_pg_step_kernel(T* __restrict__ core, const T* __restrict__ MtX, const T* __restrict__ P,
+                                                          int64_t count, T step, T sparse, const double* state, double* part) {
+  __shared__ double sh[33];
+  if (state[3] != 0.0) return;
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * RB + threadIdx.x; i < count; i += (int64_t)gridDim.x * RB) {
+    const T g = -MtX[i] + P[i] + sparse;                 // gradient, ntd.py:608
+    const T c = core[i];
+    const T st = step * g;
+    const T d = st < c ? st : c;                         // np.minimum(gradient_step * gradient, core)
+    core[i] = c - d;
+    s += (double)d * (double)d;
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+__global__ void core_pg_finish_kernel(const double* part, int nparts, double delta, double* state) {
+  if (threadIdx.x != 0 || state[3] != 0.0) return;
+  double s = 0.0;
+  for (int i = 0; i < nparts; ++i) s += part[i];         // fixed order
+  const double upd = sqrt(s);
+  if (state[2] == 1.0) state[0] = upd;                   // upd_0, ntd.py:614-615
+  state[1] = upd;
+  state[2] += 1.0;
+  if (!(state[2] <= 300.0 && upd >= delta * state[0])) state[3] = 1.0;
+}
+
 #define DISPATCH_T(dtype, CALL_F, CALL_D) \
   if ((dtype) == NNFAC_F32) { CALL_F; } else if ((dtype) == NNFAC_F64) { CALL_D; } else { \
     nnfac_set_error("bad dtype %d", (int)(dtype)); return NNFAC_ERR_ARG; }
@@ -309,6 +340,23 @@ int nnfac_hadamard(nnfac_ctx* ctx, int dtype, void* out, const void* A, const vo
   const int grid = grid_for(count, ctx->sm_count);
   DISPATCH_T(dtype, (hadamard_kernel<float><<<grid, 256, 0, st>>>((float*)out, (const float*)A, (const float*)B, count)),
              (hadamard_kernel<double><<<grid, 256, 0, st>>>((double*)out, (const double*)A, (const double*)B, count)));
+  NNFAC_LAUNCH_CHECK(ctx);
+  return NNFAC_OK;
+}
+
+int nnfac_core_pg_step(nnfac_ctx* ctx, int dtype, void* core, const void* MtX, const void* P, int64_t count, double step,
+                       double sparse, double delta, double* state, void* stream) {
+  NNFAC_ARG(ctx && core && MtX && P && state && count > 0, "nnfac_core_pg_step: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = (int)(ceil_div64(count, RB) < RMAX_BLOCKS ? ceil_div64(count, RB) : RMAX_BLOCKS);
+  // the partials live behind the mailbox area of the sweep so that they never collide with other reductions in flight
+  double* part = ctx->red + 32768;
+  DISPATCH_T(dtype, (core_pg_step_kernel<float><<<blocks, RB, 0, st>>>((float*)core, (const float*)MtX, (const float*)P, count,
+                                                                        (float)step, (float)sparse, state, part)),
+             (core_pg_step_kernel<double><<<blocks, RB, 0, st>>>((double*)core, (const double*)MtX, (const double*)P, count, step,
+                                                                  sparse, state, part)));
+  NNFAC_LAUNCH_CHECK(ctx);
+  core_pg_finish_kernel<<<1, 32, 0, st>>>(part, blocks, delta, state);
   NNFAC_LAUNCH_CHECK(ctx);
   return NNFAC_OK;
 }

@@ -42,6 +42,7 @@ SIGNATURES = {
     "nnfac_khatri_rao": [_P, _INT, _P, _P, _I64, _P, _I64, _I64, _P],
     "nnfac_hadamard": [_P, _INT, _P, _P, _P, _I64, _P],
     "nnfac_normalize_rows": [_P, _INT, _P, _I64, _I64, _I64, _P],
+    "nnfac_core_pg_step": [_P, _INT, _P, _P, _P, _I64, _DBL, _DBL, _DBL, _P, _P],
     "nnfac_nmf_plan_create": [_P, _I64, _I64, _INT, _c.POINTER(_P)],
     "nnfac_nmf_plan_bytes": [_P, _I64, _I64, _INT, _c.POINTER(_c.c_size_t)],
     "nnfac_nmf_plan_create_in": [_P, _I64, _I64, _INT, _P, _c.c_size_t, _P, _c.POINTER(_P)],

@@ -153,6 +153,12 @@ def normalize_rows_(A):
 
 
 # ---- tensor helpers (C-order N-way tensors, no unfolding copies) ---------------------------------
+def core_pg_step(core, MtX, P, step, sparse, delta, state):
+    """In-place projected-gradient step on the Tucker core (ntd.py:607-617); `state` = device double[4]."""
+    L.check(_lib().nnfac_core_pg_step(L.ctx(core.device), L.code_of(core.dtype), L.ptr(core), L.ptr(MtX), L.ptr(P), core.numel(),
+                                      float(step), float(sparse), float(delta), L.ptr(state), L.stream_ptr()))
+
+
 def _split(shape, mode):
     left = 1
     for s in shape[:mode]:

@@ -1,10 +1,9 @@
 """Nonnegative Tucker decomposition (NTD), B200 path (reference: nn_fac/ntd.py).
 
-Covered: the multiplicative-update algorithm (``update_rule="mu"``, any beta >= 0), i.e.
-``one_ntd_step_mu`` = per-mode ``mu_betadivmin`` on the implicit unfoldings followed by
-``mu_tensorial`` on the core and the beta-divergence cost (ntd.py:658-698).
-Not covered yet: ``update_rule="hals"`` (the projected-gradient core update of ntd.py:436-645 is
-row N2 of SURVEY.md section 8(f)); it raises NotImplementedError rather than falling back to a CPU.
+``update_rule="mu"`` (any beta >= 0): ``one_ntd_step_mu`` = per-mode ``mu_betadivmin`` on the implicit unfoldings
+followed by ``mu_tensorial`` on the core and the beta-divergence cost (ntd.py:658-698).
+``update_rule="hals"`` (the reference's default): ``one_ntd_step`` = per-mode HALS solve on the Tucker Grams and a
+projected-gradient loop on the core whose stop test runs on the device (ntd.py:436-645), deterministic inner rule.
 """
 import os
 import time
@@ -71,6 +70,7 @@ class DeviceNTD:
         self.T = L.to_device(tensor, dtype, device)
         self.core = L.to_device(core, dtype, device)
         self.factors = [L.to_device(f, dtype, device) for f in factors]
+        self.stats = torch.zeros(4, dtype=torch.float64, device=self.T.device)
         # fp32, every rank <= 64: the beta = 1 factor update of a mode is the NMF update of U for X = unfold(T, mode),
         # V = unfold(G x_{j != mode} F_j, mode), i.e. one fused tcgen05 pass over the planes of that unfolding
         # (model tile, ratio and contraction on chip; nothing of the size of the tensor is written).
@@ -109,6 +109,74 @@ class DeviceNTD:
             den_vec = ops.unfold_times(ones, B, mode)                       # row sums of unfold(B, mode), mu.py:86
             return ops.mu_apply(F, num, den_vec=den_vec, vec_per_row=False, gamma=g, floor=mu.epsilon)
         return ops.mu_apply(F, num, den_mat=ops.unfold_times(Q, B, mode), gamma=g, floor=mu.epsilon)
+
+    # ---- HALS factor updates + projected-gradient core update (ntd.py:436-645) ------------------------------
+    @staticmethod
+    def _unfold(t, mode):
+        return t.movedim(mode, 0).reshape(t.shape[mode], -1).contiguous()
+
+    def step_hals_async(self, norm_tensor, sparsity, fixed_modes, normalize, mode_core_norm, delta=0.01):
+        """One outer iteration of one_ntd_step (deterministic inner rule); returns the device vector of cost terms
+        [<all_MtX, core>, <core x_n MtM_n, core>, l1 norms of the sparse factors..., l1 norm of the core]."""
+        import nn_fac.update_rules.nnls as nnls
+        nm = self.T.dim()
+        modes = [m for m in range(nm) if m not in fixed_modes]
+        temp = elemprod = None
+        for mode in modes:
+            elemprod = list(self.factors)                                    # ntd.py:534-537
+            for i, f in enumerate(self.factors):
+                if i != mode:
+                    r_i = f.shape[1]
+                    elemprod[i] = ops.gemm(f, (1, r_i), f, (r_i, 1), r_i, r_i, f.shape[0])
+            core_u = self._unfold(self.core, mode)
+            UtU = ops.matmul(self._unfold(ops.multi_mode_dot(self.core, elemprod, skip=mode), mode), core_u.T.contiguous())   # ntd.py:539-544
+            temp = ops.multi_mode_dot(self.T, self.factors, skip=mode, transpose=True)                                        # ntd.py:550
+            UtM = ops.matmul(core_u, self._unfold(temp, mode).T.contiguous())                                                 # ntd.py:555-557 (transposed)
+            Ft = ops.transpose(self.factors[mode])
+            nnls.hals_nnls_device(UtM, UtU, Ft, Ft.shape[0], maxiter=100, delta=delta, sparsity_coefficient=sparsity[mode],
+                                  normalize=normalize[mode], nonzero=False, result=self.stats)   # ntd.py:571-573
+            self.factors[mode] = ops.transpose(Ft)
+        last = modes[-1]
+        F_last = self.factors[last]
+        all_MtX = ops.mode_dot(temp, F_last, last, transpose=True)           # ntd.py:581
+        all_MtM = list(elemprod)                                             # ntd.py:582-583
+        r_l = F_last.shape[1]
+        all_MtM[last] = ops.gemm(F_last, (1, r_l), F_last, (r_l, 1), r_l, r_l, F_last.shape[0])
+        # step = prod 1 / sigma_max(MtM) rounded to 6 decimals (ntd.py:590-594): control scalar from three tiny Grams
+        gradient_step = 1.0
+        for MtM in all_MtM:
+            gradient_step *= 1.0 / float(np.linalg.svd(MtM.double().cpu().numpy(), compute_uv=False)[0])
+        gradient_step = round(gradient_step, 6)
+        sparse = 0.0 if sparsity[-1] is None else float(sparsity[-1])       # ntd.py:600-603
+        core = self.core.clone()
+        state = torch.tensor([0.0, 1.0, 1.0, 0.0], dtype=torch.float64, device=core.device)
+        for it in range(300):                                                # ntd.py:607-617, stop test on the device
+            P = ops.multi_mode_dot(core, all_MtM)
+            ops.core_pg_step(core, all_MtX, P, gradient_step, sparse, delta, state)
+            if it % 25 == 24 and float(state[3].item()) != 0.0:
+                break
+        self.core_steps = state
+        if normalize[-1]:                                                    # ntd.py:619-624
+            moved = core.movedim(mode_core_norm, 0).contiguous()
+            ops.normalize_rows_(moved.reshape(moved.shape[0], -1))
+            core = moved.movedim(0, mode_core_norm).contiguous()
+        self.core = core
+        terms = [ops.dot(all_MtX, core), ops.dot(ops.multi_mode_dot(core, all_MtM), core)]      # ntd.py:637
+        for idx, sp in enumerate(sparsity):                                  # ntd.py:627-635
+            if sp:
+                if idx < nm:
+                    terms.append(ops.norm1(self.factors[idx]))
+                else:
+                    terms.append(ops.row_sums(core.reshape(1, -1)))          # ||core||_1: the core is nonnegative
+        return torch.cat([t.reshape(1).to(torch.float64) for t in terms])
+
+    @staticmethod
+    def finish_cost_hals(terms_host, norm_tensor, sparsity):
+        rec_error = norm_tensor ** 2 - 2 * terms_host[0] + terms_host[1]
+        sparsity_error = 0.0
+        for sp, l1 in zip([sp for sp in sparsity if sp], terms_host[2:]):
+            sparsity_error += 2 * (sp * float(l1))
+        return float((rec_error + sparsity_error) / (norm_tensor ** 2))      # ntd.py:638 (normalised)
 
     def step_mu(self, beta, fixed_modes, normalize, mode_core_norm):
         return float(self.step_mu_async(beta, fixed_modes, normalize, mode_core_norm).item())
@@ -156,10 +224,7 @@ def compute_ntd(tensor_in, ranks, core_in, factors_in, n_iter_max=100, tol=1e-6,
         normalize[-1] = False
     if not normalize[-1] and (mode_core_norm is not None and 0 <= mode_core_norm < nb_modes):
         print("The core was asked NOT to be normalized, but mode_core_norm was set to a valid norm. Is this a mistake?")
-    if update_rule == "hals":
-        raise NotImplementedError("ntd(update_rule='hals') is not part of this build yet (SURVEY.md 8(f) N2); "
-                                  "use update_rule='mu'. There is no CPU fallback.")
-    if update_rule != "mu":
+    if update_rule not in ("hals", "mu"):
         raise err.InvalidArgumentValue(
             f"The update rule provided is not valid. Please choose between 'hals' and 'mu' (Got {update_rule}).")
     if beta < 0:
@@ -170,15 +235,28 @@ def compute_ntd(tensor_in, ranks, core_in, factors_in, n_iter_max=100, tol=1e-6,
     tic = time.time()
     # The cost of iteration t is read while iteration t+1 is already queued; if the stop test (ntd.py:421) fires on it,
     # the speculative iteration is dropped (core and factors are replaced, never modified in place).
-    host = torch.zeros(1, dtype=torch.float64).pin_memory()
+    hals = update_rule == "hals"
+    norm_tensor = None
+    if hals:
+        norm_tensor = float(np.sqrt(ops.sq_diff(state.T).item()))           # ntd.py:361
+        for fixed_value in fixed_modes:                                      # ntd.py:515-516 (caller's list, as in the reference)
+            sparsity_coefficients[fixed_value] = None
+    host = torch.zeros(8, dtype=torch.float64).pin_memory()
     pending = None
+    nterms = 1
     for iteration in range(n_iter_max + 1):
         if iteration < n_iter_max:
             before = (state.core, list(state.factors))
-            cost_dev = state.step_mu_async(beta, fixed_modes, normalize, mode_core_norm)
+            if hals:
+                cost_dev = state.step_hals_async(norm_tensor, sparsity_coefficients, fixed_modes, normalize, mode_core_norm)
+            else:
+                cost_dev = state.step_mu_async(beta, fixed_modes, normalize, mode_core_norm).reshape(1).to(torch.float64)
         if pending is not None:
             pending.synchronize()
-            cost = float(host[0])
+            if hals:
+                cost = state.finish_cost_hals(host[:nterms].numpy().copy(), norm_tensor, sparsity_coefficients)
+            else:
+                cost = float(host[0])
             toc.append(time.time() - tic)
             cost_fct_vals.append(cost)
             if verbose:
@@ -196,7 +274,8 @@ def compute_ntd(tensor_in, ranks, core_in, factors_in, n_iter_max=100, tol=1e-6,
                 break
         if iteration == n_iter_max:
             break
-        host.copy_(cost_dev.reshape(1).to(torch.float64), non_blocking=True)
+        nterms = cost_dev.numel()
+        host[:nterms].copy_(cost_dev, non_blocking=True)
         pending = torch.cuda.Event()
         pending.record()
     if isinstance(tensor_in, torch.Tensor):
@@ -206,6 +285,21 @@ def compute_ntd(tensor_in, ranks, core_in, factors_in, n_iter_max=100, tol=1e-6,
     if return_costs:
         return core, factors, cost_fct_vals, toc
     return core, factors
+
+
+def one_ntd_step(tensor, ranks, in_core, in_factors, norm_tensor, sparsity_coefficients, fixed_modes, normalize,
+                 mode_core_norm, alpha=0.5, delta=0.01):
+    """ntd.py:436-645: HALS on every non-fixed factor, projected gradient on the core; returns (core, factors, cost)
+    with the cost normalised by ||tensor||^2.  `alpha` is ignored (deterministic inner rule)."""
+    for fixed_value in fixed_modes:                                          # ntd.py:515-516
+        sparsity_coefficients[fixed_value] = None
+    dt = L.resolve_dtype(tensor, in_core, *in_factors)
+    state = DeviceNTD(tensor, in_core, in_factors, dt)
+    terms = state.step_hals_async(float(norm_tensor), sparsity_coefficients, fixed_modes, normalize, mode_core_norm, delta)
+    cost = state.finish_cost_hals(terms.cpu().numpy(), float(norm_tensor), sparsity_coefficients)
+    if isinstance(tensor, torch.Tensor):
+        return state.core, state.factors, cost
+    return state.core.cpu().numpy(), [f.cpu().numpy() for f in state.factors], cost
 
 
 def one_ntd_step_mu(tensor, ranks, in_core, in_factors, beta, norm_tensor,

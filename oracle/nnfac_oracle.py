@@ -325,3 +325,92 @@ def compute_ntd_mu(tensor, core_in, factors_in, n_iter_max=100, tol=1e-6, beta=2
         if it > 0 and abs(costs[-2] - costs[-1]) < tol:
             break
     return core, factors, costs
+
+
+# --------------------------------------------------------------------------
+# NTD with HALS factor updates and a projected-gradient core update  (ntd.py:514-645)
+# --------------------------------------------------------------------------
+def _contract_all_but(a, b, mode):
+    """tl.tenalg.contract(a, con_modes, b, con_modes) of tensorly 0.6.0 = tensordot over every mode but `mode`
+    (ntd.py:537-557): equals unfold(a, mode) @ unfold(b, mode).T."""
+    return unfold(a, mode) @ unfold(b, mode).T
+
+
+def one_ntd_step_hals(tensor, core_in, factors_in, norm_tensor, sparsity_coefficients=None, fixed_modes=(),
+                      normalize=None, mode_core_norm=None, delta=0.01, stats=None):
+    """ntd.py:514-645 with the deterministic inner stop rule (alpha = inf).  Returns (core, factors, cost)."""
+    import scipy.sparse.linalg
+    nmodes = tensor.ndim
+    sparsity = list(sparsity_coefficients) if sparsity_coefficients is not None else [None] * (nmodes + 1)
+    normalize = list(normalize) if normalize is not None else [False] * (nmodes + 1)
+    for fixed_value in fixed_modes:                                          # ntd.py:515-516
+        sparsity[fixed_value] = None
+    core = core_in.copy()
+    factors = list(factors_in)
+    modes_list = [m for m in range(nmodes) if m not in fixed_modes]          # ntd.py:523
+    temp = elemprod = None
+    for mode in modes_list:
+        elemprod = list(factors)                                             # ntd.py:534-537
+        for i, f in enumerate(factors):
+            if i != mode:
+                elemprod[i] = f.T @ f
+        UtU = _contract_all_but(multi_mode_dot(core, elemprod, skip=mode), core, mode)          # ntd.py:539-544
+        temp = multi_mode_dot(tensor, factors, skip=mode, transpose=True)    # ntd.py:550
+        UtM = _contract_all_but(temp, core, mode).T                          # ntd.py:555-557
+        V, _, cnt, sweeps = hals_nnls_acc(UtM, UtU, factors[mode].T, maxiter=100, delta=delta,
+                                          sparsity_coefficient=sparsity[mode], normalize=normalize[mode])   # ntd.py:571-573
+        if stats is not None:
+            stats.setdefault("sweeps", []).append(sweeps)
+        factors[mode] = V.T
+    last = modes_list[-1]
+    all_MtX = mode_dot(temp, factors[last].T, last)                          # ntd.py:581
+    all_MtM = list(elemprod)                                                 # ntd.py:582-583
+    all_MtM[last] = factors[last].T @ factors[last]
+    gradient_step = 1
+    for MtM in all_MtM:                                                      # ntd.py:590-592
+        gradient_step *= 1 / (scipy.sparse.linalg.svds(MtM, k=1)[1][0])
+    gradient_step = round(gradient_step, 6)                                  # ntd.py:594
+    cnt, upd_0, upd = 1, 0, 1
+    sparse = 0 if sparsity[-1] is None else sparsity[-1]                     # ntd.py:600-603
+    while cnt <= 300 and upd >= delta * upd_0:                               # ntd.py:607-617
+        gradient = -all_MtX + multi_mode_dot(core, all_MtM) + sparse * np.ones(core.shape)
+        delta_core = np.minimum(gradient_step * gradient, core)
+        core = core - delta_core
+        upd = np.sqrt(np.sum(delta_core ** 2))
+        if cnt == 1:
+            upd_0 = upd
+        cnt += 1
+    if stats is not None:
+        stats.setdefault("core_steps", []).append(cnt - 1)
+    if normalize[-1]:                                                        # ntd.py:619-624
+        uc = unfold(core, mode_core_norm).copy()
+        for i in range(uc.shape[0]):
+            nrm = np.linalg.norm(uc[i])
+            if nrm != 0:
+                uc[i] = uc[i] / nrm
+        core = fold(uc, mode_core_norm, core.shape)
+    sparsity_error = 0                                                       # ntd.py:627-635
+    for index, sp in enumerate(sparsity):
+        if sp:
+            if index < len(factors):
+                sparsity_error += 2 * (sp * np.linalg.norm(factors[index], ord=1))
+            else:
+                sparsity_error += 2 * (sp * np.sum(np.abs(core)))
+    rec_error = norm_tensor ** 2 - 2 * np.sum(all_MtX * core) + np.sum(multi_mode_dot(core, all_MtM) * core)   # ntd.py:637
+    return core, factors, float((rec_error + sparsity_error) / (norm_tensor ** 2))                             # ntd.py:638
+
+
+def compute_ntd_hals(tensor, core_in, factors_in, n_iter_max=100, tol=1e-6, sparsity_coefficients=None,
+                     fixed_modes=(), normalize=None, mode_core_norm=None, stats=None):
+    """ntd.py:356-433 for update_rule='hals' (deterministic).  Returns (core, factors, costs)."""
+    core = core_in.copy()
+    factors = [f.copy() for f in factors_in]
+    norm_tensor = float(np.sqrt(np.sum(np.asarray(tensor, dtype=np.float64) ** 2)))      # ntd.py:361
+    costs = []
+    for it in range(n_iter_max):
+        core, factors, c = one_ntd_step_hals(tensor, core, factors, norm_tensor, sparsity_coefficients, fixed_modes,
+                                             normalize, mode_core_norm, stats=stats)
+        costs.append(c)
+        if it > 0 and abs(costs[-2] - costs[-1]) < tol:
+            break
+    return core, factors, costs

@@ -187,6 +187,17 @@ def ntd_cases():
         for i in range(3):
             out[f"sm_mu{beta}_F{i}"] = factors[i]
         out[f"sm_mu{beta}_costs"] = np.array(costs)
+    # HALS factor updates + projected-gradient core update (ntd.py:514-645), plain / sparse / core-normalised
+    for tag, kw in (("hals", dict(sparsity_coefficients=[None] * 4, normalize=[False] * 4)),
+                    ("hals_sp", dict(sparsity_coefficients=[0.05, None, 0.02, 0.01], normalize=[False] * 4)),
+                    ("hals_cn", dict(sparsity_coefficients=[None] * 4, normalize=[False, True, False, True], mode_core_norm=2))):
+        core, factors, costs, _ = ref_ntd.ntd(T, list(ranks), init="custom", core_0=G0, factors_0=[f.copy() for f in F0],
+                                              n_iter_max=8, tol=0, update_rule="hals", fixed_modes=[],
+                                              return_costs=True, deterministic=True, **kw)
+        out[f"sm_{tag}_G"] = core
+        for i in range(3):
+            out[f"sm_{tag}_F{i}"] = factors[i]
+        out[f"sm_{tag}_costs"] = np.array(costs)
     # core normalisation branch (ntd.py:676-681)
     core, factors, costs, _ = ref_ntd.ntd(T, list(ranks), init="custom", core_0=G0, factors_0=[f.copy() for f in F0],
                                           n_iter_max=5, tol=0, update_rule="mu", beta=1,
@@ -214,6 +225,13 @@ def ntd_cases():
         for i in range(3):
             out[f"fx_mu{beta}_F{i}"] = factors[i]
         out[f"fx_mu{beta}_costs"] = np.array(costs)
+    core, factors, costs, _ = ref_ntd.ntd(T, list(ranks), init="random", n_iter_max=10, tol=1e-8, update_rule="hals",
+                                          sparsity_coefficients=[None] * 4, fixed_modes=[], normalize=[False] * 4,
+                                          return_costs=True, deterministic=True, seed=0)   # tests/NTD_tests.py:138-155
+    out["fx_hals_G"] = core
+    for i in range(3):
+        out[f"fx_hals_F{i}"] = factors[i]
+    out["fx_hals_costs"] = np.array(costs)
     save("ntd", **out)
 
 

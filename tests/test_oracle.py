@@ -202,3 +202,30 @@ def test_ntd_mu_reference_golden_scalars(beta, golden):
     g = golden("ntd")
     np.testing.assert_allclose(costs, g[f"fx_mu{beta}_costs"], rtol=1e-9)
     np.testing.assert_allclose(core, g[f"fx_mu{beta}_G"], rtol=1e-8, atol=1e-11)
+
+
+# ---- NTD with HALS factor updates and the projected-gradient core update (ntd.py:514-645) ----
+@pytest.mark.parametrize("tag,kw", [("hals", {}),
+                                    ("hals_sp", {"sparsity_coefficients": [0.05, None, 0.02, 0.01]}),
+                                    ("hals_cn", {"normalize": [False, True, False, True], "mode_core_norm": 2})])
+def test_ntd_hals_small_matches_reference(tag, kw, golden):
+    g = golden("ntd")
+    F0 = [g["sm_F0_0"], g["sm_F0_1"], g["sm_F0_2"]]
+    core, factors, costs = orc.compute_ntd_hals(g["sm_T"], g["sm_G0"], F0, n_iter_max=8, tol=-1, **kw)
+    np.testing.assert_allclose(costs, g[f"sm_{tag}_costs"], rtol=1e-9)
+    np.testing.assert_allclose(core, g[f"sm_{tag}_G"], rtol=1e-8, atol=1e-12)
+    for i in range(3):
+        np.testing.assert_allclose(factors[i], g[f"sm_{tag}_F{i}"], rtol=1e-8, atol=1e-12)
+
+
+def test_ntd_hals_reference_golden_scalars(golden):
+    """/root/reference/tests/NTD_tests.py:138-155 (HALS, random init, seed 0) through the oracle."""
+    T, ranks = ntd_reference_fixture()
+    core0, fac0 = ntd_random_init(T, ranks, seed=0)
+    core, factors, costs = orc.compute_ntd_hals(T, core0, fac0, n_iter_max=10, tol=1e-8)
+    for got, ref in ((factors[0][0][0], 0.5501411956914489), (factors[1][0][0], 0.9680069293664532),
+                     (factors[2][0][0], 0.965086018254149), (core[0, 0, 0], 0.3744157888431357),
+                     (costs[0], 2.6164388105612055e-08), (costs[-1], 2.603936417799217e-08)):
+        assert round(float(got) - ref, 7) == 0
+    g = golden("ntd")
+    np.testing.assert_allclose(costs, g["fx_hals_costs"], rtol=1e-7)
