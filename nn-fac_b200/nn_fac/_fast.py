@@ -66,6 +66,26 @@ class Comm:
         lo = min(self.rank * chunk, length)
         return chunk, lo, min(lo + chunk, length)
 
+    def reduce_scatter_columns(self, M, tail, chunk):
+        """Sum over the ranks of M (r x length) and of `tail` (r x t), of which this rank only receives its own column slice
+        [rank*chunk, (rank+1)*chunk) of M (zero-padded) plus the whole summed tail: one reduce-scatter instead of an
+        all-reduce (half the bytes on the wire).  Returns (slice r x chunk, tail r x t)."""
+        r, length = M.shape
+        t = tail.shape[1]
+        if length == self.world * chunk:
+            send = torch.empty((self.world, r, chunk + t), dtype=M.dtype, device=M.device)
+            send[:, :, :chunk].copy_(M.view(r, self.world, chunk).permute(1, 0, 2))       # one strided copy
+        else:
+            send = torch.zeros((self.world, r, chunk + t), dtype=M.dtype, device=M.device)
+            for p in range(self.world):
+                lo, hi = min(p * chunk, length), min((p + 1) * chunk, length)
+                if hi > lo:
+                    send[p, :, :hi - lo].copy_(M[:, lo:hi])
+        send[:, :, chunk:].copy_(tail.unsqueeze(0).expand(self.world, r, t))
+        recv = torch.empty((r, chunk + t), dtype=M.dtype, device=M.device)
+        self.dist.reduce_scatter_tensor(recv, send.view(self.world * r, chunk + t), op=self.dist.ReduceOp.SUM, group=self.group)
+        return recv[:, :chunk], recv[:, chunk:]
+
     def gather_columns_(self, Ft, chunk, lo, hi):
         """Every rank owns columns [lo, hi) of Ft (r x length); afterwards every rank holds all of them."""
         if self.world == 1:
@@ -201,13 +221,20 @@ class FusedNMF:
             with self._phase("gram_U"):
                 if comm.world == 1:
                     VVt = VVt_join() if VVt_join is not None else eng.gram(V)      # nmf.py:407
-                else:
-                    # partial V_p X_p^T and V_p V_p^T of this column block, summed over the blocks
+                elif normalize[0]:
+                    # partial V_p X_p^T and V_p V_p^T of this column block, summed over the blocks (every rank needs all of
+                    # it: a normalised row of U^T spans every slice)
                     xb = self._xbuf
                     xb[:r * m].view(r, m).copy_(VMt)
                     eng.gram(V, out=xb[r * m:].view(r, r))
                     comm.sum_(xb)
                     VMt, VVt = xb[:r * m].view(r, m), xb[r * m:].view(r, r)
+                else:
+                    # the U solve is split by rows of U: this rank only needs its own columns of the summed V X^T (and the
+                    # summed Gram) -> reduce-scatter
+                    chunk, lo, hi = comm.slice_of(m)
+                    VMt_slice, VVt = comm.reduce_scatter_columns(VMt, eng.gram(V), chunk)
+                    VVt = VVt.contiguous()
             with self._phase("sweep_U"):
                 if (comm.world == 1 or normalize[0]) and hasattr(eng, "solve_install"):
                     Ut = eng.solve_install(0, VMt, VVt, Ut, r, sparsity[0], normalize[0], self.hals_stats[0])   # nmf.py:415
@@ -217,9 +244,8 @@ class FusedNMF:
                     eng.set_factor(0, Ut)
                 else:
                     Ut = Ut.clone()
-                    chunk, lo, hi = comm.slice_of(m)
                     if hi > lo:
-                        eng.sweep(VMt[:, lo:hi], VVt, Ut[:, lo:hi], r, sparsity[0], False, self.hals_stats[0])
+                        eng.sweep(VMt_slice[:, :hi - lo], VVt, Ut[:, lo:hi], r, sparsity[0], False, self.hals_stats[0])
                     comm.gather_columns_(Ut, chunk, lo, hi)
                     eng.set_factor(0, Ut)
         if 1 not in fixed_modes:
