@@ -32,7 +32,7 @@ MODE_RES, MODE_MU = 0, 1
 
 
 def eligible(dtype, rank, update_rule, beta):
-    return dtype == torch.float32 and rank <= 64 and (update_rule == "hals" or (update_rule == "mu" and beta == 1))
+    return dtype == torch.float32 and rank <= 64 and (update_rule == "hals" or (update_rule == "mu" and beta in (1, 2)))
 
 
 class Comm:
@@ -144,6 +144,11 @@ class CudaEngine:
         return ops.mu_apply(F, num, den_vec=den_vec, vec_per_row=True, gamma=1.0, floor=mu.epsilon)   # mu.py:88
 
     row_sums = staticmethod(ops.row_sums)
+    matmul = staticmethod(ops.matmul)
+
+    @staticmethod
+    def mu_apply_mat(F, num, den):
+        return ops.mu_apply(F, num, den_mat=den, gamma=1.0, floor=mu.epsilon)       # mu.py:89-91
 
     @staticmethod
     def max_col_abs_sum(F):
@@ -262,6 +267,25 @@ class FusedNMF:
                     eng.set_factor(1, V)
         return Ut, V
 
+    def _apply_mu2(self, VXt, fixed_modes, VVt_join):
+        """beta = 2 multiplicative update (mu.py:89-91): U <- U * (X V^T) / (U V V^T), V <- V * (U^T X) / (U^T U V).  The
+        denominators never need the model U V: they are small products with the Grams; the numerators are the two cross
+        products (first one fused with the cost of the previous iteration)."""
+        Ut, V, eng = self.Ut, self.V, self.eng
+        if 0 not in fixed_modes:
+            with self._phase("apply_U"):
+                den = eng.matmul(VVt_join(), Ut)                                   # (V V^T) U^T = (U V V^T)^T
+                Ut = eng.mu_apply_mat(Ut, VXt, den)
+                eng.set_factor(0, Ut)
+        if 1 not in fixed_modes:
+            with self._phase("pass_V"):
+                join = self._gram_async(1, Ut)
+                UtX = eng.cross(1, None)
+            with self._phase("apply_V"):
+                V = eng.mu_apply_mat(V, UtX, eng.matmul(join(), V))                # (U^T U) V
+                eng.set_factor(1, V)
+        return Ut, V
+
     def _apply_mu(self, numU, fixed_modes):
         r, m = self.r, self.m
         Ut, V, comm, eng = self.Ut, self.V, self.comm, self.eng
@@ -286,9 +310,12 @@ class FusedNMF:
         return Ut, V
 
     def run(self, n_iter_max, tol, update_rule, sparsity=(None, None), fixed_modes=(), normalize=(False, False),
-            verbose=False):
+            verbose=False, beta=None):
         """The reference's outer loop (nmf.py:298-324).  Returns (costs, toc)."""
-        mode = MODE_RES if update_rule == "hals" else MODE_MU
+        mu2 = update_rule == "mu" and beta == 2       # Frobenius MU: cross products + squared residual, like HALS
+        if mu2 and self.comm.world > 1:
+            raise NotImplementedError("the column-sharded path covers update_rule 'hals' and 'mu' with beta = 1")
+        mode = MODE_RES if (update_rule == "hals" or mu2) else MODE_MU
         sp = [0.0 if s is None else float(s) for s in sparsity]
         with_sparsity = update_rule == "hals" and (sp[0] != 0.0 or sp[1] != 0.0)
         if self.comm.world > 1 and update_rule == "hals" and normalize[1]:
@@ -316,7 +343,9 @@ class FusedNMF:
                     done.record()
             # launch iteration `it` before looking at the cost of iteration it-1
             if it < n_iter_max:
-                if mode == MODE_RES:
+                if mu2:
+                    new_Ut, new_V = self._apply_mu2(outA, fixed_modes, VVt_join)
+                elif mode == MODE_RES:
                     new_Ut, new_V = self._apply_hals(outA, sparsity, fixed_modes, normalize, VVt_join)
                 else:
                     new_Ut, new_V = self._apply_mu(outA, fixed_modes)
@@ -324,6 +353,8 @@ class FusedNMF:
                 if done is not None:
                     done.synchronize()
                 cost = float(self._host[0])
+                if mu2:
+                    cost *= 0.5                         # beta_divergence(., ., 2) = ||X - U V||^2 / 2 (beta_divergence.py:51-52)
                 if with_sparsity:
                     cost += 2 * (sp[0] * float(self._host[1]) + sp[1] * float(self._host[2]))
                 toc.append(time.time() - tic)
@@ -345,7 +376,7 @@ class FusedNMF:
                     break
             if it == n_iter_max:
                 break
-            if mode == MODE_RES:
+            if mode == MODE_RES and not mu2:
                 self.sweep_log.append(self.hals_stats[:, 3].clone())
             self.Ut, self.V = new_Ut, new_V
         return costs, toc

@@ -179,7 +179,8 @@ def compute_nmf(data, rank, U_in, V_in, n_iter_max=100, tol=1e-8,
         # fp32, rank <= 64: two X passes per iteration on tcgen05, cost fused with a lag of one pass
         _check_step_arguments(update_rule, beta, sparsity_coefficients)
         fast = _fast.FusedNMF(data, U_in, V_in)
-        cost_fct_vals, toc = fast.run(n_iter_max, tol, update_rule, sparsity_coefficients, fixed_modes, normalize, verbose)
+        cost_fct_vals, toc = fast.run(n_iter_max, tol, update_rule, sparsity_coefficients, fixed_modes, normalize, verbose,
+                                      beta=beta)
         U_dev, V_dev = fast.factors()
         U_out, V_out = _to_output(U_dev, data), _to_output(V_dev, data)
         if return_costs:

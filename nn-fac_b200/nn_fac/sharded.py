@@ -31,7 +31,7 @@ def compute_nmf_sharded(data_block, rank, U_in, V_block, n_iter_max=100, tol=1e-
     if group is None and torch.distributed.is_available() and torch.distributed.is_initialized():
         group = torch.distributed.group.WORLD
     state = _fast.FusedNMF(data_block, U_in, V_block, group=group)
-    costs, toc = state.run(n_iter_max, tol, update_rule, sparsity_coefficients, fixed_modes, normalize, verbose)
+    costs, toc = state.run(n_iter_max, tol, update_rule, sparsity_coefficients, fixed_modes, normalize, verbose, beta=beta)
     U_dev, V_dev = state.factors()
     as_out = (lambda t: t) if isinstance(data_block, torch.Tensor) else (lambda t: t.cpu().numpy())
     if return_costs:

@@ -87,6 +87,14 @@ class OracleEngine:
         return new
 
     @staticmethod
+    def mu_apply_mat(F, num, den):
+        return torch.clamp(F * (num / den), min=EPS)
+
+    @staticmethod
+    def matmul(A, B):
+        return A @ B
+
+    @staticmethod
     def row_sums(F):
         return F.sum(dim=1)
 
@@ -215,3 +223,14 @@ def test_two_ranks_hals_per_slice_stop_rule_close_to_reference(two_ranks):
     assert np.all(np.diff(costs) <= 1e-12)
     assert abs(costs[-1] - co[-1]) / co[-1] < 5e-2
     assert two_ranks[0]["cols"].tolist() == [0, 36] and two_ranks[1]["cols"].tolist() == [36, 72]
+
+
+def test_single_rank_mu_beta2_matches_oracle():
+    """The beta = 2 driver logic (cross products + Gram denominators, lagged cost / 2) on one CPU rank."""
+    from nn_fac import _fast
+    X, U0, V0 = problem()
+    st = _fast.FusedNMF(torch.from_numpy(X), torch.from_numpy(U0), torch.from_numpy(V0.copy()), group=_fast.Comm(None, align=8),
+                        engine=OracleEngine(X))
+    costs, _ = st.run(6, 0.0, "mu", [None, None], [], [False, False], beta=2)
+    _, _, ref, _ = orc.compute_nmf(X, U0, V0, n_iter_max=6, tol=0, update_rule="mu", beta=2)
+    np.testing.assert_allclose(costs, ref, rtol=1e-9)
