@@ -27,5 +27,5 @@ for t in f32:float f64:double; do
   done
 done
 for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
-"$NVCC" -shared -o "$LIB/libnnfac_b200.so" "$OBJ"/*.o -lcudart_static -ldl -lrt -lpthread
+"$NVCC" -Wno-deprecated-gpu-targets -shared -o "$LIB/libnnfac_b200.so" "$OBJ"/*.o -lcudart_static -ldl -lrt -lpthread
 echo "built $LIB/libnnfac_b200.so"

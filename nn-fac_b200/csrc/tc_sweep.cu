@@ -1,23 +1,25 @@
 // Tensor-core HALS sweep (fp32 path, rank <= 64): blocked Gauss-Seidel that reproduces the exact
 // row-by-row recurrence of nn_fac/update_rules/nnls.py:158-170.
 //
-// Formulation: the kernel keeps the (sparsity-shifted) residual  W = UtM - sp - UtU V  of every column
-// in a tensor-memory accumulator for the whole call and updates it incrementally.  For a block of 16
-// rows the step of row k is  d_k = max(W[k] / UtU[k,k], -V[k])  (nnls.py:163/167); inside the block the
-// rows see each other's steps through 120 FMAs per column whose Gram operands come from __constant__
+// Formulation: the kernel keeps the scaled, sparsity-shifted residual  W[k] = (UtM[k] - sp - UtU[k,:] V) / UtU[k,k]
+// of every column in a tensor-memory accumulator for the whole call and updates it incrementally.  For a block
+// of 16 rows the step of row k is  d_k = max(W[k], -V[k])  (nnls.py:163/167); inside the block the rows see each
+// other's steps through 120 FMAs per column whose operands (-UtU[k2,k] / UtU[k2,k2]) come from __constant__
 // memory (the same for every column); once the 16 steps of a block are known, ONE rank-16 update
-//        W[:, col] -= UtU[:, block] d[block]
-// runs on tcgen05 ([128 columns x 16] x [16 x 64] per column tile, 3-term bf16 splits of the steps and
-// of the Gram, 6 of the 9 partial products kept -> fp32-equivalent, accumulated into TMEM).  Because the
-// operand of the tensor core is the STEP (not V), rounding is relative to the step, and the accumulator
-// error is relative to the residual: more accurate than re-forming UtM - UtU V each time.
+//        W[:, col] -= (UtU / diag)[:, block] d[block]
+// runs on tcgen05 ([128 columns x 16] x [16 x 64] per column tile, accumulated into TMEM).  The initial residual
+// uses 3-term bf16 splits of V and of the Gram (6 of 9 products: fp32-equivalent).  In the loop the operand of the
+// tensor core is the STEP (not V), so rounding is relative to the step and the accumulator error relative to the
+// residual: two terms of the step against two of the Gram (3 products) suffice -- the solve stops once the steps have
+// shrunk by a factor 10 -- and the result is more accurate than re-forming UtM - UtU V each time.
 //
 // One thread owns one column of V.  The fp32 masters of V and the residual both live in tensor memory
 // (2 x 64 columns per 128-column tile); shared memory only holds the operand planes.  A CTA carries up
 // to 4 column tiles (512 update threads) plus one MMA-issuing warp per tile, so issuing never competes
 // with the update chain.  The per-sweep stop test (nnls.py:156) is an all-to-all exchange of the CTAs'
 // partial sums through tagged 64-bit mailboxes (one L2 hop, no atomics), summed in a fixed order so that
-// every CTA takes the same decision; block 0 of the next sweep runs speculatively meanwhile.
+// every CTA takes the same decision; the first three blocks of the next sweep run speculatively meanwhile.
+// The final write-out also produces the bf16 operand planes of the result for the NMF plan (optional).
 #include <type_traits>
 
 #include "common.cuh"
@@ -42,7 +44,6 @@ constexpr int NPLANES = 3;
 struct alignas(16) SweepConst {
   float nh[NBLK][BLK][BLK];     // [B][e][e2] = -UtU[k2][k] / UtU[k2][k2] (source row k = 16B+e, target row k2 = 16B+e2)
   float invd[RP];               // 1 / UtU[k][k], 0 when the diagonal entry is 0 or k >= r
-  float lbs[RP];                // -1 when the row is updated, 0 when it is skipped (nnls.py:160)
   int has_zero_diag;            // some row k < r has UtU[k][k] == 0
 };
 __constant__ SweepConst c_sw;
@@ -57,7 +58,6 @@ __global__ void sweep_prep_kernel(const float* __restrict__ G, int64_t ld_g, int
   for (int k = threadIdx.x; k < RP; k += blockDim.x) {
     const float d = k < r ? G[(int64_t)k * ld_g + k] : 0.f;
     out->invd[k] = d != 0.f ? 1.f / d : 0.f;
-    out->lbs[k] = d != 0.f ? -1.f : 0.f;
   }
   if (threadIdx.x == 0) {
     int z = 0;
