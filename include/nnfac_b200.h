@@ -163,13 +163,16 @@ int nnfac_nmf_plan_enable_f32(nnfac_nmf_plan* plan, void* workspace, size_t work
 /* which = 0: out (r x m) = F X^T with F = V (r x n)      -- VMt, nmf.py:408
  * which = 1: out (r x n) = F X   with F = U^T (r x m)    -- UtM, nmf.py:433
  * F and out are device fp32, row-major.  Deterministic.  F == NULL: use the factor installed in the plan
- * (nnfac_nmf_plan_set_factor / nnfac_nmf_plan_mu_finish), whose operand planes already exist. */
+ * (nnfac_nmf_plan_set_factor / nnfac_nmf_plan_mu_finish), whose operand planes already exist.  out == NULL: the split-K
+ * partials stay in the plan for nnfac_nmf_plan_hals_solve(UtM = NULL) or nnfac_nmf_plan_reduce. */
 int nnfac_nmf_plan_cross(nnfac_nmf_plan* plan, int which, const float* F, int64_t ldf, float* out,
                          int64_t ld_out, void* stream);
 /* MTTKRP operand (ntf.py:448-449): the Khatri-Rao product of two rank-major factors At (r x I), Bt (r x J), I*J == n,
  * written straight into the operand planes that nnfac_nmf_plan_cross(which = 0, F = NULL) reads. */
 int nnfac_nmf_plan_set_krao(nnfac_nmf_plan* plan, const float* At, int64_t lda, int64_t I, const float* Bt, int64_t ldb,
                             int64_t J, void* stream);
+/* out (r x R of `side`) = sum of the split-K partials of the last X pass over `side` run with out == NULL. */
+int nnfac_nmf_plan_reduce(nnfac_nmf_plan* plan, int side, float* out, int64_t ld_out, void* stream);
 /* Install a factor into the plan (builds all of its bf16 operand planes):
  * which = 0: U, passed as U^T (r x m, row-major); which = 1: V (r x n). */
 int nnfac_nmf_plan_set_factor(nnfac_nmf_plan* plan, int which, const float* Ft, int64_t ld, void* stream);
@@ -177,7 +180,8 @@ int nnfac_nmf_plan_set_factor(nnfac_nmf_plan* plan, int which, const float* Ft, 
  * result F_out (r x len, may not alias F_in) is installed in the plan by the sweep kernel itself (no separate pass over
  * the factor).  result: double[4] = {eps, cnt, -1, sweeps}.  Returns NNFAC_ERR_UNSUPPORTED without an error text when
  * the shape is outside the tensor-core sweep (rank > 64 or more than 512 columns per SM): use nnfac_hals_nnls +
- * nnfac_nmf_plan_set_factor then. */
+ * nnfac_nmf_plan_set_factor then.  UtM == NULL: the right-hand side is the sum of the split-K partials the last X pass
+ * over side `which` left in the plan (the solve adds them in the reduction kernel's order). */
 int nnfac_nmf_plan_hals_solve(nnfac_nmf_plan* plan, int which, const float* UtM, int64_t ld_utm, const float* UtU,
                               int64_t ld_utu, const float* F_in, int64_t ld_in, float* F_out, int64_t ld_out, int maxiter,
                               double delta, double sparsity, double* result, void* stream);

@@ -32,7 +32,7 @@ struct nnfac_sweep_planes {
 };
 int nnfac_tc_sweep_run(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const float* UtU, int64_t ld_utu, const float* Vin,
                        int64_t ld_vin, float* V, int64_t ld_v, int r, int64_t n, int maxiter, double delta, double sparsity,
-                       double* result, const nnfac_sweep_planes* planes, cudaStream_t st);
+                       double* result, const nnfac_sweep_planes* planes, cudaStream_t st, int nsplit, int64_t split_stride);
 int nnfac_ws_reserve(nnfac_ctx* ctx, size_t bytes, cudaStream_t st);
 
 #define NNFAC_CUDA(call)                                                                   \

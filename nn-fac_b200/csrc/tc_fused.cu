@@ -534,16 +534,35 @@ int nnfac_nmf_plan_set_factor(nnfac_nmf_plan* p, int which, const float* Ft, int
 int nnfac_nmf_plan_hals_solve(nnfac_nmf_plan* p, int which, const float* UtM, int64_t ld_utm, const float* UtU, int64_t ld_utu,
                               const float* F_in, int64_t ld_in, float* F_out, int64_t ld_out, int maxiter, double delta,
                               double sparsity, double* result, void* stream) {
-  NNFAC_ARG(p && UtM && UtU && F_in && F_out && result && (which == 0 || which == 1), "nnfac_nmf_plan_hals_solve: bad argument");
+  NNFAC_ARG(p && UtU && F_in && F_out && result && (which == 0 || which == 1), "nnfac_nmf_plan_hals_solve: bad argument");
   const int64_t len = which == 0 ? p->m : p->n;
-  NNFAC_ARG(ld_utm >= len && ld_in >= len && ld_out >= len && ld_utu >= p->r, "nnfac_nmf_plan_hals_solve: leading dimension too small");
+  NNFAC_ARG((!UtM || ld_utm >= len) && ld_in >= len && ld_out >= len && ld_utu >= p->r, "nnfac_nmf_plan_hals_solve: leading dimension too small");
+  // UtM == NULL: the right-hand side is what the last X pass over side `which` left in the plan as split-K partials
+  // (nnfac_nmf_plan_fused / _cross with out = NULL); the solve adds them up itself, in the order of the reduction kernel
+  int nsplit = 1;
+  int64_t split_stride = 0;
+  if (!UtM) {
+    const CrossParams& cp = p->side[which].cp;
+    UtM = p->partial; ld_utm = cp.ld_partial; nsplit = cp.splits; split_stride = (int64_t)p->r_pad * cp.ld_partial;
+  }
   Side* cs = &p->side[which == 0 ? 1 : 0];
   nnfac_sweep_planes pl;
   pl.fh = cs->fh; pl.fl = cs->fl; pl.ld_plane = cs->ld; pl.r_pad = p->r_pad;
   pl.rowh = p->fused_ok ? p->rowp_h[which] : nullptr;
   pl.rowl = p->fused_ok ? p->rowp_l[which] : nullptr;
   return nnfac_tc_sweep_run(p->ctx, UtM, ld_utm, UtU, ld_utu, F_in, ld_in, F_out, ld_out, p->r, len, maxiter, delta, sparsity,
-                            result, &pl, (cudaStream_t)stream);
+                            result, &pl, (cudaStream_t)stream, nsplit, split_stride);
+}
+
+// Sum the split-K partials the last X pass over `side` left in the plan into out (r x R): what nnfac_nmf_plan_fused /
+// _cross do themselves when they are given an output.
+int nnfac_nmf_plan_reduce(nnfac_nmf_plan* p, int side, float* out, int64_t ld_out, void* stream) {
+  NNFAC_ARG(p && out && (side == 0 || side == 1), "nnfac_nmf_plan_reduce: bad argument");
+  Side* s = &p->side[side];
+  NNFAC_ARG(ld_out >= s->R, "nnfac_nmf_plan_reduce: leading dimension too small");
+  nnfac_reduce_partials(p->partial, s->cp.splits, p->r, p->r_pad, s->R, s->cp.ld_partial, out, ld_out, p->ctx->sm_count, (cudaStream_t)stream);
+  NNFAC_LAUNCH_CHECK(p->ctx);
+  return NNFAC_OK;
 }
 
 // beta = 1 multiplicative update of factor `which` from the numerator partials the last fused pass over side `which`

@@ -457,9 +457,9 @@ int nnfac_nmf_plan_load_x(nnfac_nmf_plan* p, const float* X, int64_t ldx, void* 
 
 int nnfac_nmf_plan_cross(nnfac_nmf_plan* p, int which, const float* F, int64_t ldf, float* out, int64_t ld_out,
                          void* stream) {
-  NNFAC_ARG(p && out && (which == 0 || which == 1), "nnfac_nmf_plan_cross: bad argument");
+  NNFAC_ARG(p && (which == 0 || which == 1), "nnfac_nmf_plan_cross: bad argument");
   Side* s = &p->side[which];
-  NNFAC_ARG((!F || ldf >= s->C) && ld_out >= s->R, "nnfac_nmf_plan_cross: leading dimension too small");
+  NNFAC_ARG((!F || ldf >= s->C) && (!out || ld_out >= s->R), "nnfac_nmf_plan_cross: leading dimension too small");
   cudaStream_t st = (cudaStream_t)stream;
   int grid;
   if (F) {   // F == NULL: the operand planes of the factor installed by nnfac_nmf_plan_set_factor / _mu_finish are current
@@ -475,6 +475,7 @@ int nnfac_nmf_plan_cross(nnfac_nmf_plan* p, int which, const float* F, int64_t l
   else
     tc_cross_kernel<128><<<s->grid, NTHREADS, s->smem, st>>>(s->map_xh, s->map_xl, s->map_fh, s->map_fl, cp);
   NNFAC_LAUNCH_CHECK(p->ctx);
+  if (!out) return NNFAC_OK;     // the split-K partials stay in the plan (nnfac_nmf_plan_hals_solve / _reduce)
   const int64_t tot2 = (int64_t)p->r * s->R;
   grid = (int)(ceil_div64(tot2, 256) < (int64_t)p->ctx->sm_count * 8 ? ceil_div64(tot2, 256) : (int64_t)p->ctx->sm_count * 8);
   reduce_partials_kernel<<<grid, 256, 0, st>>>(p->partial, cp.splits, p->r, p->r_pad, s->R, cp.ld_partial, out, ld_out);

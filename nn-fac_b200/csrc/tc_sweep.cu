@@ -72,6 +72,8 @@ struct TcSweepArgs {
   const float* Vin; // r x n start values (may alias V)
   float* V;         // r x n result
   int64_t ld_b, ld_g, ld_v, ld_vin, n;
+  int nsplit;              // UtM = sum of nsplit slabs b + s * split_stride (split-K partials of an X pass), summed in order
+  int64_t split_stride;
   // optional: bf16 hi/lo operand planes of the result for the NMF plan (nnfac_nmf_plan_hals_solve)
   bf16 *fh, *fl;    // [r_pad x ld_plane], K-major (rank rows)
   bf16 *rowh, *rowl;// [n x 64], rank contiguous (may be NULL)
@@ -292,7 +294,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
         store_chunk(vh, row, c0 / 8 + 1, &x[8], PLANE_BYTES);
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          w[j] = __float_as_uint((valid && c0 + j < r) ? (a.b[(int64_t)(c0 + j) * a.ld_b + col] - a.sp) * c_sw.invd[c0 + j] : 0.f);
+        {
+          float bv = 0.f;
+          if (valid && c0 + j < r)
+            for (int sp = 0; sp < a.nsplit; ++sp) bv += a.b[(int64_t)sp * a.split_stride + (int64_t)(c0 + j) * a.ld_b + col];   // fixed order
+          w[j] = __float_as_uint((valid && c0 + j < r) ? (bv - a.sp) * c_sw.invd[c0 + j] : 0.f);
+        }
         tmem_st16(t_w + c0, w);
       }
       tmem_st_wait();
@@ -558,7 +565,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
 // of the result (see TcSweepArgs); Vin may alias V.
 int nnfac_tc_sweep_run(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const float* UtU, int64_t ld_utu, const float* Vin,
                        int64_t ld_vin, float* V, int64_t ld_v, int r, int64_t n, int maxiter, double delta, double sparsity,
-                       double* result, const nnfac_sweep_planes* planes, cudaStream_t st) {
+                       double* result, const nnfac_sweep_planes* planes, cudaStream_t st, int nsplit, int64_t split_stride) {
   if (r > RP || maxiter < 1) return NNFAC_ERR_UNSUPPORTED;
   int64_t cols = ceil_div64(n, ctx->sm_count);
   cols = ceil_div64(cols, 32) * 32;
@@ -574,6 +581,7 @@ int nnfac_tc_sweep_run(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const f
   TcSweepArgs a;
   a.b = UtM; a.G = UtU; a.Vin = Vin; a.V = V; a.ld_b = ld_utm; a.ld_g = ld_utu; a.ld_v = ld_v; a.ld_vin = ld_vin; a.n = n;
   a.r = r; a.maxiter = maxiter; a.cols_per_cta = (int)cols; a.delta = delta; a.sp = (float)sparsity;
+  a.nsplit = nsplit > 0 ? nsplit : 1; a.split_stride = split_stride;
   a.fh = a.fl = a.rowh = a.rowl = nullptr; a.ld_plane = 0; a.r_pad = 0;
   if (planes) {
     a.fh = (bf16*)planes->fh; a.fl = (bf16*)planes->fl; a.rowh = (bf16*)planes->rowh; a.rowl = (bf16*)planes->rowl;
@@ -597,5 +605,5 @@ int nnfac_tc_sweep_run(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const f
 int nnfac_tc_sweep_try(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const float* UtU, int64_t ld_utu, float* V,
                        int64_t ld_v, int r, int64_t n, int maxiter, double delta, double sparsity, double* result,
                        cudaStream_t st) {
-  return nnfac_tc_sweep_run(ctx, UtM, ld_utm, UtU, ld_utu, V, ld_v, V, ld_v, r, n, maxiter, delta, sparsity, result, nullptr, st);
+  return nnfac_tc_sweep_run(ctx, UtM, ld_utm, UtU, ld_utu, V, ld_v, V, ld_v, r, n, maxiter, delta, sparsity, result, nullptr, st, 1, 0);
 }

@@ -116,8 +116,8 @@ class CudaEngine:
         plus the installation of the new factor: one kernel."""
         return self.plan.mu_finish(which, F, den_vec, mu.epsilon)
 
-    def cross(self, which, F):
-        return self.plan.cross(which, F)
+    def cross(self, which, F, keep_partials=False):
+        return self.plan.cross(which, F, keep_partials=keep_partials)
 
     gram = staticmethod(ops.gram)                      # F (r x len) -> F F^T (nmf.py:407 / :432)
 
@@ -126,9 +126,11 @@ class CudaEngine:
         tensor-core sweep covers the case (it writes the operand planes itself), else solve on a copy + set_factor."""
         sp = 0.0 if sparsity is None else float(sparsity)
         if not normalize and type(self).sweep is CudaEngine.sweep:
-            new = self.plan.hals_solve(which, UtM, UtU, F, 100, 0.01, sp, result)
+            new = self.plan.hals_solve(which, UtM, UtU, F, 100, 0.01, sp, result)   # UtM None: the plan's split-K partials
             if new is not None:
                 return new
+        if UtM is None:
+            UtM = self.plan.reduce(which)
         new = F.clone()
         self.sweep(UtM, UtU, new, r, sparsity, normalize, result)
         self.set_factor(which, new)
@@ -195,6 +197,7 @@ class FusedNMF:
         # Grams of the single-GPU HALS path are computed on a side stream, under the X pass that precedes their use
         self._side = torch.cuda.Stream(self.device) if self._on_gpu else None
         self._gram = [torch.empty((self.r, self.r), dtype=self.Ut.dtype, device=self.device) for _ in range(2)]
+        self._rsum = [torch.empty(self.r, dtype=self.Ut.dtype, device=self.device) for _ in range(2)]
         # exchange buffer of the U side: [cross product or numerator (r x m) | Gram (r x r) or row sums (r)]
         self._xbuf = torch.empty(self.r * self.m + self.r * self.r, dtype=self.Ut.dtype, device=self.device)
 
@@ -216,6 +219,21 @@ class FusedNMF:
         def join():
             main.wait_stream(self._side)
             return self._gram[which]
+        return join
+
+    def _row_sums_async(self, which, F):
+        """Row sums of F (mu.py:85-87 denominators) into self._rsum[which] on the side stream, under the X pass that
+        precedes their use; returns the join like _gram_async."""
+        if self._side is None:
+            return lambda: self.eng.row_sums(F)
+        main = torch.cuda.current_stream(self.device)
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            self.eng.row_sums(F, out=self._rsum[which])
+
+        def join():
+            main.wait_stream(self._side)
+            return self._rsum[which]
         return join
 
     # one outer iteration, given the result of its first pass
@@ -286,12 +304,12 @@ class FusedNMF:
                 eng.set_factor(1, V)
         return Ut, V
 
-    def _apply_mu(self, numU, fixed_modes):
+    def _apply_mu(self, numU, fixed_modes, den_join=None):
         r, m = self.r, self.m
         Ut, V, comm, eng = self.Ut, self.V, self.comm, self.eng
         if 0 not in fixed_modes:
             with self._phase("apply_U"):
-                den = eng.row_sums(V)                                              # mu.py:85-87
+                den = den_join() if den_join is not None else eng.row_sums(V)      # mu.py:85-87
                 if comm.world > 1:
                     xb = self._xbuf[:r * m + r]
                     xb[:r * m].view(r, m).copy_(numU)
@@ -304,9 +322,10 @@ class FusedNMF:
                     Ut = eng.mu_finish(0, Ut, den)                                 # mu.py:84-88 + planes, one kernel
         if 1 not in fixed_modes:
             with self._phase("pass_V"):
+                join = self._row_sums_async(1, Ut) if comm.world == 1 else None    # column sums of U under the X pass
                 eng.fused(1, MODE_MU, False, keep_partials=True)
             with self._phase("apply_V"):
-                V = eng.mu_finish(1, V, eng.row_sums(Ut))                          # mu.py:27
+                V = eng.mu_finish(1, V, join() if join is not None else eng.row_sums(Ut))   # mu.py:27
         return Ut, V
 
     def run(self, n_iter_max, tol, update_rule, sparsity=(None, None), fixed_modes=(), normalize=(False, False),
@@ -324,11 +343,15 @@ class FusedNMF:
         tic = time.time()
         done = torch.cuda.Event() if self._on_gpu else None
         for it in range(n_iter_max + 1):
-            VVt_join = None
+            VVt_join = den_join = None
             if mode == MODE_RES and self.comm.world == 1 and it < n_iter_max and 0 not in fixed_modes:
                 VVt_join = self._gram_async(0, self.V)                             # V V^T under the first pass
+            if mode == MODE_MU and self.comm.world == 1 and it < n_iter_max and 0 not in fixed_modes:
+                den_join = self._row_sums_async(0, self.V)                         # row sums of V under the first pass
             with self._phase("pass_U"):
-                # single GPU, MU: the numerator stays in the plan as split partials and is consumed by mu_finish
+                # single GPU, MU: the numerator stays in the plan as split partials and is consumed by mu_finish.  (The
+                # HALS solve can add the partials itself too -- nnfac_nmf_plan_hals_solve(UtM = NULL) -- but its 640-thread
+                # prologue does that slower than the grid-wide reduction kernel: measured +0.07 ms per solve, not used.)
                 keep = mode == MODE_MU and self.comm.world == 1 and it < n_iter_max and 0 not in fixed_modes
                 # the cost lands directly in the scalar block that travels to the host
                 outA, _ = self.eng.fused(0, mode, True, keep_partials=keep, cost_out=self._dev_scal[0:1])
@@ -348,7 +371,7 @@ class FusedNMF:
                 elif mode == MODE_RES:
                     new_Ut, new_V = self._apply_hals(outA, sparsity, fixed_modes, normalize, VVt_join)
                 else:
-                    new_Ut, new_V = self._apply_mu(outA, fixed_modes)
+                    new_Ut, new_V = self._apply_mu(outA, fixed_modes, den_join)
             if it > 0:
                 if done is not None:
                     done.synchronize()

@@ -54,6 +54,7 @@ SIGNATURES = {
     "nnfac_nmf_plan_enable_f32": [_P, _P, _c.c_size_t, _P],
     "nnfac_nmf_plan_cross": [_P, _INT, _P, _I64, _P, _I64, _P],
     "nnfac_nmf_plan_set_factor": [_P, _INT, _P, _I64, _P],
+    "nnfac_nmf_plan_reduce": [_P, _INT, _P, _I64, _P],
     "nnfac_nmf_plan_set_krao": [_P, _P, _I64, _I64, _P, _I64, _I64, _P],
     "nnfac_nmf_plan_hals_solve": [_P, _INT, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _INT, _DBL, _DBL, _P, _P],
     "nnfac_nmf_plan_fused": [_P, _INT, _INT, _INT, _P, _I64, _P, _P],

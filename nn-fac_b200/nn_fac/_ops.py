@@ -114,9 +114,10 @@ def dot(A, B, out=None):
     return out
 
 
-def row_sums(A):
+def row_sums(A, out=None):
     rows, cols = A.shape
-    out = torch.empty(rows, dtype=A.dtype, device=A.device)
+    if out is None:
+        out = torch.empty(rows, dtype=A.dtype, device=A.device)
     L.check(_lib().nnfac_row_sums(L.ctx(A.device), L.code_of(A.dtype), L.ptr(A), A.stride(0), rows, cols, L.ptr(out),
                                   L.stream_ptr()))
     return out
@@ -284,13 +285,21 @@ class NMFPlan:
             ingested[b].record(main)
         L.check(_lib().nnfac_nmf_plan_load_x_done(self.handle, L.stream_ptr()))
 
-    def cross(self, which, F, out=None):
+    def reduce(self, side):
+        """Sum of the split-K partials the last pass over `side` left in the plan (r x rows of that side)."""
+        R = self.m if side == 0 else self.n
+        out = torch.empty((self.r, R), dtype=torch.float32, device=self.device)
+        L.check(_lib().nnfac_nmf_plan_reduce(self.handle, side, L.ptr(out), out.stride(0), L.stream_ptr()))
+        return out
+
+    def cross(self, which, F, out=None, keep_partials=False):
         """which=0: F = V (r x n) -> V X^T (r x m); which=1: F = U^T (r x m) -> U^T X (r x n).
         F=None: the factor installed with set_factor / mu_finish (its operand planes are reused)."""
         R = self.m if which == 0 else self.n
-        if out is None:
+        if out is None and not keep_partials:
             out = torch.empty((self.r, R), dtype=torch.float32, device=self.device)
-        L.check(_lib().nnfac_nmf_plan_cross(self.handle, which, L.ptr(F), F.stride(0) if F is not None else 0, L.ptr(out), out.stride(0),
+        L.check(_lib().nnfac_nmf_plan_cross(self.handle, which, L.ptr(F), F.stride(0) if F is not None else 0, L.ptr(out),
+                                            out.stride(0) if out is not None else 0,
                                             L.stream_ptr()))
         return out
 
@@ -307,7 +316,8 @@ class NMFPlan:
         """hals_nnls_acc(UtM, UtU, F) on the tensor-core sweep with the result installed in the plan by the same kernel.
         Returns the new factor (r x len), or None when the shape is outside that kernel (caller: hals_nnls + set_factor)."""
         out = torch.empty_like(F)
-        rc = _lib().nnfac_nmf_plan_hals_solve(self.handle, which, L.ptr(UtM), UtM.stride(0), L.ptr(UtU), UtU.stride(0), L.ptr(F),
+        rc = _lib().nnfac_nmf_plan_hals_solve(self.handle, which, L.ptr(UtM), UtM.stride(0) if UtM is not None else 0, L.ptr(UtU),
+                                              UtU.stride(0), L.ptr(F),
                                               F.stride(0), L.ptr(out), out.stride(0), int(maxiter), float(delta), float(sparsity),
                                               L.ptr(result), L.stream_ptr())
         if rc == L.ERR_UNSUPPORTED:

@@ -270,3 +270,62 @@ def test_ntd_mu_fp32_objective(beta, monkeypatch):
         res[flag] = costs
         assert abs(costs[-1] - ref[-1]) <= 1e-4 * abs(ref[-1])
     np.testing.assert_allclose(res["1"], res["0"], rtol=1e-4)
+
+
+def test_solve_from_split_partials_equals_solve_from_reduced_rhs():
+    """nnfac_nmf_plan_hals_solve(UtM = NULL) adds the split-K partials of the last X pass in the reduction kernel's
+    order: bit-identical to reducing first; nnfac_nmf_plan_reduce returns that reduced right-hand side."""
+    import torch
+    from nn_fac import _ops as ops
+    rng = np.random.RandomState(31)
+    m, n, r = 6000, 4096, 40
+    X = torch.from_numpy((rng.rand(m, r) @ rng.rand(r, n) + 0.3 * rng.rand(m, n)).astype(np.float32)).cuda()
+    Ut = torch.from_numpy(rng.rand(r, m).astype(np.float32)).cuda()
+    V = torch.from_numpy(rng.rand(r, n).astype(np.float32)).cuda()
+    plan = ops.NMFPlan(X).bind_rank(r)
+    plan.set_factor(0, Ut)
+    plan.set_factor(1, V)
+    G = ops.gram(V)
+    res = torch.zeros(4, dtype=torch.float64, device="cuda")
+    rhs, _ = plan.fused(0, 0)                                    # reduced V X^T
+    a = plan.hals_solve(0, rhs, G, Ut, 100, 0.01, 0.0, res)
+    sweeps_a = res.clone()
+    plan.set_factor(0, Ut)                                       # the solve installed its result: put U back
+    plan.fused(0, 0, keep_partials=True)                         # partials stay in the plan
+    assert torch.equal(plan.reduce(0), rhs)
+    b = plan.hals_solve(0, None, G, Ut, 100, 0.01, 0.0, res)
+    assert a is not None and b is not None
+    assert torch.equal(a, b) and torch.equal(res, sweeps_a)
+    # second side through the plain cross product
+    plan.set_factor(0, Ut)
+    rhs1 = plan.cross(1, None)
+    plan.cross(1, None, keep_partials=True)
+    assert torch.equal(plan.reduce(1), rhs1)
+
+
+def test_core_pg_step_state_machine():
+    """ntd.py:607-617 on the device: min(step * gradient, core) update, ||delta|| stop test, no-op once done."""
+    import torch
+    from nn_fac import _ops as ops
+    rng = np.random.RandomState(5)
+    for dt in (torch.float64, torch.float32):
+        core = torch.from_numpy(rng.rand(6, 5, 4)).to(dt).cuda()
+        MtX = torch.from_numpy(rng.rand(6, 5, 4)).to(dt).cuda()
+        P = torch.from_numpy(rng.rand(6, 5, 4)).to(dt).cuda()
+        c = core.double().cpu().numpy().copy()
+        g = -MtX.double().cpu().numpy() + P.double().cpu().numpy() + 0.01
+        state = torch.tensor([0.0, 1.0, 1.0, 0.0], dtype=torch.float64, device="cuda")
+        ops.core_pg_step(core, MtX, P, 0.3, 0.01, 0.01, state)
+        d = np.minimum(0.3 * g, c)
+        tol = dict(rtol=1e-12) if dt == torch.float64 else dict(rtol=2e-6, atol=1e-7)
+        np.testing.assert_allclose(core.double().cpu().numpy(), c - d, **tol)
+        st = state.cpu().numpy()
+        np.testing.assert_allclose(st[0], np.sqrt((d ** 2).sum()), rtol=1e-6)
+        assert st[2] == 2.0 and st[3] == 0.0 and st[0] == st[1]
+        # a vanishing second step ends the loop; further calls leave the core alone
+        Pz = MtX - 0.01
+        ops.core_pg_step(core, MtX, Pz, 0.3, 0.01, 0.01, state)          # gradient = 0 -> upd = 0 < delta * upd_0
+        assert state[3].item() == 1.0
+        before = core.clone()
+        ops.core_pg_step(core, MtX, P, 0.3, 0.01, 0.01, state)
+        assert torch.equal(core, before)

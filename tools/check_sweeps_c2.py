@@ -19,6 +19,8 @@ orig = _fast.CudaEngine.solve_install
 
 
 def solve_install(self, which, UtM, UtU, F, r_, sparsity, normalize, result):
+    if UtM is None:
+        UtM = self.plan.reduce(which)
     V64 = F.double()
     res64 = ops.hals_nnls(UtM.double().contiguous(), UtU.double().contiguous(), V64, r_, 100, 0.01, 0.0, False, False)
     new = orig(self, which, UtM, UtU, F, r_, sparsity, normalize, result)
