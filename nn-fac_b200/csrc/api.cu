@@ -56,8 +56,9 @@ int nnfac_ctx_create(int device, nnfac_ctx** out) {
   NNFAC_CUDA(cudaMalloc(&c->sync, 64 * sizeof(unsigned)));
   NNFAC_CUDA(cudaMemset(c->sync, 0, 64 * sizeof(unsigned)));
   c->mail_count = (size_t)1 << 18;
-  NNFAC_CUDA(cudaMalloc(&c->mail, c->mail_count * sizeof(unsigned long long)));
-  NNFAC_CUDA(cudaMemset(c->mail, 0, c->mail_count * sizeof(unsigned long long)));
+  // one extra word behind the mailboxes holds the call generation (advanced on the device, see csrc/tc_sweep.cu)
+  NNFAC_CUDA(cudaMalloc(&c->mail, (c->mail_count + 1) * sizeof(unsigned long long)));
+  NNFAC_CUDA(cudaMemset(c->mail, 0, (c->mail_count + 1) * sizeof(unsigned long long)));
   c->ws_bytes = (size_t)64 << 20;
   NNFAC_CUDA(cudaMalloc(&c->ws, c->ws_bytes));
   *out = c;

@@ -16,9 +16,8 @@ struct nnfac_ctx {
   double* red;      // small scratch for two-stage reductions / sweep barrier partials
   size_t red_count;
   unsigned* sync;   // grid-barrier counters (zeroed before each cooperative launch)
-  unsigned long long* mail;   // tagged mailboxes of the tensor-core HALS sweep (zeroed once; tags carry a call generation)
-  size_t mail_count;
-  unsigned sweep_gen;
+  unsigned long long* mail;   // tagged mailboxes of the tensor-core HALS sweep (zeroed once; tags carry a call generation
+  size_t mail_count;          // that lives in device memory, in the word behind the last mailbox: mail[mail_count])
 };
 
 void nnfac_set_error(const char* fmt, ...);

@@ -48,7 +48,20 @@ struct alignas(16) SweepConst {
 };
 __constant__ SweepConst c_sw;
 
-__global__ void sweep_prep_kernel(const float* __restrict__ G, int64_t ld_g, int r, SweepConst* out) {
+// Per-call preparation (one block): the constants of the in-block recurrence, and the call generation of the mailbox
+// tags.  The generation lives in device memory and is advanced HERE, not on the host, so that a solve captured into a
+// CUDA graph gets a fresh generation on every replay (a host-side counter would be frozen into the graph and the tags
+// of the previous replay would match).  When the 16-bit generation wraps, the mailboxes are cleared first.
+__global__ void sweep_prep_kernel(const float* __restrict__ G, int64_t ld_g, int r, SweepConst* out, unsigned* gen,
+                                  unsigned long long* mail, size_t mail_count) {
+  __shared__ unsigned next_gen;
+  if (threadIdx.x == 0) next_gen = (*gen + 1u) & 0xffffu;
+  __syncthreads();
+  if (next_gen == 0u) {
+    for (size_t i = threadIdx.x; i < mail_count; i += blockDim.x) mail[i] = 0ull;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *gen = next_gen == 0u ? 1u : next_gen;
   for (int idx = threadIdx.x; idx < NBLK * BLK * BLK; idx += blockDim.x) {
     const int B = idx / (BLK * BLK), e = (idx / BLK) % BLK, e2 = idx % BLK;
     const int k = B * BLK + e, k2 = B * BLK + e2;
@@ -83,7 +96,8 @@ struct TcSweepArgs {
   double delta;
   float sp;
   unsigned long long* mail;   // [2][grid][grid] tagged partial sums (tag = generation << 16 | sweep)
-  unsigned gen;               // call generation: stale mailbox contents of earlier calls never match
+  const unsigned* gen;        // call generation (device word, advanced by sweep_prep_kernel): stale mailbox contents of
+                              // earlier calls never match
   double* result;
 };
 
@@ -384,6 +398,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
     int cnt = 1;
     unsigned epoch = 0;
     const unsigned nb = gridDim.x;
+    const unsigned gen = *a.gen;
     // Stop test of nnls.py:156: it needs the sum of squared steps over ALL columns after every sweep.  Every CTA posts
     // its partial into the mailbox of every CTA (one 64-bit store each, tag | value) and adds the partials it receives
     // in a fixed order, so that all CTAs obtain the same bits and take the same decision.  While the partials travel,
@@ -406,7 +421,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
       const float t = warp_sum_f(nd);
       if (lane == 0) redf[warp] = t;
       named_bar_sync(1, UPD_THREADS);
-      const unsigned tag = (a.gen << 16) | (epoch + 1u);
+      const unsigned tag = (gen << 16) | (epoch + 1u);
       if (nb > 1 && threadIdx.x < nb) {
         float sum = 0.f;
 #pragma unroll
@@ -576,7 +591,8 @@ int nnfac_tc_sweep_run(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const f
   // invalidated at kernel boundaries, and the stream orders it before the sweep)
   static SweepConst* c_sw_dev = nullptr;
   if (!c_sw_dev) NNFAC_CUDA(cudaGetSymbolAddress((void**)&c_sw_dev, c_sw));
-  sweep_prep_kernel<<<1, 256, 0, st>>>(UtU, ld_utu, r, c_sw_dev);
+  unsigned* gen_dev = reinterpret_cast<unsigned*>(ctx->mail + ctx->mail_count);
+  sweep_prep_kernel<<<1, 256, 0, st>>>(UtU, ld_utu, r, c_sw_dev, gen_dev, ctx->mail, ctx->mail_count);
   NNFAC_LAUNCH_CHECK(ctx);
   TcSweepArgs a;
   a.b = UtM; a.G = UtU; a.Vin = Vin; a.V = V; a.ld_b = ld_utm; a.ld_g = ld_utu; a.ld_v = ld_v; a.ld_vin = ld_vin; a.n = n;
@@ -587,13 +603,8 @@ int nnfac_tc_sweep_run(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const f
     a.fh = (bf16*)planes->fh; a.fl = (bf16*)planes->fl; a.rowh = (bf16*)planes->rowh; a.rowl = (bf16*)planes->rowl;
     a.ld_plane = planes->ld_plane; a.r_pad = planes->r_pad;
   }
-  // mailbox tags carry a call generation, so that the slots never need clearing between calls
-  ctx->sweep_gen = (ctx->sweep_gen + 1) & 0xffffu;
-  if (ctx->sweep_gen == 0) {
-    NNFAC_CUDA(cudaMemsetAsync(ctx->mail, 0, ctx->mail_count * sizeof(unsigned long long), st));
-    ctx->sweep_gen = 1;
-  }
-  a.mail = ctx->mail; a.gen = ctx->sweep_gen; a.result = result;
+  // mailbox tags carry a call generation (device-side, see sweep_prep_kernel), so that the slots never need clearing
+  a.mail = ctx->mail; a.gen = gen_dev; a.result = result;
   const size_t smem = NPLANES * G_PLANE_BYTES + (size_t)MAX_TILES * NPLANES * PLANE_BYTES + 512;
   NNFAC_CUDA(cudaFuncSetAttribute(tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* params[] = {&a};

@@ -1,0 +1,42 @@
+"""One outer iteration captured into a CUDA graph and replayed (tensor models: NTD, NTF).
+
+An outer iteration of NTD / NTF on an L2-resident tensor is 40-70 small launches: the device finishes them faster
+than the host can enqueue them ("bound by launch latency -> CUDA-graph it").  The graph reads
+the model state (core / factors) from fixed buffers, parks the state it started from in `prev` (the outer loops drop a
+speculative iteration when the reference's stop test fires, ntd.py:421 / ntf.py:337) and writes the new state back into
+the same buffers, so that every replay is one more iteration.  Capture executes nothing: the caller must have run one
+iteration eagerly before (lazy initialisation, workspace growth) -- the outer loops capture at their second iteration.
+Everything captured is this library's own kernels plus torch copies; the HALS solve is capturable because its mailbox
+generation lives in device memory (csrc/tc_sweep.cu, sweep_prep_kernel).
+"""
+import torch
+
+
+class GraphedIteration:
+    def __init__(self, device, get_state, set_state, step):
+        """get_state() -> list of tensors; set_state(list) installs tensors of the same shapes as the state;
+        step() runs one iteration on the installed state and returns a device vector (the cost terms)."""
+        self._set = set_state
+        self.state = [t.clone() for t in get_state()]
+        self.prev = [torch.empty_like(t) for t in self.state]
+        self.graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize(device)
+        with torch.cuda.graph(self.graph):
+            for d, s in zip(self.prev, self.state):
+                d.copy_(s)
+            set_state(list(self.state))
+            out = step()
+            self.out = out.reshape(-1).to(torch.float64).clone()
+            for d, s in zip(self.state, get_state()):
+                d.copy_(s)
+        set_state(list(self.state))
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
+
+    def roll_back(self):
+        """Undo the last replay."""
+        for d, s in zip(self.state, self.prev):
+            d.copy_(s)
+        self._set(list(self.state))

@@ -16,6 +16,7 @@ import nn_fac.update_rules.mu as mu
 import nn_fac.utils.errors as err
 import nn_fac.utils.initialize_factors as init_factors
 from nn_fac import _lib as L
+from nn_fac._graph import GraphedIteration
 from nn_fac import _ops as ops
 from nn_fac.utils.beta_divergence import gamma_beta
 
@@ -82,6 +83,12 @@ class DeviceNTD:
                 Xm = self.T.movedim(mode, 0).reshape(self.T.shape[mode], -1).contiguous()
                 self.plans.append(ops.NMFPlan(Xm).bind_rank(int(self.factors[mode].shape[1])))
                 del Xm
+
+    def get_state(self):
+        return [self.core] + list(self.factors)
+
+    def set_state(self, tensors):
+        self.core, self.factors = tensors[0], list(tensors[1:])
 
     def factor_update(self, mode, beta):
         """mu_betadivmin(F, unfold(G x_{j != mode} F_j, mode), unfold(T, mode), beta), ntd.py:672."""
@@ -244,13 +251,23 @@ def compute_ntd(tensor_in, ranks, core_in, factors_in, n_iter_max=100, tol=1e-6,
     host = torch.zeros(8, dtype=torch.float64).pin_memory()
     pending = None
     nterms = 1
+    # MU: from the second iteration on the outer iteration is one CUDA-graph launch (the eager iteration is bound by the
+    # host's launch rate, not by the device); NNFAC_NTD_GRAPH=0 keeps every iteration eager
+    graphed = None
+    use_graph = (not hals) and n_iter_max >= 4 and state.T.is_cuda and os.environ.get("NNFAC_NTD_GRAPH", "1") != "0"
     for iteration in range(n_iter_max + 1):
         if iteration < n_iter_max:
-            before = (state.core, list(state.factors))
-            if hals:
-                cost_dev = state.step_hals_async(norm_tensor, sparsity_coefficients, fixed_modes, normalize, mode_core_norm)
+            if use_graph and iteration == 1:
+                graphed = GraphedIteration(state.T.device, state.get_state, state.set_state,
+                                           lambda: state.step_mu_async(beta, fixed_modes, normalize, mode_core_norm))
+            if graphed is not None:
+                cost_dev = graphed.replay()
             else:
-                cost_dev = state.step_mu_async(beta, fixed_modes, normalize, mode_core_norm).reshape(1).to(torch.float64)
+                before = (state.core, list(state.factors))
+                if hals:
+                    cost_dev = state.step_hals_async(norm_tensor, sparsity_coefficients, fixed_modes, normalize, mode_core_norm)
+                else:
+                    cost_dev = state.step_mu_async(beta, fixed_modes, normalize, mode_core_norm).reshape(1).to(torch.float64)
         if pending is not None:
             pending.synchronize()
             if hals:
@@ -269,8 +286,11 @@ def compute_ntd(tensor_in, ranks, core_in, factors_in, n_iter_max=100, tol=1e-6,
             if len(cost_fct_vals) >= 2 and abs(cost_fct_vals[-2] - cost_fct_vals[-1]) < tol:
                 if verbose:
                     print('Converged in {} iterations.'.format(len(cost_fct_vals) - 1))
-                if iteration < n_iter_max:
-                    state.core, state.factors = before
+                if iteration < n_iter_max:                                   # drop the speculative iteration
+                    if graphed is not None:
+                        graphed.roll_back()
+                    else:
+                        state.core, state.factors = before
                 break
         if iteration == n_iter_max:
             break

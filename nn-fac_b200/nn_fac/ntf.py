@@ -18,6 +18,7 @@ import nn_fac.update_rules.nnls as nnls
 import nn_fac.utils.errors as err
 import nn_fac.utils.initialize_factors as init_factors
 from nn_fac import _lib as L
+from nn_fac._graph import GraphedIteration
 from nn_fac import _ops as ops
 
 
@@ -73,6 +74,13 @@ class DeviceNTF:
                 Xm = self.T.movedim(mode, 0).reshape(self.shape[mode], -1).contiguous()
                 self.plans.append(ops.NMFPlan(Xm).bind_rank(rank))
                 del Xm
+
+    def get_state(self):
+        return list(self.factors) + list(self.factors_t)
+
+    def set_state(self, tensors):
+        k = len(tensors) // 2
+        self.factors, self.factors_t = list(tensors[:k]), list(tensors[k:])
 
     def khatri_rao(self, skip):
         kept = [f for i, f in enumerate(self.factors) if i != skip]
@@ -241,10 +249,20 @@ def compute_ntf(tensor_in, rank, factors_in, n_iter_max=100, tol=1e-8,
     # modified in place, so the previous list is simply kept).
     host = torch.zeros(8, dtype=torch.float64).pin_memory()
     pending = None                                     # (terms on host buffer, event, factors after that iteration)
+    # From the second iteration on the outer iteration is one CUDA-graph launch (_graph.py); NNFAC_NTF_GRAPH=0 keeps every
+    # iteration eager.
+    graphed = None
+    use_graph = n_iter_max >= 4 and state.T.is_cuda and os.environ.get("NNFAC_NTF_GRAPH", "1") != "0"
     for iteration in range(n_iter_max + 1):
         if iteration < n_iter_max:
-            before = list(state.factors)
-            terms = state.step_async(rank, norm_tensor, update_rule, beta, sparsity_coefficients, fixed_modes, normalize)
+            if use_graph and iteration == 1:
+                graphed = GraphedIteration(state.T.device, state.get_state, state.set_state, lambda: state.step_async(
+                    rank, norm_tensor, update_rule, beta, sparsity_coefficients, fixed_modes, normalize))
+            if graphed is not None:
+                terms = graphed.replay()
+            else:
+                before = list(state.factors)
+                terms = state.step_async(rank, norm_tensor, update_rule, beta, sparsity_coefficients, fixed_modes, normalize)
         if pending is not None:
             ev, nterms, kept = pending
             ev.synchronize()
@@ -261,9 +279,12 @@ def compute_ntf(tensor_in, rank, factors_in, n_iter_max=100, tol=1e-8,
             if len(cost_fct_vals) >= 2 and abs(cost_fct_vals[-2] - cost_fct_vals[-1]) < tol:
                 if verbose:
                     print('Converged in {} iterations.'.format(len(cost_fct_vals) - 1))
-                if iteration < n_iter_max:
-                    state.factors = before             # drop the speculative iteration
-                    state.factors_t = [ops.transpose(f) for f in before]
+                if iteration < n_iter_max:             # drop the speculative iteration
+                    if graphed is not None:
+                        graphed.roll_back()
+                    else:
+                        state.factors = before
+                        state.factors_t = [ops.transpose(f) for f in before]
                 break
         if iteration == n_iter_max:
             break

@@ -6,12 +6,14 @@ import argparse, json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "nn-fac_b200"))
 import numpy as np, torch
+from nn_fac._graph import GraphedIteration
 
 ap = argparse.ArgumentParser()
 ap.add_argument("which", nargs="?", default="both")
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--size", type=int, default=0)
 ap.add_argument("--no-cpu", action="store_true")
+ap.add_argument("--eager", action="store_true", help="every iteration launched kernel by kernel (no CUDA graph)")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
@@ -36,16 +38,21 @@ if args.which in ("ntf", "both"):
     F0 = [torch.rand((I, r), generator=g, device=dev) for _ in range(3)]
     st = ntf.DeviceNTF(T, F0, torch.float32)
     norm = float(torch.linalg.vector_norm(T.double()).item())
+    step = lambda: st.step_async(r, norm, "hals", 2, [None] * 3, [], [False] * 3)
+    if not args.eager:                               # as compute_ntf does: first iteration eager, the rest replayed from a graph
+        step()
+        step = GraphedIteration(dev, st.get_state, st.set_state, step).replay
     def run(k):
         terms = None
         for _ in range(k):                           # no host synchronisation between iterations (as compute_ntf does)
-            terms = st.step_async(r, norm, "hals", 2, [None] * 3, [], [False] * 3)
+            terms = step()
         return st.finish_cost(terms.cpu().numpy(), norm, "hals", [None] * 3)
     ms, cost = timed(run, args.iters)
     bytes_iter = 3 * I ** 3 * 4
     line = {"config": f"C4: NTF HALS {I}^3 rank {r} (fp32)", "outer_iters_per_s": 1e3 / ms, "ms_per_iter": ms,
             "algorithmic_bytes_per_iter": bytes_iter, "achieved_GBps": bytes_iter / ms / 1e6, "hbm_peak_GBps": peak,
-            "frac_of_hbm_roofline": bytes_iter / ms / 1e6 / peak, "cost_after": cost}
+            "frac_of_hbm_roofline": bytes_iter / ms / 1e6 / peak, "cost_after": cost,
+            "launch": "eager" if args.eager else "cuda graph per outer iteration"}
     if not args.no_cpu:
         Is = 128                                     # bounded CPU sample: work is proportional to I^3
         rng = np.random.RandomState(0)
@@ -70,15 +77,20 @@ if args.which in ("ntd", "both"):
     G0 = torch.rand((rc, rc, rc), generator=g, device=dev)
     F0 = [torch.rand((I, rc), generator=g, device=dev) for _ in range(3)]
     st = ntd.DeviceNTD(T, G0, F0, torch.float32)
+    step = lambda: st.step_mu_async(1, [], [False] * 4, None)
+    if not args.eager:                               # as compute_ntd does
+        step()
+        step = GraphedIteration(dev, st.get_state, st.set_state, step).replay
     def run(k):
         c = None
         for _ in range(k):
-            c = st.step_mu_async(1, [], [False] * 4, None)
+            c = step()
         return float(c.item())
     ms, cost = timed(run, args.iters)
     flop = 3 * 2 * (2 * I ** 3 * rc) + 2 * 2 * I ** 3 * rc       # per mode: model + contraction over the tensor; core: up + down (leading terms)
     line = {"config": f"C5: NTD MU beta=1 {I}^3 core {rc}^3 (fp32)", "outer_iters_per_s": 1e3 / ms, "ms_per_iter": ms,
             "leading_GFLOP_per_iter": flop / 1e9, "achieved_TFLOPs": flop / ms / 1e9, "cost_after": cost,
+            "launch": "eager" if args.eager else "cuda graph per outer iteration",
             "note": "tensor (67 MB) is L2-resident: bounded by launch latency / tensor throughput, not HBM (SURVEY 8(d))"}
     if not args.no_cpu:
         Is = 64
