@@ -192,7 +192,8 @@ class DeviceNTD:
         """One outer iteration; returns the cost as a device scalar (no synchronisation)."""
         for mode in [m for m in range(self.T.dim()) if m not in fixed_modes]:
             self.factors[mode] = self.factor_update(mode, beta)
-        self.core = mu.mu_tensorial_device(self.core, self.factors, self.T, beta)   # ntd.py:674
+        plan0 = self.plans[0] if (self.plans is not None and beta == 1) else None
+        self.core = mu.mu_tensorial_device(self.core, self.factors, self.T, beta, plan0)   # ntd.py:674
         if normalize[-1]:                                                    # ntd.py:676-681
             moved = self.core.movedim(mode_core_norm, 0).contiguous()
             flat = moved.reshape(moved.shape[0], -1)

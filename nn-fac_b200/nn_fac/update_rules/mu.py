@@ -76,18 +76,43 @@ def mu_betadivmin(U, V, M, beta):
     return _out(mu_update_device(L.to_device(U, dt), L.to_device(V, dt), L.to_device(M, dt), beta, "U"), U)
 
 
-def mu_tensorial_device(G, factors, T, beta):
-    """Tucker-core multiplicative update on device tensors (mu.py:138-159)."""
+def _ones_contracted(factors):
+    """ones x_n F_n^T (mu.py:144, 159 for beta = 1) in closed form: the outer product of the factors' column sums.  The
+    reference contracts a tensor of ones of the size of the data through every mode for it."""
+    dn = None
+    for mode, F in enumerate(factors):
+        s = ops.row_sums(ops.transpose(F))                                 # column sums of F_n (r_n)
+        shape = [1] * len(factors)
+        shape[mode] = s.shape[0]
+        dn = s.reshape(shape) if dn is None else dn * s.reshape(shape)
+    return dn.contiguous()
+
+
+def mu_tensorial_device(G, factors, T, beta, plan0=None):
+    """Tucker-core multiplicative update on device tensors (mu.py:138-159).
+
+    plan0 (beta = 1, fp32, ranks <= 64): the NMF plan of unfold(T, 0).  The first contraction of the numerator,
+    F_0^T unfold(T / K, 0), is then the V-side numerator of one fused tcgen05 pass over the planes of that unfolding
+    with U = F_0 and V = unfold(G x_{j>0} F_j, 0): neither K nor T / K is ever written."""
+    if beta == 1 and plan0 is not None:
+        B0 = ops.multi_mode_dot(G, factors, skip=0)                         # r_0 x I_1 x ... (K = F_0 x_0 B0, mu.py:141)
+        plan0.set_factor(0, ops.transpose(factors[0]))
+        plan0.set_factor(1, B0.reshape(B0.shape[0], -1))
+        P, _ = plan0.fused(1, 1, want_cost=False)                           # F_0^T unfold(T / K, 0): r_0 x (I_1 ...)
+        up = ops.multi_mode_dot(P.reshape(B0.shape), factors, skip=0, transpose=True)
+        dn = _ones_contracted(factors)
+        return ops.mu_apply(G.reshape(G.shape[0], -1), up.reshape(G.shape[0], -1), den_mat=dn.reshape(G.shape[0], -1),
+                            gamma=gamma_beta(beta), floor=epsilon).reshape(G.shape)
     K = ops.multi_mode_dot(G, factors)                                     # mu.py:141
     if beta == 2:
         L2, L1 = T, K
     elif beta == 1:
         L2 = ops.mu_terms(K, T, beta, want_q=False, out_p=K)[0]
-        L1 = torch.ones_like(T)                                            # mu.py:144 (np.ones)
+        L1 = None                                                          # mu.py:144 (np.ones): closed form below
     else:
         L2, L1 = ops.mu_terms(K, T, beta, want_q=True, out_p=torch.empty_like(K), out_q=K)
     up = ops.multi_mode_dot(L2, factors, transpose=True)
-    dn = ops.multi_mode_dot(L1, factors, transpose=True)
+    dn = ops.multi_mode_dot(L1, factors, transpose=True) if L1 is not None else _ones_contracted(factors)
     return ops.mu_apply(G.reshape(G.shape[0], -1), up.reshape(G.shape[0], -1), den_mat=dn.reshape(G.shape[0], -1),
                         gamma=gamma_beta(beta), floor=epsilon).reshape(G.shape)
 
