@@ -76,6 +76,8 @@ class DeviceNTD:
         # V = unfold(G x_{j != mode} F_j, mode), i.e. one fused tcgen05 pass over the planes of that unfolding
         # (model tile, ratio and contraction on chip; nothing of the size of the tensor is written).
         self.plans = None
+        self._m0_ready = False                                              # see step_mu_async
+        self._m0_den = torch.empty(int(self.factors[0].shape[1]), dtype=dtype, device=self.T.device)
         if (dtype == torch.float32 and max(int(f.shape[1]) for f in self.factors) <= 64
                 and os.environ.get("NNFAC_NTD_TC", "1") != "0"):
             self.plans = []
@@ -190,8 +192,16 @@ class DeviceNTD:
 
     def step_mu_async(self, beta, fixed_modes, normalize, mode_core_norm):
         """One outer iteration; returns the cost as a device scalar (no synchronisation)."""
+        tc = self.plans is not None and beta == 1
         for mode in [m for m in range(self.T.dim()) if m not in fixed_modes]:
-            self.factors[mode] = self.factor_update(mode, beta)
+            if mode == 0 and tc and self._m0_ready:
+                # the pass this update needs already ran: it is the cost pass that ended the previous iteration (same core,
+                # same factors), which left its numerator partials in the plan and the row sums of V in _m0_den
+                self.factors[0] = ops.transpose(self.plans[0].mu_finish(0, ops.transpose(self.factors[0]), self._m0_den,
+                                                                        mu.epsilon))            # mu.py:86-88
+            else:
+                self.factors[mode] = self.factor_update(mode, beta)
+        self._m0_ready = False
         plan0 = self.plans[0] if (self.plans is not None and beta == 1) else None
         self.core = mu.mu_tensorial_device(self.core, self.factors, self.T, beta, plan0)   # ntd.py:674
         if normalize[-1]:                                                    # ntd.py:676-681
@@ -202,12 +212,17 @@ class DeviceNTD:
         if self.plans is not None and beta == 1:
             # beta_divergence(T, G x_n F_n, 1) without forming the reconstruction: it is the cost output of a fused pass
             # over unfold(T, last) with U = F_last, V = unfold(G x_{j != last} F_j, last)
-            last = self.T.dim() - 1
-            plan = self.plans[last]
-            B = ops.multi_mode_dot(self.core, self.factors, skip=last)
-            plan.set_factor(0, ops.transpose(self.factors[last]))
-            plan.set_factor(1, B.movedim(last, 0).reshape(B.shape[last], -1).contiguous())
-            _, cost = plan.fused(0, 1, want_cost=True)
+            # (any mode's unfolding gives the same number; mode 0 is used because the same pass, with the same operands, is
+            # the first factor update of the NEXT iteration: its numerator partials stay in the plan for it)
+            plan = self.plans[0]
+            B = ops.multi_mode_dot(self.core, self.factors, skip=0)
+            Vm = B.reshape(B.shape[0], -1)
+            plan.set_factor(1, Vm)                                          # (factor 0's planes: installed by the core update)
+            keep = 0 not in fixed_modes
+            _, cost = plan.fused(0, 1, want_cost=True, keep_partials=keep)
+            if keep:
+                ops.row_sums(Vm, out=self._m0_den)
+                self._m0_ready = True
             return cost                                                     # ntd.py:694-696 (not normalised)
         K = ops.multi_mode_dot(self.core, self.factors)
         return ops.beta_divergence(self.T, K, beta)                         # ntd.py:694-696 (not normalised)
@@ -292,6 +307,7 @@ def compute_ntd(tensor_in, ranks, core_in, factors_in, n_iter_max=100, tol=1e-6,
                         graphed.roll_back()
                     else:
                         state.core, state.factors = before
+                    state._m0_ready = False
                 break
         if iteration == n_iter_max:
             break
