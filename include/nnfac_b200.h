@@ -131,6 +131,18 @@ int nnfac_hadamard(nnfac_ctx* ctx, int dtype, void* out, const void* A, const vo
  * {0, 1, 1, 0}): the step is a no-op once `done` is set (cnt > 300 or upd < delta * upd_0).  P = core x_n (F_n^T F_n). */
 int nnfac_core_pg_step(nnfac_ctx* ctx, int dtype, void* core, const void* MtX, const void* P, int64_t count, double step,
                        double sparse, double delta, double* state, void* stream);
+/* Same step with the step size and the sparsity coefficient read from the device: state = double[6] =
+ * {upd_0, upd, cnt, done, step, sparse}.  No per-call host scalars besides delta, so a batch of steps captured into a CUDA
+ * graph can be replayed for every outer iteration (the step size changes with the factors, ntd.py:590-594). */
+int nnfac_core_pg_step_dev(nnfac_ctx* ctx, int dtype, void* core, const void* MtX, const void* P, int64_t count, double delta,
+                           double* state, void* stream);
+/* The same step for a 3-way core (r0 x r1 x r2, row-major, every rank <= 64) INCLUDING the product
+ * P = core x_0 M0 x_1 M1 x_2 M2 of ntd.py:610 (M_n: r_n x r_n, row-major, the Grams F_n^T F_n): two kernels per step instead
+ * of three generic GEMMs + the step.  Z: workspace of r0*r1*r2 elements.  dev_scalars != 0: step / sparse from state[4],
+ * state[5] (state = double[6]) as in nnfac_core_pg_step_dev, else from the arguments (state = double[4]). */
+int nnfac_core_pg_step3(nnfac_ctx* ctx, int dtype, void* core, const void* MtX, const void* M0, const void* M1, const void* M2,
+                        int r0, int r1, int r2, void* Z, double step, double sparse, int dev_scalars, double delta, double* state,
+                        void* stream);
 int nnfac_normalize_rows(nnfac_ctx* ctx, int dtype, void* A, int64_t lda, int64_t rows,
                          int64_t cols, void* stream);
 

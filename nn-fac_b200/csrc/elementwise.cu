@@ -193,9 +193,14 @@ inline int grid_for(int64_t count, int sm) {
 // `done` is set the remaining launches of a batch return at once (the host looks at the flag only every few steps).
 template <typename T>
 __global__ void __launch_bounds__(RB) core_pg_step_kernel(T* __restrict__ core, const T* __restrict__ MtX, const T* __restrict__ P,
-                                                          int64_t count, T step, T sparse, const double* state, double* part) {
+                                                          int64_t count, T step, T sparse, int dev_scalars, const double* state,
+                                                          double* part) {
   __shared__ double sh[33];
   if (state[3] != 0.0) return;
+  if (dev_scalars) {                                     // step and sparsity from state[4], state[5] (graph-replayable launch)
+    step = (T)state[4];
+    sparse = (T)state[5];
+  }
   double s = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * RB + threadIdx.x; i < count; i += (int64_t)gridDim.x * RB) {
     const T g = -MtX[i] + P[i] + sparse;                 // gradient, ntd.py:608
@@ -217,6 +222,86 @@ __global__ void core_pg_finish_kernel(const double* part, int nparts, double del
   state[1] = upd;
   state[2] += 1.0;
   if (!(state[2] <= 300.0 && upd >= delta * state[0])) state[3] = 1.0;
+  // A first step that moves nothing (typically: the reference's round(step, 6) gave a step of 0, ntd.py:594) leaves the
+  // loop condition `0 >= delta * 0` true, and every further step repeats the same no-op on the same core until cnt
+  // exceeds 300: those steps are counted, not executed.
+  if (state[2] == 2.0 && upd == 0.0) {
+    state[2] = 301.0;
+    state[3] = 1.0;
+  }
+}
+
+// ---- projected-gradient step on a 3-way Tucker core, every rank <= 64 (ntd.py:607-617) -----------------------------
+// P = core x_0 M0 x_1 M1 x_2 M2 (ntd.py:610, the M are the r x r Grams of the factors) in two kernels instead of three
+// generic strided GEMMs of ~9 us each: (1) one CTA per slab i contracts modes 2 and 1 in shared memory,
+// Z[i] = M1 (core[i] M2^T); (2) one thread per column (b, c) contracts mode 0, P[:, col] = M0 Z[:, col], and applies
+// the step to its r0 elements at once (gradient, clamp, squared-step partial).  The step is ~3 MFLOP on 128 KB: what
+// matters is the number of launches per step, because the loop runs up to 300 steps per outer iteration.
+template <typename T>
+__global__ void __launch_bounds__(256) core_modes12_kernel(const T* __restrict__ core, const T* __restrict__ M1,
+                                                           const T* __restrict__ M2, T* __restrict__ Z, int r1, int r2,
+                                                           const double* state) {
+  if (state[3] != 0.0) return;
+  extern __shared__ __align__(16) unsigned char pg_smem[];
+  T* Gs = reinterpret_cast<T*>(pg_smem);        // [r1][r2]
+  T* Ys = Gs + r1 * r2;                         // [r1][r2]
+  T* M1s = Ys + r1 * r2;                        // [r1][r1]
+  T* M2s = M1s + r1 * r1;                       // [r2][r2 + 1]  (padded: lanes read a column)
+  const int i = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  for (int x = tid; x < r1 * r2; x += nt) Gs[x] = core[(int64_t)i * r1 * r2 + x];
+  for (int x = tid; x < r1 * r1; x += nt) M1s[x] = M1[x];
+  for (int x = tid; x < r2 * r2; x += nt) M2s[(x / r2) * (r2 + 1) + x % r2] = M2[x];
+  __syncthreads();
+  for (int x = tid; x < r1 * r2; x += nt) {     // Y[j][c] = sum_k core[i][j][k] M2[c][k]
+    const int j = x / r2, c = x % r2;
+    T acc = 0;
+    for (int k = 0; k < r2; ++k) acc += Gs[j * r2 + k] * M2s[c * (r2 + 1) + k];
+    Ys[x] = acc;
+  }
+  __syncthreads();
+  for (int x = tid; x < r1 * r2; x += nt) {     // Z[i][b][c] = sum_j M1[b][j] Y[j][c]
+    const int b = x / r2, c = x % r2;
+    T acc = 0;
+    for (int j = 0; j < r1; ++j) acc += M1s[b * r1 + j] * Ys[j * r2 + c];
+    Z[(int64_t)i * r1 * r2 + x] = acc;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) core_mode0_step_kernel(T* __restrict__ core, const T* __restrict__ MtX,
+                                                              const T* __restrict__ Z, const T* __restrict__ M0, int r0, int ncol,
+                                                              T step, T sparse, int dev_scalars, const double* state,
+                                                              double* part) {
+  __shared__ double sh[33];
+  extern __shared__ __align__(16) unsigned char pg_smem[];
+  if (state[3] != 0.0) return;
+  if (dev_scalars) {
+    step = (T)state[4];
+    sparse = (T)state[5];
+  }
+  T* M0s = reinterpret_cast<T*>(pg_smem);       // [r0][r0]
+  T* Zs = M0s + r0 * r0;                        // [r0][128]
+  const int tid = threadIdx.x, col = blockIdx.x * 128 + tid;
+  for (int x = tid; x < r0 * r0; x += 128) M0s[x] = M0[x];
+  if (col < ncol)
+    for (int i = 0; i < r0; ++i) Zs[i * 128 + tid] = Z[(int64_t)i * ncol + col];
+  __syncthreads();
+  double s = 0.0;
+  if (col < ncol) {
+    for (int a = 0; a < r0; ++a) {
+      T p = 0;
+      for (int i = 0; i < r0; ++i) p += M0s[a * r0 + i] * Zs[i * 128 + tid];
+      const int64_t idx = (int64_t)a * ncol + col;
+      const T g = -MtX[idx] + p + sparse;                 // gradient, ntd.py:608
+      const T c = core[idx];
+      const T st = step * g;
+      const T d = st < c ? st : c;                         // np.minimum(gradient_step * gradient, core)
+      core[idx] = c - d;
+      s += (double)d * (double)d;
+    }
+  }
+  s = block_sum(s, sh);
+  if (tid == 0) part[blockIdx.x] = s;
 }
 
 #define DISPATCH_T(dtype, CALL_F, CALL_D) \
@@ -344,21 +429,70 @@ int nnfac_hadamard(nnfac_ctx* ctx, int dtype, void* out, const void* A, const vo
   return NNFAC_OK;
 }
 
-int nnfac_core_pg_step(nnfac_ctx* ctx, int dtype, void* core, const void* MtX, const void* P, int64_t count, double step,
-                       double sparse, double delta, double* state, void* stream) {
-  NNFAC_ARG(ctx && core && MtX && P && state && count > 0, "nnfac_core_pg_step: bad argument");
+static int core_pg_step_impl(nnfac_ctx* ctx, int dtype, void* core, const void* MtX, const void* P, int64_t count, double step,
+                             double sparse, int dev_scalars, double delta, double* state, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   int blocks = (int)(ceil_div64(count, RB) < RMAX_BLOCKS ? ceil_div64(count, RB) : RMAX_BLOCKS);
   // the partials live behind the mailbox area of the sweep so that they never collide with other reductions in flight
   double* part = ctx->red + 32768;
   DISPATCH_T(dtype, (core_pg_step_kernel<float><<<blocks, RB, 0, st>>>((float*)core, (const float*)MtX, (const float*)P, count,
-                                                                        (float)step, (float)sparse, state, part)),
+                                                                        (float)step, (float)sparse, dev_scalars, state, part)),
              (core_pg_step_kernel<double><<<blocks, RB, 0, st>>>((double*)core, (const double*)MtX, (const double*)P, count, step,
-                                                                  sparse, state, part)));
+                                                                  sparse, dev_scalars, state, part)));
   NNFAC_LAUNCH_CHECK(ctx);
   core_pg_finish_kernel<<<1, 32, 0, st>>>(part, blocks, delta, state);
   NNFAC_LAUNCH_CHECK(ctx);
   return NNFAC_OK;
+}
+
+int nnfac_core_pg_step(nnfac_ctx* ctx, int dtype, void* core, const void* MtX, const void* P, int64_t count, double step,
+                       double sparse, double delta, double* state, void* stream) {
+  NNFAC_ARG(ctx && core && MtX && P && state && count > 0, "nnfac_core_pg_step: bad argument");
+  return core_pg_step_impl(ctx, dtype, core, MtX, P, count, step, sparse, 0, delta, state, stream);
+}
+
+}  // extern "C"
+
+template <typename T>
+static int core_pg_step3_launch(nnfac_ctx* ctx, T* core, const T* MtX, const T* M0, const T* M1, const T* M2, int r0, int r1, int r2,
+                                T* Z, double step, double sparse, int dev_scalars, double delta, double* state, cudaStream_t st) {
+  const size_t smem_a = sizeof(T) * ((size_t)2 * r1 * r2 + (size_t)r1 * r1 + (size_t)r2 * (r2 + 1));
+  const size_t smem_b = sizeof(T) * ((size_t)r0 * r0 + (size_t)r0 * 128);
+  NNFAC_CUDA(cudaFuncSetAttribute(core_modes12_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+  NNFAC_CUDA(cudaFuncSetAttribute(core_mode0_step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+  const int ncol = r1 * r2, blocks = (ncol + 127) / 128;
+  double* part = ctx->red + 32768;
+  core_modes12_kernel<T><<<r0, 256, smem_a, st>>>(core, M1, M2, Z, r1, r2, state);
+  NNFAC_LAUNCH_CHECK(ctx);
+  core_mode0_step_kernel<T><<<blocks, 128, smem_b, st>>>(core, MtX, Z, M0, r0, ncol, (T)step, (T)sparse, dev_scalars, state, part);
+  NNFAC_LAUNCH_CHECK(ctx);
+  core_pg_finish_kernel<<<1, 32, 0, st>>>(part, blocks, delta, state);
+  NNFAC_LAUNCH_CHECK(ctx);
+  return NNFAC_OK;
+}
+
+extern "C" {
+
+int nnfac_core_pg_step3(nnfac_ctx* ctx, int dtype, void* core, const void* MtX, const void* M0, const void* M1, const void* M2,
+                        int r0, int r1, int r2, void* Z, double step, double sparse, int dev_scalars, double delta, double* state,
+                        void* stream) {
+  NNFAC_ARG(ctx && core && MtX && M0 && M1 && M2 && Z && state, "nnfac_core_pg_step3: bad argument");
+  NNFAC_ARG(r0 >= 1 && r1 >= 1 && r2 >= 1 && r0 <= 64 && r1 <= 64 && r2 <= 64, "nnfac_core_pg_step3: ranks must be in 1..64");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == NNFAC_F32)
+    return core_pg_step3_launch<float>(ctx, (float*)core, (const float*)MtX, (const float*)M0, (const float*)M1, (const float*)M2, r0,
+                                       r1, r2, (float*)Z, step, sparse, dev_scalars, delta, state, st);
+  if (dtype == NNFAC_F64)
+    return core_pg_step3_launch<double>(ctx, (double*)core, (const double*)MtX, (const double*)M0, (const double*)M1,
+                                        (const double*)M2, r0, r1, r2, (double*)Z, step, sparse, dev_scalars, delta, state, st);
+  nnfac_set_error("bad dtype %d", dtype);
+  return NNFAC_ERR_ARG;
+}
+
+int nnfac_core_pg_step_dev(nnfac_ctx* ctx, int dtype, void* core, const void* MtX, const void* P, int64_t count, double delta,
+                           double* state, void* stream) {
+  NNFAC_ARG(ctx && core && MtX && P && state && count > 0, "nnfac_core_pg_step_dev: bad argument");
+  return core_pg_step_impl(ctx, dtype, core, MtX, P, count, 0.0, 0.0, 1, delta, state, stream);
 }
 
 int nnfac_normalize_rows(nnfac_ctx* ctx, int dtype, void* A, int64_t lda, int64_t rows,

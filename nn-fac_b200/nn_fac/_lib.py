@@ -43,6 +43,8 @@ SIGNATURES = {
     "nnfac_hadamard": [_P, _INT, _P, _P, _P, _I64, _P],
     "nnfac_normalize_rows": [_P, _INT, _P, _I64, _I64, _I64, _P],
     "nnfac_core_pg_step": [_P, _INT, _P, _P, _P, _I64, _DBL, _DBL, _DBL, _P, _P],
+    "nnfac_core_pg_step_dev": [_P, _INT, _P, _P, _P, _I64, _DBL, _P, _P],
+    "nnfac_core_pg_step3": [_P, _INT, _P, _P, _P, _P, _P, _INT, _INT, _INT, _P, _DBL, _DBL, _INT, _DBL, _P, _P],
     "nnfac_nmf_plan_create": [_P, _I64, _I64, _INT, _c.POINTER(_P)],
     "nnfac_nmf_plan_bytes": [_P, _I64, _I64, _INT, _c.POINTER(_c.c_size_t)],
     "nnfac_nmf_plan_create_in": [_P, _I64, _I64, _INT, _P, _c.c_size_t, _P, _c.POINTER(_P)],

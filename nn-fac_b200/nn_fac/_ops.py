@@ -160,6 +160,25 @@ def core_pg_step(core, MtX, P, step, sparse, delta, state):
                                       float(step), float(sparse), float(delta), L.ptr(state), L.stream_ptr()))
 
 
+def core_pg_step_dev(core, MtX, P, delta, state):
+    """core_pg_step with the step size and the sparsity coefficient in state[4], state[5] (`state` = device double[6])."""
+    L.check(_lib().nnfac_core_pg_step_dev(L.ctx(core.device), L.code_of(core.dtype), L.ptr(core), L.ptr(MtX), L.ptr(P), core.numel(),
+                                          float(delta), L.ptr(state), L.stream_ptr()))
+
+
+def core_pg_step3(core, MtX, MtM, Z, step, sparse, delta, state, dev_scalars=False):
+    """Projected-gradient step on a 3-way core with ranks <= 64, product core x_n MtM_n included (ntd.py:607-617)."""
+    r0, r1, r2 = core.shape
+    assert core.is_contiguous() and MtX.is_contiguous() and all(M.is_contiguous() for M in MtM) and Z.numel() >= core.numel()
+    L.check(_lib().nnfac_core_pg_step3(L.ctx(core.device), L.code_of(core.dtype), L.ptr(core), L.ptr(MtX), L.ptr(MtM[0]),
+                                       L.ptr(MtM[1]), L.ptr(MtM[2]), r0, r1, r2, L.ptr(Z), float(step), float(sparse),
+                                       1 if dev_scalars else 0, float(delta), L.ptr(state), L.stream_ptr()))
+
+
+def core_pg_fast(core):
+    return core.dim() == 3 and max(core.shape) <= 64
+
+
 def _split(shape, mode):
     left = 1
     for s in shape[:mode]:

@@ -77,6 +77,7 @@ class DeviceNTD:
         # (model tile, ratio and contraction on chip; nothing of the size of the tensor is written).
         self.plans = None
         self._m0_ready = False                                              # see step_mu_async
+        self._pg, self._pg_calls = None, 0                                  # see _core_loop_graphed
         self._m0_den = torch.empty(int(self.factors[0].shape[1]), dtype=dtype, device=self.T.device)
         if (dtype == torch.float32 and max(int(f.shape[1]) for f in self.factors) <= 64
                 and os.environ.get("NNFAC_NTD_TC", "1") != "0"):
@@ -157,13 +158,23 @@ class DeviceNTD:
             gradient_step *= 1.0 / float(np.linalg.svd(MtM.double().cpu().numpy(), compute_uv=False)[0])
         gradient_step = round(gradient_step, 6)
         sparse = 0.0 if sparsity[-1] is None else float(sparsity[-1])       # ntd.py:600-603
-        core = self.core.clone()
-        state = torch.tensor([0.0, 1.0, 1.0, 0.0], dtype=torch.float64, device=core.device)
-        for it in range(300):                                                # ntd.py:607-617, stop test on the device
-            P = ops.multi_mode_dot(core, all_MtM)
-            ops.core_pg_step(core, all_MtX, P, gradient_step, sparse, delta, state)
-            if it % 25 == 24 and float(state[3].item()) != 0.0:
-                break
+        if self._pg_calls >= 1 and os.environ.get("NNFAC_NTD_GRAPH", "1") != "0":
+            core, state = self._core_loop_graphed(all_MtX, all_MtM, gradient_step, sparse, delta)
+        else:
+            core = self.core.clone()
+            state = torch.tensor([0.0, 1.0, 1.0, 0.0], dtype=torch.float64, device=core.device)
+            fast = ops.core_pg_fast(core)
+            MtM_c = [M.contiguous() for M in all_MtM] if fast else None
+            Z = torch.empty_like(core) if fast else None
+            for it in range(300):                                            # ntd.py:607-617, stop test on the device
+                if fast:
+                    ops.core_pg_step3(core, all_MtX, MtM_c, Z, gradient_step, sparse, delta, state)
+                else:
+                    P = ops.multi_mode_dot(core, all_MtM)
+                    ops.core_pg_step(core, all_MtX, P, gradient_step, sparse, delta, state)
+                if it % self.PG_BATCH == self.PG_BATCH - 1 and float(state[3].item()) != 0.0:
+                    break
+        self._pg_calls += 1
         self.core_steps = state
         if normalize[-1]:                                                    # ntd.py:619-624
             moved = core.movedim(mode_core_norm, 0).contiguous()
@@ -178,6 +189,42 @@ class DeviceNTD:
                 else:
                     terms.append(ops.row_sums(core.reshape(1, -1)))          # ||core||_1: the core is nonnegative
         return torch.cat([t.reshape(1).to(torch.float64) for t in terms])
+
+    PG_BATCH = 25       # projected-gradient steps between two looks of the host at the `done` flag
+
+    def _core_loop_graphed(self, all_MtX, all_MtM, gradient_step, sparse, delta):
+        """The loop of ntd.py:607-617 as replays of ONE CUDA graph of PG_BATCH steps (captured at the second outer
+        iteration of this object, replayed by every later one): a step is 3 tiny mode products + 2 kernels on a 32^3 core,
+        far below the host's launch rate.  Operands live in fixed buffers; step size and sparsity coefficient travel in
+        the device state vector (nnfac_core_pg_step_dev), so nothing call-specific is frozen into the graph but delta."""
+        pg = self._pg
+        if pg is None or pg["delta"] != delta:
+            dev = self.core.device
+            pg = {"delta": delta, "core": torch.empty_like(self.core), "MtX": torch.empty_like(all_MtX),
+                  "MtM": [torch.empty_like(M) for M in all_MtM],
+                  "state": torch.zeros(6, dtype=torch.float64, device=dev), "graph": torch.cuda.CUDAGraph()}
+            fast = ops.core_pg_fast(self.core)
+            Z = torch.empty_like(self.core)
+            torch.cuda.synchronize(dev)
+            with torch.cuda.graph(pg["graph"]):
+                for _ in range(self.PG_BATCH):
+                    if fast:
+                        ops.core_pg_step3(pg["core"], pg["MtX"], pg["MtM"], Z, 0.0, 0.0, delta, pg["state"], dev_scalars=True)
+                    else:
+                        P = ops.multi_mode_dot(pg["core"], pg["MtM"])
+                        ops.core_pg_step_dev(pg["core"], pg["MtX"], P, delta, pg["state"])
+            pg["Z"] = Z
+            self._pg = pg
+        pg["core"].copy_(self.core)
+        pg["MtX"].copy_(all_MtX)
+        for d, s_ in zip(pg["MtM"], all_MtM):
+            d.copy_(s_)
+        pg["state"].copy_(torch.tensor([0.0, 1.0, 1.0, 0.0, gradient_step, sparse], dtype=torch.float64))
+        for _ in range(300 // self.PG_BATCH):
+            pg["graph"].replay()
+            if float(pg["state"][3].item()) != 0.0:
+                break
+        return pg["core"].clone(), pg["state"][:4].clone()
 
     @staticmethod
     def finish_cost_hals(terms_host, norm_tensor, sparsity):

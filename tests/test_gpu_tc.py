@@ -329,3 +329,94 @@ def test_core_pg_step_state_machine():
         before = core.clone()
         ops.core_pg_step(core, MtX, P, 0.3, 0.01, 0.01, state)
         assert torch.equal(core, before)
+        # a first step of size 0 (ntd.py:594 rounds the step to 6 decimals): the reference repeats the no-op 300 times;
+        # here they are counted, not executed
+        state0 = torch.tensor([0.0, 1.0, 1.0, 0.0], dtype=torch.float64, device="cuda")
+        ops.core_pg_step(core, MtX, P, 0.0, 0.0, 0.01, state0)
+        assert torch.equal(core, before) and state0.tolist() == [0.0, 0.0, 301.0, 1.0]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_graph_replayed_iterations_equal_eager_iterations(dtype, monkeypatch):
+    """compute_ntd (MU) / compute_ntf replay the outer iteration from a CUDA graph from the second iteration on
+    (nn_fac/_graph.py): same costs and same results bit for bit as launching every iteration kernel by kernel, both for a
+    fixed iteration count and when the reference's stop test (ntd.py:421 / ntf.py:337) drops the speculative iteration."""
+    import nn_fac.ntd as ntd
+    import nn_fac.ntf as ntf
+    rng = np.random.RandomState(3)
+    shape, ranks = (40, 36, 50), [6, 5, 7]
+    Fs = [rng.rand(s, r) for s, r in zip(shape, ranks)]
+    T = (np.einsum("abc,ia,jb,kc->ijk", rng.rand(*ranks), *Fs) + 0.05 * rng.rand(*shape) + 1e-3).astype(dtype)
+    G0, F0 = rng.rand(*ranks).astype(dtype), [rng.rand(s, r).astype(dtype) for s, r in zip(shape, ranks)]
+    C0 = [rng.rand(s, 8).astype(dtype) for s in shape]
+
+    def run_ntd(tol):
+        return ntd.ntd(T, list(ranks), init="custom", core_0=G0.copy(), factors_0=[f.copy() for f in F0], n_iter_max=12, tol=tol,
+                       update_rule="mu", beta=1, sparsity_coefficients=[None] * 4, fixed_modes=[], normalize=[False] * 4,
+                       return_costs=True, deterministic=True)
+
+    def run_ntf(tol):
+        return ntf.ntf(T, 8, init="custom", factors_0=[f.copy() for f in C0], n_iter_max=12, tol=tol, return_costs=True,
+                       sparsity_coefficients=[None] * 3, fixed_modes=[], normalize=[False] * 3)
+
+    def run_ntd_hals():
+        return ntd.ntd(T, list(ranks), init="custom", core_0=G0.copy(), factors_0=[f.copy() for f in F0], n_iter_max=4, tol=0,
+                       update_rule="hals", sparsity_coefficients=[None] * 4, fixed_modes=[], normalize=[False] * 4,
+                       return_costs=True, deterministic=True)
+
+    res, hals = {}, {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("NNFAC_NTD_GRAPH", flag)
+        monkeypatch.setenv("NNFAC_NTF_GRAPH", flag)
+        hals[flag] = run_ntd_hals()                          # core loop of ntd.py:607-617 as graph replays from iteration 2
+        core, factors, costs, _ = run_ntd(0)
+        tol = abs(costs[4] - costs[5]) * 1.01                # the stop test fires at the sixth cost at the latest
+        core_s, factors_s, costs_s, _ = run_ntd(tol)
+        fac, fcosts, _ = run_ntf(0)
+        ftol = abs(fcosts[4] - fcosts[5]) * 1.01
+        fac_s, fcosts_s, _ = run_ntf(ftol)
+        res[flag] = (core, factors, costs, core_s, factors_s, costs_s, fac, fcosts, fac_s, fcosts_s)
+    assert hals["1"][2] == hals["0"][2]
+    np.testing.assert_array_equal(hals["1"][0], hals["0"][0])
+    for x, y in zip(hals["1"][1], hals["0"][1]):
+        np.testing.assert_array_equal(x, y)
+    a, b = res["1"], res["0"]
+    assert 2 <= len(a[5]) <= 6 and 2 <= len(a[9]) <= 6
+    assert a[2] == b[2] and a[5] == b[5] and a[7] == b[7] and a[9] == b[9]
+    for i in (0, 3):
+        np.testing.assert_array_equal(a[i], b[i])
+    for i in (1, 4, 6, 8):
+        for x, y in zip(a[i], b[i]):
+            np.testing.assert_array_equal(x, y)
+    # the early-stopped run returns the state of the iteration whose cost fired the test: a prefix of the full trajectory
+    assert a[5] == a[2][:len(a[5])] and a[9] == a[7][:len(a[9])]
+
+
+@pytest.mark.parametrize("dt_name", ["float32", "float64"])
+@pytest.mark.parametrize("ranks", [(32, 32, 32), (9, 9, 3), (64, 17, 40)])
+def test_core_pg_step3_equals_mode_products_plus_step(dt_name, ranks):
+    """nnfac_core_pg_step3 (two kernels per projected-gradient step of ntd.py:607-617) against the generic route:
+    P = core x_n MtM_n by three mode products, then nnfac_core_pg_step."""
+    import torch
+    from nn_fac import _ops as ops
+    dt = getattr(torch, dt_name)
+    rng = np.random.RandomState(17)
+    core0 = torch.from_numpy(rng.rand(*ranks)).to(dt).cuda()
+    MtX = torch.from_numpy(rng.rand(*ranks) * 30).to(dt).cuda()
+    MtM = []
+    for r in ranks:
+        F = rng.rand(50, r)
+        MtM.append(torch.from_numpy(F.T @ F).to(dt).cuda().contiguous())
+    step = 1.0 / float(np.prod([np.linalg.svd(M.double().cpu().numpy(), compute_uv=False)[0] for M in MtM]))
+    a, b = core0.clone(), core0.clone()
+    sa = torch.tensor([0.0, 1.0, 1.0, 0.0], dtype=torch.float64, device="cuda")
+    sb = torch.tensor([0.0, 1.0, 1.0, 0.0, step, 0.02], dtype=torch.float64, device="cuda")
+    Z = torch.empty_like(b)
+    for _ in range(5):
+        P = ops.multi_mode_dot(a, MtM)
+        ops.core_pg_step(a, MtX, P, step, 0.02, 0.01, sa)
+        ops.core_pg_step3(b, MtX, MtM, Z, 0.0, 0.0, 0.01, sb, dev_scalars=True)
+    tol = dict(rtol=1e-11, atol=1e-13) if dt == torch.float64 else dict(rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(b.double().cpu().numpy(), a.double().cpu().numpy(), **tol)
+    np.testing.assert_allclose(sb[:3].cpu().numpy(), sa[:3].cpu().numpy(), rtol=1e-9 if dt == torch.float64 else 1e-4)
+    assert sb[3].item() == sa[3].item() and (a != core0).any()
