@@ -125,6 +125,22 @@ class DeviceNTD:
     def _unfold(t, mode):
         return t.movedim(mode, 0).reshape(t.shape[mode], -1).contiguous()
 
+    def _project_all_but(self, mode):
+        """T x_{j != mode} F_j^T (ntd.py:550).  With the tcgen05 plans (fp32, ranks <= 64) the first contraction -- the only
+        one that reads the whole tensor -- is the cross product F_j^T unfold(T, j) over the bf16 planes of that unfolding;
+        the remaining ones act on a tensor r_j / I_j times smaller."""
+        nm = self.T.dim()
+        if self.plans is None or nm < 2:
+            return ops.multi_mode_dot(self.T, self.factors, skip=mode, transpose=True)
+        j = 0 if mode != 0 else 1
+        rest = [d for d in range(nm) if d != j]
+        P = self.plans[j].cross(1, ops.transpose(self.factors[j]))         # r_j x prod(rest), mode j in front
+        P = P.reshape([P.shape[0]] + [self.T.shape[d] for d in rest])
+        for pos, d in enumerate(rest):
+            if d != mode:
+                P = ops.mode_dot(P, self.factors[d], pos + 1, transpose=True)
+        return P.movedim(0, j).contiguous()
+
     def step_hals_async(self, norm_tensor, sparsity, fixed_modes, normalize, mode_core_norm, delta=0.01):
         """One outer iteration of one_ntd_step (deterministic inner rule); returns the device vector of cost terms
         [<all_MtX, core>, <core x_n MtM_n, core>, l1 norms of the sparse factors..., l1 norm of the core]."""
@@ -140,7 +156,7 @@ class DeviceNTD:
                     elemprod[i] = ops.gemm(f, (1, r_i), f, (r_i, 1), r_i, r_i, f.shape[0])
             core_u = self._unfold(self.core, mode)
             UtU = ops.matmul(self._unfold(ops.multi_mode_dot(self.core, elemprod, skip=mode), mode), core_u.T.contiguous())   # ntd.py:539-544
-            temp = ops.multi_mode_dot(self.T, self.factors, skip=mode, transpose=True)                                        # ntd.py:550
+            temp = self._project_all_but(mode)                                                                                # ntd.py:550
             UtM = ops.matmul(core_u, self._unfold(temp, mode).T.contiguous())                                                 # ntd.py:555-557 (transposed)
             Ft = ops.transpose(self.factors[mode])
             nnls.hals_nnls_device(UtM, UtU, Ft, Ft.shape[0], maxiter=100, delta=delta, sparsity_coefficient=sparsity[mode],
