@@ -20,6 +20,7 @@ The V side needs no exchange.  The HALS stop test (nnls.py:156) is evaluated PER
 (each rank stops on the squared-step ratio of the columns it owns): a grid-wide scalar per sweep
 across GPUs would cost more than the sweep itself.  Costs are summed with a scalar all-reduce.
 """
+import os
 import time
 
 import torch
@@ -160,6 +161,12 @@ class CudaEngine:
     transpose = staticmethod(ops.transpose)
 
 
+# HALS solve reads the split-K partials of the X pass itself instead of a reduced right-hand side: "u" = the U solve only
+# (measured at C2: -0.025 ms, the reduction kernel disappears), "1" = both (the V solve has 64 columns per CTA and 16+ slabs:
+# +0.05 ms), "0" = neither
+_SPLIT_RHS = os.environ.get("NNFAC_HALS_SPLIT_RHS", "u")
+
+
 class FusedNMF:
     events = None   # set to [] to collect (name, start_event, end_event) per phase
 
@@ -274,7 +281,8 @@ class FusedNMF:
         if 1 not in fixed_modes:
             with self._phase("cross_V"):
                 join = self._gram_async(1, Ut) if comm.world == 1 else None        # nmf.py:432, under the X pass
-                UtM = eng.cross(1, None)                                           # nmf.py:433 (planes of the U just installed)
+                keepV = _SPLIT_RHS == "1" and hasattr(eng, "plan") and not normalize[1]   # the V solve adds the split-K partials itself
+                UtM = eng.cross(1, None, keep_partials=True) if keepV else eng.cross(1, None)   # nmf.py:433
                 UtU = join() if join is not None else eng.gram(Ut)
             with self._phase("sweep_V"):
                 if hasattr(eng, "solve_install"):
@@ -350,9 +358,9 @@ class FusedNMF:
                 den_join = self._row_sums_async(0, self.V)                         # row sums of V under the first pass
             with self._phase("pass_U"):
                 # single GPU, MU: the numerator stays in the plan as split partials and is consumed by mu_finish.  (The
-                # HALS solve can add the partials itself too -- nnfac_nmf_plan_hals_solve(UtM = NULL) -- but its 640-thread
-                # prologue does that slower than the grid-wide reduction kernel: measured +0.07 ms per solve, not used.)
-                keep = mode == MODE_MU and self.comm.world == 1 and it < n_iter_max and 0 not in fixed_modes
+                # HALS solve can add the partials itself too -- nnfac_nmf_plan_hals_solve(UtM = NULL), NNFAC_HALS_SPLIT_RHS=1.)
+                keep = self.comm.world == 1 and it < n_iter_max and 0 not in fixed_modes and (
+                    mode == MODE_MU or (_SPLIT_RHS in ("u", "1") and not mu2 and not normalize[0] and hasattr(self.eng, "plan")))
                 # the cost lands directly in the scalar block that travels to the host
                 outA, _ = self.eng.fused(0, mode, True, keep_partials=keep, cost_out=self._dev_scal[0:1])
             if it > 0:
