@@ -398,8 +398,16 @@ __global__ void __launch_bounds__(256) factor_finish_kernel(const float* __restr
     if (k < r && c < R) {
       f = F_in[(int64_t)k * ld_in + c];
       if (APPLY) {
-        float num = 0.f;
-        for (int sp = 0; sp < splits; ++sp) num += partial[((int64_t)sp * r_pad + k) * ldp + c];   // fixed order
+        float num = 0.f;                            // fixed order; loads issued eight at a time (few blocks, many splits
+        int sp = 0;                                 // when the other dimension is short: NTD has 64 splits for 256 rows)
+        for (; sp + 8 <= splits; sp += 8) {
+          float t[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) t[u] = partial[((int64_t)(sp + u) * r_pad + k) * ldp + c];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) num += t[u];
+        }
+        for (; sp < splits; ++sp) num += partial[((int64_t)sp * r_pad + k) * ldp + c];
         const float v = f * (num / den[k]);
         f = v > floor_value ? v : floor_value;      // np.maximum(., epsilon); NaN propagates like numpy
         if (v != v) f = v;

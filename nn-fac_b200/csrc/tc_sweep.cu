@@ -20,6 +20,7 @@
 // partial sums through tagged 64-bit mailboxes (one L2 hop, no atomics), summed in a fixed order so that
 // every CTA takes the same decision; the first three blocks of the next sweep run speculatively meanwhile.
 // The final write-out also produces the bf16 operand planes of the result for the NMF plan (optional).
+#include <stdlib.h>
 #include <type_traits>
 
 #include "common.cuh"
@@ -591,6 +592,10 @@ int nnfac_tc_sweep_run(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const f
   if (r > RP || maxiter < 1) return NNFAC_ERR_UNSUPPORTED;
   int64_t cols = ceil_div64(n, ctx->sm_count);
   cols = ceil_div64(cols, 32) * 32;
+  if (const char* force = getenv("NNFAC_SWEEP_COLS")) {   // experiment switch: columns per CTA (multiple of 32)
+    const int64_t f = atoll(force);
+    if (f >= 32 && f % 32 == 0 && f > cols) cols = f;
+  }
   if (cols > MAX_TILES * TILE) return NNFAC_ERR_UNSUPPORTED;
   const int64_t grid = ceil_div64(n, cols);
   if ((size_t)(2 * grid * grid) > ctx->mail_count || maxiter > 65000) return NNFAC_ERR_UNSUPPORTED;
@@ -614,6 +619,8 @@ int nnfac_tc_sweep_run(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const f
   a.mail = ctx->mail; a.gen = gen_dev; a.result = result;
   const size_t smem = NPLANES * G_PLANE_BYTES + (size_t)MAX_TILES * NPLANES * PLANE_BYTES + 512;
   NNFAC_CUDA(cudaFuncSetAttribute(tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // every CTA waits for every other one once per sweep: the cooperative launch guarantees that all of them are resident
+  // (a plain launch was measured: no difference in launch cost)
   void* params[] = {&a};
   NNFAC_CUDA(cudaLaunchCooperativeKernel((const void*)tc_sweep_kernel, dim3((unsigned)grid), dim3(NTHREADS), params, smem, st));
   ctx->launches++;
