@@ -420,3 +420,63 @@ def test_core_pg_step3_equals_mode_products_plus_step(dt_name, ranks):
     np.testing.assert_allclose(b.double().cpu().numpy(), a.double().cpu().numpy(), **tol)
     np.testing.assert_allclose(sb[:3].cpu().numpy(), sa[:3].cpu().numpy(), rtol=1e-9 if dt == torch.float64 else 1e-4)
     assert sb[3].item() == sa[3].item() and (a != core0).any()
+
+
+@pytest.mark.parametrize("case", ["fixed0", "fixed2", "4way", "normalized_core"])
+def test_ntd_mu_fp32_variants_vs_oracle(case):
+    """fp32 NTD-MU beta = 1 on the tcgen05 path (fused factor passes, fused core-update contraction, shared cost / mode-0
+    pass, graph replay) for the cases that change which pass is shared with which: a fixed first or last mode, a 4-way
+    tensor (generic core step), a normalised core.  Objective within 1e-4 relative of the float64 oracle after 8 iterations."""
+    import nn_fac.ntd as ntd
+    from oracle import nnfac_oracle as orc
+    rng = np.random.RandomState(29)
+    if case == "4way":
+        shape, ranks = (14, 12, 16, 10), [3, 4, 2, 3]
+        sub = "abcd,ia,jb,kc,ld->ijkl"
+    else:
+        shape, ranks = (40, 36, 50), [6, 5, 7]
+        sub = "abc,ia,jb,kc->ijk"
+    nm = len(shape)
+    Fs = [rng.rand(s, r) for s, r in zip(shape, ranks)]
+    T = np.einsum(sub, rng.rand(*ranks), *Fs) + 0.05 * rng.rand(*shape) + 1e-3
+    G0, F0 = rng.rand(*ranks), [rng.rand(s, r) for s, r in zip(shape, ranks)]
+    fixed = {"fixed0": [0], "fixed2": [2]}.get(case, [])
+    normalize = [False] * nm + [case == "normalized_core"]
+    mcn = 1 if case == "normalized_core" else None
+    _, _, ref = orc.compute_ntd_mu(T, G0, F0, n_iter_max=8, tol=0, beta=1, fixed_modes=fixed, normalize=normalize, mode_core_norm=mcn)
+    f32 = lambda x: x.astype(np.float32)  # noqa: E731
+    core, factors, costs, _ = ntd.ntd(f32(T), list(ranks), init="custom", core_0=f32(G0), factors_0=[f32(f) for f in F0], n_iter_max=8,
+                                      tol=0, update_rule="mu", beta=1, sparsity_coefficients=[None] * (nm + 1), fixed_modes=list(fixed),
+                                      normalize=list(normalize), mode_core_norm=mcn, return_costs=True, deterministic=True)
+    assert len(costs) == 8
+    np.testing.assert_allclose(costs, ref, rtol=1e-4)
+    for m in fixed:
+        np.testing.assert_array_equal(factors[m], f32(F0[m]))
+
+
+@pytest.mark.parametrize("nway", [3, 4])
+def test_ntd_hals_fp32_tensor_core_contraction_matches_generic_path(nway, monkeypatch):
+    """ntd(update_rule="hals") in fp32: T x_j F_j^T (ntd.py:550) through the tcgen05 cross product over the planes of an
+    unfolding against the strided CUDA-core route (NNFAC_NTD_TC=0), and against the float64 oracle.  The normalised cost
+    (ntd.py:637-638) subtracts numbers of the size of ||T||^2, so fp32 paths agree to ~1e-6 absolute on it."""
+    import nn_fac.ntd as ntd
+    from oracle import nnfac_oracle as orc
+    rng = np.random.RandomState(41)
+    if nway == 4:
+        shape, ranks, sub = (14, 12, 16, 10), [3, 4, 2, 3], "abcd,ia,jb,kc,ld->ijkl"
+    else:
+        shape, ranks, sub = (40, 36, 50), [6, 5, 7], "abc,ia,jb,kc->ijk"
+    Fs = [rng.rand(s, r) for s, r in zip(shape, ranks)]
+    T = np.einsum(sub, rng.rand(*ranks), *Fs) + 0.05 * rng.rand(*shape)
+    G0, F0 = rng.rand(*ranks), [rng.rand(s, r) for s, r in zip(shape, ranks)]
+    _, _, ref = orc.compute_ntd_hals(T, G0, F0, n_iter_max=5, tol=0)
+    f32 = lambda x: x.astype(np.float32)  # noqa: E731
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("NNFAC_NTD_TC", flag)
+        _, _, costs, _ = ntd.ntd(f32(T), list(ranks), init="custom", core_0=f32(G0), factors_0=[f32(f) for f in F0], n_iter_max=5, tol=0,
+                                 update_rule="hals", sparsity_coefficients=[None] * (nway + 1), fixed_modes=[],
+                                 normalize=[False] * (nway + 1), return_costs=True, deterministic=True)
+        out[flag] = costs
+        np.testing.assert_allclose(costs, ref, atol=3e-6, rtol=2e-2)
+    np.testing.assert_allclose(out["1"], out["0"], atol=3e-6, rtol=2e-2)
