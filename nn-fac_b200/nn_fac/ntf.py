@@ -62,6 +62,7 @@ class DeviceNTF:
         self.factors = [L.to_device(f, dtype, device) for f in factors]
         self.factors_t = [ops.transpose(f) for f in self.factors]           # rank-major copies (r x I): sweep / Gram / MTTKRP layout
         self.norm_sq = None
+        self._grams, self._gram_ok = None, [False] * len(self.factors)      # see _gram
         self.stats = torch.zeros(4, dtype=torch.float64, device=self.T.device)
         # fp32, rank <= 128: the MTTKRP of every mode runs on tcgen05.  One plan per mode holds unfold(T, mode)
         # (I_mode x rest, C order) as K-major bf16 hi/lo planes -- the same bytes as the fp32 unfolded copies the
@@ -74,6 +75,22 @@ class DeviceNTF:
                 Xm = self.T.movedim(mode, 0).reshape(self.shape[mode], -1).contiguous()
                 self.plans.append(ops.NMFPlan(Xm).bind_rank(rank))
                 del Xm
+
+    def _gram(self, i):
+        """F_i^T F_i of the HALS path, kept until factor i changes (the reference recomputes the Gram of every other factor
+        for every mode, ntf.py:442-445: each one twice per iteration).  Fixed buffers, so that a graph-replayed iteration
+        reads what the previous replay wrote."""
+        if self._grams is None:
+            r = int(self.factors_t[0].shape[0])
+            self._grams = [torch.empty((r, r), dtype=self.T.dtype, device=self.T.device) for _ in self.factors_t]
+        if not self._gram_ok[i]:
+            ops.gram(self.factors_t[i], out=self._grams[i])
+            self._gram_ok[i] = True
+        return self._grams[i]
+
+    def invalidate(self):
+        """The factors were replaced from outside (roll-back of a speculative iteration)."""
+        self._gram_ok = [False] * len(self.factors)
 
     def get_state(self):
         return list(self.factors) + list(self.factors_t)
@@ -127,8 +144,8 @@ class DeviceNTF:
             if update_rule == "hals":
                 cross = None
                 for i in others:
-                    gram = ops.gram(self.factors_t[i])                       # F_i^T F_i, ntf.py:445
-                    cross = gram if cross is None else ops.hadamard_(cross, gram)
+                    gram = self._gram(i)                                     # F_i^T F_i, ntf.py:445
+                    cross = gram.clone() if cross is None else ops.hadamard_(cross, gram)
                 if fused_krao:
                     # MTTKRP (ntf.py:448-449) on tcgen05: the Khatri-Rao operand goes straight into its bf16 planes
                     self.plans[mode].set_krao(self.factors_t[others[0]], self.factors_t[others[1]])
@@ -146,17 +163,19 @@ class DeviceNTF:
                                       nonzero=False, result=self.stats)    # ntf.py:454-456
                 self.factors_t[mode] = Ft
                 self.factors[mode] = ops.transpose(Ft)
+                self._gram_ok[mode] = False
             else:
                 F = self.factors[mode]
                 K = self.reconstruct_unfolded(mode, krao)
                 self.factors[mode] = self._mu_factor(F, krao, K, mode, beta)   # ntf.py:459-460
                 self.factors_t[mode] = ops.transpose(self.factors[mode])
+                self._gram_ok[mode] = False
         # the cost terms stay on the device: [rec part a, rec part b, sparsity l1 norms...] (see finish_cost)
         terms = []
         F = self.factors[mode]
         if update_rule == "hals":
             # ntf.py:470; ||F krao^T||^2 = <F^T F, krao^T krao> and krao^T krao = cross (Hadamard of Grams)
-            ftf = ops.gram(self.factors_t[mode])
+            ftf = self._gram(mode)
             inner = ops.dot(F, rhs) if rhs is not None else ops.dot(Ft, rhs_t)     # <F, rhs>, either layout
             terms += [inner, ops.dot(ftf, cross)]
         else:
@@ -285,6 +304,7 @@ def compute_ntf(tensor_in, rank, factors_in, n_iter_max=100, tol=1e-8,
                     else:
                         state.factors = before
                         state.factors_t = [ops.transpose(f) for f in before]
+                    state.invalidate()
                 break
         if iteration == n_iter_max:
             break
