@@ -9,7 +9,24 @@ iteration eagerly before (lazy initialisation, workspace growth) -- the outer lo
 Everything captured is this library's own kernels plus torch copies; the HALS solve is capturable because its mailbox
 generation lives in device memory (csrc/tc_sweep.cu, sweep_prep_kernel).
 """
+import warnings
+
 import torch
+
+
+def try_capture(device, get_state, set_state, step, on_fail=None):
+    """GraphedIteration, or None (with a warning) when the iteration cannot be captured on this system: the caller then
+    keeps launching kernel by kernel -- same kernels, same results, only slower."""
+    keep = [t.clone() for t in get_state()]
+    try:
+        return GraphedIteration(device, get_state, set_state, step)
+    except RuntimeError as exc:                      # capture refused (driver / allocator state): not an arithmetic problem
+        warnings.warn(f"CUDA graph capture of the outer iteration failed ({exc}); continuing with eager launches")
+        torch.cuda.synchronize(device)
+        set_state(keep)
+        if on_fail is not None:                      # the host-side bookkeeping of `step` ran although its kernels did not
+            on_fail()
+        return None
 
 
 class GraphedIteration:

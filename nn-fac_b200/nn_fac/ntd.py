@@ -16,7 +16,7 @@ import nn_fac.update_rules.mu as mu
 import nn_fac.utils.errors as err
 import nn_fac.utils.initialize_factors as init_factors
 from nn_fac import _lib as L
-from nn_fac._graph import GraphedIteration
+from nn_fac._graph import try_capture
 from nn_fac import _ops as ops
 from nn_fac.utils.beta_divergence import gamma_beta
 
@@ -86,6 +86,10 @@ class DeviceNTD:
                 Xm = self.T.movedim(mode, 0).reshape(self.T.shape[mode], -1).contiguous()
                 self.plans.append(ops.NMFPlan(Xm).bind_rank(int(self.factors[mode].shape[1])))
                 del Xm
+
+    def invalidate(self):
+        """Core / factors were replaced from outside: nothing left in the plans refers to them."""
+        self._m0_ready = False
 
     def get_state(self):
         return [self.core] + list(self.factors)
@@ -336,9 +340,9 @@ def compute_ntd(tensor_in, ranks, core_in, factors_in, n_iter_max=100, tol=1e-6,
     use_graph = (not hals) and n_iter_max >= 4 and state.T.is_cuda and os.environ.get("NNFAC_NTD_GRAPH", "1") != "0"
     for iteration in range(n_iter_max + 1):
         if iteration < n_iter_max:
-            if use_graph and iteration == 1:
-                graphed = GraphedIteration(state.T.device, state.get_state, state.set_state,
-                                           lambda: state.step_mu_async(beta, fixed_modes, normalize, mode_core_norm))
+            if use_graph and iteration == 1 and graphed is None:
+                graphed = try_capture(state.T.device, state.get_state, state.set_state,
+                                      lambda: state.step_mu_async(beta, fixed_modes, normalize, mode_core_norm), state.invalidate)
             if graphed is not None:
                 cost_dev = graphed.replay()
             else:
@@ -370,7 +374,7 @@ def compute_ntd(tensor_in, ranks, core_in, factors_in, n_iter_max=100, tol=1e-6,
                         graphed.roll_back()
                     else:
                         state.core, state.factors = before
-                    state._m0_ready = False
+                    state.invalidate()
                 break
         if iteration == n_iter_max:
             break

@@ -18,7 +18,7 @@ import nn_fac.update_rules.nnls as nnls
 import nn_fac.utils.errors as err
 import nn_fac.utils.initialize_factors as init_factors
 from nn_fac import _lib as L
-from nn_fac._graph import GraphedIteration
+from nn_fac._graph import try_capture
 from nn_fac import _ops as ops
 
 
@@ -274,9 +274,9 @@ def compute_ntf(tensor_in, rank, factors_in, n_iter_max=100, tol=1e-8,
     use_graph = n_iter_max >= 4 and state.T.is_cuda and os.environ.get("NNFAC_NTF_GRAPH", "1") != "0"
     for iteration in range(n_iter_max + 1):
         if iteration < n_iter_max:
-            if use_graph and iteration == 1:
-                graphed = GraphedIteration(state.T.device, state.get_state, state.set_state, lambda: state.step_async(
-                    rank, norm_tensor, update_rule, beta, sparsity_coefficients, fixed_modes, normalize))
+            if use_graph and iteration == 1 and graphed is None:
+                graphed = try_capture(state.T.device, state.get_state, state.set_state, lambda: state.step_async(
+                    rank, norm_tensor, update_rule, beta, sparsity_coefficients, fixed_modes, normalize), state.invalidate)
             if graphed is not None:
                 terms = graphed.replay()
             else:
