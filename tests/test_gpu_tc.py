@@ -480,3 +480,19 @@ def test_ntd_hals_fp32_tensor_core_contraction_matches_generic_path(nway, monkey
         out[flag] = costs
         np.testing.assert_allclose(costs, ref, atol=3e-6, rtol=2e-2)
     np.testing.assert_allclose(out["1"], out["0"], atol=3e-6, rtol=2e-2)
+
+
+def test_nmf_hals_more_columns_than_the_tensor_core_solve_covers():
+    """m beyond 512 columns per SM: the U solve falls back from the tcgen05 sweep to the CUDA-core sweep, which needs the
+    REDUCED right-hand side although the X pass left split-K partials in the plan (nnfac_nmf_plan_reduce)."""
+    import nn_fac.nmf as nmf
+    from oracle import nnfac_oracle as orc
+    rng = np.random.RandomState(8)
+    m, n, r = 80000, 192, 8
+    X = rng.rand(m, r) @ rng.rand(r, n) + 0.2 * rng.rand(m, n)
+    U0, V0 = rng.rand(m, r), rng.rand(r, n)
+    _, _, ref, _ = orc.compute_nmf(X, U0, V0, n_iter_max=4, tol=0, update_rule="hals")
+    f32 = lambda x: x.astype(np.float32)  # noqa: E731
+    _, _, costs, _ = nmf.nmf(f32(X), r, init="custom", U_0=f32(U0), V_0=f32(V0), n_iter_max=4, tol=0, update_rule="hals",
+                             return_costs=True, deterministic=True)
+    np.testing.assert_allclose(costs, ref[:len(costs)], rtol=1e-4)
