@@ -109,8 +109,8 @@ class CudaEngine:
     def set_factor(self, which, Ft):
         self.plan.set_factor(which, Ft)
 
-    def fused(self, side, mode, want_cost, keep_partials=False, cost_out=None):
-        return self.plan.fused(side, mode, want_cost=want_cost, keep_partials=keep_partials, cost_out=cost_out)
+    def fused(self, side, mode, want_cost, keep_partials=False, cost_out=None, out=None):
+        return self.plan.fused(side, mode, want_cost=want_cost, keep_partials=keep_partials, cost_out=cost_out, out=out)
 
     def mu_finish(self, which, F, den_vec):
         """mu.py:84-88 on the numerator the last fused(which, MODE_MU, keep_partials=True) left in the plan,
@@ -320,7 +320,8 @@ class FusedNMF:
                 den = den_join() if den_join is not None else eng.row_sums(V)      # mu.py:85-87
                 if comm.world > 1:
                     xb = self._xbuf[:r * m + r]
-                    xb[:r * m].view(r, m).copy_(numU)
+                    if numU.data_ptr() != xb.data_ptr():
+                        xb[:r * m].view(r, m).copy_(numU)
                     xb[r * m:].copy_(den)
                     comm.sum_(xb)
                     numU, den = xb[:r * m].view(r, m), xb[r * m:]
@@ -362,7 +363,12 @@ class FusedNMF:
                 keep = self.comm.world == 1 and it < n_iter_max and 0 not in fixed_modes and (
                     mode == MODE_MU or (_SPLIT_RHS in ("u", "1") and not mu2 and not normalize[0] and hasattr(self.eng, "plan")))
                 # the cost lands directly in the scalar block that travels to the host
-                outA, _ = self.eng.fused(0, mode, True, keep_partials=keep, cost_out=self._dev_scal[0:1])
+                if self.comm.world > 1 and mode == MODE_MU and hasattr(self.eng, "plan"):
+                    # sharded MU: the partial numerator lands directly in the exchange buffer (no 16.8 MB copy before the sum)
+                    outA, _ = self.eng.fused(0, mode, True, cost_out=self._dev_scal[0:1],
+                                             out=self._xbuf[:self.r * self.m].view(self.r, self.m))
+                else:
+                    outA, _ = self.eng.fused(0, mode, True, keep_partials=keep, cost_out=self._dev_scal[0:1])
             if it > 0:
                 self.comm.sum_(self._dev_scal[0:1])
                 if with_sparsity:       # nmf.py:449-452: matrix 1-norms of the factors the cost refers to
