@@ -41,7 +41,9 @@ typedef enum {
 #define NNFAC_HALS_NORMALIZE 1u /* nnls.py:179-185 */
 #define NNFAC_HALS_NONZERO 2u   /* nnls.py:173-177 */
 
-typedef struct nnfac_ctx nnfac_ctx; /* per-device workspace + launch limits; not thread-safe */
+typedef struct nnfac_ctx nnfac_ctx; /* per-device workspace + launch limits; not thread-safe.  Scratch shared by several
+                                     * kernels is guarded: a call on another stream than the last user of the same
+                                     * scratch first waits for that user, so streams are ordered, never racing. */
 
 int nnfac_abi_version(void);
 const char* nnfac_last_error(void);
@@ -50,6 +52,23 @@ int nnfac_ctx_destroy(nnfac_ctx* ctx);
 int nnfac_ctx_sm_count(const nnfac_ctx* ctx);
 /* Number of kernels this library has launched on behalf of `ctx` since creation. */
 int64_t nnfac_ctx_launch_count(const nnfac_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------------
+ * Collective HALS solves (several GPUs of one node, one process per GPU; new -- the reference is single-process).
+ * When the columns of one solve (nn_fac/update_rules/nnls.py:156-198) are spread over several GPUs, the stop test of
+ * nnls.py:156 still sums the squared steps of ALL columns (nnls.py:170,195).  Each rank owns a small "board" in its
+ * device memory; the sweep kernels of all ranks post their partial sums on every board over NVLink (peer-mapped memory)
+ * once per sweep and take the same decision, so the sharded solve stops after exactly the sweeps of the unsharded one.
+ *   1. every rank: nnfac_ctx_board_export(ctx, handle)          -> 64-byte CUDA IPC handle of its board
+ *   2. exchange the handles between the ranks (any transport; the host layer uses torch.distributed.all_gather)
+ *   3. every rank: nnfac_ctx_board_attach(ctx, world, rank, handles ( world x 64 bytes, in rank order ))
+ *   4. nnfac_ctx_collective(ctx, 1, slice_lengths ( columns of every rank's slice )) before a solve that is one slice
+ *      of a joint solve -- every rank must make the same sequence of such solves -- and (ctx, 0, NULL) after it.
+ * world <= 8.  Applies to the tensor-core sweep (fp32, rank <= 128: nnfac_nmf_plan_hals_solve, nnfac_hals_nnls).
+ * -------------------------------------------------------------------------------------------*/
+int nnfac_ctx_board_export(nnfac_ctx* ctx, void* handle_out);
+int nnfac_ctx_board_attach(nnfac_ctx* ctx, int world, int rank, const void* handles);
+int nnfac_ctx_collective(nnfac_ctx* ctx, int on, const int64_t* slice_lengths);
 
 /* ---------------------------------------------------------------------------------------------
  * HALS NNLS solver: replaces nn_fac/update_rules/nnls.py:156-198 (hals_nnls_acc sweep loop with
@@ -62,6 +81,11 @@ int64_t nnfac_ctx_launch_count(const nnfac_ctx* ctx);
 int nnfac_hals_nnls(nnfac_ctx* ctx, int dtype, const void* UtM, int64_t ld_utm, const void* UtU,
                     int64_t ld_utu, void* V, int64_t ld_v, int r, int64_t n, int maxiter,
                     double delta, double sparsity, unsigned flags, double* result, void* stream);
+/* Out-of-place fp32 variant: Vout = hals_nnls_acc(UtM, UtU, Vin), Vin is not modified (nnls.py:147 makes that copy).
+ * Same rule and result vector; no normalize / nonzero. */
+int nnfac_hals_solve_f32(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const float* UtU, int64_t ld_utu,
+                         const float* Vin, int64_t ld_vin, float* Vout, int64_t ld_vout, int r, int64_t n, int maxiter,
+                         double delta, double sparsity, double* result, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Strided, batched, K-blocked GEMM on CUDA cores (fp32 or fp64 accumulate in the operand type):
@@ -188,16 +212,21 @@ int nnfac_nmf_plan_reduce(nnfac_nmf_plan* plan, int side, float* out, int64_t ld
 /* Install a factor into the plan (builds all of its bf16 operand planes):
  * which = 0: U, passed as U^T (r x m, row-major); which = 1: V (r x n). */
 int nnfac_nmf_plan_set_factor(nnfac_nmf_plan* plan, int which, const float* Ft, int64_t ld, void* stream);
+/* The same from the output of an all-gather of column slices, G = [slices][r][chunk] (slice s = columns
+ * [s*chunk, (s+1)*chunk) of the factor); also writes the factor itself, rank-major, into Ft_out (r x len). */
+int nnfac_nmf_plan_set_factor_gathered(nnfac_nmf_plan* plan, int which, const float* G, int64_t chunk, float* Ft_out,
+                                       int64_t ld_out, void* stream);
 /* HALS solve of factor `which` (nn_fac/update_rules/nnls.py:24-198, deterministic rule, no normalize / nonzero) whose
  * result F_out (r x len, may not alias F_in) is installed in the plan by the sweep kernel itself (no separate pass over
  * the factor).  result: double[4] = {eps, cnt, -1, sweeps}.  Returns NNFAC_ERR_UNSUPPORTED without an error text when
- * the shape is outside the tensor-core sweep (rank > 64 or more than 512 columns per SM): use nnfac_hals_nnls +
+ * the shape is outside the tensor-core sweep (rank > 128, or more than 512 columns per SM at rank <= 64 / 256 at rank
+ * <= 128): use nnfac_hals_nnls +
  * nnfac_nmf_plan_set_factor then.  UtM == NULL: the right-hand side is the sum of the split-K partials the last X pass
  * over side `which` left in the plan (the solve adds them in the reduction kernel's order). */
 int nnfac_nmf_plan_hals_solve(nnfac_nmf_plan* plan, int which, const float* UtM, int64_t ld_utm, const float* UtU,
                               int64_t ld_utu, const float* F_in, int64_t ld_in, float* F_out, int64_t ld_out, int maxiter,
                               double delta, double sparsity, double* result, void* stream);
-/* One fused X pass (rank <= 64) over side 0 (rows of X) or side 1 (rows of X^T), using the installed
+/* One fused X pass (mode 0: rank <= 128, mode 1: rank <= 64) over side 0 (rows of X) or side 1 (rows of X^T), using the installed
  * factors: the model tile U V is formed and consumed on chip, never written to HBM.
  *   mode 0: out (r x rows) = the HALS cross product of nmf.py:408 / :433, cost_out = ||X - U V||_F^2 (nmf.py:452)
  *   mode 1: out (r x rows) = the beta=1 MU numerator ((X / UV) V^T)^T of mu.py:84-88 (side 0) or its
@@ -214,6 +243,14 @@ int nnfac_nmf_plan_mu_finish(nnfac_nmf_plan* plan, int which, const float* F_in,
 /* Work decomposition chosen for one side (for benchmarks / DESIGN.md); any pointer may be NULL. */
 int nnfac_nmf_plan_info(const nnfac_nmf_plan* plan, int which, int* splits, int* stages_per_unit,
                         int* num_units, int* num_stages, int* grid);
+
+/* ---------------------------------------------------------------------------------------------
+ * Synthetic data for benchmarks and tests (not on the factorisation path): out[i][j] (+)= scale * u, u uniform in [0, 1),
+ * a pure function of (seed, stream_id, row0 + i, col0 + j) -- Philox4x32-10, counter (row, column, stream, 0) -- so that
+ * any shard of a matrix on any number of GPUs regenerates the same values.  Device fp32, row-major.
+ * -------------------------------------------------------------------------------------------*/
+int nnfac_philox_uniform(nnfac_ctx* ctx, float* out, int64_t ld, int64_t rows, int64_t cols, int64_t row0, int64_t col0,
+                         uint64_t seed, uint32_t stream_id, double scale, int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

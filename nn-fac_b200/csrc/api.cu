@@ -29,6 +29,28 @@ int nnfac_ws_reserve(nnfac_ctx* ctx, size_t bytes, cudaStream_t st) {
   return NNFAC_OK;
 }
 
+int nnfac_guard_enter(nnfac_ctx* ctx, int which, cudaStream_t st) {
+  nnfac_guard* g = &ctx->guard[which];
+  if (g->valid && g->last != st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) cudaGetLastError();
+    if (cs != cudaStreamCaptureStatusNone) return NNFAC_OK;       // a captured sequence is single-stream by construction
+    if (!g->ev) NNFAC_CUDA(cudaEventCreateWithFlags(&g->ev, cudaEventDisableTiming));
+    if (cudaEventRecord(g->ev, g->last) == cudaSuccess) {
+      NNFAC_CUDA(cudaStreamWaitEvent(st, g->ev, 0));
+    } else {
+      cudaGetLastError();                                          // the last user's stream is gone: drain the device instead
+      NNFAC_CUDA(cudaDeviceSynchronize());
+    }
+  }
+  g->last = st;
+  g->valid = 1;
+  return NNFAC_OK;
+}
+
+// layout of a stop-scalar board: 4 banks x NNFAC_MAX_PEERS ranks x 160 CTAs of 8 bytes (see csrc/tc_sweep.cu)
+static const size_t kBoardBytes = (size_t)4 * NNFAC_MAX_PEERS * 160 * sizeof(unsigned long long);
+
 extern "C" {
 
 int nnfac_abi_version(void) { return NNFAC_ABI_VERSION; }
@@ -72,7 +94,58 @@ int nnfac_ctx_destroy(nnfac_ctx* ctx) {
   cudaFree(ctx->red);
   cudaFree(ctx->sync);
   cudaFree(ctx->mail);
+  for (int q = 0; q < ctx->peers.world; ++q)
+    if (q != ctx->peers.rank && ctx->peers.board[q]) cudaIpcCloseMemHandle(ctx->peers.board[q]);
+  cudaFree(ctx->board);
+  for (int i = 0; i < NNFAC_NGUARD; ++i)
+    if (ctx->guard[i].ev) cudaEventDestroy(ctx->guard[i].ev);
   free(ctx);
+  return NNFAC_OK;
+}
+
+// ---- collective HALS solves over several GPUs (one process each) -------------------------------------------------
+// 1. every rank: nnfac_ctx_board_export -> 64-byte IPC handle of its board; 2. exchange the handles (any transport);
+// 3. every rank: nnfac_ctx_board_attach(world, rank, handles); 4. around a solve that is one slice of a joint solve:
+// nnfac_ctx_collective(ctx, 1, slice_lengths) ... nnfac_ctx_collective(ctx, 0, NULL).
+int nnfac_ctx_board_export(nnfac_ctx* ctx, void* handle_out) {
+  NNFAC_ARG(ctx && handle_out, "nnfac_ctx_board_export: NULL argument");
+  NNFAC_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->board) {
+    NNFAC_CUDA(cudaMalloc(&ctx->board, kBoardBytes));
+    NNFAC_CUDA(cudaMemset(ctx->board, 0, kBoardBytes));
+    NNFAC_CUDA(cudaDeviceSynchronize());
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  NNFAC_CUDA(cudaIpcGetMemHandle(&h, ctx->board));
+  memcpy(handle_out, &h, sizeof(h));
+  return NNFAC_OK;
+}
+
+int nnfac_ctx_board_attach(nnfac_ctx* ctx, int world, int rank, const void* handles) {
+  NNFAC_ARG(ctx && handles && world >= 1 && world <= NNFAC_MAX_PEERS && rank >= 0 && rank < world, "nnfac_ctx_board_attach: bad argument");
+  NNFAC_ARG(ctx->board != nullptr, "nnfac_ctx_board_attach: call nnfac_ctx_board_export first");
+  NNFAC_CUDA(cudaSetDevice(ctx->device));
+  for (int q = 0; q < ctx->peers.world; ++q)
+    if (q != ctx->peers.rank && ctx->peers.board[q]) cudaIpcCloseMemHandle(ctx->peers.board[q]);
+  memset(&ctx->peers, 0, sizeof(ctx->peers));
+  for (int q = 0; q < world; ++q) {
+    if (q == rank) { ctx->peers.board[q] = ctx->board; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)q * sizeof(h), sizeof(h));
+    NNFAC_CUDA(cudaIpcOpenMemHandle(&ctx->peers.board[q], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  ctx->peers.world = world;
+  ctx->peers.rank = rank;
+  return NNFAC_OK;
+}
+
+int nnfac_ctx_collective(nnfac_ctx* ctx, int on, const int64_t* slice_lengths) {
+  NNFAC_ARG(ctx != nullptr, "nnfac_ctx_collective: ctx is NULL");
+  if (!on) { ctx->collective = 0; return NNFAC_OK; }
+  NNFAC_ARG(ctx->peers.world > 1 && slice_lengths, "nnfac_ctx_collective: no peer group attached");
+  for (int q = 0; q < ctx->peers.world; ++q) ctx->collective_n[q] = slice_lengths[q];
+  ctx->collective = 1;
   return NNFAC_OK;
 }
 

@@ -7,6 +7,25 @@
 
 #include "../../include/nnfac_b200.h"
 
+// Scratch of a context that several kernels share (split-K workspace, reduction partials, the sweep's constant bank and
+// mailboxes).  A context is used from one stream at a time; when a call arrives on ANOTHER stream than the last user of
+// the same scratch, that stream is first made to wait for the last user (nnfac_guard_enter), so calls on different
+// streams are ordered instead of racing.
+enum { NNFAC_GUARD_WS = 0, NNFAC_GUARD_RED = 1, NNFAC_GUARD_SWEEP = 2, NNFAC_NGUARD = 3 };
+struct nnfac_guard {
+  cudaStream_t last;
+  cudaEvent_t ev;
+  int valid;
+};
+
+// Ranks of a collective HALS solve (one process per GPU): board[q] is rank q's stop-scalar board as mapped into this
+// process (cudaIpcOpenMemHandle; board[rank] is the local allocation).
+#define NNFAC_MAX_PEERS 8
+struct nnfac_peer_group {
+  int world, rank;
+  void* board[NNFAC_MAX_PEERS];
+};
+
 struct nnfac_ctx {
   int device;
   int sm_count;
@@ -18,6 +37,13 @@ struct nnfac_ctx {
   unsigned* sync;   // grid-barrier counters (zeroed before each cooperative launch)
   unsigned long long* mail;   // tagged mailboxes of the tensor-core HALS sweep (zeroed once; tags carry a call generation
   size_t mail_count;          // that lives in device memory, in the word behind the last mailbox: mail[mail_count])
+  void* sweep_const[2];       // device address of the sweep's __constant__ bank for padded rank 64 / 128 (per device)
+  nnfac_guard guard[NNFAC_NGUARD];
+  void* board;                // local stop-scalar board of collective solves (cudaMalloc, IPC-exported)
+  nnfac_peer_group peers;
+  int collective;             // the next tensor-core sweeps are collective over `peers`
+  int64_t collective_n[NNFAC_MAX_PEERS];   // columns of every rank's slice
+  unsigned collective_gen;    // collective call counter (advances identically on every rank)
 };
 
 void nnfac_set_error(const char* fmt, ...);
@@ -25,14 +51,16 @@ void nnfac_set_error(const char* fmt, ...);
 // operand planes the tensor-core HALS sweep can write for the NMF plan (all bf16; see csrc/tc_sweep.cu)
 struct nnfac_sweep_planes {
   void *fh, *fl;      // [r_pad x ld_plane] K-major hi / lo
-  void *rowh, *rowl;  // [n x 64] rank-contiguous hi / lo (NULL: not wanted)
+  void *rowh, *rowl;  // [n x row_pitch] rank-contiguous hi / lo (NULL: not wanted)
   int64_t ld_plane;
   int r_pad;
+  int row_pitch;      // 64 or 128
 };
 int nnfac_tc_sweep_run(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const float* UtU, int64_t ld_utu, const float* Vin,
                        int64_t ld_vin, float* V, int64_t ld_v, int r, int64_t n, int maxiter, double delta, double sparsity,
                        double* result, const nnfac_sweep_planes* planes, cudaStream_t st, int nsplit, int64_t split_stride);
 int nnfac_ws_reserve(nnfac_ctx* ctx, size_t bytes, cudaStream_t st);
+int nnfac_guard_enter(nnfac_ctx* ctx, int which, cudaStream_t st);
 
 #define NNFAC_CUDA(call)                                                                   \
   do {                                                                                     \

@@ -59,8 +59,10 @@ __device__ __forceinline__ double red_term(int op, double beta, const T* A, cons
   if (op == 5) return a * a;
   const double b = (double)B[i];
   switch (op) {
-    case 0: return a * log(a / b) - a + b;
-    case 1: { const double q = a / b; return q - log(q) - 1.0; }
+    // beta_divergence.py:45-50 masks the logarithm where its argument is 0 (`where=`): an entry with a == 0 contributes
+    // b (beta = 1) or a / b - 1 (beta = 0), not 0 * log(0) = NaN / +inf -- sparse and count data have exact zeros
+    case 0: return (a != 0.0 ? a * log(a / b) : 0.0) - a + b;
+    case 1: { const double q = a / b; return q - (a != 0.0 ? log(q) : 0.0) - 1.0; }
     case 2: return (pow(a, beta) + (beta - 1.0) * pow(b, beta) - beta * a * pow(b, beta - 1.0)) / (beta * (beta - 1.0));
     case 3: { const double d = a - b; return d * d; }
     default: return a * b;
@@ -91,6 +93,8 @@ int run_reduce(nnfac_ctx* ctx, int op, double beta, const T* A, const T* B, int6
                cudaStream_t st) {
   int blocks = (int)(ceil_div64(count, RB * 4) < RMAX_BLOCKS ? ceil_div64(count, RB * 4) : RMAX_BLOCKS);
   if (blocks < 1) blocks = 1;
+  const int grc = nnfac_guard_enter(ctx, NNFAC_GUARD_RED, st);
+  if (grc) return grc;
   reduce_stage1<T><<<blocks, RB, 0, st>>>(op, beta, A, B, count, ctx->red);
   NNFAC_LAUNCH_CHECK(ctx);
   reduce_stage2<<<1, RB, 0, st>>>(ctx->red, blocks, out, 0);
@@ -387,6 +391,8 @@ int nnfac_norm1(nnfac_ctx* ctx, int dtype, const void* A, int64_t lda, int64_t r
   NNFAC_ARG(ctx && A && out && rows > 0 && cols > 0, "nnfac_norm1: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   int blocks = (int)(ceil_div64(cols, RB) < RMAX_BLOCKS ? ceil_div64(cols, RB) : RMAX_BLOCKS);
+  const int grc = nnfac_guard_enter(ctx, NNFAC_GUARD_RED, st);
+  if (grc) return grc;
   DISPATCH_T(dtype, (norm1_stage1<float><<<blocks, RB, 0, st>>>((const float*)A, lda, rows, cols, ctx->red)),
              (norm1_stage1<double><<<blocks, RB, 0, st>>>((const double*)A, lda, rows, cols, ctx->red)));
   NNFAC_LAUNCH_CHECK(ctx);
@@ -435,6 +441,8 @@ static int core_pg_step_impl(nnfac_ctx* ctx, int dtype, void* core, const void* 
   int blocks = (int)(ceil_div64(count, RB) < RMAX_BLOCKS ? ceil_div64(count, RB) : RMAX_BLOCKS);
   // the partials live behind the mailbox area of the sweep so that they never collide with other reductions in flight
   double* part = ctx->red + 32768;
+  const int grc = nnfac_guard_enter(ctx, NNFAC_GUARD_RED, st);
+  if (grc) return grc;
   DISPATCH_T(dtype, (core_pg_step_kernel<float><<<blocks, RB, 0, st>>>((float*)core, (const float*)MtX, (const float*)P, count,
                                                                         (float)step, (float)sparse, dev_scalars, state, part)),
              (core_pg_step_kernel<double><<<blocks, RB, 0, st>>>((double*)core, (const double*)MtX, (const double*)P, count, step,
@@ -462,6 +470,8 @@ static int core_pg_step3_launch(nnfac_ctx* ctx, T* core, const T* MtX, const T* 
   NNFAC_CUDA(cudaFuncSetAttribute(core_mode0_step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
   const int ncol = r1 * r2, blocks = (ncol + 127) / 128;
   double* part = ctx->red + 32768;
+  const int grc = nnfac_guard_enter(ctx, NNFAC_GUARD_RED, st);
+  if (grc) return grc;
   core_modes12_kernel<T><<<r0, 256, smem_a, st>>>(core, M1, M2, Z, r1, r2, state);
   NNFAC_LAUNCH_CHECK(ctx);
   core_mode0_step_kernel<T><<<blocks, 128, smem_b, st>>>(core, MtX, Z, M0, r0, ncol, (T)step, (T)sparse, dev_scalars, state, part);

@@ -146,7 +146,8 @@ int run_gemm(nnfac_ctx* ctx, T* C, int64_t ldc, int64_t sc_b, const T* A, int64_
   g.partial = nullptr;
   if (splits > 1) {
     const size_t need = (size_t)splits * batch * M * N * sizeof(T);
-    int rc = nnfac_ws_reserve(ctx, need, st);
+    int rc = nnfac_guard_enter(ctx, NNFAC_GUARD_WS, st);
+    if (!rc) rc = nnfac_ws_reserve(ctx, need, st);
     if (rc) return rc;
     g.partial = (T*)ctx->ws;
   }
@@ -227,7 +228,8 @@ int run_gram(nnfac_ctx* ctx, T* out, int64_t ld_out, const T* F, int64_t ld_f, i
   cols = ceil_div64(cols, GC) * GC;
   const int grid = (int)ceil_div64(len, cols);
   const size_t need = (size_t)grid * GR * GR * sizeof(T);
-  const int rc = nnfac_ws_reserve(ctx, need, st);
+  int rc = nnfac_guard_enter(ctx, NNFAC_GUARD_WS, st);
+  if (!rc) rc = nnfac_ws_reserve(ctx, need, st);
   if (rc != NNFAC_OK) return rc;
   gram_partial_kernel<T><<<grid, 256, 0, st>>>(F, ld_f, r, len, cols, (T*)ctx->ws);
   NNFAC_LAUNCH_CHECK(ctx);

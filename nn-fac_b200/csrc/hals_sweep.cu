@@ -68,3 +68,26 @@ extern "C" int nnfac_hals_nnls(nnfac_ctx* ctx, int dtype, const void* UtM, int64
   nnfac_set_error("nnfac_hals_nnls: bad dtype %d", dtype);
   return NNFAC_ERR_ARG;
 }
+
+// Out-of-place fp32 solve: Vout (r x n) = hals_nnls_acc(UtM, UtU, Vin) with Vin untouched (the copy of nnls.py:147 happens
+// inside the kernel: the tensor-core sweep reads its start values from Vin and writes the result to Vout).  Used for the
+// slice solves of the sharded path, whose input is a strided view of the full factor and whose output is the contiguous
+// send buffer of the all-gather.  Shapes outside the tensor-core sweep: a strided copy, then the in-place solver.
+extern "C" int nnfac_hals_solve_f32(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const float* UtU, int64_t ld_utu,
+                                    const float* Vin, int64_t ld_vin, float* Vout, int64_t ld_vout, int r, int64_t n, int maxiter,
+                                    double delta, double sparsity, double* result, void* stream) {
+  NNFAC_ARG(ctx && UtM && UtU && Vin && Vout && result, "nnfac_hals_solve_f32: NULL argument");
+  NNFAC_ARG(r > 0 && n > 0, "nnfac_hals_solve_f32: empty problem (r=%d, n=%lld)", r, (long long)n);
+  NNFAC_ARG(ld_utm >= n && ld_vin >= n && ld_vout >= n && ld_utu >= r, "nnfac_hals_solve_f32: leading dimension too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  static const bool force_fma = getenv("NNFAC_SWEEP") && !strcmp(getenv("NNFAC_SWEEP"), "fma");
+  if (!force_fma) {
+    const int rc = nnfac_tc_sweep_run(ctx, UtM, ld_utm, UtU, ld_utu, Vin, ld_vin, Vout, ld_vout, r, n, maxiter, delta, sparsity,
+                                      result, nullptr, st, 1, 0);
+    if (rc != NNFAC_ERR_UNSUPPORTED) return rc;
+  }
+  if (Vin != Vout)
+    NNFAC_CUDA(cudaMemcpy2DAsync(Vout, ld_vout * sizeof(float), Vin, ld_vin * sizeof(float), n * sizeof(float), r,
+                                 cudaMemcpyDeviceToDevice, st));
+  return nnfac_hals_nnls(ctx, NNFAC_F32, UtM, ld_utm, UtU, ld_utu, Vout, ld_vout, r, n, maxiter, delta, sparsity, 0u, result, stream);
+}

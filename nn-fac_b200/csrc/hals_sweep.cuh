@@ -276,8 +276,10 @@ __global__ void __launch_bounds__(MAXT, 1) hals_sweep_kernel(SweepArgs<T> a) {
     if (cnt == 1) eps0 = tot;                                   // nnls.py:187-188
     eps = tot;
     ++cnt;
-    if (tot == 0.0 && !normalize) {                             // remaining sweeps are no-ops (nnls.py:156 '>=')
-      if (cnt < a.maxiter + 1) cnt = a.maxiter + 1;
+    if (tot == 0.0 && !normalize) {
+      // remaining sweeps are no-ops.  nnls.py:156 keeps looping on `0 >= delta * 0` only when the first sweep already moved
+      // nothing (eps0 == 0: it then burns all maxiter sweeps, cnt = maxiter + 1); otherwise the test fails and cnt stays
+      if (eps0 == 0.0 && cnt < a.maxiter + 1) cnt = a.maxiter + 1;
       break;
     }
   }
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(MAXT, 1) hals_sweep_chunked_kernel(SweepArgs<T
     eps = tot;
     ++cnt;
     if (tot == 0.0) {
-      if (cnt < a.maxiter + 1) cnt = a.maxiter + 1;
+      if (eps0 == 0.0 && cnt < a.maxiter + 1) cnt = a.maxiter + 1;     // see above (nnls.py:156)
       break;
     }
   }
@@ -545,6 +547,8 @@ int launch(nnfac_ctx* ctx, SweepArgs<T> a, cudaStream_t st) {
     nnfac_set_error("hals_nnls: barrier scratch too small");
     return NNFAC_ERR_UNSUPPORTED;
   }
+  const int grc = nnfac_guard_enter(ctx, NNFAC_GUARD_RED, st);
+  if (grc) return grc;
   a.part = ctx->red;
   a.counter = ctx->sync;
   NNFAC_CUDA(cudaMemsetAsync(ctx->sync, 0, sizeof(unsigned), st));

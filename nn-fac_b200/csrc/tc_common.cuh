@@ -192,6 +192,21 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// One lane of a converged warp (elect.sync): tcgen05.mma / commit are issued inside `if (elect_one())` by a warp that
+// runs its loop converged, so that descriptors stay in uniform registers and the MMAs issue back to back (a branch on
+// lane == 0 makes ptxas wrap every UTCHMMA in an ELECT / BRA.U.ANY loop: ~8 instructions per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " elect.sync _|p, 0xffffffff;\n"
+      " selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // bf16x2 split of an fp32 value: x ~= hi + lo with |x - hi - lo| <= 2^-18 |x|
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);

@@ -19,25 +19,37 @@ namespace {
 using namespace tcplan;
 
 constexpr int NSP = 4;               // column splits of a stage among the transform warps
-constexpr int CW = 64 / NSP;         // X columns (and D2 columns) per transform thread and stage
+constexpr int CW = 64 / NSP;         // X columns per transform thread and stage
 constexpr int NCHK = CW / 8;         // 16-byte chunks per thread, plane and stage
 constexpr int NWT = 4 * NSP;         // transform warps: 4 TMEM lane quadrants x NSP column parts
 constexpr int FUSED_THREADS = 128 + 32 * NWT;   // warp0 TMA, warps 1/3 MMA issuers, warp2 TMEM, then transform warps
 static_assert(CW == 16, "the transform below moves 16 columns per tcgen05.ld / 8 words per tcgen05.st");
-constexpr int FSTAGES = 4;
-constexpr int ND1 = 3;               // model-tile buffers in tensor memory: the model GEMM runs up to two stages ahead of the transform
 constexpr uint32_t X_BYTES = TILE_ROWS * BK * sizeof(bf16);   // 16 KiB per plane tile
-constexpr uint32_t FK_BYTES = 64 * BK * sizeof(bf16);         // 8 KiB  (64 columns of X x rank 64)
-constexpr uint32_t STAGE_BYTES = 2 * X_BYTES + 2 * FK_BYTES;  // 48 KiB
-constexpr uint32_t A1_BYTES = 2 * X_BYTES;                    // 32 KiB
 constexpr int MODE_RES = 0, MODE_MU = 1;
 constexpr int DRAIN = 2;             // stages per TMEM accumulation chain of the contraction GEMM (the tensor core accumulates with truncation)
+
+// Per padded rank RK (64 or 128).  RK = 128 (ranks 65..128, MODE_RES only): the factor slab of a stage is two 64-rank
+// atoms per plane (64 KiB stages, 3 of them), the contraction GEMM is 128 wide, and the rows of the aligned factor go
+// global -> registers -> tensor memory (no 64 KiB staging buffer); tensor memory: D1 2 x 64 | D2 2 x 128 | A1 128.
+template <int RK>
+struct Cfg {
+  static constexpr int KR = RK / 64;                                              // 64-rank atoms
+  static constexpr uint32_t FK_BYTES = (uint32_t)KR * 64 * BK * sizeof(bf16);     // one plane of the slab: 64 columns of X x RK ranks
+  static constexpr uint32_t STAGE_BYTES = 2 * X_BYTES + 2 * FK_BYTES;             // 48 / 64 KiB
+  static constexpr int FSTAGES = RK == 64 ? 4 : 3;
+  static constexpr int ND1 = RK == 64 ? 3 : 2;   // model-tile buffers in tensor memory: the model GEMM runs up to ND1 - 1 stages ahead of the transform
+  static constexpr uint32_t A1_BYTES = RK == 64 ? 2 * X_BYTES : 0;
+  static constexpr int CWD = RK / NSP;           // D2 columns per transform thread
+  static constexpr size_t SMEM = A1_BYTES + (size_t)FSTAGES * STAGE_BYTES + 512;
+};
 
 struct FusedParams {
   int r_pad, splits, stages_per_unit, num_units, drain, want_cost;
   int64_t ld_partial;
   float* partial;
   double* cost_part;
+  const bf16 *a1h, *a1l;   // RK = 128: rank-contiguous planes [R x RK] of the factor aligned with the rows of this side
+  int64_t R;               // rows of this side
 };
 
 __device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, <= 1 ulp: no IEEE fix-up branch
@@ -53,18 +65,22 @@ __device__ __forceinline__ float lg2_approx(float x) {   // MUFU.LG2 without the
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
-template <int MODE, bool COST, bool XF32>
+template <int MODE, bool COST, bool XF32, int RK>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                 const __grid_constant__ CUtensorMap map_fkh, const __grid_constant__ CUtensorMap map_fkl,
                 const __grid_constant__ CUtensorMap map_a1h, const __grid_constant__ CUtensorMap map_a1l,
                 const FusedParams p) {
+  using C = Cfg<RK>;
+  static_assert(RK == 64 || (MODE == MODE_RES && !XF32), "rank 65..128: residual + cross-product pass only");
+  constexpr int FSTAGES = C::FSTAGES, ND1 = C::ND1, CWD = C::CWD;
+  constexpr uint32_t FK_BYTES = C::FK_BYTES, STAGE_BYTES = C::STAGE_BYTES, A1_BYTES = C::A1_BYTES;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* a1 = smem;                                   // [hi | lo]
+  uint8_t* a1 = smem;                                   // [hi | lo]  (RK = 64 only)
   uint8_t* ring = smem + A1_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)FSTAGES * STAGE_BYTES);
   uint64_t* full = bars;                 // [4]
-  uint64_t* empty = bars + 4;            // [4]  count 9: GEMM-2 commit + 8 transform warps
+  uint64_t* empty = bars + 4;            // [4]  count NWT + 1: GEMM-2 commit + the transform warps
   uint64_t* a1_full = bars + 9;
   uint64_t* a1_empty = bars + 10;
   uint64_t* d1_full = bars + 11;         // [ND1]
@@ -79,11 +95,11 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
   double* cost_sh = reinterpret_cast<double*>(bars + 28);   // [2 * NWT]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t stage_tx = STAGE_BYTES;
 
   if (warp == 0 && lane == 0) {
-    tc::prefetch_tmap(&map_xh); tc::prefetch_tmap(&map_xl); 
-    tc::prefetch_tmap(&map_fkh); tc::prefetch_tmap(&map_fkl); tc::prefetch_tmap(&map_a1h); tc::prefetch_tmap(&map_a1l);
+    tc::prefetch_tmap(&map_xh); tc::prefetch_tmap(&map_xl);
+    tc::prefetch_tmap(&map_fkh); tc::prefetch_tmap(&map_fkl);
+    if (RK == 64) { tc::prefetch_tmap(&map_a1h); tc::prefetch_tmap(&map_a1l); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < FSTAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], NWT + 1); }
@@ -99,8 +115,8 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // tensor-memory map (columns): D1 ND1 x 64 | D2 2x64 | A1 hi 32 + lo 32 | Q 2 x (hi 32 + lo 32)  (512 in all)
-  const uint32_t D1 = tmem_base, D2 = tmem_base + 64 * ND1, A1T = D2 + 128, QT = A1T + 64;
+  // tensor-memory map (columns): D1 ND1 x 64 | D2 2 x RK | A1 hi RK/2 + lo RK/2 | Q 2 x (hi 32 + lo 32) (MU)  (512 in all)
+  const uint32_t D1 = tmem_base, D2 = tmem_base + 64 * ND1, A1T = D2 + 2 * RK, QT = A1T + RK;
   const int S = p.stages_per_unit;
 
   if (warp == 0 && lane == 0) {
@@ -109,29 +125,34 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
       const int tile = u / p.splits, split = u % p.splits;
       const int row0 = tile * TILE_ROWS, k0 = split * S * BK;
-      tc::mbar_wait(a1_empty, a1_phase ^ 1);
-      a1_phase ^= 1;
-      tc::mbar_arrive_expect_tx(a1_full, A1_BYTES);
-      tc::tma_load_2d_hint(a1, &map_a1h, a1_full, 0, row0, tc::kEvictLast);
-      tc::tma_load_2d_hint(a1 + X_BYTES, &map_a1l, a1_full, 0, row0, tc::kEvictLast);
+      if (RK == 64) {
+        tc::mbar_wait(a1_empty, a1_phase ^ 1);
+        a1_phase ^= 1;
+        tc::mbar_arrive_expect_tx(a1_full, A1_BYTES);
+        tc::tma_load_2d_hint(a1, &map_a1h, a1_full, 0, row0, tc::kEvictLast);
+        tc::tma_load_2d_hint(a1 + X_BYTES, &map_a1l, a1_full, 0, row0, tc::kEvictLast);
+      }
       for (int ks = 0; ks < S; ++ks) {
         tc::mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* st = ring + (size_t)stage * STAGE_BYTES;
-        tc::mbar_arrive_expect_tx(&full[stage], stage_tx);
+        tc::mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
         const int c = k0 + ks * BK;
         // XF32: map_xh is the fp32 copy of X; the two 16 KiB halves of the tile are its columns [c, c+32) and [c+32, c+64)
         tc::tma_load_2d_hint(st, &map_xh, &full[stage], c, row0, tc::kEvictFirst);
         tc::tma_load_2d_hint(st + X_BYTES, XF32 ? &map_xh : &map_xl, &full[stage], XF32 ? c + 32 : c, row0, tc::kEvictFirst);
-        tc::tma_load_2d_hint(st + 2 * X_BYTES, &map_fkh, &full[stage], 0, c, tc::kEvictLast);
-        tc::tma_load_2d_hint(st + 2 * X_BYTES + FK_BYTES, &map_fkl, &full[stage], 0, c, tc::kEvictLast);
+#pragma unroll
+        for (int kr = 0; kr < C::KR; ++kr) {   // 64 columns of X x 64 ranks per box
+          tc::tma_load_2d_hint(st + 2 * X_BYTES + kr * 8192, &map_fkh, &full[stage], kr * 64, c, tc::kEvictLast);
+          tc::tma_load_2d_hint(st + 2 * X_BYTES + FK_BYTES + kr * 8192, &map_fkl, &full[stage], kr * 64, c, tc::kEvictLast);
+        }
         if (++stage == FSTAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ===================== MMA issuer 1: model GEMM  D1 = A1 * Fk^T =====================
-    // (two issuing threads: a single thread needs ~100 cycles per tcgen05.mma for descriptor set-up,
-    //  which alone would cap a 24-MMA stage below the HBM rate)
+    // (two issuing warps, each running its loop converged with one elected lane issuing: see tc::elect_one)
     const uint32_t idesc1 = tc::umma_idesc_bf16(TILE_ROWS, 64);
+    const int ksteps = p.r_pad / UMMA_K;             // the planes are zero beyond r_pad: shorter contraction for small ranks
     int st1 = 0; uint32_t ph1 = 0;
     int b1 = 0; uint32_t b1_phase = 0;
     uint32_t a1_phase = 0;
@@ -142,23 +163,28 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         tc::mbar_wait(&full[st1], ph1);
         tc::mbar_wait(&d1_empty[b1], b1_phase ^ 1);
         tc::tcgen05_fence_after();
-        const uint32_t sb = tc::smem_u32(ring + (size_t)st1 * STAGE_BYTES);
-        const uint64_t fkh = tc::umma_desc_k_sw128(sb + 2 * X_BYTES), fkl = tc::umma_desc_k_sw128(sb + 2 * X_BYTES + FK_BYTES);
-        const uint32_t d = D1 + (uint32_t)b1 * 64;
+        if (tc::elect_one()) {
+          const uint32_t sb = tc::smem_u32(ring + (size_t)st1 * STAGE_BYTES);
+          const uint64_t fkh = tc::umma_desc_k_sw128(sb + 2 * X_BYTES), fkl = tc::umma_desc_k_sw128(sb + 2 * X_BYTES + FK_BYTES);
+          const uint32_t d = D1 + (uint32_t)b1 * 64;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t ko = (uint64_t)(k * 2);
-          tc::umma_bf16_ts(d, A1T + 8 * k, fkh + ko, idesc1, k != 0);
-          tc::umma_bf16_ts(d, A1T + 32 + 8 * k, fkh + ko, idesc1, true);
-          tc::umma_bf16_ts(d, A1T + 8 * k, fkl + ko, idesc1, true);
+          for (int k = 0; k < RK / UMMA_K; ++k) {
+            if (k < ksteps) {
+              const uint64_t bo = (uint64_t)((k >> 2) * (8192 >> 4) + (k & 3) * 2);   // 64-rank atom, 32 B inside its 128 B row
+              tc::umma_bf16_ts(d, A1T + 8 * k, fkh + bo, idesc1, k != 0);
+              tc::umma_bf16_ts(d, A1T + RK / 2 + 8 * k, fkh + bo, idesc1, true);
+              tc::umma_bf16_ts(d, A1T + 8 * k, fkl + bo, idesc1, true);
+            }
+          }
+          tc::umma_commit(&d1_full[b1]);
+          if (i == S - 1) tc::umma_commit(a1t_free);
         }
-        tc::umma_commit(&d1_full[b1]);
-        if (i == S - 1) tc::umma_commit(a1t_free);
+        __syncwarp();
         if (++b1 == ND1) { b1 = 0; b1_phase ^= 1; }
         if (++st1 == FSTAGES) { st1 = 0; ph1 ^= 1; }
       }
     }
-  } else if (warp == 3 && lane == 0) {
+  } else if (warp == 3) {
     // ===================== MMA issuer 2: contraction GEMM  D2 += A2 * Fn^T =====================
     const uint32_t idesc2 = tc::umma_idesc_bf16(TILE_ROWS, p.r_pad) | (1u << 16);   // B operand MN-major
     int qb = 0; uint32_t qb_phase = 0;      // Q buffer (MU)
@@ -172,37 +198,36 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         if (MODE == MODE_MU) tc::mbar_wait(&q_ready[qb], qb_phase);
         if (chain_start) tc::mbar_wait(&d2_empty[b2], b2_phase ^ 1);
         tc::tcgen05_fence_after();
-        const uint32_t sb = tc::smem_u32(ring + (size_t)st2 * STAGE_BYTES);
-        const uint64_t xh = tc::umma_desc_k_sw128(sb), xl = tc::umma_desc_k_sw128(sb + X_BYTES);
-        // B operand = the SAME 64-column slab of the other factor that the model GEMM reads K-major, addressed
-        // MN-major here (rank contiguous = N, columns = K): no second copy of the factor travels through L2
-        const uint64_t fnh = tc::umma_desc_mn_sw128(sb + 2 * X_BYTES);
-        const uint64_t fnl = tc::umma_desc_mn_sw128(sb + 2 * X_BYTES + FK_BYTES);
-        const uint32_t d = D2 + (uint32_t)b2 * 64;
+        if (tc::elect_one()) {
+          const uint32_t sb = tc::smem_u32(ring + (size_t)st2 * STAGE_BYTES);
+          const uint64_t xh = tc::umma_desc_k_sw128(sb), xl = tc::umma_desc_k_sw128(sb + X_BYTES);
+          // B operand = the SAME 64-column slab of the other factor that the model GEMM reads K-major, addressed
+          // MN-major here (rank contiguous = N, columns = K): no second copy of the factor travels through L2
+          const uint64_t fnh = tc::umma_desc_mn_sw128(sb + 2 * X_BYTES);
+          const uint64_t fnl = tc::umma_desc_mn_sw128(sb + 2 * X_BYTES + FK_BYTES);
+          const uint32_t d = D2 + (uint32_t)b2 * RK;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t ko = (uint64_t)(k * 2);            // A (K-major): 16 bf16 = 32 B inside the 128 B row
-          const uint64_t kb = (uint64_t)(k * 128);          // B (MN-major): 16 rows of 128 B = 2048 B
-          if (MODE == MODE_MU) {
-            const uint32_t qa = QT + (uint32_t)qb * 64 + 8 * k;
-            tc::umma_bf16_ts(d, qa, fnh + kb, idesc2, !(chain_start && k == 0));
-            tc::umma_bf16_ts(d, qa + 32, fnh + kb, idesc2, true);
-            tc::umma_bf16_ts(d, qa, fnl + kb, idesc2, true);
-          } else {
-            tc::umma_bf16(d, xh + ko, fnh + kb, idesc2, !(chain_start && k == 0));
-            tc::umma_bf16(d, xl + ko, fnh + kb, idesc2, true);
-            tc::umma_bf16(d, xh + ko, fnl + kb, idesc2, true);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t ko = (uint64_t)(k * 2);            // A (K-major): 16 bf16 = 32 B inside the 128 B row
+            const uint64_t kb = (uint64_t)(k * 128);          // B (MN-major): 16 rows of 128 B = 2048 B
+            if (MODE == MODE_MU) {
+              const uint32_t qa = QT + (uint32_t)qb * 64 + 8 * k;
+              tc::umma_bf16_ts(d, qa, fnh + kb, idesc2, !(chain_start && k == 0));
+              tc::umma_bf16_ts(d, qa + 32, fnh + kb, idesc2, true);
+              tc::umma_bf16_ts(d, qa, fnl + kb, idesc2, true);
+            } else {
+              tc::umma_bf16(d, xh + ko, fnh + kb, idesc2, !(chain_start && k == 0));
+              tc::umma_bf16(d, xl + ko, fnh + kb, idesc2, true);
+              tc::umma_bf16(d, xh + ko, fnl + kb, idesc2, true);
+            }
           }
+          tc::umma_commit(&empty[st2]);
+          if (MODE == MODE_MU) tc::umma_commit(&q_free[qb]);
+          if (chain_end) tc::umma_commit(&d2_full[b2]);
         }
-        tc::umma_commit(&empty[st2]);
-        if (MODE == MODE_MU) {
-          tc::umma_commit(&q_free[qb]);
-          if (++qb == 2) { qb = 0; qb_phase ^= 1; }
-        }
-        if (chain_end) {
-          tc::umma_commit(&d2_full[b2]);
-          if (++b2 == 2) { b2 = 0; b2_phase ^= 1; }
-        }
+        __syncwarp();
+        if (MODE == MODE_MU) { if (++qb == 2) { qb = 0; qb_phase ^= 1; } }
+        if (chain_end) { if (++b2 == 2) { b2 = 0; b2_phase ^= 1; } }
         if (++st2 == FSTAGES) { st2 = 0; ph2 ^= 1; }
       }
     }
@@ -211,7 +236,6 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     const int q = warp & 3, part = (warp - 4) >> 2;           // TMEM lane quadrant, column part (0..NSP-1)
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const bool has_d2 = CW * part < p.r_pad;                   // r_pad is a multiple of 16 = CW
     int st = 0; uint32_t ph = 0;
     int b1 = 0; uint32_t b1_phase = 0;
     int b2 = 0; uint32_t b2_phase = 0;
@@ -220,10 +244,10 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     double cost = 0.0, costk = 0.0;
     for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
       const int tile = u / p.splits, split = u % p.splits;
-      float sum[CW];
+      float sum[CWD];
 #pragma unroll
-      for (int j = 0; j < CW; ++j) sum[j] = 0.f;
-      {
+      for (int j = 0; j < CWD; ++j) sum[j] = 0.f;
+      if (RK == 64) {
         // A1 (this unit's rows of the aligned factor): shared memory -> tensor memory, this thread's row and K part
         tc::mbar_wait(a1_full, a1_phase);
         tc::mbar_wait(a1t_free, a1_phase ^ 1);
@@ -244,16 +268,42 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         tc::tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) { tc::mbar_arrive(a1t_ready); tc::mbar_arrive(a1_empty); }
+      } else {
+        // rank 65..128: this thread's row of the aligned factor, ranks [32 part, 32 part + 32) of both planes, straight from
+        // the rank-contiguous planes in global memory (64 B per plane) into tensor memory
+        const int64_t grow = (int64_t)tile * TILE_ROWS + row;
+        uint32_t w[2][16];
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+          const uint4* src = reinterpret_cast<const uint4*>((pl ? p.a1l : p.a1h) + grow * RK + part * (RK / 4));
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 v4 = grow < p.R ? __ldg(src + c) : make_uint4(0u, 0u, 0u, 0u);
+            w[pl][4 * c] = v4.x; w[pl][4 * c + 1] = v4.y; w[pl][4 * c + 2] = v4.z; w[pl][4 * c + 3] = v4.w;
+          }
+        }
+        tc::mbar_wait(a1t_free, a1_phase ^ 1);
+        a1_phase ^= 1;
+        tc::tcgen05_fence_after();
+        tc::tmem_st16(A1T + lane_base + (RK / 8) * part, w[0]);
+        tc::tmem_st16(A1T + lane_base + RK / 2 + (RK / 8) * part, w[1]);
+        tc::tmem_st_wait();
+        tc::tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(a1t_ready);
       }
       auto drain_chain = [&]() {
         tc::mbar_wait(&d2_full[b2], b2_phase);
         tc::tcgen05_fence_after();
-        if (has_d2) {
-          uint32_t v[16];
-          tc::tmem_ld16(D2 + (uint32_t)b2 * 64 + lane_base + CW * part, v);
-          tc::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) sum[j] += __uint_as_float(v[j]);
+        for (int c0 = 0; c0 < CWD; c0 += 16) {
+          if (CWD * part + c0 < p.r_pad) {                       // r_pad is a multiple of 16; warp-uniform
+            uint32_t v[16];
+            tc::tmem_ld16(D2 + (uint32_t)b2 * RK + lane_base + CWD * part + c0, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sum[c0 + j] += __uint_as_float(v[j]);
+          }
         }
         tc::tcgen05_fence_before();
         __syncwarp();
@@ -354,10 +404,11 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         if (i >= 3 && (i & 1)) { drain_chain(); ++drained; }
       }
       for (; drained < (S + DRAIN - 1) / DRAIN; ++drained) drain_chain();
-      if (has_d2) {
-        float* out = p.partial + ((int64_t)split * p.r_pad + CW * part) * p.ld_partial + (int64_t)tile * TILE_ROWS + row;
+      {
+        float* out = p.partial + ((int64_t)split * p.r_pad + CWD * part) * p.ld_partial + (int64_t)tile * TILE_ROWS + row;
 #pragma unroll
-        for (int j = 0; j < CW; ++j) out[(int64_t)j * p.ld_partial] = sum[j];
+        for (int j = 0; j < CWD; ++j)
+          if (CWD * part + j < p.r_pad) out[(int64_t)j * p.ld_partial] = sum[j];
       }
     }
     // per-CTA cost partials (fixed order): [blockIdx] = sum of squares or sum of x log2(x/k); [512 + blockIdx] = sum of k
@@ -384,19 +435,22 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
 //   else : F = F_in                                                                                 (after a HALS solve)
 // and writes F (fp32, rank-major), its K-major bf16 hi/lo planes [r_pad x ld_plane] (operand of the cross product)
 // and its rank-contiguous planes [R x 64] (operands of the fused pass).  Block = 32 columns x all ranks.
-template <bool APPLY>
+template <bool APPLY, int RK>
 __global__ void __launch_bounds__(256) factor_finish_kernel(const float* __restrict__ partial, int splits, int r, int r_pad, int64_t R,
                                                             int64_t ldp, const float* __restrict__ F_in, int64_t ld_in,
+                                                            int64_t in_chunk, int64_t in_slab,
                                                             const float* __restrict__ den, float floor_value, float* __restrict__ F_out,
                                                             int64_t ld_out, bf16* __restrict__ fh, bf16* __restrict__ fl, int64_t ld_plane,
                                                             bf16* __restrict__ rowh, bf16* __restrict__ rowl) {
-  __shared__ float tile[64][33];
+  __shared__ float tile[RK][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t c0 = (int64_t)blockIdx.x * 32, c = c0 + tx;
-  for (int k = ty; k < 64; k += 8) {
+  // in_chunk > 0: F_in is the output of an all-gather of column slices, [slice][r][in_chunk] with slab pitch in_slab
+  const int64_t cin = in_chunk > 0 ? (c / in_chunk) * in_slab + (c % in_chunk) : c;
+  for (int k = ty; k < RK; k += 8) {
     float f = 0.f;
     if (k < r && c < R) {
-      f = F_in[(int64_t)k * ld_in + c];
+      f = F_in[(int64_t)k * ld_in + cin];
       if (APPLY) {
         float num = 0.f;                            // fixed order; loads issued eight at a time (few blocks, many splits
         int sp = 0;                                 // when the other dimension is short: NTD has 64 splits for 256 rows)
@@ -426,12 +480,12 @@ __global__ void __launch_bounds__(256) factor_finish_kernel(const float* __restr
     const int64_t cc = c0 + i;
     if (cc < R) {
 #pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
+      for (int h2 = 0; h2 < RK / 32; ++h2) {
         const int k = tx + 32 * h2;
         bf16 h, l;
         tc::split_bf16(tile[k][i], h, l);
-        rowh[cc * 64 + k] = h;
-        rowl[cc * 64 + k] = l;
+        rowh[cc * RK + k] = h;
+        rowl[cc * RK + k] = l;
       }
     }
   }
@@ -474,20 +528,25 @@ __global__ void __launch_bounds__(256) planes_to_f32_kernel(const bf16* __restri
 
 }  // namespace
 
-static int finish_factor(nnfac_nmf_plan* p, int which, bool apply, const float* F_in, int64_t ld_in, const float* den,
-                         float floor_value, float* F_out, int64_t ld_out, cudaStream_t st) {
+static int finish_factor(nnfac_nmf_plan* p, int which, bool apply, const float* F_in, int64_t ld_in, int64_t in_chunk, int64_t in_slab,
+                         const float* den, float floor_value, float* F_out, int64_t ld_out, cudaStream_t st) {
   const int64_t len = which == 0 ? p->m : p->n;
   Side* cs = &p->side[which == 0 ? 1 : 0];        // U^T planes are the Fn operand of side 1, V planes of side 0
   Side* ps = &p->side[which];                     // the pass whose partials feed this factor
   const unsigned grid = (unsigned)ceil_div64(len, 32);
   bf16* rh = p->fused_ok ? p->rowp_h[which] : nullptr;
   bf16* rl = p->fused_ok ? p->rowp_l[which] : nullptr;
-  if (apply)
-    factor_finish_kernel<true><<<grid, 256, 0, st>>>(p->partial, ps->cp.splits, p->r, p->r_pad, len, ps->cp.ld_partial, F_in, ld_in, den,
-                                                     floor_value, F_out, ld_out, cs->fh, cs->fl, cs->ld, rh, rl);
-  else
-    factor_finish_kernel<false><<<grid, 256, 0, st>>>(nullptr, 0, p->r, p->r_pad, len, 0, F_in, ld_in, nullptr, 0.f, F_out, ld_out,
-                                                      cs->fh, cs->fl, cs->ld, rh, rl);
+#define NNFAC_FINISH(RKV)                                                                                                          \
+  do {                                                                                                                             \
+    if (apply)                                                                                                                     \
+      factor_finish_kernel<true, RKV><<<grid, 256, 0, st>>>(p->partial, ps->cp.splits, p->r, p->r_pad, len, ps->cp.ld_partial,    \
+          F_in, ld_in, in_chunk, in_slab, den, floor_value, F_out, ld_out, cs->fh, cs->fl, cs->ld, rh, rl);                        \
+    else                                                                                                                           \
+      factor_finish_kernel<false, RKV><<<grid, 256, 0, st>>>(nullptr, 0, p->r, p->r_pad, len, 0, F_in, ld_in, in_chunk, in_slab,  \
+          nullptr, 0.f, F_out, ld_out, cs->fh, cs->fl, cs->ld, rh, rl);                                                            \
+  } while (0)
+  if (p->rk == 64) NNFAC_FINISH(64); else NNFAC_FINISH(128);
+#undef NNFAC_FINISH
   NNFAC_LAUNCH_CHECK(p->ctx);
   return NNFAC_OK;
 }
@@ -510,7 +569,7 @@ int nnfac_nmf_plan_enable_f32(nnfac_nmf_plan* p, void* workspace, size_t workspa
   size_t need = 0;
   nnfac_nmf_plan_f32_bytes(p, &need);
   NNFAC_ARG(workspace_bytes >= need, "nnfac_nmf_plan_enable_f32: workspace of %zu bytes needed, got %zu", need, workspace_bytes);
-  if (!p->fused_ok) { nnfac_set_error("nnfac_nmf_plan_enable_f32: rank %d > 64 is not covered by the fused pass", p->r); return NNFAC_ERR_UNSUPPORTED; }
+  if (!p->fused_ok || p->rk != 64) { nnfac_set_error("nnfac_nmf_plan_enable_f32: rank %d > 64 is not covered by the beta = 1 fused pass", p->r); return NNFAC_ERR_UNSUPPORTED; }
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* base = (uint8_t*)workspace;
   for (int i = 0; i < 2; ++i) {
@@ -532,7 +591,18 @@ int nnfac_nmf_plan_set_factor(nnfac_nmf_plan* p, int which, const float* Ft, int
   NNFAC_ARG(p && Ft && (which == 0 || which == 1), "nnfac_nmf_plan_set_factor: bad argument");
   const int64_t len = which == 0 ? p->m : p->n;
   NNFAC_ARG(ld >= len, "nnfac_nmf_plan_set_factor: leading dimension too small");
-  return finish_factor(p, which, false, Ft, ld, nullptr, 0.f, nullptr, 0, (cudaStream_t)stream);
+  return finish_factor(p, which, false, Ft, ld, 0, 0, nullptr, 0.f, nullptr, 0, (cudaStream_t)stream);
+}
+
+// The same from the output of an all-gather of column slices: G = [slices][r][chunk] (slice s holds columns
+// [s * chunk, (s + 1) * chunk) of the factor, the last slice may be short).  Also writes the factor itself, rank-major,
+// into Ft_out (r x len, leading dimension ld_out) -- one kernel instead of an un-permuting copy followed by set_factor.
+int nnfac_nmf_plan_set_factor_gathered(nnfac_nmf_plan* p, int which, const float* G, int64_t chunk, float* Ft_out, int64_t ld_out,
+                                       void* stream) {
+  NNFAC_ARG(p && G && Ft_out && chunk > 0 && (which == 0 || which == 1), "nnfac_nmf_plan_set_factor_gathered: bad argument");
+  const int64_t len = which == 0 ? p->m : p->n;
+  NNFAC_ARG(ld_out >= len, "nnfac_nmf_plan_set_factor_gathered: leading dimension too small");
+  return finish_factor(p, which, false, G, chunk, chunk, (int64_t)p->r * chunk, nullptr, 0.f, Ft_out, ld_out, (cudaStream_t)stream);
 }
 
 // HALS solve of factor `which` (nnls.py:24-198, deterministic rule) that also installs the result in the plan:
@@ -558,6 +628,7 @@ int nnfac_nmf_plan_hals_solve(nnfac_nmf_plan* p, int which, const float* UtM, in
   pl.fh = cs->fh; pl.fl = cs->fl; pl.ld_plane = cs->ld; pl.r_pad = p->r_pad;
   pl.rowh = p->fused_ok ? p->rowp_h[which] : nullptr;
   pl.rowl = p->fused_ok ? p->rowp_l[which] : nullptr;
+  pl.row_pitch = p->rk;
   return nnfac_tc_sweep_run(p->ctx, UtM, ld_utm, UtU, ld_utu, F_in, ld_in, F_out, ld_out, p->r, len, maxiter, delta, sparsity,
                             result, &pl, (cudaStream_t)stream, nsplit, split_stride);
 }
@@ -581,8 +652,8 @@ int nnfac_nmf_plan_mu_finish(nnfac_nmf_plan* p, int which, const float* F_in, in
   NNFAC_ARG(p && F_in && den && F_out && (which == 0 || which == 1), "nnfac_nmf_plan_mu_finish: bad argument");
   const int64_t len = which == 0 ? p->m : p->n;
   NNFAC_ARG(ld_in >= len && ld_out >= len, "nnfac_nmf_plan_mu_finish: leading dimension too small");
-  if (!p->fused_ok) { nnfac_set_error("nnfac_nmf_plan_mu_finish: rank %d > 64 is not covered by the fused pass", p->r); return NNFAC_ERR_UNSUPPORTED; }
-  return finish_factor(p, which, true, F_in, ld_in, den, (float)floor_value, F_out, ld_out, (cudaStream_t)stream);
+  if (!p->fused_ok) { nnfac_set_error("nnfac_nmf_plan_mu_finish: rank %d > 128 is not covered by the fused pass", p->r); return NNFAC_ERR_UNSUPPORTED; }
+  return finish_factor(p, which, true, F_in, ld_in, 0, 0, den, (float)floor_value, F_out, ld_out, (cudaStream_t)stream);
 }
 
 // One fused pass over side `side` (0: planes of X, rows = m; 1: planes of X^T, rows = n).
@@ -592,7 +663,8 @@ int nnfac_nmf_plan_mu_finish(nnfac_nmf_plan* p, int which, const float* F_in, in
 int nnfac_nmf_plan_fused(nnfac_nmf_plan* p, int side, int mode, int want_cost, float* out, int64_t ld_out, double* cost_out,
                          void* stream) {
   NNFAC_ARG(p && (side == 0 || side == 1) && (mode == 0 || mode == 1), "nnfac_nmf_plan_fused: bad argument");
-  if (!p->fused_ok) { nnfac_set_error("nnfac_nmf_plan_fused: rank %d > 64 is not covered by the fused pass", p->r); return NNFAC_ERR_UNSUPPORTED; }
+  if (!p->fused_ok) { nnfac_set_error("nnfac_nmf_plan_fused: rank %d > 128 is not covered by the fused pass", p->r); return NNFAC_ERR_UNSUPPORTED; }
+  if (mode == 1 && p->rk != 64) { nnfac_set_error("nnfac_nmf_plan_fused: the beta = 1 pass covers rank <= 64 (rank %d)", p->r); return NNFAC_ERR_UNSUPPORTED; }
   Side* s = &p->side[side];
   NNFAC_ARG(!out || ld_out >= s->R, "nnfac_nmf_plan_fused: leading dimension too small");
   cudaStream_t st = (cudaStream_t)stream;
@@ -600,21 +672,23 @@ int nnfac_nmf_plan_fused(nnfac_nmf_plan* p, int side, int mode, int want_cost, f
   fp.r_pad = p->r_pad; fp.splits = s->cp.splits; fp.stages_per_unit = s->cp.stages_per_unit; fp.num_units = s->cp.num_units;
   fp.drain = DRAIN; fp.want_cost = (mode == 0 || want_cost) ? 1 : 0;
   fp.ld_partial = s->cp.ld_partial; fp.partial = p->partial; fp.cost_part = p->cost_part;
-  const size_t smem = A1_BYTES + (size_t)FSTAGES * STAGE_BYTES + 512;
+  fp.a1h = p->rowp_h[side]; fp.a1l = p->rowp_l[side]; fp.R = s->R;
   const int other = 1 - side;
-#define NNFAC_LAUNCH_FUSED(M, C, XF, MAPH, MAPL)                                                                             \
-  do {                                                                                                                   \
-    NNFAC_CUDA(cudaFuncSetAttribute(tc_fused_kernel<M, C, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    tc_fused_kernel<M, C, XF><<<s->grid, FUSED_THREADS, smem, st>>>(MAPH, MAPL, p->map_row_b_h[other],                  \
-        p->map_row_b_l[other], p->map_row_a_h[side], p->map_row_a_l[side], fp);                                          \
+#define NNFAC_LAUNCH_FUSED(M, C, XF, RKV, MAPH, MAPL)                                                                             \
+  do {                                                                                                                        \
+    const size_t smem = Cfg<RKV>::SMEM;                                                                                       \
+    NNFAC_CUDA(cudaFuncSetAttribute(tc_fused_kernel<M, C, XF, RKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    tc_fused_kernel<M, C, XF, RKV><<<s->grid, FUSED_THREADS, smem, st>>>(MAPH, MAPL, p->map_row_b_h[other],                  \
+        p->map_row_b_l[other], p->map_row_a_h[side], p->map_row_a_l[side], fp);                                               \
   } while (0)
-  if (mode == 0) NNFAC_LAUNCH_FUSED(MODE_RES, true, false, s->map_xh, s->map_xl);
+  if (mode == 0 && p->rk == 128) NNFAC_LAUNCH_FUSED(MODE_RES, true, false, 128, s->map_xh, s->map_xl);
+  else if (mode == 0) NNFAC_LAUNCH_FUSED(MODE_RES, true, false, 64, s->map_xh, s->map_xl);
   else if (p->xf_ready) {   // beta = 1: X only travels through registers -> read its fp32 copy
-    if (fp.want_cost) NNFAC_LAUNCH_FUSED(MODE_MU, true, true, p->map_xf[side], p->map_xf[side]);
-    else NNFAC_LAUNCH_FUSED(MODE_MU, false, true, p->map_xf[side], p->map_xf[side]);
+    if (fp.want_cost) NNFAC_LAUNCH_FUSED(MODE_MU, true, true, 64, p->map_xf[side], p->map_xf[side]);
+    else NNFAC_LAUNCH_FUSED(MODE_MU, false, true, 64, p->map_xf[side], p->map_xf[side]);
   } else {
-    if (fp.want_cost) NNFAC_LAUNCH_FUSED(MODE_MU, true, false, s->map_xh, s->map_xl);
-    else NNFAC_LAUNCH_FUSED(MODE_MU, false, false, s->map_xh, s->map_xl);
+    if (fp.want_cost) NNFAC_LAUNCH_FUSED(MODE_MU, true, false, 64, s->map_xh, s->map_xl);
+    else NNFAC_LAUNCH_FUSED(MODE_MU, false, false, 64, s->map_xh, s->map_xl);
   }
 #undef NNFAC_LAUNCH_FUSED
   NNFAC_LAUNCH_CHECK(p->ctx);

@@ -103,8 +103,8 @@ tc_cross_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===== MMA issuer =====
+  } else if (warp == 1) {
+    // ===== MMA issuer (the warp runs converged, one elected lane issues: see tc::elect_one) =====
     // The tensor core adds into the fp32 accumulator with truncation, so a long chain drifts low
     // (measured: -1.9e-5 relative over 768 accumulations).  Chains are therefore cut every
     // `drain` stages; the epilogue warps sum the chain results in registers (round-to-nearest).
@@ -120,22 +120,25 @@ tc_cross_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         for (int ks = ks0; ks < ks1; ++ks) {
           tc::mbar_wait(&full[stage], phase);
           tc::tcgen05_fence_after();
-          const uint32_t st = tc::smem_u32(ring + (size_t)stage * stage_bytes);
+          if (tc::elect_one()) {
+            const uint32_t st = tc::smem_u32(ring + (size_t)stage * stage_bytes);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint32_t koff = k * UMMA_K * sizeof(bf16);   // 32 B inside the 128 B swizzle row
-            const uint64_t xh = tc::umma_desc_k_sw128(st + koff);
-            const uint64_t xl = tc::umma_desc_k_sw128(st + x_bytes + koff);
-            const uint64_t fh = tc::umma_desc_k_sw128(st + 2 * x_bytes + koff);
-            const uint64_t fl = tc::umma_desc_k_sw128(st + 2 * x_bytes + f_bytes + koff);
-            tc::umma_bf16(d, xh, fh, idesc, (ks != ks0) || (k != 0));
-            tc::umma_bf16(d, xl, fh, idesc, true);
-            tc::umma_bf16(d, xh, fl, idesc, true);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint32_t koff = k * UMMA_K * sizeof(bf16);   // 32 B inside the 128 B swizzle row
+              const uint64_t xh = tc::umma_desc_k_sw128(st + koff);
+              const uint64_t xl = tc::umma_desc_k_sw128(st + x_bytes + koff);
+              const uint64_t fh = tc::umma_desc_k_sw128(st + 2 * x_bytes + koff);
+              const uint64_t fl = tc::umma_desc_k_sw128(st + 2 * x_bytes + f_bytes + koff);
+              tc::umma_bf16(d, xh, fh, idesc, (ks != ks0) || (k != 0));
+              tc::umma_bf16(d, xl, fh, idesc, true);
+              tc::umma_bf16(d, xh, fl, idesc, true);
+            }
+            tc::umma_commit(&empty[stage]);                      // frees the smem slot when the MMAs retire
+            if (ks == ks1 - 1) tc::umma_commit(&acc_full[acc]);  // chain result ready for the epilogue
           }
-          tc::umma_commit(&empty[stage]);                      // frees the smem slot when the MMAs retire
+          __syncwarp();
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
-        tc::umma_commit(&acc_full[acc]);                       // chain result ready for the epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -310,7 +313,8 @@ static int plan_build(nnfac_ctx* ctx, int64_t m, int64_t n, int r, void* buffer,
   if (!p) return NNFAC_ERR_ALLOC;
   p->ctx = ctx; p->m = m; p->n = n; p->r = r;
   p->r_pad = (int)round_up(r, 16);
-  p->fused_ok = p->r_pad <= 64;
+  p->rk = p->r_pad <= 64 ? 64 : 128;
+  p->fused_ok = 1;                       // rank <= 128: residual pass; the beta = 1 pass needs rk == 64
   // ---- sizes ----
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
@@ -331,7 +335,7 @@ static int plan_build(nnfac_ctx* ctx, int64_t m, int64_t n, int r, void* buffer,
   const size_t o_partial = take(partial_bytes);
   if (p->fused_ok)
     for (int i = 0; i < 2; ++i) {
-      rb[i] = (size_t)(i == 0 ? m : n) * 64 * sizeof(bf16);
+      rb[i] = (size_t)(i == 0 ? m : n) * p->rk * sizeof(bf16);
       o_rh[i] = take(rb[i]); o_rl[i] = take(rb[i]);
     }
   const size_t o_cost = take(sizeof(double) * 2048);
@@ -381,10 +385,10 @@ static int plan_build(nnfac_ctx* ctx, int64_t m, int64_t n, int r, void* buffer,
       p->rowp_h[i] = (bf16*)(base + o_rh[i]); p->rowp_l[i] = (bf16*)(base + o_rl[i]);
       cudaMemsetAsync(p->rowp_h[i], 0, rb[i], st);
       cudaMemsetAsync(p->rowp_l[i], 0, rb[i], st);
-      int rc = make_map(&p->map_row_a_h[i], p->rowp_h[i], len, 64, 64, TILE_ROWS);
-      if (!rc) rc = make_map(&p->map_row_a_l[i], p->rowp_l[i], len, 64, 64, TILE_ROWS);
-      if (!rc) rc = make_map(&p->map_row_b_h[i], p->rowp_h[i], len, 64, 64, 64);
-      if (!rc) rc = make_map(&p->map_row_b_l[i], p->rowp_l[i], len, 64, 64, 64);
+      int rc = make_map(&p->map_row_a_h[i], p->rowp_h[i], len, p->rk, p->rk, TILE_ROWS);
+      if (!rc) rc = make_map(&p->map_row_a_l[i], p->rowp_l[i], len, p->rk, p->rk, TILE_ROWS);
+      if (!rc) rc = make_map(&p->map_row_b_h[i], p->rowp_h[i], len, p->rk, p->rk, 64);
+      if (!rc) rc = make_map(&p->map_row_b_l[i], p->rowp_l[i], len, p->rk, p->rk, 64);
       if (rc) { nnfac_nmf_plan_destroy(p); return rc; }
     }
   }
@@ -441,6 +445,8 @@ int nnfac_nmf_plan_load_x_done(nnfac_nmf_plan* p, void* stream) {
   if (p->fused_ok) {
     // sum of X as the passes see it (hi + lo planes), fp64, fixed order: the constant term of the KL cost
     const int blocks = p->ctx->sm_count * 4;
+    const int grc = nnfac_guard_enter(p->ctx, NNFAC_GUARD_RED, st);
+    if (grc) return grc;
     plane_total_kernel<<<blocks, 256, 0, st>>>(p->side[0].xh, p->side[0].xl, p->side[0].ld, p->m, p->n, p->ctx->red);
     NNFAC_LAUNCH_CHECK(p->ctx);
     plane_total_finish_kernel<<<1, 32, 0, st>>>(p->ctx->red, blocks, p->sums);

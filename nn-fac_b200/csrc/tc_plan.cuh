@@ -89,9 +89,10 @@ struct nnfac_nmf_plan {
   tcplan::Side side[2];         // [0]: planes of X (m x n), used for V X^T;  [1]: planes of X^T (n x m), used for U^T X
   float* partial;
   size_t partial_bytes;
-  // fused passes (rank <= 64): factor "row planes" with the rank axis contiguous, padded to 64:
-  //   rowp[0] = U [m x 64], rowp[1] = V^T [n x 64]; map_row_a: 128-row boxes (A operand of the model GEMM),
-  //   map_row_b: 64-row boxes (B operand of the model GEMM)
+  // fused passes: factor "row planes" with the rank axis contiguous, padded to rk = 64 (rank <= 64) or 128:
+  //   rowp[0] = U [m x rk], rowp[1] = V^T [n x rk]; map_row_a: 128-row boxes (A operand of the model GEMM, rk = 64 only),
+  //   map_row_b: boxes of 64 rows x 64 ranks (B operand of the model GEMM)
+  int rk;
   __nv_bfloat16 *rowp_h[2], *rowp_l[2];
   CUtensorMap map_row_a_h[2], map_row_a_l[2], map_row_b_h[2], map_row_b_l[2];
   double* cost_part;    // [1024] per-CTA cost partials of a fused pass ([512 + i]: second partial of CTA i)

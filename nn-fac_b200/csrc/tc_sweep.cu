@@ -30,31 +30,51 @@ namespace {
 
 using bf16 = __nv_bfloat16;
 
-constexpr int RP = 64;            // padded rank
 constexpr int BLK = 16;           // rows per Gauss-Seidel block (K extent of the rank update)
-constexpr int NBLK = RP / BLK;
 constexpr int TILE = 128;         // columns per tile (UMMA M)
-constexpr int MAX_TILES = 4;
-constexpr int UPD_THREADS = MAX_TILES * TILE;   // 512
-constexpr int NTHREADS = UPD_THREADS + MAX_TILES * 32;   // + one issuing warp per tile
-constexpr int TMEM_PER_TILE = 128;              // 64 columns residual + 64 columns V
-constexpr uint32_t PLANE_BYTES = TILE * RP * sizeof(bf16);   // 16 KiB
-constexpr uint32_t G_PLANE_BYTES = RP * RP * sizeof(bf16);   // 8 KiB
+constexpr uint32_t PLANE_BYTES = TILE * 64 * sizeof(bf16);   // 16 KiB: one 64-wide K atom of an operand plane of a tile
 constexpr int NPLANES = 3;
+constexpr int XMAXW = 8;          // ranks of a collective solve (cross-GPU stop scalar)
+constexpr int XMAXG = 160;        // board entries per rank (>= CTAs of a solve)
 
+// Per padded rank RP (64 or 128): a tile keeps RP residual + RP master columns in tensor memory, so a CTA carries
+// 256 / RP tiles; the Gram operand planes are RP / 64 K atoms of [RP rows x 128 B].
+template <int RP>
+struct Cfg {
+  static constexpr int NBLK = RP / BLK;
+  static constexpr int KR = RP / 64;
+  static constexpr int MAX_TILES = 256 / RP;                       // 4 (RP = 64) or 2 (RP = 128): 512 tensor-memory columns
+  static constexpr int UPD_THREADS = MAX_TILES * TILE;
+  static constexpr int NTHREADS = UPD_THREADS + MAX_TILES * 32;    // + one issuing warp per tile
+  static constexpr int TMEM_PER_TILE = 2 * RP;
+  static constexpr uint32_t G_ATOM_BYTES = RP * 128;               // [RP rows x 64 K] bf16
+  static constexpr uint32_t G_PLANE_BYTES = KR * G_ATOM_BYTES;     // 8 / 32 KiB
+  static constexpr size_t SMEM = NPLANES * G_PLANE_BYTES + (size_t)MAX_TILES * NPLANES * PLANE_BYTES + 512;
+};
+
+template <int RP>
 struct alignas(16) SweepConst {
-  float nh[NBLK][BLK][BLK];     // [B][e][e2] = -UtU[k2][k] / UtU[k2][k2] (source row k = 16B+e, target row k2 = 16B+e2)
+  float nh[RP / BLK][BLK][BLK]; // [B][e][e2] = -UtU[k2][k] / UtU[k2][k2] (source row k = 16B+e, target row k2 = 16B+e2)
   float invd[RP];               // 1 / UtU[k][k], 0 when the diagonal entry is 0 or k >= r
   int has_zero_diag;            // some row k < r has UtU[k][k] == 0
 };
-__constant__ SweepConst c_sw;
+// One bank per padded rank and device.  It is written by a one-block kernel on the stream of the solve, right before the
+// solve; solves of one context on different streams are ordered by the context's scratch guard (nnfac_guard_enter).
+__constant__ SweepConst<64> c_sw64;
+__constant__ SweepConst<128> c_sw128;
+template <int RP>
+__device__ __forceinline__ const SweepConst<RP>& csw() {
+  if constexpr (RP == 64) return c_sw64; else return c_sw128;
+}
 
 // Per-call preparation (one block): the constants of the in-block recurrence, and the call generation of the mailbox
 // tags.  The generation lives in device memory and is advanced HERE, not on the host, so that a solve captured into a
 // CUDA graph gets a fresh generation on every replay (a host-side counter would be frozen into the graph and the tags
 // of the previous replay would match).  When the 16-bit generation wraps, the mailboxes are cleared first.
-__global__ void sweep_prep_kernel(const float* __restrict__ G, int64_t ld_g, int r, SweepConst* out, unsigned* gen,
+template <int RP>
+__global__ void sweep_prep_kernel(const float* __restrict__ G, int64_t ld_g, int r, SweepConst<RP>* out, unsigned* gen,
                                   unsigned long long* mail, size_t mail_count) {
+  constexpr int NBLK = RP / BLK;
   __shared__ unsigned next_gen;
   if (threadIdx.x == 0) next_gen = (*gen + 1u) & 0xffffu;
   __syncthreads();
@@ -90,9 +110,9 @@ struct TcSweepArgs {
   int64_t split_stride;
   // optional: bf16 hi/lo operand planes of the result for the NMF plan (nnfac_nmf_plan_hals_solve)
   bf16 *fh, *fl;    // [r_pad x ld_plane], K-major (rank rows)
-  bf16 *rowh, *rowl;// [n x 64], rank contiguous (may be NULL)
+  bf16 *rowh, *rowl;// [n x row_pitch], rank contiguous (may be NULL)
   int64_t ld_plane;
-  int r_pad;
+  int r_pad, row_pitch;
   int r, maxiter, cols_per_cta;
   double delta;
   float sp;
@@ -100,6 +120,14 @@ struct TcSweepArgs {
   const unsigned* gen;        // call generation (device word, advanced by sweep_prep_kernel): stale mailbox contents of
                               // earlier calls never match
   double* result;
+  // Collective solve (several GPUs, one slice of the columns each): the stop test of nnls.py:156 sums the squared steps
+  // over ALL columns.  Every CTA posts its partial on the board of every rank (peer-mapped memory, one 8-byte store
+  // each over NVLink) and adds up all P x grid partials it finds on its own board, in (rank, CTA) order, so that every
+  // CTA of every GPU obtains the same bits.  xworld <= 1: single-GPU exchange through the private mailboxes above.
+  int xworld, xrank;
+  unsigned xgen;                              // collective call counter (host side, the same on every rank)
+  unsigned long long* xboard[XMAXW];          // [q]: board of rank q as mapped here; [xrank]: the local one
+  int xgrid[XMAXW];                           // CTAs of rank q's solve
 };
 
 using tc::tmem_st16;
@@ -154,17 +182,7 @@ __device__ __forceinline__ float warp_sum_f(float v) {
   return v;
 }
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n"
-      " .reg .pred p;\n"
-      " elect.sync _|p, 0xffffffff;\n"
-      " selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
+using tc::elect_one;
 
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
   unsigned long long v;
@@ -174,32 +192,61 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 // The six partial products of one 16-wide K slice:  acc += (a_hi + a_mid + a_lo) (g_hi + g_mid + g_lo)^T
 // without the three terms below 2^-24.  `koff` is the K offset inside the 128-byte swizzled row (>> 4).
 // Rank update of one block inside the sweep: the operand is the STEP of the block, whose rounding only has to
 // be small against the step itself (the solve stops when the steps have shrunk by a factor 10, nnls.py:156):
 // two terms of the step against two terms of the Gram, three products (error 2^-16 of the update).
-__device__ __forceinline__ void issue_step_update(uint64_t a_hi, uint64_t g_hi, uint32_t d, uint64_t koff, uint32_t idesc) {
-  constexpr uint64_t AP = PLANE_BYTES >> 4, GP = G_PLANE_BYTES >> 4;
-  tc::umma_bf16(d, a_hi + koff, g_hi + koff, idesc, true);
-  tc::umma_bf16(d, a_hi + koff, g_hi + GP + koff, idesc, true);
-  tc::umma_bf16(d, a_hi + AP + koff, g_hi + koff, idesc, true);
+// `a_hi` / `g_hi`: descriptors of the hi planes, already advanced to the 16-wide K slice; AP / GP: plane pitches (>> 4).
+__device__ __forceinline__ void issue_step_update(uint64_t a_hi, uint64_t g_hi, uint32_t d, uint32_t idesc, uint64_t GP) {
+  constexpr uint64_t AP = PLANE_BYTES >> 4;
+  tc::umma_bf16(d, a_hi, g_hi, idesc, true);
+  tc::umma_bf16(d, a_hi, g_hi + GP, idesc, true);
+  tc::umma_bf16(d, a_hi + AP, g_hi, idesc, true);
 }
 
-__device__ __forceinline__ void issue_kslice(uint64_t a_hi, uint64_t g_hi, uint32_t d, uint64_t koff, uint32_t idesc) {
-  constexpr uint64_t AP = PLANE_BYTES >> 4, GP = G_PLANE_BYTES >> 4;
-  tc::umma_bf16(d, a_hi + koff, g_hi + koff, idesc, true);
-  tc::umma_bf16(d, a_hi + koff, g_hi + GP + koff, idesc, true);
-  tc::umma_bf16(d, a_hi + AP + koff, g_hi + koff, idesc, true);
-  tc::umma_bf16(d, a_hi + koff, g_hi + 2 * GP + koff, idesc, true);
-  tc::umma_bf16(d, a_hi + AP + koff, g_hi + GP + koff, idesc, true);
-  tc::umma_bf16(d, a_hi + 2 * AP + koff, g_hi + koff, idesc, true);
+__device__ __forceinline__ void issue_kslice(uint64_t a_hi, uint64_t g_hi, uint32_t d, uint32_t idesc, uint64_t GP) {
+  constexpr uint64_t AP = PLANE_BYTES >> 4;
+  tc::umma_bf16(d, a_hi, g_hi, idesc, true);
+  tc::umma_bf16(d, a_hi, g_hi + GP, idesc, true);
+  tc::umma_bf16(d, a_hi + AP, g_hi, idesc, true);
+  tc::umma_bf16(d, a_hi, g_hi + 2 * GP, idesc, true);
+  tc::umma_bf16(d, a_hi + AP, g_hi + GP, idesc, true);
+  tc::umma_bf16(d, a_hi + 2 * AP, g_hi, idesc, true);
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs a) {
+// compile-time loop over the blocks of a sweep
+template <int B, int N>
+struct BlockLoop {
+  template <class F>
+  static __device__ __forceinline__ void run(F& f) {
+    f(std::integral_constant<int, B>{});
+    BlockLoop<B + 1, N>::run(f);
+  }
+};
+template <int N>
+struct BlockLoop<N, N> {
+  template <class F>
+  static __device__ __forceinline__ void run(F&) {}
+};
+
+template <int RP>
+__global__ void __launch_bounds__(Cfg<RP>::NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs a) {
+  using C = Cfg<RP>;
+  constexpr int MAX_TILES = C::MAX_TILES, UPD_THREADS = C::UPD_THREADS, TMEM_PER_TILE = C::TMEM_PER_TILE, KR = C::KR;
+  constexpr uint32_t G_PLANE_BYTES = C::G_PLANE_BYTES, G_ATOM_BYTES = C::G_ATOM_BYTES;
+  constexpr uint64_t GP = G_PLANE_BYTES >> 4;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* g_planes = smem;                                            // -UtU: hi | mid | lo, rows j, K-major (24 KiB)
+  uint8_t* g_planes = smem;                                            // -UtU / diag: hi | mid | lo, [K atom][row j][128 B]
   uint8_t* v_planes = smem + NPLANES * G_PLANE_BYTES;                  // [tile][hi|mid|lo][16 KiB]
   uint8_t* tail = v_planes + (size_t)MAX_TILES * NPLANES * PLANE_BYTES;
   uint64_t* s_full = reinterpret_cast<uint64_t*>(tail);                // [MAX_TILES] MMA batch complete
@@ -231,16 +278,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
   // Operand planes of -UtU[j][:] / UtU[j][j] (K-major, 128B swizzle): row j = output row of the rank update, K = source
   // row.  With the rows scaled by the diagonal the accumulator holds the SCALED residual, i.e. the unclamped step.
   if (threadIdx.x < UPD_THREADS) {
-    const int j = threadIdx.x >> 3, c = threadIdx.x & 7;
-    const float dj = j < r ? a.G[(int64_t)j * a.ld_g + j] : 0.f;
-    const float sj = dj != 0.f ? -1.f / dj : 0.f;
-    float x[8];
+    for (int idx = threadIdx.x; idx < RP * (RP / 8); idx += UPD_THREADS) {
+      const int j = idx / (RP / 8), c = idx % (RP / 8);                // row j, 16-byte chunk c = source rows 8c .. 8c+7
+      const float dj = j < r ? a.G[(int64_t)j * a.ld_g + j] : 0.f;
+      const float sj = dj != 0.f ? -1.f / dj : 0.f;
+      float x[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int l = c * 8 + i;
-      x[i] = (j < r && l < r) ? a.G[(int64_t)j * a.ld_g + l] * sj : 0.f;
+      for (int i = 0; i < 8; ++i) {
+        const int l = c * 8 + i;
+        x[i] = (j < r && l < r) ? a.G[(int64_t)j * a.ld_g + l] * sj : 0.f;
+      }
+      store_chunk(g_planes + (c >> 3) * G_ATOM_BYTES, j, c & 7, x, G_PLANE_BYTES);
     }
-    store_chunk(g_planes, j, c, x, G_PLANE_BYTES);
   }
   tc::fence_proxy_async_smem();
   tc::tcgen05_fence_before();
@@ -252,7 +301,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
 
   // ------------------------------------------------------------------------------------------------
   // MMA-issuing warps: one per tile.  Every arrival of the tile's 128 update threads on s_ready hands
-  // over one operand set: first the full V (initial residual), then one 16-row block of steps each.
+  // over one operand set: first V (initial residual; one 64-row K atom per hand-over), then one 16-row
+  // block of steps each.
   // ------------------------------------------------------------------------------------------------
   if (warp >= UPD_THREADS / 32) {
     // warp-uniform by construction (shuffle), so that descriptors live in uniform registers
@@ -261,21 +311,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
       const uint64_t a_desc = tc::umma_desc_k_sw128(tc::smem_u32(v_planes + (size_t)tile * NPLANES * PLANE_BYTES));
       const uint32_t d = tmem_base + (uint32_t)(tile * TMEM_PER_TILE);
       uint32_t phase = 0;
-      tc::mbar_wait(&s_ready[tile], phase);
-      phase ^= 1;
-      tc::tcgen05_fence_after();
-      if (elect_one()) {
-        for (int ks = 0; ks < nblk; ++ks) issue_kslice(a_desc, g_desc, d, (uint64_t)(ks * 2), idesc);
-        tc::umma_commit(&s_full[tile]);
+      for (int kr = 0; kr < KR; ++kr) {
+        if (kr * 4 >= nblk) break;
+        tc::mbar_wait(&s_ready[tile], phase);
+        phase ^= 1;
+        tc::tcgen05_fence_after();
+        if (elect_one()) {
+          for (int ks = 0; ks < 4 && kr * 4 + ks < nblk; ++ks)
+            issue_kslice(a_desc + (uint64_t)(ks * 2), g_desc + (uint64_t)(kr * (G_ATOM_BYTES >> 4) + ks * 2), d, idesc, GP);
+          tc::umma_commit(&s_full[tile]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
       for (int B = 0;; B = (B + 1 < nblk) ? B + 1 : 0) {
         tc::mbar_wait(&s_ready[tile], phase);
         phase ^= 1;
         if (s_done[tile]) break;
         tc::tcgen05_fence_after();
         if (elect_one()) {
-          issue_step_update(a_desc, g_desc, d, (uint64_t)(B * 2), idesc);
+          issue_step_update(a_desc + (uint64_t)((B & 3) * 2), g_desc + (uint64_t)((B >> 2) * (G_ATOM_BYTES >> 4) + (B & 3) * 2), d, idesc, GP);
           tc::umma_commit(&s_full[tile]);
         }
         __syncwarp();
@@ -293,44 +347,62 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
     uint8_t* vh = v_planes + (size_t)tile * NPLANES * PLANE_BYTES;
     const uint32_t t_w = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile * TMEM_PER_TILE);
     const uint32_t t_v = t_w + RP;
+    uint32_t s_phase = 0;
 
     if (active) {
       // V -> TMEM masters and operand planes; UtM - sp -> residual accumulator (the issuer adds -UtU V)
 #pragma unroll
-      for (int c0 = 0; c0 < RP; c0 += 16) {
-        float x[16];
-        uint32_t w[16];
+      for (int kr = 0; kr < KR; ++kr) {
+        if (kr * 4 < nblk) {
+          if (kr > 0) {                                                  // the planes are reused: the products of the previous
+            tc::mbar_wait(&s_full[tile], s_phase);                       // K atom must have retired
+            s_phase ^= 1;
+          }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = (valid && c0 + j < r) ? a.Vin[(int64_t)(c0 + j) * a.ld_vin + col] : 0.f;
+          for (int c1 = 0; c1 < 64; c1 += 16) {
+            const int c0 = kr * 64 + c1;
+            float x[16];
+            uint32_t w[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) w[j] = __float_as_uint(c_sw.invd[c0 + j] != 0.f ? x[j] : 0.f);   // skipped rows: master 0
-        tmem_st16(t_v + c0, w);
-        store_chunk(vh, row, c0 / 8, &x[0], PLANE_BYTES);
-        store_chunk(vh, row, c0 / 8 + 1, &x[8], PLANE_BYTES);
-        // right-hand side: 16 independent loads in flight per slab (a loop over the slabs INSIDE the row loop serialises
-        // them: measured +0.07 ms per solve); the slabs of split-K partials are added in order, like the reduction kernel
-        float bv[16];
+            for (int j = 0; j < 16; ++j) x[j] = (valid && c0 + j < r) ? a.Vin[(int64_t)(c0 + j) * a.ld_vin + col] : 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) bv[j] = (valid && c0 + j < r) ? a.b[(int64_t)(c0 + j) * a.ld_b + col] : 0.f;
-        for (int sp = 1; sp < a.nsplit; ++sp) {
-          float t[16];
+            for (int j = 0; j < 16; ++j) w[j] = __float_as_uint(csw<RP>().invd[c0 + j] != 0.f ? x[j] : 0.f);   // skipped rows: master 0
+            tmem_st16(t_v + c0, w);
+            store_chunk(vh, row, c1 / 8, &x[0], PLANE_BYTES);
+            store_chunk(vh, row, c1 / 8 + 1, &x[8], PLANE_BYTES);
+            // right-hand side: 16 independent loads in flight per slab (a loop over the slabs INSIDE the row loop serialises
+            // them: measured +0.07 ms per solve); the slabs of split-K partials are added in order, like the reduction kernel
+            float bv[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            t[j] = (valid && c0 + j < r) ? a.b[(int64_t)sp * a.split_stride + (int64_t)(c0 + j) * a.ld_b + col] : 0.f;
+            for (int j = 0; j < 16; ++j) bv[j] = (valid && c0 + j < r) ? a.b[(int64_t)(c0 + j) * a.ld_b + col] : 0.f;
+            for (int sp = 1; sp < a.nsplit; ++sp) {
+              float t[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) bv[j] += t[j];
+              for (int j = 0; j < 16; ++j)
+                t[j] = (valid && c0 + j < r) ? a.b[(int64_t)sp * a.split_stride + (int64_t)(c0 + j) * a.ld_b + col] : 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) bv[j] += t[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w[j] = __float_as_uint((valid && c0 + j < r) ? (bv[j] - a.sp) * csw<RP>().invd[c0 + j] : 0.f);
+            tmem_st16(t_w + c0, w);
+          }
+          tmem_st_wait();
+          tc::fence_proxy_async_smem();
+          tc::tcgen05_fence_before();
+          tc::mbar_arrive(&s_ready[tile]);
+        } else {
+          // rank rows beyond the last block: masters and residual are zero
+          uint32_t z[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) z[j] = 0u;
+#pragma unroll
+          for (int c1 = 0; c1 < 64; c1 += 16) { tmem_st16(t_v + kr * 64 + c1, z); tmem_st16(t_w + kr * 64 + c1, z); }
+          tmem_st_wait();
         }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) w[j] = __float_as_uint((valid && c0 + j < r) ? (bv[j] - a.sp) * c_sw.invd[c0 + j] : 0.f);
-        tmem_st16(t_w + c0, w);
       }
-      tmem_st_wait();
-      tc::fence_proxy_async_smem();
-      tc::tcgen05_fence_before();
-      tc::mbar_arrive(&s_ready[tile]);
     }
 
-    uint32_t s_phase = 0;
     uint8_t* bkrow = vh + 2 * PLANE_BYTES + (uint32_t)row * 128u;       // 128 B: masters of up to 2 speculative blocks
 #ifdef SWEEP_PROF
     long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -382,17 +454,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
         // nnls.py:163/167.  A skipped row (zero diagonal, nnls.py:160) has u = 0 and a master of 0 (its true value only
         // enters the initial residual and is left untouched in memory), so its step is max(0, -0) = 0.
         const float d = fmaxf(u[e], -cur);
-        if (e + 1 < BLK) u[e + 1] = fmaf(c_sw.nh[B][e][e + 1], d, u[e + 1]);
+        if (e + 1 < BLK) u[e + 1] = fmaf(csw<RP>().nh[B][e][e + 1], d, u[e + 1]);
         dd[e] = d;
         vn[e] = __float_as_uint(cur + d);
         nd = fmaf(d, d, nd);                                           // nnls.py:170
 #pragma unroll
-        for (int e2 = e + 2; e2 < BLK; ++e2) u[e2] = fmaf(c_sw.nh[B][e][e2], d, u[e2]);
+        for (int e2 = e + 2; e2 < BLK; ++e2) u[e2] = fmaf(csw<RP>().nh[B][e][e2], d, u[e2]);
       }
       PROF_T(2)
       tmem_st16(t_v + B * BLK, vn);
-      store_chunk2(vh, row, 2 * B, &dd[0], PLANE_BYTES);
-      store_chunk2(vh, row, 2 * B + 1, &dd[8], PLANE_BYTES);
+      store_chunk2(vh, row, 2 * (B & 3), &dd[0], PLANE_BYTES);
+      store_chunk2(vh, row, 2 * (B & 3) + 1, &dd[8], PLANE_BYTES);
       PROF_T(3)
       tc::fence_proxy_async_smem();
       tmem_st_wait();
@@ -407,6 +479,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
     unsigned epoch = 0;
     const unsigned nb = gridDim.x;
     const unsigned gen = *a.gen;
+    const bool collective = a.xworld > 1;
     // Stop test of nnls.py:156: it needs the sum of squared steps over ALL columns after every sweep.  Every CTA posts
     // its partial into the mailbox of every CTA (one 64-bit store each, tag | value) and adds the partials it receives
     // in a fixed order, so that all CTAs obtain the same bits and take the same decision.  While the partials travel,
@@ -420,17 +493,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
     while (true) {
       float nd = nd_spec;
       if (active) {
-        if (nspec < 1) nd += block_update(std::integral_constant<int, 0>{}, plain);
-        if (nblk > 1 && nspec < 2) nd += block_update(std::integral_constant<int, 1>{}, plain);
-        if (nblk > 2 && nspec < 3) nd += block_update(std::integral_constant<int, 2>{}, plain);
-        if (nblk > 3) nd += block_update(std::integral_constant<int, 3>{}, plain);
+        auto body = [&](auto Bc) {
+          constexpr int B = decltype(Bc)::value;
+          if (B < nblk && B >= nspec) nd += block_update(Bc, plain);
+        };
+        BlockLoop<0, C::NBLK>::run(body);
       }
       // (fp32 trees: every CTA adds the same numbers in the same order)
       const float t = warp_sum_f(nd);
       if (lane == 0) redf[warp] = t;
       named_bar_sync(1, UPD_THREADS);
-      const unsigned tag = (gen << 16) | (epoch + 1u);
-      if (nb > 1 && threadIdx.x < nb) {
+      const unsigned tag = collective ? ((a.xgen & 0xffffu) << 16) | (epoch + 1u) : (gen << 16) | (epoch + 1u);
+      // collective: 4 banks of XMAXW x XMAXG entries, bank = 2 (call parity) + sweep parity, so that a rank that is a
+      // whole sweep (or the start of the next call) ahead never overwrites an entry a slower rank still has to read
+      const size_t xbank = (size_t)(((a.xgen & 1u) << 1) | (epoch & 1u)) * (XMAXW * XMAXG);
+      if (collective) {
+        if (threadIdx.x < (unsigned)a.xworld) {
+          float sum = 0.f;
+#pragma unroll
+          for (int w = 0; w < UPD_THREADS / 32; ++w) sum += redf[w];
+          const unsigned long long bits = ((unsigned long long)tag << 32) | __float_as_uint(sum);
+          st_relaxed_sys_u64(a.xboard[threadIdx.x] + xbank + (size_t)a.xrank * XMAXG + blockIdx.x, bits);
+        }
+      } else if (nb > 1 && threadIdx.x < nb) {
         float sum = 0.f;
 #pragma unroll
         for (int w = 0; w < UPD_THREADS / 32; ++w) sum += redf[w];
@@ -440,7 +525,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
       // ---- speculative blocks of the next sweep; the first look into the mailbox is issued before the last of them,
       //      so that its L2 round trip runs under that block ----
       const unsigned long long* slot = a.mail + ((size_t)(epoch & 1u) * nb + blockIdx.x) * nb + threadIdx.x;
-      const bool poller = nb > 1 && threadIdx.x < nb;
+      const bool poller = !collective && nb > 1 && threadIdx.x < nb;
       unsigned long long early = 0ull;
       nspec = 0;
       nd_spec = 0.f;
@@ -462,7 +547,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
       const long long tg0 = clock64();
 #endif
       float totf = 0.f;
-      if (nb > 1) {
+      if (collective) {
+        // every entry of the local board: thread t adds entries t, t + UPD_THREADS, ... (rank-major), then the usual trees
+        float got = 0.f;
+        const unsigned long long* board = a.xboard[a.xrank] + xbank;
+        for (int e = threadIdx.x; e < a.xworld * XMAXG; e += UPD_THREADS) {
+          const int qr = e / XMAXG, c = e - qr * XMAXG;
+          if (c < a.xgrid[qr]) {
+            unsigned long long bits = ld_relaxed_sys_u64(board + e);
+            uint32_t spins = 0;
+            while ((unsigned)(bits >> 32) != tag) {
+              bits = ld_relaxed_sys_u64(board + e);
+              if (++spins > (1u << 26)) __trap();
+            }
+            got += __uint_as_float((unsigned)bits);
+          }
+        }
+        got = warp_sum_f(got);
+        if (lane == 0) redf[16 + warp] = got;
+        named_bar_sync(1, UPD_THREADS);
+#pragma unroll
+        for (int w = 0; w < UPD_THREADS / 32; ++w) totf += redf[16 + w];
+      } else if (nb > 1) {
         float got = 0.f;
         if (poller) {
           unsigned long long bits = early;
@@ -497,8 +603,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
       epsf = totf;
       ++cnt;
       bool stop = !(epsf >= thr && cnt <= a.maxiter);
-      if (totf == 0.f) {                                                  // further sweeps are no-ops (nnls.py:156)
-        if (cnt < a.maxiter + 1) cnt = a.maxiter + 1;
+      if (totf == 0.f) {
+        // every further sweep is a no-op.  nnls.py:156 keeps looping on `0 >= delta * 0` only when the FIRST sweep already
+        // moved nothing (eps0 == 0): then it burns all maxiter sweeps and returns cnt = maxiter + 1; otherwise
+        // 0 >= delta * eps0 is false and the loop ends with the current count.
+        if (thr == 0.f && cnt < a.maxiter + 1) cnt = a.maxiter + 1;
         stop = true;
       }
       if (stop) break;
@@ -513,50 +622,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
     if (active) {                                                         // tcgen05.ld is warp-collective: no per-lane branch around it
 #pragma unroll
       for (int c0 = 0; c0 < RP; c0 += 16) {
-        uint32_t w[16];
-        tc::tmem_ld16(t_v + c0, w);
-        tc::tmem_ld_wait();
-        if (c0 / BLK == 2 && nspec > 2) {                                   // undo the speculative blocks
+        if (c0 < nblk * BLK) {
+          uint32_t w[16];
+          tc::tmem_ld16(t_v + c0, w);
+          tc::tmem_ld_wait();
+          if (c0 / BLK == 2 && nspec > 2) {                                   // undo the speculative blocks
 #pragma unroll
-          for (int e = 0; e < BLK; ++e) w[e] = bk2[e];
-        } else if (c0 / BLK < nspec) {
+            for (int e = 0; e < BLK; ++e) w[e] = bk2[e];
+          } else if (c0 / BLK < 2 && c0 / BLK < nspec) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint4 b4 = *reinterpret_cast<const uint4*>(bkrow + ((((c0 / BLK) * 4 + c) ^ (row & 7)) << 4));
-            w[4 * c] = b4.x; w[4 * c + 1] = b4.y; w[4 * c + 2] = b4.z; w[4 * c + 3] = b4.w;
-          }
-        }
-        float x[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          x[j] = __uint_as_float(w[j]);
-          // a skipped row (zero diagonal) keeps its start value (its master was a placeholder 0)
-          if (c_sw.has_zero_diag && valid && c0 + j < r && c_sw.invd[c0 + j] == 0.f) x[j] = a.Vin[(int64_t)(c0 + j) * a.ld_vin + col];
-          if (valid && c0 + j < r) a.V[(int64_t)(c0 + j) * a.ld_v + col] = x[j];
-        }
-        if (a.fh != nullptr) {
-          // operand planes of the new factor, straight from the registers (replaces a separate pass over the factor)
-          uint32_t hw[8], lw[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float p0 = (valid && c0 + 2 * j < r) ? x[2 * j] : 0.f, p1 = (valid && c0 + 2 * j + 1 < r) ? x[2 * j + 1] : 0.f;
-            hw[j] = pack_bf16(p0, p1);
-            lw[j] = pack_bf16(p0 - __uint_as_float(hw[j] << 16), p1 - __uint_as_float(hw[j] & 0xffff0000u));
-          }
-          if (valid) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (c0 + j < a.r_pad) {
-                const uint32_t h = (j & 1) ? (hw[j >> 1] >> 16) : (hw[j >> 1] & 0xffffu), l = (j & 1) ? (lw[j >> 1] >> 16) : (lw[j >> 1] & 0xffffu);
-                reinterpret_cast<unsigned short*>(a.fh)[(int64_t)(c0 + j) * a.ld_plane + col] = (unsigned short)h;
-                reinterpret_cast<unsigned short*>(a.fl)[(int64_t)(c0 + j) * a.ld_plane + col] = (unsigned short)l;
-              }
+            for (int c = 0; c < 4; ++c) {
+              const uint4 b4 = *reinterpret_cast<const uint4*>(bkrow + ((((c0 / BLK) * 4 + c) ^ (row & 7)) << 4));
+              w[4 * c] = b4.x; w[4 * c + 1] = b4.y; w[4 * c + 2] = b4.z; w[4 * c + 3] = b4.w;
             }
-            if (a.rowh != nullptr) {
-              uint4* rh = reinterpret_cast<uint4*>(a.rowh + col * 64 + c0);
-              uint4* rl = reinterpret_cast<uint4*>(a.rowl + col * 64 + c0);
-              rh[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]); rh[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-              rl[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]); rl[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+          }
+          float x[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            x[j] = __uint_as_float(w[j]);
+            // a skipped row (zero diagonal) keeps its start value (its master was a placeholder 0)
+            if (csw<RP>().has_zero_diag && valid && c0 + j < r && csw<RP>().invd[c0 + j] == 0.f) x[j] = a.Vin[(int64_t)(c0 + j) * a.ld_vin + col];
+            if (valid && c0 + j < r) a.V[(int64_t)(c0 + j) * a.ld_v + col] = x[j];
+          }
+          if (a.fh != nullptr) {
+            // operand planes of the new factor, straight from the registers (replaces a separate pass over the factor)
+            uint32_t hw[8], lw[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float p0 = (valid && c0 + 2 * j < r) ? x[2 * j] : 0.f, p1 = (valid && c0 + 2 * j + 1 < r) ? x[2 * j + 1] : 0.f;
+              hw[j] = pack_bf16(p0, p1);
+              lw[j] = pack_bf16(p0 - __uint_as_float(hw[j] << 16), p1 - __uint_as_float(hw[j] & 0xffff0000u));
+            }
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (c0 + j < a.r_pad) {
+                  const uint32_t h = (j & 1) ? (hw[j >> 1] >> 16) : (hw[j >> 1] & 0xffffu), l = (j & 1) ? (lw[j >> 1] >> 16) : (lw[j >> 1] & 0xffffu);
+                  reinterpret_cast<unsigned short*>(a.fh)[(int64_t)(c0 + j) * a.ld_plane + col] = (unsigned short)h;
+                  reinterpret_cast<unsigned short*>(a.fl)[(int64_t)(c0 + j) * a.ld_plane + col] = (unsigned short)l;
+                }
+              }
+              if (a.rowh != nullptr) {
+                uint4* rh = reinterpret_cast<uint4*>(a.rowh + col * a.row_pitch + c0);
+                uint4* rl = reinterpret_cast<uint4*>(a.rowl + col * a.row_pitch + c0);
+                rh[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]); rh[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+                rl[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]); rl[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+              }
             }
           }
         }
@@ -583,48 +694,83 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs
 
 }  // namespace
 
+template <int RP>
+static int sweep_launch(nnfac_ctx* ctx, TcSweepArgs& a, const float* UtU, int64_t ld_utu, int64_t grid, cudaStream_t st) {
+  using C = Cfg<RP>;
+  // the per-call constants are written straight into the __constant__ bank of this device by a one-block kernel (constant
+  // caches are invalidated at kernel boundaries, and the stream orders it before the sweep); the bank address is resolved
+  // once per context, i.e. per device
+  void*& bank = ctx->sweep_const[RP == 64 ? 0 : 1];
+  if (!bank) {
+    if (RP == 64) NNFAC_CUDA(cudaGetSymbolAddress(&bank, c_sw64));
+    else NNFAC_CUDA(cudaGetSymbolAddress(&bank, c_sw128));
+  }
+  unsigned* gen_dev = reinterpret_cast<unsigned*>(ctx->mail + ctx->mail_count);
+  sweep_prep_kernel<RP><<<1, 256, 0, st>>>(UtU, ld_utu, a.r, (SweepConst<RP>*)bank, gen_dev, ctx->mail, ctx->mail_count);
+  NNFAC_LAUNCH_CHECK(ctx);
+  a.mail = ctx->mail; a.gen = gen_dev;
+  NNFAC_CUDA(cudaFuncSetAttribute(tc_sweep_kernel<RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+  // every CTA waits for every other one once per sweep: the cooperative launch guarantees that all of them are resident
+  // (a plain launch was measured: no difference in launch cost)
+  void* params[] = {&a};
+  NNFAC_CUDA(cudaLaunchCooperativeKernel((const void*)tc_sweep_kernel<RP>, dim3((unsigned)grid), dim3(C::NTHREADS), params, C::SMEM, st));
+  ctx->launches++;
+  return NNFAC_OK;
+}
+
 // Returns NNFAC_ERR_UNSUPPORTED (without setting an error) when the shape is outside this kernel's
 // envelope, so that the caller can use the FMA kernel instead.  `planes` (optional) receives the bf16 operand planes
 // of the result (see TcSweepArgs); Vin may alias V.
 int nnfac_tc_sweep_run(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const float* UtU, int64_t ld_utu, const float* Vin,
                        int64_t ld_vin, float* V, int64_t ld_v, int r, int64_t n, int maxiter, double delta, double sparsity,
                        double* result, const nnfac_sweep_planes* planes, cudaStream_t st, int nsplit, int64_t split_stride) {
-  if (r > RP || maxiter < 1) return NNFAC_ERR_UNSUPPORTED;
+  if (r > 128 || maxiter < 1 || n < 1) return NNFAC_ERR_UNSUPPORTED;
+  const int rp = r <= 64 ? 64 : 128;
+  const int max_cols = (256 / rp) * TILE;                  // columns a CTA can keep in tensor memory
   int64_t cols = ceil_div64(n, ctx->sm_count);
   cols = ceil_div64(cols, 32) * 32;
   if (const char* force = getenv("NNFAC_SWEEP_COLS")) {   // experiment switch: columns per CTA (multiple of 32)
     const int64_t f = atoll(force);
     if (f >= 32 && f % 32 == 0 && f > cols) cols = f;
   }
-  if (cols > MAX_TILES * TILE) return NNFAC_ERR_UNSUPPORTED;
+  const nnfac_peer_group* pg = ctx->collective ? &ctx->peers : nullptr;
+  if (pg) {
+    // collective solve: every rank must take the same kernel; the widest slice decides whether the shape fits
+    int64_t widest = n;
+    for (int q = 0; q < pg->world; ++q) if (ctx->collective_n[q] > widest) widest = ctx->collective_n[q];
+    int64_t wc = ceil_div64(ceil_div64(widest, ctx->sm_count), 32) * 32;
+    if (wc > max_cols) { nnfac_set_error("collective HALS solve: a slice of %lld columns at rank %d exceeds the tensor-core sweep", (long long)widest, r); return NNFAC_ERR_UNSUPPORTED; }
+  }
+  if (cols > max_cols) return NNFAC_ERR_UNSUPPORTED;
   const int64_t grid = ceil_div64(n, cols);
-  if ((size_t)(2 * grid * grid) > ctx->mail_count || maxiter > 65000) return NNFAC_ERR_UNSUPPORTED;
-  // the per-call constants are written straight into the __constant__ bank by a one-block kernel (constant caches are
-  // invalidated at kernel boundaries, and the stream orders it before the sweep)
-  static SweepConst* c_sw_dev = nullptr;
-  if (!c_sw_dev) NNFAC_CUDA(cudaGetSymbolAddress((void**)&c_sw_dev, c_sw));
-  unsigned* gen_dev = reinterpret_cast<unsigned*>(ctx->mail + ctx->mail_count);
-  sweep_prep_kernel<<<1, 256, 0, st>>>(UtU, ld_utu, r, c_sw_dev, gen_dev, ctx->mail, ctx->mail_count);
-  NNFAC_LAUNCH_CHECK(ctx);
+  if ((size_t)(2 * grid * grid) > ctx->mail_count || maxiter > 65000 || grid > XMAXG) return NNFAC_ERR_UNSUPPORTED;
+  int rc = nnfac_guard_enter(ctx, NNFAC_GUARD_SWEEP, st);
+  if (rc) return rc;
   TcSweepArgs a;
   a.b = UtM; a.G = UtU; a.Vin = Vin; a.V = V; a.ld_b = ld_utm; a.ld_g = ld_utu; a.ld_v = ld_v; a.ld_vin = ld_vin; a.n = n;
   a.r = r; a.maxiter = maxiter; a.cols_per_cta = (int)cols; a.delta = delta; a.sp = (float)sparsity;
   a.nsplit = nsplit > 0 ? nsplit : 1; a.split_stride = split_stride;
-  a.fh = a.fl = a.rowh = a.rowl = nullptr; a.ld_plane = 0; a.r_pad = 0;
+  a.fh = a.fl = a.rowh = a.rowl = nullptr; a.ld_plane = 0; a.r_pad = 0; a.row_pitch = 64;
   if (planes) {
     a.fh = (bf16*)planes->fh; a.fl = (bf16*)planes->fl; a.rowh = (bf16*)planes->rowh; a.rowl = (bf16*)planes->rowl;
-    a.ld_plane = planes->ld_plane; a.r_pad = planes->r_pad;
+    a.ld_plane = planes->ld_plane; a.r_pad = planes->r_pad; a.row_pitch = planes->row_pitch;
+  }
+  a.result = result;
+  a.xworld = 0; a.xrank = 0; a.xgen = 0;
+  for (int q = 0; q < XMAXW; ++q) { a.xboard[q] = nullptr; a.xgrid[q] = 0; }
+  if (pg) {
+    a.xworld = pg->world; a.xrank = pg->rank; a.xgen = ++ctx->collective_gen;
+    for (int q = 0; q < pg->world; ++q) {
+      a.xboard[q] = (unsigned long long*)pg->board[q];
+      const int64_t nq = ctx->collective_n[q];
+      int64_t cq = ceil_div64(ceil_div64(nq, ctx->sm_count), 32) * 32;
+      a.xgrid[q] = nq > 0 ? (int)ceil_div64(nq, cq) : 0;
+    }
+    if (a.xgrid[pg->rank] != (int)grid) { nnfac_set_error("collective HALS solve: slice length %lld does not match the announced one", (long long)n); return NNFAC_ERR_ARG; }
   }
   // mailbox tags carry a call generation (device-side, see sweep_prep_kernel), so that the slots never need clearing
-  a.mail = ctx->mail; a.gen = gen_dev; a.result = result;
-  const size_t smem = NPLANES * G_PLANE_BYTES + (size_t)MAX_TILES * NPLANES * PLANE_BYTES + 512;
-  NNFAC_CUDA(cudaFuncSetAttribute(tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // every CTA waits for every other one once per sweep: the cooperative launch guarantees that all of them are resident
-  // (a plain launch was measured: no difference in launch cost)
-  void* params[] = {&a};
-  NNFAC_CUDA(cudaLaunchCooperativeKernel((const void*)tc_sweep_kernel, dim3((unsigned)grid), dim3(NTHREADS), params, smem, st));
-  ctx->launches++;
-  return NNFAC_OK;
+  rc = rp == 64 ? sweep_launch<64>(ctx, a, UtU, ld_utu, grid, st) : sweep_launch<128>(ctx, a, UtU, ld_utu, grid, st);
+  return rc;
 }
 
 int nnfac_tc_sweep_try(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const float* UtU, int64_t ld_utu, float* V,

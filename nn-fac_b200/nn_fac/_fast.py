@@ -16,10 +16,14 @@ U is replicated.  Per outer iteration there is one exchange step on each side of
     summed with one all-reduce (HALS), or the partial MU numerator and the partial row sums of V (MU);
   * for HALS the U solve is split by rows of U (columns of U^T): every rank sweeps its own m/P slice and
     the slices are all-gathered, so the solve shrinks with P instead of being repeated on every rank.
-The V side needs no exchange.  The HALS stop test (nnls.py:156) is evaluated PER SLICE in this mode
-(each rank stops on the squared-step ratio of the columns it owns): a grid-wide scalar per sweep
-across GPUs would cost more than the sweep itself.  Costs are summed with a scalar all-reduce.
+The V side needs no exchange of factor data.  The HALS stop test (nnls.py:156) sums the squared steps over ALL columns
+of a solve, also when they are spread over several GPUs: the sweep kernels of all ranks exchange their partial sums once per
+sweep through peer-mapped "boards" (8-byte stores over NVLink, csrc/tc_sweep.cu), so a sharded solve stops after exactly
+the sweeps of the unsharded one.  (Solves outside the tensor-core sweep -- normalize, slices too wide for tensor memory --
+fall back to the CUDA-core kernel with the rule applied per slice.)  Costs are summed with a scalar all-reduce.
 """
+import contextlib
+import ctypes
 import os
 import time
 
@@ -33,7 +37,12 @@ MODE_RES, MODE_MU = 0, 1
 
 
 def eligible(dtype, rank, update_rule, beta):
-    return dtype == torch.float32 and rank <= 64 and (update_rule == "hals" or (update_rule == "mu" and beta in (1, 2)))
+    """fp32 on the tcgen05 path: HALS and Frobenius MU up to rank 128 (residual + cross-product pass), KL MU up to rank 64."""
+    if dtype != torch.float32:
+        return False
+    if update_rule == "hals" or (update_rule == "mu" and beta == 2):
+        return rank <= 128
+    return update_rule == "mu" and beta == 1 and rank <= 64
 
 
 class Comm:
@@ -67,6 +76,64 @@ class Comm:
         lo = min(self.rank * chunk, length)
         return chunk, lo, min(lo + chunk, length)
 
+    def slice_lengths(self, length):
+        """Columns of every rank's slice of range(length) (see slice_of)."""
+        chunk = -(-length // self.world)
+        chunk = -(-chunk // self.align) * self.align
+        return [max(0, min((p + 1) * chunk, length) - min(p * chunk, length)) for p in range(self.world)]
+
+    def all_lengths(self, n_local, device):
+        """The local column counts of all ranks (the V blocks need not be equal)."""
+        if self.world == 1:
+            return [int(n_local)]
+        t = torch.zeros(self.world, dtype=torch.int64, device=device)
+        t[self.rank] = int(n_local)
+        self.sum_(t)
+        return [int(v) for v in t.cpu().tolist()]
+
+    # ---- the cross-GPU stop scalar of collective HALS solves (GPU ranks only) ----
+    _boards_device = None
+
+    def attach_boards(self, device):
+        """Once per (group, device): every rank exports the CUDA IPC handle of its board, the handles are all-gathered and
+        every rank maps the boards of its peers (nnfac_ctx_board_export / _attach)."""
+        if self.world == 1 or self._boards_device == device:
+            return self._boards_device is not None
+        if self.world > 8:
+            return False
+        lib = L.load_library()
+        mine = (ctypes.c_ubyte * 64)()
+        L.check(lib.nnfac_ctx_board_export(L.ctx(device), mine))
+        send = torch.tensor(list(mine), dtype=torch.uint8, device=device)
+        recv = torch.empty(self.world * 64, dtype=torch.uint8, device=device)
+        self.dist.all_gather_into_tensor(recv, send, group=self.group)
+        handles = (ctypes.c_ubyte * (64 * self.world))(*recv.cpu().tolist())
+        rc = lib.nnfac_ctx_board_attach(L.ctx(device), self.world, self.rank, handles)
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int64, device=device)
+        self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN, group=self.group)      # all ranks or none
+        if int(ok.item()) == 1:
+            self._boards_device = device
+            return True
+        import warnings
+        warnings.warn("nn_fac: peer access between the GPUs of this group is not available (%s); the sharded HALS solves "
+                      "apply the stop rule per slice" % L.load_library().nnfac_last_error().decode())
+        return False
+
+    @contextlib.contextmanager
+    def collective(self, lengths):
+        """The tensor-core HALS solves issued inside are one slice each of a joint solve over the group: `lengths` = columns of
+        every rank's slice.  No-op for a single rank or without attached boards."""
+        if self.world == 1 or self._boards_device is None:
+            yield
+            return
+        lib = L.load_library()
+        arr = (ctypes.c_int64 * self.world)(*[int(v) for v in lengths])
+        L.check(lib.nnfac_ctx_collective(L.ctx(self._boards_device), 1, arr))
+        try:
+            yield
+        finally:
+            L.check(lib.nnfac_ctx_collective(L.ctx(self._boards_device), 0, None))
+
     def reduce_scatter_columns(self, M, tail, chunk):
         """Sum over the ranks of M (r x length) and of `tail` (r x t), of which this rank only receives its own column slice
         [rank*chunk, (rank+1)*chunk) of M (zero-padded) plus the whole summed tail: one reduce-scatter instead of an
@@ -86,6 +153,13 @@ class Comm:
         recv = torch.empty((r, chunk + t), dtype=M.dtype, device=M.device)
         self.dist.reduce_scatter_tensor(recv, send.view(self.world * r, chunk + t), op=self.dist.ReduceOp.SUM, group=self.group)
         return recv[:, :chunk], recv[:, chunk:]
+
+    def gather_slices(self, send):
+        """send: this rank's slice (r x chunk, zero-padded).  Returns [world][r][chunk] (all-gather, no staging copies)."""
+        r, chunk = send.shape
+        recv = torch.empty((self.world, r, chunk), dtype=send.dtype, device=send.device)
+        self.dist.all_gather_into_tensor(recv.view(self.world * r, chunk), send, group=self.group)
+        return recv
 
     def gather_columns_(self, Ft, chunk, lo, hi):
         """Every rank owns columns [lo, hi) of Ft (r x length); afterwards every rank holds all of them."""
@@ -141,6 +215,19 @@ class CudaEngine:
     def sweep(UtM, UtU, V, r, sparsity, normalize, result):
         sp = 0.0 if sparsity is None else float(sparsity)
         ops.hals_nnls(UtM, UtU, V, r, 100, 0.01, sp, bool(normalize), False, result)   # nmf.py:415 / :440
+
+    @staticmethod
+    def solve_slice(UtM, UtU, F_in, out, r, sparsity, result, comm, lengths):
+        """out <- hals_nnls_acc(UtM, UtU, F_in) for this rank's column slice of a solve that spans the group (F_in: strided view
+        of the full factor, out: the contiguous send buffer of the all-gather); global stop rule of nnls.py:156."""
+        sp = 0.0 if sparsity is None else float(sparsity)
+        with comm.collective(lengths):
+            if out.shape[1] > 0:
+                ops.hals_solve(UtM, UtU, F_in, out, r, 100, 0.01, sp, result)
+
+    def install_gathered(self, which, gathered, length):
+        """gathered: [world][r][chunk] slices of the new factor -> the factor (r x length) and all of its operand planes."""
+        return self.plan.set_factor_gathered(which, gathered, length)
 
     @staticmethod
     def mu_apply(F, num, den_vec):
@@ -207,6 +294,10 @@ class FusedNMF:
         self._rsum = [torch.empty(self.r, dtype=self.Ut.dtype, device=self.device) for _ in range(2)]
         # exchange buffer of the U side: [cross product or numerator (r x m) | Gram (r x r) or row sums (r)]
         self._xbuf = torch.empty(self.r * self.m + self.r * self.r, dtype=self.Ut.dtype, device=self.device)
+        self._usend = None
+        self._vlens = self.comm.all_lengths(self.n, self.device)
+        if self.comm.world > 1 and self._on_gpu and engine is None:
+            self.comm.attach_boards(self.device)
 
     def _phase(self, name):
         from nn_fac.nmf import _Phase
@@ -272,6 +363,15 @@ class FusedNMF:
                     Ut = Ut.clone()
                     eng.sweep(VMt, VVt, Ut, r, sparsity[0], normalize[0], self.hals_stats[0])
                     eng.set_factor(0, Ut)
+                elif hasattr(eng, "solve_slice"):
+                    # every rank solves its slice of the rows of U straight into the send buffer of the all-gather; the
+                    # gathered slices become the new U^T and its operand planes in one kernel
+                    send = self._usend if self._usend is not None and self._usend.shape[1] == chunk else None
+                    if send is None:
+                        send = self._usend = torch.zeros((r, chunk), dtype=Ut.dtype, device=Ut.device)
+                    eng.solve_slice(VMt_slice[:, :hi - lo], VVt, Ut[:, lo:hi], send[:, :hi - lo], r, sparsity[0],
+                                    self.hals_stats[0], comm, comm.slice_lengths(m))
+                    Ut = eng.install_gathered(0, comm.gather_slices(send), m)
                 else:
                     Ut = Ut.clone()
                     if hi > lo:
@@ -286,7 +386,12 @@ class FusedNMF:
                 UtU = join() if join is not None else eng.gram(Ut)
             with self._phase("sweep_V"):
                 if hasattr(eng, "solve_install"):
-                    V = eng.solve_install(1, UtM, UtU, V, r, sparsity[1], normalize[1], self.hals_stats[1])   # nmf.py:440
+                    with comm.collective(self._vlens):       # the columns of V are spread over the ranks: joint stop rule
+                        V = eng.solve_install(1, UtM, UtU, V, r, sparsity[1], normalize[1], self.hals_stats[1])   # nmf.py:440
+                elif hasattr(eng, "sweep_collective") and comm.world > 1:
+                    V = V.clone()
+                    eng.sweep_collective(UtM, UtU, V, r, sparsity[1], self.hals_stats[1], comm)
+                    eng.set_factor(1, V)
                 else:
                     V = V.clone()
                     eng.sweep(UtM, UtU, V, r, sparsity[1], normalize[1], self.hals_stats[1])

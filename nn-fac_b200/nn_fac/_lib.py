@@ -27,7 +27,11 @@ SIGNATURES = {
     "nnfac_ctx_destroy": [_P],
     "nnfac_ctx_sm_count": [_P],
     "nnfac_ctx_launch_count": [_P],
+    "nnfac_ctx_board_export": [_P, _P],
+    "nnfac_ctx_board_attach": [_P, _INT, _INT, _P],
+    "nnfac_ctx_collective": [_P, _INT, _P],
     "nnfac_hals_nnls": [_P, _INT, _P, _I64, _P, _I64, _P, _I64, _INT, _I64, _INT, _DBL, _DBL, _U32, _P, _P],
+    "nnfac_hals_solve_f32": [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _INT, _I64, _INT, _DBL, _DBL, _P, _P],
     "nnfac_gemm_strided": [_P, _INT, _P, _I64, _I64, _P, _I64, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I64,
                            _I64, _I64, _I64, _I64, _I64, _P],
     "nnfac_gram": [_P, _INT, _P, _I64, _P, _I64, _INT, _I64, _P],
@@ -45,6 +49,7 @@ SIGNATURES = {
     "nnfac_core_pg_step": [_P, _INT, _P, _P, _P, _I64, _DBL, _DBL, _DBL, _P, _P],
     "nnfac_core_pg_step_dev": [_P, _INT, _P, _P, _P, _I64, _DBL, _P, _P],
     "nnfac_core_pg_step3": [_P, _INT, _P, _P, _P, _P, _P, _INT, _INT, _INT, _P, _DBL, _DBL, _INT, _DBL, _P, _P],
+    "nnfac_philox_uniform": [_P, _P, _I64, _I64, _I64, _I64, _I64, _c.c_uint64, _U32, _DBL, _INT, _P],
     "nnfac_nmf_plan_create": [_P, _I64, _I64, _INT, _c.POINTER(_P)],
     "nnfac_nmf_plan_bytes": [_P, _I64, _I64, _INT, _c.POINTER(_c.c_size_t)],
     "nnfac_nmf_plan_create_in": [_P, _I64, _I64, _INT, _P, _c.c_size_t, _P, _c.POINTER(_P)],
@@ -56,6 +61,7 @@ SIGNATURES = {
     "nnfac_nmf_plan_enable_f32": [_P, _P, _c.c_size_t, _P],
     "nnfac_nmf_plan_cross": [_P, _INT, _P, _I64, _P, _I64, _P],
     "nnfac_nmf_plan_set_factor": [_P, _INT, _P, _I64, _P],
+    "nnfac_nmf_plan_set_factor_gathered": [_P, _INT, _P, _I64, _P, _I64, _P],
     "nnfac_nmf_plan_reduce": [_P, _INT, _P, _I64, _P],
     "nnfac_nmf_plan_set_krao": [_P, _P, _I64, _I64, _P, _I64, _I64, _P],
     "nnfac_nmf_plan_hals_solve": [_P, _INT, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _INT, _DBL, _DBL, _P, _P],

@@ -68,6 +68,26 @@ def hals_nnls(UtM, UtU, V, r, maxiter, delta, sparsity, normalize, nonzero, resu
     return result
 
 
+def hals_solve(UtM, UtU, V_in, V_out, r, maxiter, delta, sparsity, result=None):
+    """V_out (r x n) <- hals_nnls_acc(UtM, UtU, V_in), out of place (fp32; V_in / V_out may be strided views)."""
+    n = UtM.shape[1]
+    if result is None:
+        result = torch.empty(4, dtype=torch.float64, device=V_in.device)
+    L.check(_lib().nnfac_hals_solve_f32(L.ctx(V_in.device), L.ptr(UtM), UtM.stride(0), L.ptr(UtU), UtU.stride(0), L.ptr(V_in),
+                                        V_in.stride(0), L.ptr(V_out), V_out.stride(0), r, n, int(maxiter), float(delta),
+                                        float(sparsity), L.ptr(result), L.stream_ptr()))
+    return result
+
+
+def philox_uniform(rows, cols, row0=0, col0=0, seed=0, stream_id=0, scale=1.0, out=None, accumulate=False, device=None):
+    """[rows x cols] float32 block of the synthetic matrix (seed, stream_id): element (i, j) = scale * u(row0 + i, col0 + j)."""
+    if out is None:
+        out = torch.empty((rows, cols), dtype=torch.float32, device=torch.device("cuda", L.device_index(device)))
+    L.check(_lib().nnfac_philox_uniform(L.ctx(out.device), L.ptr(out), out.stride(0), rows, cols, int(row0), int(col0), int(seed),
+                                        int(stream_id), float(scale), 1 if accumulate else 0, L.stream_ptr()))
+    return out
+
+
 def mu_terms(K, X, beta, want_q=True, out_p=None, out_q=None):
     """P = K^(beta-2) * X, Q = K^(beta-1).  P may alias K when Q is not wanted."""
     P = out_p if out_p is not None else torch.empty_like(K)
@@ -326,6 +346,15 @@ class NMFPlan:
         """which=0: U given as U^T (r x m); which=1: V (r x n).  Rebuilds that factor's bf16 operand planes."""
         L.check(_lib().nnfac_nmf_plan_set_factor(self.handle, which, L.ptr(Ft), Ft.stride(0), L.stream_ptr()))
 
+    def set_factor_gathered(self, which, gathered, length):
+        """gathered: [slices][r][chunk] (all-gather of column slices of the factor).  Installs the factor and returns it
+        rank-major (r x length)."""
+        slices, r, chunk = gathered.shape
+        out = torch.empty((r, length), dtype=torch.float32, device=self.device)
+        L.check(_lib().nnfac_nmf_plan_set_factor_gathered(self.handle, which, L.ptr(gathered), chunk, L.ptr(out), out.stride(0),
+                                                          L.stream_ptr()))
+        return out
+
     def set_krao(self, At, Bt):
         """The r x (I*J) Khatri-Rao factor of two rank-major factors (r x I, r x J) as the operand of cross(0, None)."""
         L.check(_lib().nnfac_nmf_plan_set_krao(self.handle, L.ptr(At), At.stride(0), At.shape[1], L.ptr(Bt), Bt.stride(0),
@@ -379,6 +408,7 @@ class NMFPlan:
 
     @property
     def fused_ok(self):
+        """The beta = 1 fused pass (and its fp32 copies of X) cover rank <= 64; the residual pass covers rank <= 128."""
         return self.r is not None and self.r <= 64
 
     def info(self, which):

@@ -72,6 +72,32 @@ def test_fused_pass_matches_float64(m, n, r):
     np.testing.assert_allclose(cost.item(), kl, rtol=2e-5)
 
 
+@pytest.mark.parametrize("m,n,r", [(384, 320, 96), (1000, 520, 128), (777, 1300, 80), (2048, 4096, 128), (130, 70, 65)])
+def test_fused_pass_rank_65_to_128_matches_float64(m, n, r):
+    """Residual + cross-product pass at padded rank 128 (two 64-rank atoms per factor slab, 128-wide contraction, rows of the
+    aligned factor loaded global -> tensor memory) against float64 numpy, both sides; ragged tiles and ranks."""
+    import torch
+    from nn_fac import _ops as ops
+    rng = np.random.RandomState(m * 7 + n + r)
+    U = rng.rand(m, r).astype(np.float32) + 0.05
+    V = rng.rand(r, n).astype(np.float32) + 0.05
+    X = ((rng.rand(m, r) @ rng.rand(r, n)) * (1 + 0.2 * rng.rand(m, n)) + 1e-3).astype(np.float32)
+    plan = ops.NMFPlan(torch.from_numpy(X).cuda()).bind_rank(r)
+    plan.set_factor(0, torch.from_numpy(np.ascontiguousarray(U.T)).cuda())
+    plan.set_factor(1, torch.from_numpy(V).cuda())
+    X64, U64, V64 = X.astype(np.float64), U.astype(np.float64), V.astype(np.float64)
+    K = U64 @ V64
+    for side, ref in ((0, V64 @ X64.T), (1, U64.T @ X64)):
+        out, cost = plan.fused(side, 0)
+        np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=2e-5)
+        np.testing.assert_allclose(cost.item(), np.sum((X64 - K) ** 2), rtol=2e-5)
+        # the split partials left in the plan add up to the same numbers
+        plan.fused(side, 0, keep_partials=True)
+        np.testing.assert_array_equal(plan.reduce(side).cpu().numpy(), out.cpu().numpy())
+    with pytest.raises(Exception):
+        plan.fused(0, 1)                              # the beta = 1 pass covers rank <= 64
+
+
 @pytest.mark.parametrize("r,length,dtype", [(10, 500, "float64"), (64, 65536, "float32"), (33, 1301, "float32"),
                                             (64, 8192, "float64"), (1, 7, "float32"), (96, 700, "float32")])
 def test_gram_matches_float64(r, length, dtype):
@@ -124,7 +150,9 @@ def test_mu_finish_equals_reduce_apply_install(m, n, r):
 # tensor-core HALS sweep (tc_sweep_kernel): shapes, edge cases and full parity of the stop rule
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("r,n,maxiter", [(64, 130, 100), (64, 20000, 100), (40, 777, 100), (17, 4096, 100), (1, 300, 50),
-                                         (64, 1, 30), (33, 5000, 1), (64, 3000, 2), (48, 70000, 7)])
+                                         (64, 1, 30), (33, 5000, 1), (64, 3000, 2), (48, 70000, 7),
+                                         (128, 5000, 100), (96, 777, 100), (100, 30000, 100), (128, 130, 100), (65, 300, 3),
+                                         (128, 37000, 20), (80, 1, 30)])
 def test_tc_sweep_matches_oracle(r, n, maxiter):
     """fp32 tcgen05 solve vs the float64 oracle on identical inputs: same sweep count (one flip near the threshold is
     allowed), solution to fp32 accuracy, ragged tiles / partial warps / partial rank blocks."""
@@ -496,3 +524,48 @@ def test_nmf_hals_more_columns_than_the_tensor_core_solve_covers():
     _, _, costs, _ = nmf.nmf(f32(X), r, init="custom", U_0=f32(U0), V_0=f32(V0), n_iter_max=4, tol=0, update_rule="hals",
                              return_costs=True, deterministic=True)
     np.testing.assert_allclose(costs, ref[:len(costs)], rtol=1e-4)
+
+
+@pytest.mark.parametrize("r", [96, 128])
+def test_nmf_hals_rank_65_to_128_fast_path_vs_oracle(r):
+    """HALS NMF at rank 65..128 on the tcgen05 path (fused residual pass, cross product, tensor-core sweep with 256 tensor-memory
+    columns per tile) against the float64 oracle at a reduced C3 shape: objective @1e-4, sweep counts +-1."""
+    import torch
+    from nn_fac import _fast
+    from oracle import nnfac_oracle as orc
+    rng = np.random.RandomState(r)
+    m, n = 4096, 2048
+    low = rng.rand(m, r) @ rng.rand(r, n)
+    X = low + low.mean() * rng.rand(m, n)
+    U0, V0 = rng.rand(m, r), rng.rand(r, n)
+    stats = {}
+    _, _, ref, _ = orc.compute_nmf(X, U0, V0, n_iter_max=4, tol=0, update_rule="hals", stats=stats)
+    f32 = lambda x: torch.from_numpy(x.astype(np.float32)).cuda()  # noqa: E731
+    assert _fast.eligible(torch.float32, r, "hals", 2)
+    st = _fast.FusedNMF(f32(X), f32(U0), f32(V0))
+    costs, _ = st.run(4, 0.0, "hals")
+    np.testing.assert_allclose(costs, ref, rtol=1e-4)
+    got = np.array([t.cpu().numpy() for t in st.sweep_log])          # [iteration][U, V]
+    want = np.stack([stats["sweeps_U"], stats["sweeps_V"]], axis=1)
+    assert np.abs(got - want).max() <= 1, (got, want)
+    # the public entry point takes the same path
+    import nn_fac.nmf as nmf
+    _, _, c2, _ = nmf.nmf(X.astype(np.float32), r, init="custom", U_0=U0.astype(np.float32), V_0=V0.astype(np.float32),
+                          n_iter_max=4, tol=0, update_rule="hals", return_costs=True, deterministic=True)
+    np.testing.assert_allclose(c2, costs, rtol=1e-12)
+
+
+def test_philox_blocks_equal_numpy_restatement_and_tile():
+    """Counter-based synthetic data (csrc/synth.cu): device blocks equal the numpy restatement bit for bit, and a matrix
+    generated as one block equals the same matrix generated shard by shard."""
+    import torch
+    from nn_fac import _ops as ops
+    from oracle import philox
+    full = ops.philox_uniform(300, 517, seed=1234567890123, stream_id=3).cpu().numpy()
+    np.testing.assert_array_equal(full, philox.uniform(300, 517, seed=1234567890123, stream_id=3))
+    part = ops.philox_uniform(100, 200, row0=150, col0=300, seed=1234567890123, stream_id=3).cpu().numpy()
+    np.testing.assert_array_equal(part, full[150:250, 300:500])
+    acc = torch.ones((100, 200), device="cuda")
+    ops.philox_uniform(100, 200, row0=150, col0=300, seed=1234567890123, stream_id=3, scale=2.0, out=acc, accumulate=True)
+    np.testing.assert_allclose(acc.cpu().numpy(), 1.0 + 2.0 * part, rtol=1e-7)
+    assert 0.0 <= full.min() and full.max() < 1.0 and abs(full.mean() - 0.5) < 0.01

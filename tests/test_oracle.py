@@ -229,3 +229,12 @@ def test_ntd_hals_reference_golden_scalars(golden):
         assert round(float(got) - ref, 7) == 0
     g = golden("ntd")
     np.testing.assert_allclose(costs, g["fx_hals_costs"], rtol=1e-7)
+
+
+def test_philox_known_answer():
+    """Random123's known-answer vector for Philox4x32-10: counter 0, key 0 -> first word 0x6627e8d5."""
+    from oracle import philox
+    u = philox.uniform(1, 1, seed=0, stream_id=0)
+    assert u[0, 0] == np.float32((0x6627e8d5 >> 8) / 16777216.0)
+    a = philox.uniform(40, 30, seed=5, stream_id=2)
+    np.testing.assert_array_equal(philox.uniform(10, 7, row0=20, col0=11, seed=5, stream_id=2), a[20:30, 11:18])
