@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: NMF outer iterations / second, HALS and MU beta=1, 65536 x 8192, rank 64.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--m M --n N --rank R]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rows M --cols N --rank R]
 
 One "step" = one HALS outer iteration + one MU (beta=1) outer iteration (U update, V update, cost
 each), every one on its own resident factor state.  `value` = 2K / T outer iterations per second
@@ -36,12 +36,21 @@ def parse_args():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--m", type=int, default=65536)
-    p.add_argument("--n", type=int, default=8192)
+    p.add_argument("--m", "--rows", dest="m", type=int, default=65536)      # (--rows / --cols: torchrun's own parser chokes on --m)
+    p.add_argument("--n", "--cols", dest="n", type=int, default=8192)
     p.add_argument("--rank", type=int, default=64)
-    p.add_argument("--cpu-rows", type=int, default=2048, help="rows of the bounded CPU sample")
+    p.add_argument("--cpu-rows", type=int, default=16384, help="rows of the bounded CPU sample (all columns are kept)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-secondary", action="store_true", help="skip the secondary configs C1 / C4 / C5 / NTD-HALS (1 GPU)")
+    p.add_argument("--c3", default="auto", choices=["auto", "on", "off"],
+                   help="also run configs[2] (HALS rank 128 on 262144x32768, column-sharded); auto = when 8 GPUs are used")
+    p.add_argument("--c3-m", type=int, default=262144)
+    p.add_argument("--c3-n", type=int, default=32768)
+    p.add_argument("--c3-rank", type=int, default=128)
+    p.add_argument("--no-parity-n1", action="store_true", help="skip the sharded-vs-single-GPU self-check (N > 1)")
+    p.add_argument("--c3-parity-full", action="store_true",
+                   help="run the single-GPU self-check of C3 also when the matrix has more than 2^31 elements")
     return p.parse_args()
 
 
@@ -135,48 +144,201 @@ def synth_host(m, n, r, seed, dtype=np.float64):
     return X.astype(dtype), rng.rand(m, r).astype(dtype), rng.rand(r, n).astype(dtype)
 
 
-def cpu_baseline(args, steps=1):
-    """The reference's algorithm (oracle port, numpy/OpenBLAS float64) on a row-subsample of the workload.
-    Work per outer iteration is linear in m, so full-shape its/s = sample its/s * rows / m."""
+def _baseline_from(res, args, kind):
+    """cpu_baseline object from the per-iteration seconds of a CPU run (scaled to the full shape, see oracle/ref_timing.py)."""
+    value = 2.0 / (res["hals_s_per_iter"] + res["mu_s_per_iter"])
+    rows = res["rows"]
+    if rows == args.m:
+        sample = f"full shape {args.m}x{args.n} r={args.rank} float64, {res['iters']} outer iteration(s) each of HALS and MU beta=1"
+    else:
+        sample = (f"{rows}x{args.n} r={args.rank} float64 row-subsample (all columns), {res['iters']} outer iteration(s) each of HALS and "
+                  f"MU beta=1; the m-proportional part of an iteration is scaled by m/rows={res['scale']:g}, the V-side HALS solve "
+                  f"(size independent of m, {res.get('hals_vsolve_s_per_iter', 0.0):.3f} s) is not")
+    return {"value": value, "unit": UNIT, "cores": int(res.get("blas_threads") or os.cpu_count() or 1), "kind": kind, "sample": sample,
+            "same_config": rows == args.m, "hals_its_per_s": 1.0 / res["hals_s_per_iter"], "mu_its_per_s": 1.0 / res["mu_s_per_iter"],
+            "hals_sweeps_per_call": res.get("hals_sweeps_per_call"), "host_cpus": res.get("host_cpus"),
+            "what": ("nn_fac.nmf.nmf(X64, r, init='custom', ..., deterministic=True) of the unmodified reference (oracle/_ref, tensorly "
+                     "stand-in oracle/ref_shim)") if kind == "reference" else "numpy float64 port of the reference (oracle/nnfac_oracle.py)"}
+
+
+def _port_timing(args, rows, iters):
+    """Fallback when oracle/_ref is absent: the oracle port, same sampling and scaling as oracle/ref_timing.py."""
     from oracle import nnfac_oracle as orc
-    try:
-        from threadpoolctl import threadpool_info
-        threads = max([i.get("num_threads", 1) for i in threadpool_info()] or [1])
-    except Exception:
-        threads = os.cpu_count() or 1
-    rows = min(args.cpu_rows, args.m)
+    from oracle.ref_timing import blas_threads
     X, U0, V0 = synth_host(rows, args.n, args.rank, seed=1)
-    t0 = time.time()
-    stats = {}
-    orc.compute_nmf(X, U0, V0, n_iter_max=steps, tol=0, update_rule="hals", stats=stats)
-    t_hals = (time.time() - t0) / steps
-    t0 = time.time()
-    orc.compute_nmf(X, U0, V0, n_iter_max=steps, tol=0, update_rule="mu", beta=1)
-    t_mu = (time.time() - t0) / steps
-    scale = rows / args.m
-    value = 2.0 / (t_hals + t_mu) * scale
-    return {"value": value, "unit": UNIT, "cores": int(threads), "kind": "port",
-            "sample": f"{rows}x{args.n} r={args.rank} float64 row-subsample, {steps} outer iteration(s) each of HALS and "
-                      f"MU beta=1, scaled by rows/m={scale:.5f} (work is linear in m)",
-            "hals_its_per_s": 1.0 / t_hals * scale, "mu_its_per_s": 1.0 / t_mu * scale,
-            "host_cpus": os.cpu_count()}
+    scale = args.m / rows
+    orig, tv = orc.hals_nnls_acc, [0.0]
+
+    def timed(UtM, *a, **kw):
+        t0 = time.perf_counter()
+        res = orig(UtM, *a, **kw)
+        if UtM.shape[1] == args.n and rows != args.n:
+            tv[0] += time.perf_counter() - t0
+        return res
+    orc.hals_nnls_acc = timed
+    try:
+        t0 = time.perf_counter()
+        orc.compute_nmf(X, U0, V0, n_iter_max=iters, tol=0, update_rule="hals")
+        t_hals = (time.perf_counter() - t0) / iters
+    finally:
+        orc.hals_nnls_acc = orig
+    t0 = time.perf_counter()
+    orc.compute_nmf(X, U0, V0, n_iter_max=iters, tol=0, update_rule="mu", beta=1)
+    t_mu = (time.perf_counter() - t0) / iters
+    v = tv[0] / iters
+    return {"rows": rows, "scale": scale, "iters": iters, "hals_s_per_iter": (t_hals - v) * scale + v, "hals_vsolve_s_per_iter": v,
+            "mu_s_per_iter": t_mu * scale, "blas_threads": blas_threads(), "host_cpus": os.cpu_count()}
+
+
+def cpu_baseline(args, iters=1, in_process=False):
+    """nn-fac's own CPU path on the host cores: the unmodified reference from oracle/_ref (kind "reference"), else the oracle
+    port (kind "port").  Bounded sample: `--cpu-rows` rows of the m rows, all columns (see oracle/ref_timing.py for the scaling).
+    The reference's package is called nn_fac like the product's, so from the GPU arm it runs in a subprocess."""
+    rows = min(args.cpu_rows, args.m)
+    have_ref = os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "nn_fac"))
+    if have_ref:
+        try:
+            if in_process:
+                from oracle import ref_timing
+                res = ref_timing.time_reference_nmf(args.m, args.n, args.rank, rows, iters, NOISE)
+            else:
+                cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_timing.py"), str(args.m), str(args.n), str(args.rank), str(rows),
+                       str(iters), str(NOISE)]
+                out = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, check=True).stdout
+                res = json.loads(out.strip().splitlines()[-1])
+            res["iters"] = iters
+            return _baseline_from(res, args, "reference")
+        except Exception as e:                      # noqa: BLE001  (stated in the line, then the port is timed instead)
+            note = f"reference run failed ({type(e).__name__}: {e}); "
+    else:
+        note = "oracle/_ref missing (python oracle/make_ref.py needs /root/reference); "
+    base = _baseline_from(_port_timing(args, rows, iters), args, "port")
+    base["sample"] = note + base["sample"]
+    return base
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     t0 = time.time()
-    base = cpu_baseline(args, steps=max(1, min(args.steps, 2)))
+    base = cpu_baseline(args, iters=max(1, min(args.steps, 3)), in_process=True)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 2000.0 / base["value"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"NMF {args.m}x{args.n} r={args.rank}: 1 HALS + 1 MU(beta=1) outer iteration per step",
-                       "noise": NOISE, "note": "reference algorithm (numpy float64 port in oracle/) on the host cores, "
-                                               "bounded row-subsample scaled to the full shape"},
+                       "noise": NOISE, "note": "nn-fac's CPU path on the host cores (no GPU): " + base["what"] + "; " + base["sample"]},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t0}
     print(json.dumps(line))
+
+
+def philox_problem(m, n, r, lo, hi, seed=20261018):
+    """This rank's column block [lo, hi) of the synthetic problem (m x n, rank r): X = W0 H0 + NOISE * (r/4) * E with every
+    entry a pure function of (seed, stream, global row, global column) (csrc/synth.cu), so any number of GPUs regenerates
+    the same matrix shard by shard.  r/4 = E[W0 H0].  Returns device fp32 (X_p, U0, V0_p)."""
+    import torch
+    from nn_fac import _ops as ops
+    W0 = ops.philox_uniform(m, r, seed=seed, stream_id=0)
+    H0 = ops.philox_uniform(r, hi - lo, col0=lo, seed=seed, stream_id=1)
+    X = torch.matmul(W0, H0)                       # data generation, not the timed path
+    del W0, H0
+    ops.philox_uniform(m, hi - lo, col0=lo, seed=seed, stream_id=2, scale=NOISE * r / 4.0, out=X, accumulate=True)
+    U0 = ops.philox_uniform(m, r, seed=seed, stream_id=3)
+    V0 = ops.philox_uniform(r, hi - lo, col0=lo, seed=seed, stream_id=4)
+    return X, U0, V0
+
+
+def run_c3(args, dev, world, rank, group, peak):
+    """configs[2]: NMF HALS rank 128 on 262144 x 32768, column-sharded with the Gram / cross-product exchange on the U side
+    (nmf.py:407-441, nnls.py:156-198).  Same timing rules as the headline; reports whole-job it/s and the per-GPU fraction of
+    the 2 m n_p 4 + 4 (m + n_p) r 4 bytes per iteration and GPU of SURVEY.md 8(d)."""
+    import torch
+    import torch.distributed as dist
+    from nn_fac import _fast
+    from nn_fac.sharded import column_block
+    m, n, r = args.c3_m, args.c3_n, args.c3_rank
+    lo, hi = column_block(n, world, rank)
+    torch.cuda.empty_cache()
+    X, U0, V0 = philox_problem(m, n, r, lo, hi)
+    st = _fast.FusedNMF(X, U0, V0, group=group)
+    del X
+    torch.cuda.empty_cache()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    st.run(args.warmup, 0.0, "hals")
+    st.events, st.sweep_log = [], []
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    barrier()
+    ev[0].record()
+    costs = st.run(args.steps, 0.0, "hals")[0]
+    ev[1].record()
+    barrier()
+    ms = ev[0].elapsed_time(ev[1])
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    phases = {}
+    for name, e0, e1 in st.events:
+        phases.setdefault(name, []).append(e0.elapsed_time(e1))
+    its = args.steps / (ms / 1e3)
+    n_p = hi - lo
+    bytes_gpu = 2 * m * n_p * 4 + 4 * (m + n_p) * r * 4
+    out = {"config": f"C3: NMF HALS {m}x{n} r={r}, columns sharded over {world} GPU(s) ({n_p} columns each), fp32 storage",
+           "outer_iters_per_s": its, "ms_per_iter": ms / args.steps, "n_gpus": world,
+           "algorithmic_bytes_per_iter_per_gpu": bytes_gpu, "frac_of_hbm_roofline_per_gpu": bytes_gpu * its / 1e9 / peak,
+           "phase_ms": {k: sum(v) / len(v) for k, v in phases.items()}, "final_cost": costs[-1],
+           "hals_sweeps_per_call": [[float(v) for v in t.cpu().tolist()] for t in st.sweep_log[-3:]],
+           "data": "synthetic, Philox keyed on (seed, global row, global column): identical for any number of GPUs"}
+    sharded_sweeps = [[float(v) for v in t.cpu().tolist()] for t in st.sweep_log]
+    del st
+    torch.cuda.empty_cache()
+    if world > 1 and not args.no_parity_n1 and (m * n <= 2 ** 31 or args.c3_parity_full):
+        # self-check: rank 0 regenerates the WHOLE matrix from the same counters and repeats the run unsharded
+        if rank == 0:
+            X, U0, V0 = philox_problem(m, n, r, 0, n)
+            one = _fast.FusedNMF(X, U0, V0)
+            del X
+            c1 = one.run(args.warmup + args.steps, 0.0, "hals")[0]
+            single_sweeps = [[float(v) for v in t.cpu().tolist()] for t in one.sweep_log[-len(sharded_sweeps):]]
+            out["parity_vs_n1"] = {"iterations": args.warmup + args.steps, "cost_single": c1[-1], "cost_sharded": costs[-1],
+                                   "cost_rel_diff": abs(c1[-1] - costs[-1]) / abs(c1[-1]),
+                                   "sweeps_equal": single_sweeps == sharded_sweeps,
+                                   "sweep_count_max_abs_diff": max((abs(a - b) for x, y in zip(single_sweeps, sharded_sweeps)
+                                                                    for a, b in zip(x, y)), default=None)}
+            del one
+            torch.cuda.empty_cache()
+        barrier()
+    return out
+
+
+def parity_vs_single_gpu(args, dev, world, rank, X_full, U0, V0_full, sharded_costs, sharded_sweeps):
+    """Self-check of the sharded run (the driver's GPU tests are single-GPU): rank 0 repeats the SAME problem unsharded for the
+    same number of iterations and compares objectives and HALS sweep counts."""
+    import torch
+    from nn_fac import _fast
+    if rank != 0:
+        return None
+    iters = args.warmup + args.steps
+    out = {"iterations": iters, "shape": list(X_full.shape), "rank": int(U0.shape[1])}
+    for rule in ("hals", "mu"):
+        st = _fast.FusedNMF(X_full, U0, V0_full)
+        costs = st.run(iters, 0.0, rule)[0]
+        out[f"{rule}_cost_single"] = costs[-1]
+        out[f"{rule}_cost_sharded"] = sharded_costs[rule]
+        out[f"{rule}_cost_rel_diff"] = abs(costs[-1] - sharded_costs[rule]) / abs(costs[-1])
+        if rule == "hals":
+            single = [[float(v) for v in t.cpu().tolist()] for t in st.sweep_log[-len(sharded_sweeps):]] if sharded_sweeps else []
+            out["hals_sweeps_single_last"] = single
+            out["hals_sweeps_sharded_last"] = sharded_sweeps
+            out["hals_sweeps_equal"] = single == sharded_sweeps
+        del st
+        torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -215,10 +377,13 @@ def main():
     from nn_fac.sharded import column_block
     fused = args.rank <= 64
     group = None
+    X_full = V0_full = None
     if world > 1:
         # every rank generated the same X (same seed, same generator); it keeps its own column block only
-        assert fused, "the sharded path covers rank <= 64"
+        assert fused, "the sharded headline covers rank <= 64 (MU beta = 1)"
         lo, hi = column_block(n, world, rank)
+        if rank == 0 and not args.no_parity_n1:
+            X_full, V0_full = X, V0
         X, V0 = X[:, lo:hi].contiguous(), V0[:, lo:hi].contiguous()
         group = dist.group.WORLD
         torch.cuda.empty_cache()
@@ -305,6 +470,13 @@ def main():
 
     if rank == 0:
         line["clocks"] = clocks.summary()
+    if world > 1 and not args.no_parity_n1:
+        sharded_sweeps = [[float(v) for v in t.cpu().tolist()] for t in states["hals"].sweep_log[-3:]] if fused else []
+        chk = parity_vs_single_gpu(args, dev, world, rank, X_full, U0, V0_full, {"hals": costs[0], "mu": costs[1]}, sharded_sweeps)
+        del X_full, V0_full
+        barrier()
+        if rank == 0:
+            line["parity_vs_n1"] = chk
 
     # ---- end to end through the public API with host buffers ----
     if not args.no_e2e:
@@ -344,8 +516,23 @@ def main():
                        "note": f"{api}(pinned host arrays, n_iter_max={k}) once per rule: X uploaded once per call, "
                                "bytes (per rank) amortised over the call's iterations; one untimed 1-iteration call per rule first; "
                                "wall clock, max over ranks"}
+    run_c3_now = args.c3 == "on" or (args.c3 == "auto" and world == 8)
+    if run_c3_now:
+        try:
+            states = s = X = U0 = V0 = None            # noqa: F841  (free the headline's state before the 4.3 GB blocks of C3)
+            torch.cuda.empty_cache()
+            line["c3"] = run_c3(args, dev, world, rank, group, peak)
+        except Exception as e:                        # noqa: BLE001
+            line["c3"] = {"error": f"{type(e).__name__}: {e}"}
+    if rank == 0 and world == 1 and not args.no_secondary:
+        states = s = X = U0 = V0 = None                # noqa: F841
+        torch.cuda.empty_cache()
+        from tools import secondary
+        line["secondary"] = secondary.all_secondary(peak_gbs=peak, iters=10)
+        line["secondary"]["note"] = ("BASELINE.json configs[0], [3], [4] and the reference's default NTD rule on this GPU, run after "
+                                     "the headline (outside its timed region); CUDA events except c1 (wall clock of the public call)")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args, steps=1)
+        line["cpu_baseline"] = cpu_baseline(args, iters=1)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -311,7 +311,10 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         if (++b2 == 2) { b2 = 0; b2_phase ^= 1; }
       };
       int drained = 0;
-      float acc = 0.f, acck = 0.f;      // fp32 partial sums of up to 8 stages (128 elements); FP64 adds are scarce on this part
+      // fp32 partial sums of up to 8 stages (128 elements) per lane pair; FP64 adds are scarce on this part.  The element-wise
+      // math runs on PACKED fp32 pairs (FADD2 / FMUL2 / FFMA2 of sm_100): two columns per instruction.
+      float2 acc2 = make_float2(0.f, 0.f), acck2 = make_float2(0.f, 0.f);
+      const float2 neg1 = make_float2(-1.f, -1.f), tiny2 = make_float2(1e-30f, 1e-30f);
       for (int i = 0; i < S; ++i) {
         // ---- model tile for this stage ----
         tc::mbar_wait(&d1_full[b1], b1_phase);
@@ -331,7 +334,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         uint32_t qhw[4 * NCHK], qlw[4 * NCHK];
 #pragma unroll
         for (int cc = 0; cc < NCHK; ++cc) {
-          float xv[8];
+          float2 xv[4];
           if (XF32) {
             // fp32 tile: half (part >> 1) holds 32 columns = 8 chunks of 4 floats per row; this thread's 16 columns are
             // chunks 4 (part & 1) .. +3, two of them per iteration
@@ -340,7 +343,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
             for (int h = 0; h < 2; ++h) {
               const int chunk = 4 * (part & 1) + 2 * cc + h;
               const float4 v4 = *reinterpret_cast<const float4*>(xb + ((chunk ^ (row & 7)) << 4));
-              xv[4 * h] = v4.x; xv[4 * h + 1] = v4.y; xv[4 * h + 2] = v4.z; xv[4 * h + 3] = v4.w;
+              xv[2 * h] = make_float2(v4.x, v4.y); xv[2 * h + 1] = make_float2(v4.z, v4.w);
             }
           } else {
             const int chunk = NCHK * part + cc;
@@ -349,39 +352,41 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
             const uint4 l4 = *reinterpret_cast<const uint4*>(xl + off);
             const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
-            for (int w = 0; w < 4; ++w) { xv[2 * w] = bf_lo(hw[w]) + bf_lo(lw[w]); xv[2 * w + 1] = bf_hi(hw[w]) + bf_hi(lw[w]); }
+            for (int w = 0; w < 4; ++w)
+              xv[w] = __fadd2_rn(make_float2(bf_lo(hw[w]), bf_hi(hw[w])), make_float2(bf_lo(lw[w]), bf_hi(lw[w])));
           }
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
-            const float x0 = xv[2 * w], x1 = xv[2 * w + 1];
-            const float k0 = __uint_as_float(kk[cc * 8 + 2 * w]), k1 = __uint_as_float(kk[cc * 8 + 2 * w + 1]);
+            const float2 x2 = xv[w];
+            const float2 k2 = make_float2(__uint_as_float(kk[cc * 8 + 2 * w]), __uint_as_float(kk[cc * 8 + 2 * w + 1]));
             if (MODE == MODE_RES) {
-              const float r0 = x0 - k0, r1 = x1 - k1;
-              acc = fmaf(r0, r0, acc);
-              acc = fmaf(r1, r1, acc);
+              const float2 r2 = __ffma2_rn(k2, neg1, x2);            // x - k
+              acc2 = __ffma2_rn(r2, r2, acc2);
             } else {
-              // padded rows / columns have x = 0 and k = 0: the floor keeps 0 * (1/k) = 0 there
-              const float i0 = rcp_approx(fmaxf(k0, 1e-30f)), i1 = rcp_approx(fmaxf(k1, 1e-30f));
-              const float q0 = x0 * i0, q1 = x1 * i1;
+              // padded rows / columns have x = 0 and k = 0: k + 1e-30 keeps 0 * (1/k) = 0 there and changes no real k
+              // (k >= r * 1e-24 through the 1e-12 floor of the factors)
+              const float2 kt = __fadd2_rn(k2, tiny2);
+              const float2 q2 = __fmul2_rn(x2, make_float2(rcp_approx(kt.x), rcp_approx(kt.y)));
               if (COST) {
                 // sum of x log2(x / k) and sum of k (the model tile as the tensor core produced it, so that the two terms
-                // stay consistent); the sum of x is a constant of the plan (see kl_cost_finish_kernel)
-                acc = fmaf(x0, lg2_approx(fmaxf(q0, 1e-30f)), acc);
-                acc = fmaf(x1, lg2_approx(fmaxf(q1, 1e-30f)), acc);
-                acck += k0 + k1;
+                // stay consistent); the sum of x is a constant of the plan (see kl_cost_finish_kernel).  x = 0: 0 * log2(1e-30).
+                const float2 qt = __fadd2_rn(q2, tiny2);
+                acc2 = __ffma2_rn(x2, make_float2(lg2_approx(qt.x), lg2_approx(qt.y)), acc2);
+                acck2 = __fadd2_rn(acck2, k2);
               }
-              const __nv_bfloat162 hq = __floats2bfloat162_rn(q0, q1);
+              const __nv_bfloat162 hq = __floats2bfloat162_rn(q2.x, q2.y);
               const uint32_t hqw = *reinterpret_cast<const uint32_t*>(&hq);
-              const __nv_bfloat162 lq = __floats2bfloat162_rn(q0 - bf_lo(hqw), q1 - bf_hi(hqw));
+              const float2 rem = __ffma2_rn(make_float2(bf_lo(hqw), bf_hi(hqw)), neg1, q2);    // q - hi(q), exact
+              const __nv_bfloat162 lq = __floats2bfloat162_rn(rem.x, rem.y);
               qhw[4 * cc + w] = hqw;
               qlw[4 * cc + w] = *reinterpret_cast<const uint32_t*>(&lq);
             }
           }
         }
         if (COST && ((i & 7) == 7 || i == S - 1)) {
-          cost += (double)acc;
-          acc = 0.f;
-          if (MODE == MODE_MU) { costk += (double)acck; acck = 0.f; }
+          cost += (double)(acc2.x + acc2.y);
+          acc2 = make_float2(0.f, 0.f);
+          if (MODE == MODE_MU) { costk += (double)(acck2.x + acck2.y); acck2 = make_float2(0.f, 0.f); }
         }
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&empty[st]);          // done with the stage's X tile

@@ -350,7 +350,34 @@ __global__ void __launch_bounds__(Cfg<RP>::NTHREADS, 1) tc_sweep_kernel(const Tc
     uint32_t s_phase = 0;
 
     if (active) {
-      // V -> TMEM masters and operand planes; UtM - sp -> residual accumulator (the issuer adds -UtU V)
+      // UtM - sp -> residual accumulator, for ALL rank rows before the first hand-over (the products of the first K atom
+      // already add -UtU[:, atom] V[atom] into every one of the RP residual columns)
+#pragma unroll
+      for (int c0 = 0; c0 < RP; c0 += 16) {
+        uint32_t w[16];
+        if (c0 < nblk * BLK) {
+          // right-hand side: 16 independent loads in flight per slab (a loop over the slabs INSIDE the row loop serialises
+          // them: measured +0.07 ms per solve); the slabs of split-K partials are added in order, like the reduction kernel
+          float bv[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) bv[j] = (valid && c0 + j < r) ? a.b[(int64_t)(c0 + j) * a.ld_b + col] : 0.f;
+          for (int sp = 1; sp < a.nsplit; ++sp) {
+            float t[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              t[j] = (valid && c0 + j < r) ? a.b[(int64_t)sp * a.split_stride + (int64_t)(c0 + j) * a.ld_b + col] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) bv[j] += t[j];
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] = __float_as_uint((valid && c0 + j < r) ? (bv[j] - a.sp) * csw<RP>().invd[c0 + j] : 0.f);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] = 0u;
+        }
+        tmem_st16(t_w + c0, w);
+      }
+      // V -> TMEM masters and operand planes, one 64-row K atom per hand-over (the issuer adds -UtU[:, atom] V[atom])
 #pragma unroll
       for (int kr = 0; kr < KR; ++kr) {
         if (kr * 4 < nblk) {
@@ -370,34 +397,17 @@ __global__ void __launch_bounds__(Cfg<RP>::NTHREADS, 1) tc_sweep_kernel(const Tc
             tmem_st16(t_v + c0, w);
             store_chunk(vh, row, c1 / 8, &x[0], PLANE_BYTES);
             store_chunk(vh, row, c1 / 8 + 1, &x[8], PLANE_BYTES);
-            // right-hand side: 16 independent loads in flight per slab (a loop over the slabs INSIDE the row loop serialises
-            // them: measured +0.07 ms per solve); the slabs of split-K partials are added in order, like the reduction kernel
-            float bv[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) bv[j] = (valid && c0 + j < r) ? a.b[(int64_t)(c0 + j) * a.ld_b + col] : 0.f;
-            for (int sp = 1; sp < a.nsplit; ++sp) {
-              float t[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                t[j] = (valid && c0 + j < r) ? a.b[(int64_t)sp * a.split_stride + (int64_t)(c0 + j) * a.ld_b + col] : 0.f;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) bv[j] += t[j];
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) w[j] = __float_as_uint((valid && c0 + j < r) ? (bv[j] - a.sp) * csw<RP>().invd[c0 + j] : 0.f);
-            tmem_st16(t_w + c0, w);
           }
           tmem_st_wait();
           tc::fence_proxy_async_smem();
           tc::tcgen05_fence_before();
           tc::mbar_arrive(&s_ready[tile]);
         } else {
-          // rank rows beyond the last block: masters and residual are zero
-          uint32_t z[16];
+          uint32_t z[16];                                                // rank rows beyond the last block: masters are zero
 #pragma unroll
           for (int j = 0; j < 16; ++j) z[j] = 0u;
 #pragma unroll
-          for (int c1 = 0; c1 < 64; c1 += 16) { tmem_st16(t_v + kr * 64 + c1, z); tmem_st16(t_w + kr * 64 + c1, z); }
+          for (int c1 = 0; c1 < 64; c1 += 16) tmem_st16(t_v + kr * 64 + c1, z);
           tmem_st_wait();
         }
       }

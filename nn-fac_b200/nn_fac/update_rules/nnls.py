@@ -54,6 +54,10 @@ def hals_nnls_acc(UtM, UtU, in_V, maxiter=500, atime=None, alpha=0.5, delta=0.01
         V = L.to_device(in_V, dt)                                          # the copy of nnls.py:147
         if V.data_ptr() == (in_V.data_ptr() if isinstance(in_V, torch.Tensor) else 0):
             V = V.clone()
+    if G.shape[1] > r and V.shape[0] == G.shape[1]:
+        # nnls.py:163/167 multiply the WHOLE row UtU[k,:] with V: rows >= r of in_V are never updated but enter every product
+        # (tests/nnls_tests.py:44-45).  They are constants of the solve: fold them into the right-hand side.
+        b = b - ops.matmul(G[:r, r:], V[r:, :])
     res = hals_nnls_device(b, G, V, r, maxiter, delta, sparsity_coefficient, normalize, nonzero).cpu().numpy()
     raise_if_zero_column(res)
     out = V if isinstance(in_V, torch.Tensor) else V.cpu().numpy()

@@ -108,7 +108,9 @@ def hals_nnls_acc(UtM, UtU, in_V, maxiter=500, delta=0.01,
         nodelta = 0.0
         for k in range(r):
             if UtU[k, k] != 0:                                # nnls.py:160
-                step = np.maximum((UtM[k, :] - UtU[k, :r] @ V[:r, :] - sp) / UtU[k, k], -V[k, :])  # :163/:167
+                # :163/:167 -- `UtU[k,:] @ V` runs over ALL rows of V: when UtU / in_V are larger than r (tests/nnls_tests.py:44-45)
+                # the rows >= r of in_V are never updated but do enter the products
+                step = np.maximum((UtM[k, :] - UtU[k, :V.shape[0]] @ V - sp) / UtU[k, k], -V[k, :])
                 V[k, :] = V[k, :] + step
                 nodelta += float(step @ step)                 # nnls.py:170
                 if nonzero and not V[k, :].any():             # nnls.py:173-174
@@ -125,9 +127,10 @@ def hals_nnls_acc(UtM, UtU, in_V, maxiter=500, delta=0.01,
             eps0 = nodelta                                    # nnls.py:187-188
         eps = nodelta
         cnt += 1
-        if nodelta == 0.0 and not normalize:
-            cnt = max(cnt, maxiter + 1)                       # remaining sweeps are no-ops
-            break
+        if nodelta == 0.0 and eps0 == 0.0 and not normalize:
+            cnt = max(cnt, maxiter + 1)                       # `0 >= delta * 0`: nnls.py:156 burns the remaining sweeps as
+            break                                             # no-ops; they are counted, not run.  (With eps0 > 0 a sweep
+                                                              # that moves nothing fails the test and the loop ends by itself.)
     return V, eps, cnt, cnt - 1
 
 
