@@ -148,6 +148,10 @@ int nnfac_khatri_rao(nnfac_ctx* ctx, int dtype, void* out, const void* A, int64_
 /* out[i][j] = A[i][j] * B[i][j] (Hadamard of Grams, ntf.py:445); in place allowed. */
 int nnfac_hadamard(nnfac_ctx* ctx, int dtype, void* out, const void* A, const void* B,
                    int64_t count, void* stream);
+/* out = a X + b Y, element-wise (contiguous, `count` elements): the coupled right-hand side UtM + mu Vtarget of
+ * nn_fac/update_rules/nnls.py:318 (hals_coupling_nnls_acc). */
+int nnfac_axpby(nnfac_ctx* ctx, int dtype, void* out, double a, const void* X, double b, const void* Y, int64_t count,
+                void* stream);
 
 /* Row-wise L2 normalisation of the Tucker core unfolding (ntd.py:676-681), in place. */
 /* One projected-gradient step on the Tucker core, ntd.py:607-617:  delta = min(step * (-MtX + P + sparse), core);
@@ -184,6 +188,11 @@ int nnfac_nmf_plan_create(nnfac_ctx* ctx, int64_t m, int64_t n, int r, nnfac_nmf
 int nnfac_nmf_plan_bytes(nnfac_ctx* ctx, int64_t m, int64_t n, int r, size_t* bytes);
 int nnfac_nmf_plan_create_in(nnfac_ctx* ctx, int64_t m, int64_t n, int r, void* workspace, size_t workspace_bytes,
                              void* stream, nnfac_nmf_plan** out);
+/* One-sided plans: sides = 1 keeps only the planes of X (passes over side 0), 2 only those of X^T (side 1), 3 both.  The
+ * MTTKRP of a tensor unfolding (ntf.py:449) only ever reads side 0: half the memory.  A pass over an absent side is refused. */
+int nnfac_nmf_plan_bytes_sided(nnfac_ctx* ctx, int64_t m, int64_t n, int r, int sides, size_t* bytes);
+int nnfac_nmf_plan_create_sided(nnfac_ctx* ctx, int64_t m, int64_t n, int r, int sides, void* workspace, size_t workspace_bytes,
+                                void* stream, nnfac_nmf_plan** out);
 int nnfac_nmf_plan_destroy(nnfac_nmf_plan* plan);
 /* Ingest X (device fp32, row-major, leading dimension ldx >= n): one read of X, two plane writes. */
 int nnfac_nmf_plan_load_x(nnfac_nmf_plan* plan, const float* X, int64_t ldx, void* stream);
@@ -209,6 +218,11 @@ int nnfac_nmf_plan_set_krao(nnfac_nmf_plan* plan, const float* At, int64_t lda, 
                             int64_t J, void* stream);
 /* out (r x R of `side`) = sum of the split-K partials of the last X pass over `side` run with out == NULL. */
 int nnfac_nmf_plan_reduce(nnfac_nmf_plan* plan, int side, float* out, int64_t ld_out, void* stream);
+/* The same sum in the send layout of a reduce-scatter over `slabs` ranks (column-sharded U side, nn_fac/_fast.py):
+ * out = [slabs][r][chunk + tail_cols]; column `row` of the result goes to out[row / chunk][k][row % chunk], and the small
+ * matrix `tail` (r x tail_cols, the partial Gram; NULL with tail_cols = 0) is copied behind every chunk. */
+int nnfac_nmf_plan_reduce_chunked(nnfac_nmf_plan* plan, int side, float* out, int64_t chunk, int slabs, const float* tail,
+                                  int64_t ld_tail, int tail_cols, void* stream);
 /* Install a factor into the plan (builds all of its bf16 operand planes):
  * which = 0: U, passed as U^T (r x m, row-major); which = 1: V (r x n). */
 int nnfac_nmf_plan_set_factor(nnfac_nmf_plan* plan, int which, const float* Ft, int64_t ld, void* stream);

@@ -173,6 +173,14 @@ __global__ void hadamard_kernel(T* out, const T* A, const T* B, int64_t count) {
     out[i] = A[i] * B[i];
 }
 
+// out = a X + b Y (the coupled right-hand side UtM + mu Vtarget of nnls.py:318, and the extra-row correction of nnls.py:163)
+template <typename T>
+__global__ void axpby_kernel(T* out, T a, const T* X, T b, const T* Y, int64_t count) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = a * X[i] + b * Y[i];
+}
+
 // one block per row: row /= ||row||_2 when the norm is non-zero (ntd.py:678-680)
 template <typename T>
 __global__ void __launch_bounds__(RB) normalize_rows_kernel(T* A, int64_t lda, int64_t cols) {
@@ -431,6 +439,16 @@ int nnfac_hadamard(nnfac_ctx* ctx, int dtype, void* out, const void* A, const vo
   const int grid = grid_for(count, ctx->sm_count);
   DISPATCH_T(dtype, (hadamard_kernel<float><<<grid, 256, 0, st>>>((float*)out, (const float*)A, (const float*)B, count)),
              (hadamard_kernel<double><<<grid, 256, 0, st>>>((double*)out, (const double*)A, (const double*)B, count)));
+  NNFAC_LAUNCH_CHECK(ctx);
+  return NNFAC_OK;
+}
+
+int nnfac_axpby(nnfac_ctx* ctx, int dtype, void* out, double a, const void* X, double b, const void* Y, int64_t count, void* stream) {
+  NNFAC_ARG(ctx && out && X && Y && count > 0, "nnfac_axpby: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(count, ctx->sm_count);
+  DISPATCH_T(dtype, (axpby_kernel<float><<<grid, 256, 0, st>>>((float*)out, (float)a, (const float*)X, (float)b, (const float*)Y, count)),
+             (axpby_kernel<double><<<grid, 256, 0, st>>>((double*)out, a, (const double*)X, b, (const double*)Y, count)));
   NNFAC_LAUNCH_CHECK(ctx);
   return NNFAC_OK;
 }

@@ -238,6 +238,78 @@ int run_gram(nnfac_ctx* ctx, T* out, int64_t ld_out, const T* F, int64_t ld_f, i
   return NNFAC_OK;
 }
 
+// ---- the same for 64 < r <= 128 (fp32): the Gram as 64 x 64 blocks (0,0), (0,1), (1,1) -- blockIdx.y -- of the row blocks
+// F[0:64] and F[64:128]; block (1,0) is the mirror of (0,1).  32-column slabs (17 KiB of shared memory for the two tiles), so
+// that a CTA still fits beside the tcgen05 X pass it runs under.
+constexpr int GC2 = 32;
+
+__global__ void __launch_bounds__(256, 4) gram2_partial_kernel(const float* __restrict__ F, int64_t ld_f, int r, int64_t len,
+                                                               int64_t cols_per_cta, float* __restrict__ part) {
+  __shared__ __align__(16) float ta[GC2][GPADF], tb[GC2][GPADF];
+  const int t = threadIdx.x, ti = t >> 4, tj = t & 15;
+  const int pair = blockIdx.y, ra = pair == 2 ? 64 : 0, rb = pair == 0 ? 0 : 64;       // row blocks of the two operands
+  const int64_t c_begin = (int64_t)blockIdx.x * cols_per_cta;
+  int64_t c_end = c_begin + cols_per_cta;
+  if (c_end > len) c_end = len;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int64_t c0 = c_begin; c0 < c_end; c0 += GC2) {
+    __syncthreads();
+    for (int idx = t; idx < GR * GC2; idx += 256) {
+      const int k = idx >> 5, cx = idx & 31;
+      const int64_t c = c0 + cx;
+      ta[cx][k] = (ra + k < r && c < c_end) ? F[(int64_t)(ra + k) * ld_f + c] : 0.f;
+      tb[cx][k] = (rb + k < r && c < c_end) ? F[(int64_t)(rb + k) * ld_f + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int cx = 0; cx < GC2; ++cx) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = ta[cx][4 * ti + i]; b[i] = tb[cx][4 * tj + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+  }
+  float* out = part + ((size_t)pair * gridDim.x + blockIdx.x) * GR * GR;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[(4 * ti + i) * GR + 4 * tj + j] = acc[i][j];
+}
+
+__global__ void gram2_reduce_kernel(const float* __restrict__ part, int nparts, int r, float* __restrict__ out, int64_t ld_out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= r * r) return;
+  const int i = idx / r, j = idx % r;
+  const int bi = i >> 6, bj = j >> 6;
+  const int pair = bi + bj;                                         // (0,0) -> 0, (0,1) / (1,0) -> 1, (1,1) -> 2
+  const int li = (bi <= bj ? i : j) & 63, lj = (bi <= bj ? j : i) & 63;   // block (1,0) reads block (0,1) transposed
+  double s = 0.0;
+  for (int p = 0; p < nparts; ++p) s += (double)part[((size_t)pair * nparts + p) * GR * GR + li * GR + lj];   // fixed order
+  out[(int64_t)i * ld_out + j] = (float)s;
+}
+
+int run_gram2(nnfac_ctx* ctx, float* out, int64_t ld_out, const float* F, int64_t ld_f, int r, int64_t len, cudaStream_t st) {
+  int64_t cols = ceil_div64(len, (int64_t)ctx->sm_count * 2);
+  cols = ceil_div64(cols, GC2) * GC2;
+  const int grid = (int)ceil_div64(len, cols);
+  const size_t need = (size_t)3 * grid * GR * GR * sizeof(float);
+  int rc = nnfac_guard_enter(ctx, NNFAC_GUARD_WS, st);
+  if (!rc) rc = nnfac_ws_reserve(ctx, need, st);
+  if (rc != NNFAC_OK) return rc;
+  gram2_partial_kernel<<<dim3((unsigned)grid, 3), 256, 0, st>>>(F, ld_f, r, len, cols, (float*)ctx->ws);
+  NNFAC_LAUNCH_CHECK(ctx);
+  gram2_reduce_kernel<<<(r * r + 255) / 256, 256, 0, st>>>((const float*)ctx->ws, grid, r, out, ld_out);
+  NNFAC_LAUNCH_CHECK(ctx);
+  return NNFAC_OK;
+}
+
 }  // namespace
 
 extern "C" int nnfac_gram(nnfac_ctx* ctx, int dtype, void* out, int64_t ld_out, const void* F, int64_t ld_f, int r,
@@ -245,6 +317,7 @@ extern "C" int nnfac_gram(nnfac_ctx* ctx, int dtype, void* out, int64_t ld_out, 
   NNFAC_ARG(ctx && out && F && r > 0 && len > 0 && ld_out >= r && ld_f >= len, "nnfac_gram: bad argument");
   NNFAC_ARG(dtype == NNFAC_F32 || dtype == NNFAC_F64, "nnfac_gram: bad dtype %d", dtype);
   cudaStream_t st = (cudaStream_t)stream;
+  if (r > GR && r <= 2 * GR && dtype == NNFAC_F32) return run_gram2(ctx, (float*)out, ld_out, (const float*)F, ld_f, r, len, st);
   if (r > GR) {   // wider factors go through the general kernel
     if (dtype == NNFAC_F32)
       return run_gemm<float>(ctx, (float*)out, ld_out, 0, (const float*)F, ld_f, 1, 0, 0, (const float*)F, 1, ld_f, 0, 0, r, r, len, 1, 1, st);

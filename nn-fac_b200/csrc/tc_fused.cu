@@ -574,6 +574,7 @@ int nnfac_nmf_plan_enable_f32(nnfac_nmf_plan* p, void* workspace, size_t workspa
   size_t need = 0;
   nnfac_nmf_plan_f32_bytes(p, &need);
   NNFAC_ARG(workspace_bytes >= need, "nnfac_nmf_plan_enable_f32: workspace of %zu bytes needed, got %zu", need, workspace_bytes);
+  NNFAC_ARG(p->sides == 3, "nnfac_nmf_plan_enable_f32: needs a two-sided plan");
   if (!p->fused_ok || p->rk != 64) { nnfac_set_error("nnfac_nmf_plan_enable_f32: rank %d > 64 is not covered by the beta = 1 fused pass", p->r); return NNFAC_ERR_UNSUPPORTED; }
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* base = (uint8_t*)workspace;
@@ -649,6 +650,22 @@ int nnfac_nmf_plan_reduce(nnfac_nmf_plan* p, int side, float* out, int64_t ld_ou
   return NNFAC_OK;
 }
 
+// The sum of nnfac_nmf_plan_reduce, written as the send buffer of a reduce-scatter over `slabs` ranks (see the kernel in
+// tc_nmf.cu): out = [slabs][r][chunk + tail_cols], `tail` (r x tail_cols, may be NULL with tail_cols = 0) copied behind
+// every chunk.  Replaces a reduction + a permuting copy + a broadcast copy by one kernel.
+int nnfac_nmf_plan_reduce_chunked(nnfac_nmf_plan* p, int side, float* out, int64_t chunk, int slabs, const float* tail, int64_t ld_tail,
+                                  int tail_cols, void* stream) {
+  NNFAC_ARG(p && out && (side == 0 || side == 1) && chunk > 0 && slabs > 0 && tail_cols >= 0 && (tail || tail_cols == 0),
+            "nnfac_nmf_plan_reduce_chunked: bad argument");
+  Side* s = &p->side[side];
+  NNFAC_ARG((int64_t)slabs * chunk >= s->R, "nnfac_nmf_plan_reduce_chunked: %d slabs of %lld columns do not cover %lld", slabs,
+            (long long)chunk, (long long)s->R);
+  nnfac_reduce_partials_chunked(p->partial, s->cp.splits, p->r, p->r_pad, s->R, s->cp.ld_partial, out, chunk, slabs, tail, ld_tail,
+                                tail_cols, p->ctx->sm_count, (cudaStream_t)stream);
+  NNFAC_LAUNCH_CHECK(p->ctx);
+  return NNFAC_OK;
+}
+
 // beta = 1 multiplicative update of factor `which` from the numerator partials the last fused pass over side `which`
 // left in the plan (call nnfac_nmf_plan_fused with out = NULL): F_out = max(F_in * num / den[k], floor), mu.py:84-88,
 // and F_out is installed in the plan (as nnfac_nmf_plan_set_factor would).  den: r row sums of the other factor.
@@ -668,6 +685,7 @@ int nnfac_nmf_plan_mu_finish(nnfac_nmf_plan* p, int which, const float* F_in, in
 int nnfac_nmf_plan_fused(nnfac_nmf_plan* p, int side, int mode, int want_cost, float* out, int64_t ld_out, double* cost_out,
                          void* stream) {
   NNFAC_ARG(p && (side == 0 || side == 1) && (mode == 0 || mode == 1), "nnfac_nmf_plan_fused: bad argument");
+  NNFAC_ARG((p->sides >> side) & 1, "nnfac_nmf_plan_fused: this plan keeps no planes of side %d", side);
   if (!p->fused_ok) { nnfac_set_error("nnfac_nmf_plan_fused: rank %d > 128 is not covered by the fused pass", p->r); return NNFAC_ERR_UNSUPPORTED; }
   if (mode == 1 && p->rk != 64) { nnfac_set_error("nnfac_nmf_plan_fused: the beta = 1 pass covers rank <= 64 (rank %d)", p->r); return NNFAC_ERR_UNSUPPORTED; }
   Side* s = &p->side[side];

@@ -193,6 +193,27 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int sp
   }
 }
 
+// The same sum written in the send layout of a reduce-scatter over `slabs` ranks: column `row` of the (r x R) result goes to
+// out[row / chunk][k][row % chunk] (slab pitch `slab`, row pitch `pitch` >= chunk + tail_cols), columns beyond R are zero, and
+// every slab also receives a copy of the small matrix `tail` (r x tail_cols: the partial Gram) behind its chunk.
+__global__ void reduce_partials_chunked_kernel(const float* __restrict__ partial, int splits, int r, int r_pad, int64_t R,
+                                               int64_t ld_partial, float* __restrict__ out, int64_t chunk, int64_t pitch, int64_t slab,
+                                               int slabs, const float* __restrict__ tail, int64_t ld_tail, int tail_cols) {
+  const int64_t width = chunk + tail_cols, total = (int64_t)slabs * r * width;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i % width, k = (i / width) % r, s = i / (width * r);
+    float v = 0.f;
+    if (c < chunk) {
+      const int64_t row = s * chunk + c;
+      if (row < R)
+        for (int sp = 0; sp < splits; ++sp) v += partial[((int64_t)sp * r_pad + k) * ld_partial + row];   // fixed order
+    } else {
+      v = tail[k * ld_tail + (c - chunk)];
+    }
+    out[s * slab + k * pitch + c] = v;
+  }
+}
+
 }  // namespace
 
 namespace {
@@ -292,6 +313,15 @@ void nnfac_reduce_partials(const float* partial, int splits, int r, int r_pad, i
   reduce_partials_kernel<<<grid, 256, 0, st>>>(partial, splits, r, r_pad, R, ld_partial, out, ld_out);
 }
 
+void nnfac_reduce_partials_chunked(const float* partial, int splits, int r, int r_pad, int64_t R, int64_t ld_partial, float* out,
+                                   int64_t chunk, int slabs, const float* tail, int64_t ld_tail, int tail_cols, int sm_count,
+                                   cudaStream_t st) {
+  const int64_t total = (int64_t)slabs * r * (chunk + tail_cols);
+  const int grid = (int)(ceil_div64(total, 256) < (int64_t)sm_count * 8 ? ceil_div64(total, 256) : (int64_t)sm_count * 8);
+  reduce_partials_chunked_kernel<<<grid, 256, 0, st>>>(partial, splits, r, r_pad, R, ld_partial, out, chunk, chunk + tail_cols,
+                                                       (int64_t)r * (chunk + tail_cols), slabs, tail, ld_tail, tail_cols);
+}
+
 extern "C" {
 
 int nnfac_nmf_plan_destroy(nnfac_nmf_plan* p) {
@@ -304,14 +334,15 @@ int nnfac_nmf_plan_destroy(nnfac_nmf_plan* p) {
 // Every device buffer of a plan is carved out of ONE allocation (256-byte aligned pieces): either the caller's
 // workspace (`buffer`, at least nnfac_nmf_plan_bytes() bytes -- e.g. a block of a caching allocator, so that repeated
 // factorisations of same-shaped data never reach cudaMalloc / cudaFree) or one cudaMalloc owned by the plan.
-static int plan_build(nnfac_ctx* ctx, int64_t m, int64_t n, int r, void* buffer, size_t buffer_bytes, cudaStream_t st,
+static int plan_build(nnfac_ctx* ctx, int64_t m, int64_t n, int r, int sides, void* buffer, size_t buffer_bytes, cudaStream_t st,
                       nnfac_nmf_plan** out, size_t* bytes_out) {
-  NNFAC_ARG(ctx && m > 0 && n > 0 && r > 0, "nnfac_nmf_plan_create: bad argument");
+  NNFAC_ARG(ctx && m > 0 && n > 0 && r > 0 && sides >= 1 && sides <= 3, "nnfac_nmf_plan_create: bad argument");
   if (r > 128) { nnfac_set_error("nnfac_nmf_plan_create: rank %d > 128 is not covered by the tensor-core path", r); return NNFAC_ERR_UNSUPPORTED; }
   if (m >= (1ll << 31) - 256 || n >= (1ll << 31) - 256) { nnfac_set_error("nnfac_nmf_plan_create: dimension too large"); return NNFAC_ERR_UNSUPPORTED; }
   nnfac_nmf_plan* p = (nnfac_nmf_plan*)calloc(1, sizeof(nnfac_nmf_plan));
   if (!p) return NNFAC_ERR_ALLOC;
   p->ctx = ctx; p->m = m; p->n = n; p->r = r;
+  p->sides = sides;
   p->r_pad = (int)round_up(r, 16);
   p->rk = p->r_pad <= 64 ? 64 : 128;
   p->fused_ok = 1;                       // rank <= 128: residual pass; the beta = 1 pass needs rk == 64
@@ -325,12 +356,12 @@ static int plan_build(nnfac_ctx* ctx, int64_t m, int64_t n, int r, void* buffer,
     s->R = i == 0 ? m : n;
     s->C = i == 0 ? n : m;
     s->ld = round_up(s->C, 64);
-    xb[i] = (size_t)s->R * s->ld * sizeof(bf16);
+    xb[i] = (sides >> i) & 1 ? (size_t)s->R * s->ld * sizeof(bf16) : 0;     // an absent side keeps no planes of X
     fb[i] = (size_t)p->r_pad * s->ld * sizeof(bf16);
     o_xh[i] = take(xb[i]); o_xl[i] = take(xb[i]); o_fh[i] = take(fb[i]); o_fl[i] = take(fb[i]);
     choose_partition(ctx->sm_count, s->R, s->C, p->r_pad, s);
     const size_t pb = (size_t)s->cp.splits * p->r_pad * s->cp.ld_partial * sizeof(float);
-    if (pb > partial_bytes) partial_bytes = pb;
+    if (((sides >> i) & 1) && pb > partial_bytes) partial_bytes = pb;
   }
   const size_t o_partial = take(partial_bytes);
   if (p->fused_ok)
@@ -402,18 +433,31 @@ static int plan_build(nnfac_ctx* ctx, int64_t m, int64_t n, int r, void* buffer,
 
 int nnfac_nmf_plan_create(nnfac_ctx* ctx, int64_t m, int64_t n, int r, nnfac_nmf_plan** out) {
   NNFAC_ARG(out != nullptr, "nnfac_nmf_plan_create: out is NULL");
-  return plan_build(ctx, m, n, r, nullptr, 0, (cudaStream_t)0, out, nullptr);
+  return plan_build(ctx, m, n, r, 3, nullptr, 0, (cudaStream_t)0, out, nullptr);
 }
 
 int nnfac_nmf_plan_bytes(nnfac_ctx* ctx, int64_t m, int64_t n, int r, size_t* bytes) {
   NNFAC_ARG(bytes != nullptr, "nnfac_nmf_plan_bytes: bytes is NULL");
-  return plan_build(ctx, m, n, r, nullptr, 0, (cudaStream_t)0, nullptr, bytes);
+  return plan_build(ctx, m, n, r, 3, nullptr, 0, (cudaStream_t)0, nullptr, bytes);
 }
 
 int nnfac_nmf_plan_create_in(nnfac_ctx* ctx, int64_t m, int64_t n, int r, void* workspace, size_t workspace_bytes,
                              void* stream, nnfac_nmf_plan** out) {
   NNFAC_ARG(out != nullptr && workspace != nullptr, "nnfac_nmf_plan_create_in: NULL argument");
-  return plan_build(ctx, m, n, r, workspace, workspace_bytes, (cudaStream_t)stream, out, nullptr);
+  return plan_build(ctx, m, n, r, 3, workspace, workspace_bytes, (cudaStream_t)stream, out, nullptr);
+}
+
+// One-sided plans: sides = 1 keeps only the planes of X (passes over side 0: V X^T, the MTTKRP of an unfolding),
+// sides = 2 only those of X^T, 3 both.  A pass over an absent side is refused.
+int nnfac_nmf_plan_bytes_sided(nnfac_ctx* ctx, int64_t m, int64_t n, int r, int sides, size_t* bytes) {
+  NNFAC_ARG(bytes != nullptr, "nnfac_nmf_plan_bytes_sided: bytes is NULL");
+  return plan_build(ctx, m, n, r, sides, nullptr, 0, (cudaStream_t)0, nullptr, bytes);
+}
+
+int nnfac_nmf_plan_create_sided(nnfac_ctx* ctx, int64_t m, int64_t n, int r, int sides, void* workspace, size_t workspace_bytes,
+                                void* stream, nnfac_nmf_plan** out) {
+  NNFAC_ARG(out != nullptr && workspace != nullptr, "nnfac_nmf_plan_create_sided: NULL argument");
+  return plan_build(ctx, m, n, r, sides, workspace, workspace_bytes, (cudaStream_t)stream, out, nullptr);
 }
 
 // Rows [row0, row0 + rows) of X (device fp32, `Xrows` points at row row0): both plane orientations of that slab.
@@ -423,12 +467,14 @@ int nnfac_nmf_plan_load_x_rows(nnfac_nmf_plan* p, const float* Xrows, int64_t ld
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t total = rows * p->n;
   int grid = (int)(ceil_div64(total, 256) < (int64_t)p->ctx->sm_count * 32 ? ceil_div64(total, 256) : (int64_t)p->ctx->sm_count * 32);
-  split_planes_kernel<<<grid, 256, 0, st>>>(Xrows, ldx, rows, p->n, p->side[0].xh + row0 * p->side[0].ld,
-                                            p->side[0].xl + row0 * p->side[0].ld, p->side[0].ld);
-  NNFAC_LAUNCH_CHECK(p->ctx);
+  if (p->sides & 1) {
+    split_planes_kernel<<<grid, 256, 0, st>>>(Xrows, ldx, rows, p->n, p->side[0].xh + row0 * p->side[0].ld,
+                                              p->side[0].xl + row0 * p->side[0].ld, p->side[0].ld);
+    NNFAC_LAUNCH_CHECK(p->ctx);
+  }
   // grid.y is limited to 65535 blocks of 32 rows: walk the rows in slabs
   const int64_t slab = 65535ll * 32;
-  for (int64_t r0 = 0; r0 < rows; r0 += slab) {
+  for (int64_t r0 = 0; (p->sides & 2) && r0 < rows; r0 += slab) {
     const int64_t nr = rows - r0 < slab ? rows - r0 : slab;
     dim3 g((unsigned)ceil_div64(p->n, 32), (unsigned)ceil_div64(nr, 32)), b(32, 8);
     split_planes_transposed_kernel<<<g, b, 0, st>>>(Xrows + r0 * ldx, ldx, nr, p->n, p->side[1].xh + row0 + r0,
@@ -442,7 +488,7 @@ int nnfac_nmf_plan_load_x_rows(nnfac_nmf_plan* p, const float* Xrows, int64_t ld
 int nnfac_nmf_plan_load_x_done(nnfac_nmf_plan* p, void* stream) {
   NNFAC_ARG(p != nullptr, "nnfac_nmf_plan_load_x_done: plan is NULL");
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->fused_ok) {
+  if (p->fused_ok && (p->sides & 1)) {
     // sum of X as the passes see it (hi + lo planes), fp64, fixed order: the constant term of the KL cost
     const int blocks = p->ctx->sm_count * 4;
     const int grc = nnfac_guard_enter(p->ctx, NNFAC_GUARD_RED, st);
@@ -464,6 +510,7 @@ int nnfac_nmf_plan_load_x(nnfac_nmf_plan* p, const float* X, int64_t ldx, void* 
 int nnfac_nmf_plan_cross(nnfac_nmf_plan* p, int which, const float* F, int64_t ldf, float* out, int64_t ld_out,
                          void* stream) {
   NNFAC_ARG(p && (which == 0 || which == 1), "nnfac_nmf_plan_cross: bad argument");
+  NNFAC_ARG((p->sides >> which) & 1, "nnfac_nmf_plan_cross: this plan keeps no planes of side %d", which);
   Side* s = &p->side[which];
   NNFAC_ARG((!F || ldf >= s->C) && (!out || ld_out >= s->R), "nnfac_nmf_plan_cross: leading dimension too small");
   cudaStream_t st = (cudaStream_t)stream;

@@ -98,6 +98,7 @@ struct nnfac_nmf_plan {
   double* cost_part;    // [1024] per-CTA cost partials of a fused pass ([512 + i]: second partial of CTA i)
   double* sums;         // cost_part + 1024: [0] sum of X (as stored in the planes)
   int fused_ok;
+  int sides;            // bit i: the planes of side i exist (one-sided plans: the MTTKRP of a tensor unfolding only reads side 0)
   void* buffer;         // the one device allocation every pointer above points into
   size_t buffer_bytes;
   int owns_buffer;      // 0: caller's workspace (nnfac_nmf_plan_create_in)
@@ -116,3 +117,6 @@ void nnfac_split_planes_transposed(const float* in, int64_t ld_in, int64_t rows,
                                    __nv_bfloat16* loT, int64_t ld_out, cudaStream_t st);
 void nnfac_reduce_partials(const float* partial, int splits, int r, int r_pad, int64_t R, int64_t ld_partial, float* out,
                            int64_t ld_out, int sm_count, cudaStream_t st);
+void nnfac_reduce_partials_chunked(const float* partial, int splits, int r, int r_pad, int64_t R, int64_t ld_partial, float* out,
+                                   int64_t chunk, int slabs, const float* tail, int64_t ld_tail, int tail_cols, int sm_count,
+                                   cudaStream_t st);

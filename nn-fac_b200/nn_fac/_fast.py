@@ -154,6 +154,13 @@ class Comm:
         self.dist.reduce_scatter_tensor(recv, send.view(self.world * r, chunk + t), op=self.dist.ReduceOp.SUM, group=self.group)
         return recv[:, :chunk], recv[:, chunk:]
 
+    def reduce_scatter_send(self, send):
+        """send: [world][r][w] (slab p = what rank p is to receive).  Returns the (r x w) sum over the ranks of this rank's slab."""
+        world, r, w = send.shape
+        recv = torch.empty((r, w), dtype=send.dtype, device=send.device)
+        self.dist.reduce_scatter_tensor(recv, send.view(world * r, w), op=self.dist.ReduceOp.SUM, group=self.group)
+        return recv
+
     def gather_slices(self, send):
         """send: this rank's slice (r x chunk, zero-padded).  Returns [world][r][chunk] (all-gather, no staging copies)."""
         r, chunk = send.shape
@@ -354,8 +361,15 @@ class FusedNMF:
                     # the U solve is split by rows of U: this rank only needs its own columns of the summed V X^T (and the
                     # summed Gram) -> reduce-scatter
                     chunk, lo, hi = comm.slice_of(m)
-                    VMt_slice, VVt = comm.reduce_scatter_columns(VMt, eng.gram(V), chunk)
-                    VVt = VVt.contiguous()
+                    if VMt is None:
+                        # the pass left its split-K partials in the plan: ONE kernel sums them straight into the send layout of the
+                        # reduce-scatter and appends the partial Gram (computed under the pass, on the side stream)
+                        gram = VVt_join() if VVt_join is not None else eng.gram(V)
+                        recv = comm.reduce_scatter_send(eng.plan.reduce_chunked(0, comm.world, chunk, gram))
+                        VMt_slice, VVt = recv[:, :chunk], recv[:, chunk:]
+                    else:
+                        VMt_slice, VVt = comm.reduce_scatter_columns(VMt, eng.gram(V), chunk)
+                        VVt = VVt.contiguous()
             with self._phase("sweep_U"):
                 if (comm.world == 1 or normalize[0]) and hasattr(eng, "solve_install"):
                     Ut = eng.solve_install(0, VMt, VVt, Ut, r, sparsity[0], normalize[0], self.hals_stats[0])   # nmf.py:415
@@ -380,7 +394,7 @@ class FusedNMF:
                     eng.set_factor(0, Ut)
         if 1 not in fixed_modes:
             with self._phase("cross_V"):
-                join = self._gram_async(1, Ut) if comm.world == 1 else None        # nmf.py:432, under the X pass
+                join = self._gram_async(1, Ut) if self._side is not None else None    # nmf.py:432, under the X pass
                 keepV = _SPLIT_RHS == "1" and hasattr(eng, "plan") and not normalize[1]   # the V solve adds the split-K partials itself
                 UtM = eng.cross(1, None, keep_partials=True) if keepV else eng.cross(1, None)   # nmf.py:433
                 UtU = join() if join is not None else eng.gram(Ut)
@@ -458,7 +472,8 @@ class FusedNMF:
         done = torch.cuda.Event() if self._on_gpu else None
         for it in range(n_iter_max + 1):
             VVt_join = den_join = None
-            if mode == MODE_RES and self.comm.world == 1 and it < n_iter_max and 0 not in fixed_modes:
+            if mode == MODE_RES and self._side is not None and it < n_iter_max and 0 not in fixed_modes and not (
+                    self.comm.world > 1 and normalize[0]):
                 VVt_join = self._gram_async(0, self.V)                             # V V^T under the first pass
             if mode == MODE_MU and self.comm.world == 1 and it < n_iter_max and 0 not in fixed_modes:
                 den_join = self._row_sums_async(0, self.V)                         # row sums of V under the first pass
@@ -467,6 +482,9 @@ class FusedNMF:
                 # HALS solve can add the partials itself too -- nnfac_nmf_plan_hals_solve(UtM = NULL), NNFAC_HALS_SPLIT_RHS=1.)
                 keep = self.comm.world == 1 and it < n_iter_max and 0 not in fixed_modes and (
                     mode == MODE_MU or (_SPLIT_RHS in ("u", "1") and not mu2 and not normalize[0] and hasattr(self.eng, "plan")))
+                # sharded HALS: the partials stay in the plan too; the reduce-scatter's send buffer is built from them
+                keep = keep or (self.comm.world > 1 and mode == MODE_RES and not mu2 and it < n_iter_max and 0 not in fixed_modes
+                                and not normalize[0] and hasattr(self.eng, "plan"))
                 # the cost lands directly in the scalar block that travels to the host
                 if self.comm.world > 1 and mode == MODE_MU and hasattr(self.eng, "plan"):
                     # sharded MU: the partial numerator lands directly in the exchange buffer (no 16.8 MB copy before the sum)

@@ -45,6 +45,7 @@ SIGNATURES = {
     "nnfac_transpose": [_P, _INT, _P, _I64, _P, _I64, _I64, _I64, _P],
     "nnfac_khatri_rao": [_P, _INT, _P, _P, _I64, _P, _I64, _I64, _P],
     "nnfac_hadamard": [_P, _INT, _P, _P, _P, _I64, _P],
+    "nnfac_axpby": [_P, _INT, _P, _DBL, _P, _DBL, _P, _I64, _P],
     "nnfac_normalize_rows": [_P, _INT, _P, _I64, _I64, _I64, _P],
     "nnfac_core_pg_step": [_P, _INT, _P, _P, _P, _I64, _DBL, _DBL, _DBL, _P, _P],
     "nnfac_core_pg_step_dev": [_P, _INT, _P, _P, _P, _I64, _DBL, _P, _P],
@@ -53,6 +54,8 @@ SIGNATURES = {
     "nnfac_nmf_plan_create": [_P, _I64, _I64, _INT, _c.POINTER(_P)],
     "nnfac_nmf_plan_bytes": [_P, _I64, _I64, _INT, _c.POINTER(_c.c_size_t)],
     "nnfac_nmf_plan_create_in": [_P, _I64, _I64, _INT, _P, _c.c_size_t, _P, _c.POINTER(_P)],
+    "nnfac_nmf_plan_bytes_sided": [_P, _I64, _I64, _INT, _INT, _c.POINTER(_c.c_size_t)],
+    "nnfac_nmf_plan_create_sided": [_P, _I64, _I64, _INT, _INT, _P, _c.c_size_t, _P, _c.POINTER(_P)],
     "nnfac_nmf_plan_destroy": [_P],
     "nnfac_nmf_plan_load_x": [_P, _P, _I64, _P],
     "nnfac_nmf_plan_load_x_rows": [_P, _P, _I64, _I64, _I64, _P],
@@ -63,6 +66,7 @@ SIGNATURES = {
     "nnfac_nmf_plan_set_factor": [_P, _INT, _P, _I64, _P],
     "nnfac_nmf_plan_set_factor_gathered": [_P, _INT, _P, _I64, _P, _I64, _P],
     "nnfac_nmf_plan_reduce": [_P, _INT, _P, _I64, _P],
+    "nnfac_nmf_plan_reduce_chunked": [_P, _INT, _P, _I64, _INT, _P, _I64, _INT, _P],
     "nnfac_nmf_plan_set_krao": [_P, _P, _I64, _I64, _P, _I64, _I64, _P],
     "nnfac_nmf_plan_hals_solve": [_P, _INT, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _INT, _DBL, _DBL, _P, _P],
     "nnfac_nmf_plan_fused": [_P, _INT, _INT, _INT, _P, _I64, _P, _P],
@@ -167,3 +171,13 @@ def resolve_dtype(*arrays):
             continue
         return torch.float64
     return torch.float32
+
+
+def working_dtype(numel, *arrays):
+    """(arithmetic dtype, dtype of the returned arrays): resolve_dtype, except that in "auto" mode a float32 problem of at most
+    config.small_problem_elements data elements computes in float64 (see nn_fac/config.py)."""
+    from . import config
+    dt = resolve_dtype(*arrays)
+    if dt == torch.float32 and config.precision == "auto" and int(numel) <= config.small_problem_elements:
+        return torch.float64, torch.float32
+    return dt, dt

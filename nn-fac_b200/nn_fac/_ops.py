@@ -166,6 +166,14 @@ def hadamard_(A, B):
     return A
 
 
+def axpby(a, X, b, Y):
+    """a X + b Y for contiguous tensors of the same shape."""
+    out = torch.empty_like(X)
+    L.check(_lib().nnfac_axpby(L.ctx(X.device), L.code_of(X.dtype), L.ptr(out), float(a), L.ptr(X), float(b), L.ptr(Y), X.numel(),
+                               L.stream_ptr()))
+    return out
+
+
 def normalize_rows_(A):
     rows, cols = A.shape
     L.check(_lib().nnfac_normalize_rows(L.ctx(A.device), L.code_of(A.dtype), L.ptr(A), A.stride(0), rows, cols,
@@ -281,16 +289,17 @@ class NMFPlan:
         self._xf32 = None
         self._X = X
 
-    def bind_rank(self, r):
+    def bind_rank(self, r, sides=3):
+        """sides: 3 = planes of X and of X^T; 1 = only X (passes over side 0, e.g. the MTTKRP of an unfolding); 2 = only X^T."""
         import ctypes
         self.r = r
         # the plan lives in one block of torch's caching allocator: a second factorisation of same-shaped data
         # reuses it without any cudaMalloc / cudaFree
         nbytes = ctypes.c_size_t()
-        L.check(_lib().nnfac_nmf_plan_bytes(L.ctx(self.device), self.m, self.n, r, ctypes.byref(nbytes)))
+        L.check(_lib().nnfac_nmf_plan_bytes_sided(L.ctx(self.device), self.m, self.n, r, sides, ctypes.byref(nbytes)))
         self._workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
-        L.check(_lib().nnfac_nmf_plan_create_in(L.ctx(self.device), self.m, self.n, r, L.ptr(self._workspace), nbytes.value,
-                                                L.stream_ptr(), ctypes.byref(self.handle)))
+        L.check(_lib().nnfac_nmf_plan_create_sided(L.ctx(self.device), self.m, self.n, r, sides, L.ptr(self._workspace), nbytes.value,
+                                                   L.stream_ptr(), ctypes.byref(self.handle)))
         if self._X.is_cuda:
             L.check(_lib().nnfac_nmf_plan_load_x(self.handle, L.ptr(self._X), self._X.stride(0), L.stream_ptr()))
         else:
@@ -329,6 +338,15 @@ class NMFPlan:
         R = self.m if side == 0 else self.n
         out = torch.empty((self.r, R), dtype=torch.float32, device=self.device)
         L.check(_lib().nnfac_nmf_plan_reduce(self.handle, side, L.ptr(out), out.stride(0), L.stream_ptr()))
+        return out
+
+    def reduce_chunked(self, side, slabs, chunk, tail=None):
+        """The sum of reduce(side) as the send buffer of a reduce-scatter over `slabs` ranks: [slabs][r][chunk + t] with the small
+        matrix `tail` (r x t) copied behind every chunk."""
+        t = 0 if tail is None else int(tail.shape[1])
+        out = torch.empty((slabs, self.r, chunk + t), dtype=torch.float32, device=self.device)
+        L.check(_lib().nnfac_nmf_plan_reduce_chunked(self.handle, side, L.ptr(out), chunk, slabs, L.ptr(tail),
+                                                     tail.stride(0) if tail is not None else 0, t, L.stream_ptr()))
         return out
 
     def cross(self, which, F, out=None, keep_partials=False):

@@ -159,7 +159,9 @@ class DeviceNMF:
         return self.mu_iteration(beta, fixed_modes)
 
 
-def _to_output(t, like):
+def _to_output(t, like, dtype=None):
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)                               # small float32 problems compute in float64 (nn_fac/config.py)
     return t if isinstance(like, torch.Tensor) else t.cpu().numpy()
 
 
@@ -174,7 +176,7 @@ def compute_nmf(data, rank, U_in, V_in, n_iter_max=100, tol=1e-8,
         fixed_modes = []
     if normalize is None or normalize is False:
         normalize = [False, False]
-    dt = L.resolve_dtype(data, U_in, V_in)
+    dt, dt_out = L.working_dtype(int(np.prod(np.shape(data))), data, U_in, V_in)
     if n_iter_max > 0 and _fast.eligible(dt, int(np.shape(U_in)[1]), update_rule, beta):
         # fp32, rank <= 64: two X passes per iteration on tcgen05, cost fused with a lag of one pass
         _check_step_arguments(update_rule, beta, sparsity_coefficients)
@@ -210,7 +212,7 @@ def compute_nmf(data, rank, U_in, V_in, n_iter_max=100, tol=1e-8,
     if state is None:
         U_out, V_out = np.array(U_in), np.array(V_in)
     else:
-        U_out, V_out = _to_output(state.U, data), _to_output(state.V, data)
+        U_out, V_out = _to_output(state.U, data, dt_out), _to_output(state.V, data, dt_out)
     if return_costs:
         return U_out, V_out, cost_fct_vals, toc
     return U_out, V_out
@@ -225,7 +227,7 @@ def one_nmf_step(data, rank, U_in, V_in, norm_data, update_rule, beta,
     nmf.py:457, and the inner stop rule is always the deterministic one).
     """
     _check_step_arguments(update_rule, beta, sparsity_coefficients)
-    dt = L.resolve_dtype(data, U_in, V_in)
+    dt, dt_out = L.working_dtype(int(np.prod(np.shape(data))), data, U_in, V_in)
     state = DeviceNMF(data, U_in, V_in, dt)
     cost = state.step(update_rule, beta, sparsity_coefficients, fixed_modes, normalize)
-    return _to_output(state.U, data), _to_output(state.V, data), cost
+    return _to_output(state.U, data, dt_out), _to_output(state.V, data, dt_out), cost

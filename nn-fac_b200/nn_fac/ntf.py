@@ -64,17 +64,22 @@ class DeviceNTF:
         self.norm_sq = None
         self._grams, self._gram_ok = None, [False] * len(self.factors)      # see _gram
         self.stats = torch.zeros(4, dtype=torch.float64, device=self.T.device)
-        # fp32, rank <= 128: the MTTKRP of every mode runs on tcgen05.  One plan per mode holds unfold(T, mode)
-        # (I_mode x rest, C order) as K-major bf16 hi/lo planes -- the same bytes as the fp32 unfolded copies the
-        # reference keeps (ntf.py:309-311) -- and the MTTKRP is the plan's cross product F X^T with F = krao^T.
+        # fp32, rank <= 128: the MTTKRP of every mode runs on tcgen05.  One ONE-SIDED plan per mode holds unfold(T, mode)
+        # (I_mode x rest, C order) as K-major bf16 hi/lo planes -- 4 bytes per element and mode, the same bytes as the fp32
+        # unfolded copies the reference keeps (ntf.py:309-311) -- and the MTTKRP is the plan's cross product F X^T with
+        # F = krao^T.  Not enough memory for the planes: the strided CUDA-core MTTKRP on the tensor itself (self.plans None).
         self.plans = None
         rank = int(self.factors[0].shape[1])
         if dtype == torch.float32 and rank <= 128 and self.T.dim() >= 2 and os.environ.get("NNFAC_NTF_TC", "1") != "0":
-            self.plans = []
-            for mode in range(self.T.dim()):
-                Xm = self.T.movedim(mode, 0).reshape(self.shape[mode], -1).contiguous()
-                self.plans.append(ops.NMFPlan(Xm).bind_rank(rank))
-                del Xm
+            try:
+                self.plans = []
+                for mode in range(self.T.dim()):
+                    Xm = self.T.movedim(mode, 0).reshape(self.shape[mode], -1).contiguous()
+                    self.plans.append(ops.NMFPlan(Xm).bind_rank(rank, sides=1))
+                    del Xm
+            except torch.cuda.OutOfMemoryError:
+                self.plans = None
+                torch.cuda.empty_cache()
 
     def _gram(self, i):
         """F_i^T F_i of the HALS path, kept until factor i changes (the reference recomputes the Gram of every other factor

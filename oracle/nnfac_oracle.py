@@ -71,17 +71,22 @@ def gamma_beta(beta):
 
 
 def beta_divergence(a, b, beta):
-    """beta_divergence.py:42-52.  Inputs are assumed strictly positive (the
-    reference's ``where=`` masks leave masked entries uninitialised)."""
+    """beta_divergence.py:42-52.  The reference masks the logarithm where its argument is zero (``where=``) and leaves the
+    masked entries uninitialised; the well-defined reading -- the limit, and what fresh (zeroed) memory gives -- is that an
+    entry with a == 0 contributes b (beta = 1) or a/b - 1 (beta = 0)."""
     if beta < 0:
         raise ValueError("negative beta")
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     if beta == 1:
-        return float(np.sum(a * np.log(a / b) - a + b))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t = np.where(a != 0, a * np.log(np.where(a != 0, a / b, 1.0)), 0.0)
+        return float(np.sum(t - a + b))
     if beta == 0:
         q = a / b
-        return float(np.sum(q - np.log(q) - 1.0))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            lg = np.where(a != 0, np.log(np.where(a != 0, q, 1.0)), 0.0)
+        return float(np.sum(q - lg - 1.0))
     return float(np.sum((a ** beta + (beta - 1.0) * b ** beta - beta * a * b ** (beta - 1.0))
                         / (beta * (beta - 1.0))))
 
@@ -131,6 +136,42 @@ def hals_nnls_acc(UtM, UtU, in_V, maxiter=500, delta=0.01,
             cnt = max(cnt, maxiter + 1)                       # `0 >= delta * 0`: nnls.py:156 burns the remaining sweeps as
             break                                             # no-ops; they are counted, not run.  (With eps0 > 0 a sweep
                                                               # that moves nothing fails the test and the loop ends by itself.)
+    return V, eps, cnt, cnt - 1
+
+
+def hals_coupling_nnls_acc(UtM, UtU, in_V, Vtarget, mu, maxiter=500, delta=0.01, normalize=False, nonzero=False):
+    """nnls.py:204-352 with alpha = inf: min_{V>=0} ||M - UV||^2 + mu ||V - Vtarget||^2.  Returns (V, eps, cnt, sweeps)."""
+    UtM = np.asarray(UtM, dtype=np.float64)
+    UtU = np.asarray(UtU, dtype=np.float64)
+    Vt = np.asarray(Vtarget, dtype=np.float64)
+    r, n = UtM.shape
+    V = np.array(in_V, dtype=np.float64, copy=True)          # nnls.py:300
+    eps0, eps, cnt = 0.0, 1.0, 1
+    while cnt <= maxiter and eps >= delta * eps0:             # nnls.py:311
+        nodelta = 0.0
+        for k in range(r):
+            if UtU[k, k] != 0:                                # nnls.py:316
+                step = np.maximum((UtM[k, :] - UtU[k, :V.shape[0]] @ V + mu * (Vt[k, :] - V[k, :])) / (UtU[k, k] + mu),
+                                  -V[k, :])                   # nnls.py:318
+                V[k, :] = V[k, :] + step
+                nodelta += float(step @ step)
+                if nonzero and not V[k, :].any():
+                    V[k, :] = 1e-16 * np.max(V)
+            elif nonzero:
+                raise ValueError(f"Column {k} is zero with nonzero condition")   # nnls.py:330
+            if normalize:                                     # nnls.py:332-338
+                nrm = np.linalg.norm(V[k, :])
+                if nrm != 0:
+                    V[k, :] /= nrm
+                else:
+                    V[k, :] = 1.0 / math.sqrt(n)
+        if cnt == 1:
+            eps0 = nodelta
+        eps = nodelta
+        cnt += 1
+        if nodelta == 0.0 and eps0 == 0.0 and not normalize:
+            cnt = max(cnt, maxiter + 1)
+            break
     return V, eps, cnt, cnt - 1
 
 

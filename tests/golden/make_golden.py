@@ -235,7 +235,39 @@ def ntd_cases():
     save("ntd", **out)
 
 
+# ---- 6. coupled NNLS (nnls.py:204-352, untested by the reference) and the larger-UtU / in_V case of nnls_tests.py:40-47 ----
+def coupling_cases():
+    rng = np.random.RandomState(23)
+    out = {}
+    for tag, (m, r, n, mu) in {"a": (40, 6, 31, 0.5), "b": (90, 12, 50, 3.0), "c": (64, 16, 130, 40.0)}.items():
+        U = rng.rand(m, r)
+        M = U @ rng.rand(r, n) + 0.05 * rng.rand(m, n)
+        UtM, UtU, V0, Vt = U.T @ M, U.T @ U, rng.rand(r, n), rng.rand(r, n)
+        for opt, kw in {"plain": {}, "norm": {"normalize": True}}.items():
+            V, eps, cnt, _ = ref_nnls.hals_coupling_nnls_acc(UtM, UtU, V0, Vt, mu, maxiter=100, atime=None, alpha=math.inf,
+                                                             delta=0.01, **kw)
+            key = f"{tag}_{opt}"
+            out[key + "_UtM"], out[key + "_UtU"], out[key + "_V0"], out[key + "_Vt"] = UtM, UtU, V0, Vt
+            out[key + "_mu"], out[key + "_V"], out[key + "_eps"], out[key + "_cnt"] = np.float64(mu), V, np.float64(eps), np.int64(cnt)
+    # zero diagonal entry of UtU: the row is skipped although UtU[k,k] + mu != 0 (nnls.py:316)
+    U = rng.rand(25, 5)
+    UtU = U.T @ U
+    UtU[3, 3] = 0.0
+    UtM, V0, Vt = U.T @ rng.rand(25, 18), rng.rand(5, 18), rng.rand(5, 18)
+    V, eps, cnt, _ = ref_nnls.hals_coupling_nnls_acc(UtM, UtU, V0, Vt, 0.7, maxiter=30, atime=None, alpha=math.inf, delta=0.01)
+    out.update(zd_UtM=UtM, zd_UtU=UtU, zd_V0=V0, zd_Vt=Vt, zd_mu=np.float64(0.7), zd_V=V, zd_eps=np.float64(eps), zd_cnt=np.int64(cnt))
+    # hals_nnls_acc with UtU / in_V larger than UtM (tests/nnls_tests.py:40-47): rows >= r of in_V enter every product
+    UtU, UtM, V0 = rng.rand(15, 15), rng.rand(8, 1), rng.rand(15, 1)
+    V, eps, cnt, _ = ref_nnls.hals_nnls_acc(UtM, UtU, V0, maxiter=500, atime=None, alpha=math.inf, delta=0.01)
+    out.update(big_UtM=UtM, big_UtU=UtU, big_V0=V0, big_V=V, big_eps=np.float64(eps), big_cnt=np.int64(cnt))
+    U = rng.rand(30, 9)
+    UtU, UtM, V0 = U.T @ U, (U.T @ rng.rand(30, 12))[:6], rng.rand(9, 12)
+    V, eps, cnt, _ = ref_nnls.hals_nnls_acc(UtM, UtU, V0, maxiter=100, atime=None, alpha=math.inf, delta=0.01)
+    out.update(big2_UtM=UtM, big2_UtU=UtU, big2_V0=V0, big2_V=V, big2_eps=np.float64(eps), big2_cnt=np.int64(cnt))
+    save("coupling", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["nnls", "mu", "nmf", "ntf", "ntd"]
+    which = sys.argv[1:] or ["nnls", "mu", "nmf", "ntf", "ntd", "coupling"]
     for w in which:
         globals()[w + "_cases"]()

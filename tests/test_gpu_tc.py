@@ -99,9 +99,10 @@ def test_fused_pass_rank_65_to_128_matches_float64(m, n, r):
 
 
 @pytest.mark.parametrize("r,length,dtype", [(10, 500, "float64"), (64, 65536, "float32"), (33, 1301, "float32"),
-                                            (64, 8192, "float64"), (1, 7, "float32"), (96, 700, "float32")])
+                                            (64, 8192, "float64"), (1, 7, "float32"), (96, 700, "float32"),
+                                            (128, 70000, "float32"), (65, 33, "float32"), (100, 5000, "float64")])
 def test_gram_matches_float64(r, length, dtype):
-    """F F^T of a rank-major factor (nmf.py:407 / :432); r > 64 takes the general kernel."""
+    """F F^T of a rank-major factor (nmf.py:407 / :432); 64 < r <= 128 in fp32: 64 x 64 block pairs, else the general kernel."""
     import torch
     from nn_fac import _ops as ops
     rng = np.random.RandomState(r + length)

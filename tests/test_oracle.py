@@ -238,3 +238,24 @@ def test_philox_known_answer():
     assert u[0, 0] == np.float32((0x6627e8d5 >> 8) / 16777216.0)
     a = philox.uniform(40, 30, seed=5, stream_id=2)
     np.testing.assert_array_equal(philox.uniform(10, 7, row0=20, col0=11, seed=5, stream_id=2), a[20:30, 11:18])
+
+
+@pytest.mark.parametrize("key", ["a_plain", "a_norm", "b_plain", "b_norm", "c_plain", "c_norm", "zd"])
+def test_coupled_nnls_oracle_matches_reference(key, golden):
+    """hals_coupling_nnls_acc (nnls.py:204-352, PARAFAC2's coupled solve) against fixtures generated by the real reference."""
+    g = golden("coupling")
+    V, eps, cnt, _ = orc.hals_coupling_nnls_acc(g[key + "_UtM"], g[key + "_UtU"], g[key + "_V0"], g[key + "_Vt"], float(g[key + "_mu"]),
+                                                maxiter=30 if key == "zd" else 100, normalize=key.endswith("norm"))
+    np.testing.assert_allclose(V, g[key + "_V"], rtol=1e-12, atol=1e-14)
+    assert cnt == int(g[key + "_cnt"])
+    np.testing.assert_allclose(eps, float(g[key + "_eps"]), rtol=1e-9)
+
+
+@pytest.mark.parametrize("key,maxiter", [("big", 500), ("big2", 100)])
+def test_nnls_oracle_with_gram_and_start_larger_than_rhs(key, maxiter, golden):
+    """tests/nnls_tests.py:40-47: UtU / in_V may have more rows than UtM; nnls.py:163/167 multiply the whole row of UtU with V,
+    so the extra rows of in_V are constants of the solve (and are returned untouched)."""
+    g = golden("coupling")
+    V, eps, cnt, _ = orc.hals_nnls_acc(g[key + "_UtM"], g[key + "_UtU"], g[key + "_V0"], maxiter=maxiter)
+    np.testing.assert_allclose(V, g[key + "_V"], rtol=1e-12, atol=1e-14)
+    assert cnt == int(g[key + "_cnt"])
