@@ -472,8 +472,8 @@ class FusedNMF:
         done = torch.cuda.Event() if self._on_gpu else None
         for it in range(n_iter_max + 1):
             VVt_join = den_join = None
-            if mode == MODE_RES and self._side is not None and it < n_iter_max and 0 not in fixed_modes and not (
-                    self.comm.world > 1 and normalize[0]):
+            if mode == MODE_RES and (self.comm.world == 1 or self._side is not None) and it < n_iter_max and 0 not in fixed_modes \
+                    and not (self.comm.world > 1 and normalize[0]):
                 VVt_join = self._gram_async(0, self.V)                             # V V^T under the first pass
             if mode == MODE_MU and self.comm.world == 1 and it < n_iter_max and 0 not in fixed_modes:
                 den_join = self._row_sums_async(0, self.V)                         # row sums of V under the first pass
