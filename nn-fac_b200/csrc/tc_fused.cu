@@ -315,17 +315,28 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
       // math runs on PACKED fp32 pairs (FADD2 / FMUL2 / FFMA2 of sm_100): two columns per instruction.
       float2 acc2 = make_float2(0.f, 0.f), acck2 = make_float2(0.f, 0.f);
       const float2 neg1 = make_float2(-1.f, -1.f), tiny2 = make_float2(1e-30f, 1e-30f);
+      // The model tile of stage i + 1 is fetched from tensor memory WHILE stage i is transformed (tcgen05.ld is asynchronous
+      // until its wait): the 16 transform warps read 32 KiB of tensor memory per stage, which otherwise sits on the critical path.
+      uint32_t kn[CW];
+      int bf = b1; uint32_t bf_phase = b1_phase;                 // buffer of the next fetch
+      auto fetch_d1 = [&]() {
+        tc::mbar_wait(&d1_full[bf], bf_phase);
+        tc::tcgen05_fence_after();
+        tc::tmem_ld16(D1 + (uint32_t)bf * 64 + lane_base + CW * part, kn);
+        if (++bf == ND1) { bf = 0; bf_phase ^= 1; }
+      };
+      fetch_d1();
       for (int i = 0; i < S; ++i) {
         // ---- model tile for this stage ----
-        tc::mbar_wait(&d1_full[b1], b1_phase);
-        tc::tcgen05_fence_after();
+        tc::tmem_ld_wait16(kn);
         uint32_t kk[CW];
-        tc::tmem_ld16(D1 + (uint32_t)b1 * 64 + lane_base + CW * part, kk);
-        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < CW; ++j) kk[j] = kn[j];
         tc::tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&d1_empty[b1]);
         if (++b1 == ND1) { b1 = 0; b1_phase ^= 1; }
+        if (i + 1 < S) fetch_d1();
         // the stage's TMA data is visible to the MMA issuers; this thread must observe the barrier too
         // before reading X through the generic proxy
         tc::mbar_wait(&full[st], ph);

@@ -458,6 +458,22 @@ __global__ void __launch_bounds__(Cfg<RP>::NTHREADS, 1) tc_sweep_kernel(const Tc
       // max(u, -V[k]) and every later row of the block sees it through -UtU[k2][k] / UtU[k2][k2].
       float dd[BLK];
       uint32_t vn[BLK];
+#ifdef SWEEP_SCALAR_FMA
+#pragma unroll
+      for (int e = 0; e < BLK; ++e) {
+        const float cur = __uint_as_float(keep[e]);
+        const float d = fmaxf(u[e], -cur);
+        if (e + 1 < BLK) u[e + 1] = fmaf(csw<RP>().nh[B][e][e + 1], d, u[e + 1]);
+        dd[e] = d;
+        vn[e] = __float_as_uint(cur + d);
+        nd = fmaf(d, d, nd);                                           // nnls.py:170
+#pragma unroll
+        for (int e2 = e + 2; e2 < BLK; ++e2) u[e2] = fmaf(csw<RP>().nh[B][e][e2], d, u[e2]);
+      }
+#else
+      // the same recurrence with the off-chain updates on PACKED fp32 pairs (FFMA2): rows (e2, e2 + 1), e2 even, take
+      // u[e2 .. e2+1] += nh[B][e][e2 .. e2+1] * (d, d) in one instruction; the update of the NEXT row stays scalar and
+      // first, it is the dependent chain.  Same products and sums as the scalar form, element for element.
 #pragma unroll
       for (int e = 0; e < BLK; ++e) {
         const float cur = __uint_as_float(keep[e]);
@@ -468,9 +484,17 @@ __global__ void __launch_bounds__(Cfg<RP>::NTHREADS, 1) tc_sweep_kernel(const Tc
         dd[e] = d;
         vn[e] = __float_as_uint(cur + d);
         nd = fmaf(d, d, nd);                                           // nnls.py:170
+        const float2 d2 = make_float2(d, d);
+        constexpr int dummy = 0; (void)dummy;
+        if (((e + 2) & 1) && e + 2 < BLK) u[e + 2] = fmaf(csw<RP>().nh[B][e][e + 2], d, u[e + 2]);
 #pragma unroll
-        for (int e2 = e + 2; e2 < BLK; ++e2) u[e2] = fmaf(csw<RP>().nh[B][e][e2], d, u[e2]);
+        for (int e2 = (e + 2 + 1) & ~1; e2 + 1 < BLK; e2 += 2) {
+          const float2 c2 = *reinterpret_cast<const float2*>(&csw<RP>().nh[B][e][e2]);
+          const float2 r2 = __ffma2_rn(c2, d2, make_float2(u[e2], u[e2 + 1]));
+          u[e2] = r2.x; u[e2 + 1] = r2.y;
+        }
       }
+#endif
       PROF_T(2)
       tmem_st16(t_v + B * BLK, vn);
       store_chunk2(vh, row, 2 * (B & 3), &dd[0], PLANE_BYTES);

@@ -267,7 +267,43 @@ def coupling_cases():
     save("coupling", **out)
 
 
+# ---- 7. PARAFAC2 (parafac2.py, no reference test): the reference run with the deterministic inner rule ------------------
+def parafac2_cases():
+    import nn_fac.parafac2 as ref_p2
+    # parafac2.py:522/548/581 pass the wall-clock rule (alpha=0.5, atime=timer); parity is defined against alpha = inf, like
+    # deterministic=True does for nmf / ntd.  The solvers are wrapped at the module attribute the driver resolves at call time.
+    plain, coupled = ref_nnls.hals_nnls_acc, ref_nnls.hals_coupling_nnls_acc
+
+    def det_plain(UtM, UtU, in_V, maxiter=500, atime=None, alpha=0.5, delta=0.01, **kw):
+        return plain(UtM, UtU, in_V, maxiter=maxiter, atime=None, alpha=math.inf, delta=delta, **kw)
+
+    def det_coupled(UtM, UtU, in_V, Vtarget, mu, maxiter=500, atime=None, alpha=0.5, delta=0.01, **kw):
+        return coupled(UtM, UtU, in_V, Vtarget, mu, maxiter=maxiter, atime=None, alpha=math.inf, delta=delta, **kw)
+
+    ref_nnls.hals_nnls_acc, ref_nnls.hals_coupling_nnls_acc = det_plain, det_coupled
+    try:
+        rng = np.random.RandomState(31)
+        K, r_, n, rank = 4, 20, 30, 3
+        H = rng.rand(rank, n)
+        Wstar = rng.rand(r_, rank)
+        slices = []
+        for k in range(K):
+            Q, _ = np.linalg.qr(rng.randn(r_, r_))
+            slices.append(np.abs(Q @ Wstar) @ np.diag(rng.rand(rank) + 0.5) @ H + 0.01 * rng.rand(r_, n))
+        out = {f"slice{k}": s for k, s in enumerate(slices)}
+        out["rank"] = np.int64(rank)
+        for tag, with_P in (("P", True), ("W", False)):
+            W_list, Hh, D_list, costs, _ = ref_p2.parafac_2(slices, rank, with_P, init="random", n_iter_max=8, tol=1e-12,
+                                                           return_costs=True, deterministic=True, seed=3)
+            out[f"{tag}_H"], out[f"{tag}_costs"] = Hh, np.array(costs)
+            for k in range(K):
+                out[f"{tag}_W{k}"], out[f"{tag}_D{k}"] = W_list[k], D_list[k]
+    finally:
+        ref_nnls.hals_nnls_acc, ref_nnls.hals_coupling_nnls_acc = plain, coupled
+    save("parafac2", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["nnls", "mu", "nmf", "ntf", "ntd", "coupling"]
+    which = sys.argv[1:] or ["nnls", "mu", "nmf", "ntf", "ntd", "coupling", "parafac2"]
     for w in which:
         globals()[w + "_cases"]()
