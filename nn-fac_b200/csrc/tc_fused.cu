@@ -50,7 +50,7 @@ struct Cfg {
 };
 
 struct FusedParams {
-  int r_pad, splits, stages_per_unit, num_units, drain, want_cost;
+  int r_pad, splits, stages_per_unit, num_units, drain, want_cost, tiles, split_major;
   int64_t ld_partial;
   float* partial;
   double* cost_part;
@@ -129,7 +129,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     // ===================== TMA producer =====================
     int stage = 0; uint32_t phase = 0, a1_phase = 0;
     for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-      const int tile = u / p.splits, split = u % p.splits;
+      const int tile = p.split_major ? u % p.tiles : u / p.splits, split = p.split_major ? u / p.tiles : u % p.splits;
       const int row0 = tile * TILE_ROWS, k0 = split * S * BK;
       if (RK == 64) {
         tc::mbar_wait(a1_empty, a1_phase ^ 1);
@@ -249,7 +249,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     uint32_t a1_phase = 0;
     double cost = 0.0, costk = 0.0;
     for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-      const int tile = u / p.splits, split = u % p.splits;
+      const int tile = p.split_major ? u % p.tiles : u / p.splits, split = p.split_major ? u / p.tiles : u % p.splits;
       float sum[CWD];
 #pragma unroll
       for (int j = 0; j < CWD; ++j) sum[j] = 0.f;
@@ -748,6 +748,7 @@ int nnfac_nmf_plan_fused(nnfac_nmf_plan* p, int side, int mode, int want_cost, f
   FusedParams fp;
   fp.r_pad = p->r_pad; fp.splits = s->cp.splits; fp.stages_per_unit = s->cp.stages_per_unit; fp.num_units = s->cp.num_units;
   fp.drain = DRAIN; fp.want_cost = (mode == 0 || want_cost) ? 1 : 0;
+  fp.tiles = s->cp.tiles; fp.split_major = s->cp.split_major;
   fp.ld_partial = s->cp.ld_partial; fp.partial = p->partial; fp.cost_part = p->cost_part;
   fp.a1h = p->rowp_h[side]; fp.a1l = p->rowp_l[side]; fp.R = s->R;
   const int other = 1 - side;

@@ -88,7 +88,7 @@ tc_cross_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     // ===== TMA producer =====
     int stage = 0; uint32_t phase = 0;
     for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-      const int tile = u / p.splits, split = u % p.splits;
+      const int tile = p.split_major ? u % p.tiles : u / p.splits, split = p.split_major ? u / p.tiles : u % p.splits;
       const int row0 = tile * TILE_ROWS;
       const int k0 = split * p.stages_per_unit * BK;
       for (int ks = 0; ks < p.stages_per_unit; ++ks) {
@@ -147,7 +147,7 @@ tc_cross_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     const int q = warp & 3;                                  // TMEM lane quadrant of this warp
     int acc = 0; uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-      const int tile = u / p.splits, split = u % p.splits;
+      const int tile = p.split_major ? u % p.tiles : u / p.splits, split = p.split_major ? u / p.tiles : u % p.splits;
       const int64_t row = (int64_t)tile * TILE_ROWS + q * 32 + lane;
       float* out = p.partial + (int64_t)split * p.r_pad * p.ld_partial + row;
       float sum[MAX_RPAD];
@@ -237,6 +237,9 @@ void choose_partition(int sm, int64_t R, int64_t C, int r_pad, Side* s) {
   s->cp.stages_per_unit = (int)ceil_div64(kblocks, best_s);
   s->cp.splits = (int)ceil_div64(kblocks, s->cp.stages_per_unit);
   s->cp.num_units = (int)(tiles * s->cp.splits);
+  s->cp.tiles = (int)tiles;
+  // factor planes of this side: r_pad x ld, hi + lo.  When they do not fit L2 comfortably, order the units split-major
+  s->cp.split_major = ((size_t)r_pad * (size_t)round_up(C, 64) * 4 > ((size_t)32 << 20) && tiles <= sm) ? 1 : 0;
   const size_t stage_bytes = 2 * (size_t)TILE_ROWS * BK * 2 + 2 * (size_t)r_pad * BK * 2;
   int stages = (int)((200 * 1024) / stage_bytes);
   if (stages > 6) stages = 6;

@@ -66,6 +66,10 @@ struct CrossParams {
   int num_units;        // row_tiles * splits
   int num_stages;       // smem ring depth
   int drain;            // stages per TMEM accumulation chain (the tensor core accumulates with truncation)
+  int tiles;            // row tiles
+  int split_major;      // unit u = split * tiles + tile instead of tile * splits + split: concurrent CTAs then share the factor
+                        // columns of one split (the factor planes are re-read per tile; beyond the L2 size that order decides
+                        // whether they come from L2 or from HBM)
   int64_t ld_partial;   // row pitch of the partial buffer (multiple of 128)
   float* partial;       // [splits][r_pad][ld_partial]
 };

@@ -287,12 +287,14 @@ class NMFPlan:
         self.handle = ctypes.c_void_p()
         self.r = None
         self._xf32 = None
+        self._xf32_refused = False
         self._X = X
 
     def bind_rank(self, r, sides=3):
         """sides: 3 = planes of X and of X^T; 1 = only X (passes over side 0, e.g. the MTTKRP of an unfolding); 2 = only X^T."""
         import ctypes
         self.r = r
+        self.sides = sides
         # the plan lives in one block of torch's caching allocator: a second factorisation of same-shaped data
         # reuses it without any cudaMalloc / cudaFree
         nbytes = ctypes.c_size_t()
@@ -404,10 +406,17 @@ class NMFPlan:
         mode 1: beta=1 MU numerator + KL(X|UV).  Returns (out r x rows, cost device scalar or None).
         keep_partials: leave the split partials in the plan for mu_finish instead of reducing them into `out`."""
         R = self.m if side == 0 else self.n
-        # measured on B200: reading x from an fp32 copy (-3 instructions per element) does not shorten the pass, which is
-        # bound by its TMA -> MMA -> transform -> MMA hand-offs, so the 2 x 4mn bytes are not spent by default
-        if mode == 1 and self._xf32 is None and self.fused_ok and os.environ.get("NNFAC_MU_F32") == "1":
-            self.enable_f32()
+        # The beta = 1 pass only needs x in registers (never as a tensor-core operand): from an fp32 copy of X it saves three
+        # instructions per element (no bf16 unpack + add).  With the issuing warps converged the pass is bound by the issue
+        # slots of its transform warps, and the copy pays: MU 905 -> 950 it/s at C2.  It costs 2 x 4mn bytes, so it is made on
+        # first use only when that leaves at least as much memory free again (NNFAC_MU_F32=0 / 1 force it off / on).
+        if mode == 1 and self._xf32 is None and self.fused_ok and self.sides == 3 and not self._xf32_refused:
+            want = os.environ.get("NNFAC_MU_F32", "auto")
+            need = 2 * 4 * self.m * self.n
+            if want == "1" or (want != "0" and torch.cuda.mem_get_info(self.device)[0] > 2 * need + (1 << 30)):
+                self.enable_f32()
+            else:
+                self._xf32_refused = True
         if out is None and not keep_partials:
             out = torch.empty((self.r, R), dtype=torch.float32, device=self.device)
         if cost_out is None and (want_cost or mode == 0):
