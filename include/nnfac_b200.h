@@ -216,6 +216,11 @@ int nnfac_nmf_plan_cross(nnfac_nmf_plan* plan, int which, const float* F, int64_
  * written straight into the operand planes that nnfac_nmf_plan_cross(which = 0, F = NULL) reads. */
 int nnfac_nmf_plan_set_krao(nnfac_nmf_plan* plan, const float* At, int64_t lda, int64_t I, const float* Bt, int64_t ldb,
                             int64_t J, void* stream);
+/* The same Khatri-Rao operand as the rank-contiguous planes of factor 1, for nnfac_nmf_plan_fused(plan, 0, 0, ...): with the
+ * mode's own factor installed as factor 0 that pass yields the MTTKRP (ntf.py:449) and the direct residual
+ * ||unfold(T, mode) - F krao^T||_F^2 of the CP model (instead of the cancelling ntf.py:470) in one pass over the tensor. */
+int nnfac_nmf_plan_set_krao_rows(nnfac_nmf_plan* plan, const float* At, int64_t lda, int64_t I, const float* Bt, int64_t ldb,
+                                 int64_t J, void* stream);
 /* out (r x R of `side`) = sum of the split-K partials of the last X pass over `side` run with out == NULL. */
 int nnfac_nmf_plan_reduce(nnfac_nmf_plan* plan, int side, float* out, int64_t ld_out, void* stream);
 /* The same sum in the send layout of a reduce-scatter over `slabs` ranks (column-sharded U side, nn_fac/_fast.py):

@@ -296,6 +296,31 @@ __global__ void __launch_bounds__(256) krao_planes_kernel(const float* __restric
   }
 }
 
+// The same Khatri-Rao product as RANK-CONTIGUOUS bf16 hi/lo planes [I*J x rk] (the "row planes" the fused pass reads its
+// factor slabs from): row c = a * J + b holds At[q][a] * Bt[q][b], q < r; ranks r .. rk stay zero.  One thread per row.
+__global__ void __launch_bounds__(256) krao_row_planes_kernel(const float* __restrict__ At, int64_t lda, int64_t I, const float* __restrict__ Bt,
+                                                              int64_t ldb, int64_t J, int r, int rk, bf16* __restrict__ hi, bf16* __restrict__ lo) {
+  const int64_t total = I * J;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t a = c / J, b = c - a * J;
+    for (int q0 = 0; q0 < r; q0 += 8) {
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = q0 + 2 * j;
+        const float v0 = q < r ? At[(int64_t)q * lda + a] * Bt[(int64_t)q * ldb + b] : 0.f;
+        const float v1 = q + 1 < r ? At[(int64_t)(q + 1) * lda + a] * Bt[(int64_t)(q + 1) * ldb + b] : 0.f;
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+        hw[j] = *reinterpret_cast<const uint32_t*>(&h);
+        const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - __uint_as_float(hw[j] << 16), v1 - __uint_as_float(hw[j] & 0xffff0000u));
+        lw[j] = *reinterpret_cast<const uint32_t*>(&l);
+      }
+      *reinterpret_cast<uint4*>(hi + c * rk + q0) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4*>(lo + c * rk + q0) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+  }
+}
+
 }  // namespace
 
 void nnfac_split_planes(const float* in, int64_t ld_in, int64_t rows, int64_t cols, __nv_bfloat16* hi, __nv_bfloat16* lo,
@@ -549,6 +574,21 @@ int nnfac_nmf_plan_set_krao(nnfac_nmf_plan* p, const float* At, int64_t lda, int
   const int64_t total = I * J;
   const int grid = (int)(ceil_div64(total, 256) < (int64_t)p->ctx->sm_count * 16 ? ceil_div64(total, 256) : (int64_t)p->ctx->sm_count * 16);
   krao_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(At, lda, I, Bt, ldb, J, p->r, s->fh, s->fl, s->ld);
+  NNFAC_LAUNCH_CHECK(p->ctx);
+  return NNFAC_OK;
+}
+
+// The same operand for the FUSED pass over side 0 (nnfac_nmf_plan_fused(plan, 0, 0, ...)): the Khatri-Rao product installed as
+// the rank-contiguous planes of factor 1 ("V^T", [n x rk]).  With the mode's own factor installed as factor 0
+// (nnfac_nmf_plan_set_factor(plan, 0, F^T)) that pass yields the MTTKRP of ntf.py:449 AND ||unfold(T, mode) - F krao^T||^2, the
+// direct residual of the CP model, in one pass over the tensor.
+int nnfac_nmf_plan_set_krao_rows(nnfac_nmf_plan* p, const float* At, int64_t lda, int64_t I, const float* Bt, int64_t ldb, int64_t J,
+                                 void* stream) {
+  NNFAC_ARG(p && At && Bt && I > 0 && J > 0 && I * J == p->n && lda >= I && ldb >= J, "nnfac_nmf_plan_set_krao_rows: bad argument");
+  NNFAC_ARG(p->fused_ok, "nnfac_nmf_plan_set_krao_rows: the plan has no row planes");
+  const int64_t total = I * J;
+  const int grid = (int)(ceil_div64(total, 256) < (int64_t)p->ctx->sm_count * 16 ? ceil_div64(total, 256) : (int64_t)p->ctx->sm_count * 16);
+  krao_row_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(At, lda, I, Bt, ldb, J, p->r, p->rk, p->rowp_h[1], p->rowp_l[1]);
   NNFAC_LAUNCH_CHECK(p->ctx);
   return NNFAC_OK;
 }

@@ -36,9 +36,12 @@ class GraphedIteration:
         self._set = set_state
         self.state = [t.clone() for t in get_state()]
         self.prev = [torch.empty_like(t) for t in self.state]
-        self.graph = torch.cuda.CUDAGraph()
+        self.prev2 = [t.clone() for t in self.state]           # the state two replays back (outer loops whose cost lags by one
+        self.graph = torch.cuda.CUDAGraph()                     # iteration drop TWO speculative iterations, see roll_back)
         torch.cuda.synchronize(device)
         with torch.cuda.graph(self.graph):
+            for d, s in zip(self.prev2, self.prev):
+                d.copy_(s)
             for d, s in zip(self.prev, self.state):
                 d.copy_(s)
             set_state(list(self.state))
@@ -52,8 +55,8 @@ class GraphedIteration:
         self.graph.replay()
         return self.out
 
-    def roll_back(self):
-        """Undo the last replay."""
-        for d, s in zip(self.state, self.prev):
+    def roll_back(self, steps=1):
+        """Undo the last replay (steps = 1) or the last two (steps = 2; only valid after at least two replays)."""
+        for d, s in zip(self.state, self.prev if steps == 1 else self.prev2):
             d.copy_(s)
         self._set(list(self.state))

@@ -68,6 +68,7 @@ SIGNATURES = {
     "nnfac_nmf_plan_reduce": [_P, _INT, _P, _I64, _P],
     "nnfac_nmf_plan_reduce_chunked": [_P, _INT, _P, _I64, _INT, _P, _I64, _INT, _P],
     "nnfac_nmf_plan_set_krao": [_P, _P, _I64, _I64, _P, _I64, _I64, _P],
+    "nnfac_nmf_plan_set_krao_rows": [_P, _P, _I64, _I64, _P, _I64, _I64, _P],
     "nnfac_nmf_plan_hals_solve": [_P, _INT, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _INT, _DBL, _DBL, _P, _P],
     "nnfac_nmf_plan_fused": [_P, _INT, _INT, _INT, _P, _I64, _P, _P],
     "nnfac_nmf_plan_mu_finish": [_P, _INT, _P, _I64, _P, _DBL, _P, _I64, _P],

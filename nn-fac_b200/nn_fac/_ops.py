@@ -380,6 +380,11 @@ class NMFPlan:
         L.check(_lib().nnfac_nmf_plan_set_krao(self.handle, L.ptr(At), At.stride(0), At.shape[1], L.ptr(Bt), Bt.stride(0),
                                                Bt.shape[1], L.stream_ptr()))
 
+    def set_krao_rows(self, At, Bt):
+        """The same Khatri-Rao factor as rank-contiguous planes, the operand of fused(0, 0) (MTTKRP + direct residual)."""
+        L.check(_lib().nnfac_nmf_plan_set_krao_rows(self.handle, L.ptr(At), At.stride(0), At.shape[1], L.ptr(Bt), Bt.stride(0),
+                                                    Bt.shape[1], L.stream_ptr()))
+
     def hals_solve(self, which, UtM, UtU, F, maxiter, delta, sparsity, result):
         """hals_nnls_acc(UtM, UtU, F) on the tensor-core sweep with the result installed in the plan by the same kernel.
         Returns the new factor (r x len), or None when the shape is outside that kernel (caller: hals_nnls + set_factor)."""

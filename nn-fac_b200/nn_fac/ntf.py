@@ -81,6 +81,33 @@ class DeviceNTF:
                 self.plans = None
                 torch.cuda.empty_cache()
 
+    def direct_cost(self, update_rule):
+        """fp32 HALS on a 3-way tensor with plans: the objective is the DIRECT residual ||T - [[A, B, C]]||^2 of the state an
+        iteration starts from, formed on chip by the fused pass that also yields the first MTTKRP of that iteration (the model
+        tile never reaches HBM) -- instead of the reference's ||T||^2 - 2 <F, rhs> + ||F krao^T||^2 (ntf.py:470), which
+        subtracts numbers of the size of ||T||^2 and in fp32 keeps an error of ~7e-7 ||T||^2 (the truncation of the tensor
+        core's fp32 accumulator biases rhs by -3.5e-7): 1.4e-4 of the objective at C4, more when the fit is better."""
+        return (update_rule == "hals" and self.plans is not None and self.T.dim() == 3 and self.T.dtype == torch.float32
+                and os.environ.get("NNFAC_NTF_DIRECT", "1") != "0")
+
+    def _residual_pass(self, mode):
+        """Fused pass over unfold(T, mode): returns ((unfold(T, mode) @ krao)^T, || T - F_mode krao^T ||^2) for the CURRENT factors."""
+        others = [i for i in range(3) if i != mode]
+        plan = self.plans[mode]
+        plan.set_factor(0, self.factors_t[mode])
+        plan.set_krao_rows(self.factors_t[others[0]], self.factors_t[others[1]])
+        return plan.fused(0, 0)
+
+    def cost_terms_now(self, sparsity, fixed_modes=()):
+        """Device vector [direct residual of the current state, l1 norms for the sparsity terms...] (closing pass of a run)."""
+        mode = [m for m in range(3) if m not in fixed_modes][0] if len(fixed_modes) < 3 else 0
+        _, res = self._residual_pass(mode)
+        terms = [res]
+        for idx, sp in enumerate(sparsity):
+            if sp:
+                terms.append(ops.norm1(self.factors[idx]))
+        return torch.cat([t.reshape(1).to(torch.float64) for t in terms])
+
     def _gram(self, i):
         """F_i^T F_i of the HALS path, kept until factor i changes (the reference recomputes the Gram of every other factor
         for every mode, ntf.py:442-445: each one twice per iteration).  Fixed buffers, so that a graph-replayed iteration
@@ -138,10 +165,18 @@ class DeviceNTF:
         return K
 
     def step_async(self, rank, norm_tensor, update_rule, beta, sparsity, fixed_modes, normalize):
-        """One pass over the modes; returns the device vector of cost terms (no synchronisation)."""
+        """One pass over the modes; returns the device vector of cost terms (no synchronisation).  With direct_cost() the
+        terms describe the state the iteration STARTED from (its first pass forms that residual); else the state it ends in."""
         modes = [m for m in range(len(self.shape)) if m not in fixed_modes]
         rhs = krao = cross = None
         mode = None
+        direct = self.direct_cost(update_rule) and len(modes) > 0
+        lag_terms = None
+        if direct:
+            lag_terms = []
+            for idx, sp in enumerate(sparsity):
+                if sp:
+                    lag_terms.append(ops.norm1(self.factors[idx]))          # of the incoming state, like the residual
         for mode in modes:
             others = [i for i in range(len(self.factors)) if i != mode]
             fused_krao = update_rule == "hals" and self.plans is not None and len(others) == 2
@@ -151,7 +186,12 @@ class DeviceNTF:
                 for i in others:
                     gram = self._gram(i)                                     # F_i^T F_i, ntf.py:445
                     cross = gram.clone() if cross is None else ops.hadamard_(cross, gram)
-                if fused_krao:
+                if direct and mode == modes[0]:
+                    # first mode: the fused pass yields the MTTKRP AND the residual of the incoming state
+                    rhs_t, res_in = self._residual_pass(mode)
+                    lag_terms.insert(0, res_in)
+                    rhs = None
+                elif fused_krao:
                     # MTTKRP (ntf.py:448-449) on tcgen05: the Khatri-Rao operand goes straight into its bf16 planes
                     self.plans[mode].set_krao(self.factors_t[others[0]], self.factors_t[others[1]])
                     rhs_t = self.plans[mode].cross(0, None)                  # (unfold(T, mode) @ krao)^T
@@ -175,6 +215,8 @@ class DeviceNTF:
                 self.factors[mode] = self._mu_factor(F, krao, K, mode, beta)   # ntf.py:459-460
                 self.factors_t[mode] = ops.transpose(self.factors[mode])
                 self._gram_ok[mode] = False
+        if direct:
+            return torch.cat([t.reshape(1).to(torch.float64) for t in lag_terms])
         # the cost terms stay on the device: [rec part a, rec part b, sparsity l1 norms...] (see finish_cost)
         terms = []
         F = self.factors[mode]
@@ -192,9 +234,12 @@ class DeviceNTF:
         return torch.cat([t.reshape(1).to(torch.float64) for t in terms])
 
     @staticmethod
-    def finish_cost(terms_host, norm_tensor, update_rule, sparsity):
+    def finish_cost(terms_host, norm_tensor, update_rule, sparsity, direct=False):
         """ntf.py:463-475 from the device terms of step_async (host float64 arithmetic, as in the reference)."""
-        if update_rule == "hals":
+        if direct:
+            rec_error = terms_host[0]
+            rest = terms_host[1:]
+        elif update_rule == "hals":
             rec_error = norm_tensor ** 2 - 2 * terms_host[0] + terms_host[1]
             rest = terms_host[2:]
         else:
@@ -207,7 +252,10 @@ class DeviceNTF:
 
     def step(self, rank, norm_tensor, update_rule, beta, sparsity, fixed_modes, normalize):
         terms = self.step_async(rank, norm_tensor, update_rule, beta, sparsity, fixed_modes, normalize)
-        return self.finish_cost(terms.cpu().numpy(), norm_tensor, update_rule, sparsity)
+        direct = self.direct_cost(update_rule) and len(fixed_modes) < len(self.shape)
+        if direct:                                      # the terms of the step describe the state it started from
+            terms = self.cost_terms_now(sparsity, fixed_modes)
+        return self.finish_cost(terms.cpu().numpy(), norm_tensor, update_rule, sparsity, direct)
 
     def _mu_factor(self, F, krao, K, mode, beta):
         """mu_betadivmin(F, krao.T, unfold(T, mode), beta) with the unfolding kept implicit."""
@@ -277,32 +325,87 @@ def compute_ntf(tensor_in, rank, factors_in, n_iter_max=100, tol=1e-8,
     # iteration eager.
     graphed = None
     use_graph = n_iter_max >= 4 and state.T.is_cuda and os.environ.get("NNFAC_NTF_GRAPH", "1") != "0"
+    lagged = state.direct_cost(update_rule) and len(fixed_modes) < nb_modes
+    step = lambda: state.step_async(rank, norm_tensor, update_rule, beta, sparsity_coefficients, fixed_modes, normalize)  # noqa: E731
+
+    def record(cost):
+        """Append one objective value; returns True when the reference's stop test (ntf.py:337) fires on it."""
+        toc.append(time.time() - tic)
+        cost_fct_vals.append(cost)
+        if verbose:
+            if len(cost_fct_vals) == 1:
+                print('Normalized cost function value={}'.format(cost))
+            else:
+                gain = cost_fct_vals[-2] - cost_fct_vals[-1]
+                line = 'Normalized cost function value={}, variation={}.'.format(cost_fct_vals[-1], gain)
+                print(line if gain > 0 else '\033[91m' + line + '\033[0m')
+        if len(cost_fct_vals) >= 2 and abs(cost_fct_vals[-2] - cost_fct_vals[-1]) < tol:
+            if verbose:
+                print('Converged in {} iterations.'.format(len(cost_fct_vals) - 1))
+            return True
+        return False
+
+    if lagged:
+        # Direct residual (DeviceNTF.direct_cost): round k launches iteration k (state k -> k + 1) -- or, at k = n_iter_max, the
+        # closing pass -- and its terms are the objective of state k.  They are read one round later, while the next iteration
+        # is already queued, so a stop decision on state s is taken when the device is two iterations ahead: both are dropped.
+        hosts = [torch.zeros(8, dtype=torch.float64).pin_memory() for _ in range(2)]
+        history = []                                   # eager launches: (factors, factors_t) each iteration started from
+        pending, stopped = None, False
+        for k in range(n_iter_max + 1):
+            if k < n_iter_max:
+                if use_graph and k == 1 and graphed is None:
+                    graphed = try_capture(state.T.device, state.get_state, state.set_state, step, state.invalidate)
+                if graphed is not None:
+                    terms = graphed.replay()
+                else:
+                    history = (history + [(list(state.factors), list(state.factors_t))])[-2:]
+                    terms = step()
+            else:
+                terms = state.cost_terms_now(sparsity_coefficients, fixed_modes)
+            buf = hosts[k & 1]
+            buf[:terms.numel()].copy_(terms, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            entries = [pending] if pending is not None else []
+            pending = (ev, buf, terms.numel(), k)
+            if k == n_iter_max:
+                entries.append(pending)
+            for ev_s, buf_s, n_s, s_idx in entries:
+                if s_idx == 0:
+                    continue                           # objective of the initial factors: the reference never reports it
+                ev_s.synchronize()
+                cost = state.finish_cost(buf_s[:n_s].numpy().copy(), norm_tensor, update_rule, sparsity_coefficients, True)
+                if record(cost) and s_idx < n_iter_max:
+                    back = min(k + 1, n_iter_max) - s_idx  # iterations launched beyond state s_idx: 2, or 1 in the closing round
+                    if graphed is not None:
+                        graphed.roll_back(back)
+                    else:
+                        state.factors, state.factors_t = history[-back]
+                    state.invalidate()
+                    stopped = True
+                    break
+            if stopped:
+                break
+        out = _pack(state.factors, tensor_in)
+        if return_costs:
+            return out, cost_fct_vals, toc
+        return out
+
     for iteration in range(n_iter_max + 1):
         if iteration < n_iter_max:
             if use_graph and iteration == 1 and graphed is None:
-                graphed = try_capture(state.T.device, state.get_state, state.set_state, lambda: state.step_async(
-                    rank, norm_tensor, update_rule, beta, sparsity_coefficients, fixed_modes, normalize), state.invalidate)
+                graphed = try_capture(state.T.device, state.get_state, state.set_state, step, state.invalidate)
             if graphed is not None:
                 terms = graphed.replay()
             else:
                 before = list(state.factors)
-                terms = state.step_async(rank, norm_tensor, update_rule, beta, sparsity_coefficients, fixed_modes, normalize)
+                terms = step()
         if pending is not None:
             ev, nterms, kept = pending
             ev.synchronize()
             cost = state.finish_cost(host[:nterms].numpy().copy(), norm_tensor, update_rule, sparsity_coefficients)
-            toc.append(time.time() - tic)
-            cost_fct_vals.append(cost)
-            if verbose:
-                if len(cost_fct_vals) == 1:
-                    print('Normalized cost function value={}'.format(cost))
-                else:
-                    gain = cost_fct_vals[-2] - cost_fct_vals[-1]
-                    line = 'Normalized cost function value={}, variation={}.'.format(cost_fct_vals[-1], gain)
-                    print(line if gain > 0 else '\033[91m' + line + '\033[0m')
-            if len(cost_fct_vals) >= 2 and abs(cost_fct_vals[-2] - cost_fct_vals[-1]) < tol:
-                if verbose:
-                    print('Converged in {} iterations.'.format(len(cost_fct_vals) - 1))
+            if record(cost):
                 if iteration < n_iter_max:             # drop the speculative iteration
                     if graphed is not None:
                         graphed.roll_back()
