@@ -201,7 +201,19 @@ class DeviceNTD:
             ops.normalize_rows_(moved.reshape(moved.shape[0], -1))
             core = moved.movedim(0, mode_core_norm).contiguous()
         self.core = core
-        terms = [ops.dot(all_MtX, core), ops.dot(ops.multi_mode_dot(core, all_MtM), core)]      # ntd.py:637
+        if self.plans is not None and nm >= 2 and os.environ.get("NNFAC_NTD_DIRECT", "1") != "0":
+            # fp32 with plans: the reconstruction error as the DIRECT residual ||unfold(T, 0) - F_0 unfold(G x_{j>0} F_j, 0)||^2,
+            # formed on chip by one fused pass over the (L2-resident) tensor, instead of ntd.py:637's
+            # ||T||^2 - 2 <all_MtX, G> + <G x_n MtM_n, G>, whose terms are of the size of ||T||^2: in fp32 that formula keeps
+            # ~1e-6 ||T||^2 of noise on a normalised cost of a few 1e-4.  NaN in the second slot marks the direct form.
+            B0 = ops.multi_mode_dot(core, self.factors, skip=0)
+            self.plans[0].set_factor(0, ops.transpose(self.factors[0]))
+            self.plans[0].set_factor(1, self._unfold(B0, 0))
+            _, res = self.plans[0].fused(0, 0)
+            self._m0_ready = False
+            terms = [res, torch.full((1,), float("nan"), dtype=torch.float64, device=core.device)]
+        else:
+            terms = [ops.dot(all_MtX, core), ops.dot(ops.multi_mode_dot(core, all_MtM), core)]      # ntd.py:637
         for idx, sp in enumerate(sparsity):                                  # ntd.py:627-635
             if sp:
                 if idx < nm:
@@ -248,7 +260,10 @@ class DeviceNTD:
 
     @staticmethod
     def finish_cost_hals(terms_host, norm_tensor, sparsity):
-        rec_error = norm_tensor ** 2 - 2 * terms_host[0] + terms_host[1]
+        if np.isnan(terms_host[1]):                     # direct residual (see step_hals_async)
+            rec_error = terms_host[0]
+        else:
+            rec_error = norm_tensor ** 2 - 2 * terms_host[0] + terms_host[1]
         sparsity_error = 0.0
         for sp, l1 in zip([sp for sp in sparsity if sp], terms_host[2:]):
             sparsity_error += 2 * (sp * float(l1))

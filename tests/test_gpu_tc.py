@@ -486,8 +486,7 @@ def test_ntd_mu_fp32_variants_vs_oracle(case):
 @pytest.mark.parametrize("nway", [3, 4])
 def test_ntd_hals_fp32_tensor_core_contraction_matches_generic_path(nway, monkeypatch):
     """ntd(update_rule="hals") in fp32: T x_j F_j^T (ntd.py:550) through the tcgen05 cross product over the planes of an
-    unfolding against the strided CUDA-core route (NNFAC_NTD_TC=0), and against the float64 oracle.  The normalised cost
-    (ntd.py:637-638) subtracts numbers of the size of ||T||^2, so fp32 paths agree to ~1e-6 absolute on it."""
+    unfolding against the strided CUDA-core route (NNFAC_NTD_TC=0), and against the float64 oracle."""
     import nn_fac.ntd as ntd
     from oracle import nnfac_oracle as orc
     rng = np.random.RandomState(41)
@@ -507,7 +506,12 @@ def test_ntd_hals_fp32_tensor_core_contraction_matches_generic_path(nway, monkey
                                  update_rule="hals", sparsity_coefficients=[None] * (nway + 1), fixed_modes=[],
                                  normalize=[False] * (nway + 1), return_costs=True, deterministic=True)
         out[flag] = costs
-        np.testing.assert_allclose(costs, ref, atol=3e-6, rtol=2e-2)
+        if flag == "1":
+            # with the plans the cost is the direct residual of a fused pass (DeviceNTD.step_hals_async): north-star tolerance
+            np.testing.assert_allclose(costs, ref, rtol=1e-4)
+        else:
+            # CUDA-core route: the reference's own formula (ntd.py:637) in fp32 -- ~1e-6 ||T||^2 of cancellation noise
+            np.testing.assert_allclose(costs, ref, atol=3e-6, rtol=2e-2)
     np.testing.assert_allclose(out["1"], out["0"], atol=3e-6, rtol=2e-2)
 
 
