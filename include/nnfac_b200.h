@@ -193,6 +193,15 @@ int nnfac_nmf_plan_create_in(nnfac_ctx* ctx, int64_t m, int64_t n, int r, void* 
 int nnfac_nmf_plan_bytes_sided(nnfac_ctx* ctx, int64_t m, int64_t n, int r, int sides, size_t* bytes);
 int nnfac_nmf_plan_create_sided(nnfac_ctx* ctx, int64_t m, int64_t n, int r, int sides, void* workspace, size_t workspace_bytes,
                                 void* stream, nnfac_nmf_plan** out);
+/* View plans: the unfolding of another mode of the C-order tensor whose mode-0 unfolding `base` holds (I_0 x rest, rest % 64 == 0),
+ * addressed in place through TMA maps over the SAME planes -- the reference copies the tensor once per mode (ntf.py:309-311).
+ * The tensor is read as (left, I, right); the view is the I x (left*right) unfolding of the middle axis: the last mode
+ * (right == 1, I % 8 == 0) as an MN-major tensor-core operand, middle modes (right % 64 == 0) through a 3-D map.  A view supports
+ * nnfac_nmf_plan_set_krao, nnfac_nmf_plan_cross(which = 0), _reduce and _info; NNFAC_ERR_UNSUPPORTED when the extents do not
+ * allow it (the caller then builds a one-sided plan on a copy of that unfolding).  `base` must outlive the view. */
+int nnfac_nmf_plan_view_bytes(nnfac_ctx* ctx, const nnfac_nmf_plan* base, int64_t left, int64_t I, int64_t right, int r, size_t* bytes);
+int nnfac_nmf_plan_create_view(nnfac_ctx* ctx, const nnfac_nmf_plan* base, int64_t left, int64_t I, int64_t right, int r,
+                               void* workspace, size_t workspace_bytes, void* stream, nnfac_nmf_plan** out);
 int nnfac_nmf_plan_destroy(nnfac_nmf_plan* plan);
 /* Ingest X (device fp32, row-major, leading dimension ldx >= n): one read of X, two plane writes. */
 int nnfac_nmf_plan_load_x(nnfac_nmf_plan* plan, const float* X, int64_t ldx, void* stream);

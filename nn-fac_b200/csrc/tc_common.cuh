@@ -91,6 +91,14 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorM
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
+// 3-D tile load: c0 = coordinate along the contiguous dimension, then the two outer ones.
+__device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;  // createpolicy encodings used by CUTLASS (CacheHintSm90)
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 

@@ -649,6 +649,7 @@ int nnfac_nmf_plan_enable_f32(nnfac_nmf_plan* p, void* workspace, size_t workspa
 // which = 0: U given as U^T (r x m); which = 1: V (r x n).  Builds every bf16 operand plane of that factor.
 int nnfac_nmf_plan_set_factor(nnfac_nmf_plan* p, int which, const float* Ft, int64_t ld, void* stream) {
   NNFAC_ARG(p && Ft && (which == 0 || which == 1), "nnfac_nmf_plan_set_factor: bad argument");
+  NNFAC_ARG(!p->base, "nnfac_nmf_plan_set_factor: not available on a view plan");
   const int64_t len = which == 0 ? p->m : p->n;
   NNFAC_ARG(ld >= len, "nnfac_nmf_plan_set_factor: leading dimension too small");
   return finish_factor(p, which, false, Ft, ld, 0, 0, nullptr, 0.f, nullptr, 0, (cudaStream_t)stream);
@@ -673,6 +674,7 @@ int nnfac_nmf_plan_hals_solve(nnfac_nmf_plan* p, int which, const float* UtM, in
                               const float* F_in, int64_t ld_in, float* F_out, int64_t ld_out, int maxiter, double delta,
                               double sparsity, double* result, void* stream) {
   NNFAC_ARG(p && UtU && F_in && F_out && result && (which == 0 || which == 1), "nnfac_nmf_plan_hals_solve: bad argument");
+  NNFAC_ARG(!p->base, "nnfac_nmf_plan_hals_solve: not available on a view plan");
   const int64_t len = which == 0 ? p->m : p->n;
   NNFAC_ARG((!UtM || ld_utm >= len) && ld_in >= len && ld_out >= len && ld_utu >= p->r, "nnfac_nmf_plan_hals_solve: leading dimension too small");
   // UtM == NULL: the right-hand side is what the last X pass over side `which` left in the plan as split-K partials
@@ -740,7 +742,7 @@ int nnfac_nmf_plan_fused(nnfac_nmf_plan* p, int side, int mode, int want_cost, f
                          void* stream) {
   NNFAC_ARG(p && (side == 0 || side == 1) && (mode == 0 || mode == 1), "nnfac_nmf_plan_fused: bad argument");
   NNFAC_ARG((p->sides >> side) & 1, "nnfac_nmf_plan_fused: this plan keeps no planes of side %d", side);
-  if (!p->fused_ok) { nnfac_set_error("nnfac_nmf_plan_fused: rank %d > 128 is not covered by the fused pass", p->r); return NNFAC_ERR_UNSUPPORTED; }
+  if (!p->fused_ok) { nnfac_set_error("nnfac_nmf_plan_fused: not covered by the fused pass (rank %d > 128, or a view plan)", p->r); return NNFAC_ERR_UNSUPPORTED; }
   if (mode == 1 && p->rk != 64) { nnfac_set_error("nnfac_nmf_plan_fused: the beta = 1 pass covers rank <= 64 (rank %d)", p->r); return NNFAC_ERR_UNSUPPORTED; }
   Side* s = &p->side[side];
   NNFAC_ARG(!out || ld_out >= s->R, "nnfac_nmf_plan_fused: leading dimension too small");

@@ -50,7 +50,11 @@ __global__ void split_planes_transposed_kernel(const float* __restrict__ in, int
   }
 }
 
-template <int MAX_RPAD>
+// AMODE: how the X operand is addressed (CrossParams::amode).  0: the planes hold the rows of X K-major (TMA 2-D, 128-row box);
+// 1: the planes hold X^T -- contraction index = plane row, the 128 output rows of a tile are contiguous in memory -- and the
+// tile is an MN-major UMMA operand (two 64-wide M blocks per plane, each a 64 x 64 TMA box): the LAST mode of a C-order tensor;
+// 2: as 0 through a 3-D map, k-block b = (slab b / kb_per_slab, offset 64 (b % kb_per_slab)): a MIDDLE mode.
+template <int MAX_RPAD, int AMODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_cross_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                 const __grid_constant__ CUtensorMap map_fh, const __grid_constant__ CUtensorMap map_fl,
@@ -96,8 +100,20 @@ tc_cross_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         uint8_t* st = ring + (size_t)stage * stage_bytes;
         tc::mbar_arrive_expect_tx(&full[stage], stage_bytes);
         const int c = k0 + ks * BK;
-        tc::tma_load_2d_hint(st, &map_xh, &full[stage], c, row0, tc::kEvictFirst);
-        tc::tma_load_2d_hint(st + x_bytes, &map_xl, &full[stage], c, row0, tc::kEvictFirst);
+        if (AMODE == 0) {
+          tc::tma_load_2d_hint(st, &map_xh, &full[stage], c, row0, tc::kEvictFirst);
+          tc::tma_load_2d_hint(st + x_bytes, &map_xl, &full[stage], c, row0, tc::kEvictFirst);
+        } else if (AMODE == 1) {
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb) {             // M block mb: output rows row0 + 64 mb .. + 63, contraction rows c .. c + 63
+            tc::tma_load_2d_hint(st + mb * 8192, &map_xh, &full[stage], row0 + 64 * mb, c, tc::kEvictFirst);
+            tc::tma_load_2d_hint(st + x_bytes + mb * 8192, &map_xl, &full[stage], row0 + 64 * mb, c, tc::kEvictFirst);
+          }
+        } else {
+          const int b = c / BK, slab = b / p.kb_per_slab, off = (b - slab * p.kb_per_slab) * BK;
+          tc::tma_load_3d_hint(st, &map_xh, &full[stage], off, row0, slab, tc::kEvictFirst);
+          tc::tma_load_3d_hint(st + x_bytes, &map_xl, &full[stage], off, row0, slab, tc::kEvictFirst);
+        }
         tc::tma_load_2d_hint(st + 2 * x_bytes, &map_fh, &full[stage], c, 0, tc::kEvictLast);
         tc::tma_load_2d_hint(st + 2 * x_bytes + f_bytes, &map_fl, &full[stage], c, 0, tc::kEvictLast);
         if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
@@ -108,7 +124,7 @@ tc_cross_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     // The tensor core adds into the fp32 accumulator with truncation, so a long chain drifts low
     // (measured: -1.9e-5 relative over 768 accumulations).  Chains are therefore cut every
     // `drain` stages; the epilogue warps sum the chain results in registers (round-to-nearest).
-    const uint32_t idesc = tc::umma_idesc_bf16(TILE_ROWS, p.r_pad);
+    const uint32_t idesc = tc::umma_idesc_bf16(TILE_ROWS, p.r_pad) | (AMODE == 1 ? (1u << 15) : 0u);   // bit 15: A operand MN-major
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
@@ -125,8 +141,9 @@ tc_cross_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint32_t koff = k * UMMA_K * sizeof(bf16);   // 32 B inside the 128 B swizzle row
-              const uint64_t xh = tc::umma_desc_k_sw128(st + koff);
-              const uint64_t xl = tc::umma_desc_k_sw128(st + x_bytes + koff);
+              // MN-major A: a K step is 16 rows of 128 B inside each 64-wide M block
+              const uint64_t xh = AMODE == 1 ? tc::umma_desc_mn_sw128(st + k * 2048) : tc::umma_desc_k_sw128(st + koff);
+              const uint64_t xl = AMODE == 1 ? tc::umma_desc_mn_sw128(st + x_bytes + k * 2048) : tc::umma_desc_k_sw128(st + x_bytes + koff);
               const uint64_t fh = tc::umma_desc_k_sw128(st + 2 * x_bytes + koff);
               const uint64_t fl = tc::umma_desc_k_sw128(st + 2 * x_bytes + f_bytes + koff);
               tc::umma_bf16(d, xh, fh, idesc, (ks != ks0) || (k != 0));
@@ -238,6 +255,8 @@ void choose_partition(int sm, int64_t R, int64_t C, int r_pad, Side* s) {
   s->cp.splits = (int)ceil_div64(kblocks, s->cp.stages_per_unit);
   s->cp.num_units = (int)(tiles * s->cp.splits);
   s->cp.tiles = (int)tiles;
+  s->cp.amode = 0;
+  s->cp.kb_per_slab = 1;
   // factor planes of this side: r_pad x ld, hi + lo.  When they do not fit L2 comfortably, order the units split-major
   s->cp.split_major = ((size_t)r_pad * (size_t)round_up(C, 64) * 4 > ((size_t)32 << 20) && tiles <= sm) ? 1 : 0;
   const size_t stage_bytes = 2 * (size_t)TILE_ROWS * BK * 2 + 2 * (size_t)r_pad * BK * 2;
@@ -350,6 +369,28 @@ void nnfac_reduce_partials_chunked(const float* partial, int splits, int r, int 
                                                        (int64_t)r * (chunk + tail_cols), slabs, tail, ld_tail, tail_cols);
 }
 
+// every variant of the cross-product kernel: padded rank <= 64 / <= 128 x addressing mode of the X operand
+template <int AMODE>
+static cudaError_t cross_set_smem(int r_pad, size_t smem) {
+  return r_pad <= 64 ? cudaFuncSetAttribute(tc_cross_kernel<64, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                     : cudaFuncSetAttribute(tc_cross_kernel<128, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+static cudaError_t cross_prepare(const Side* s, int r_pad) {
+  return s->cp.amode == 0 ? cross_set_smem<0>(r_pad, s->smem) : s->cp.amode == 1 ? cross_set_smem<1>(r_pad, s->smem) : cross_set_smem<2>(r_pad, s->smem);
+}
+template <int AMODE>
+static void cross_launch_mode(const Side* s, const CrossParams& cp, int r_pad, cudaStream_t st) {
+  if (r_pad <= 64)
+    tc_cross_kernel<64, AMODE><<<s->grid, NTHREADS, s->smem, st>>>(s->map_xh, s->map_xl, s->map_fh, s->map_fl, cp);
+  else
+    tc_cross_kernel<128, AMODE><<<s->grid, NTHREADS, s->smem, st>>>(s->map_xh, s->map_xl, s->map_fh, s->map_fl, cp);
+}
+static void cross_launch(const Side* s, const CrossParams& cp, int r_pad, cudaStream_t st) {
+  if (cp.amode == 0) cross_launch_mode<0>(s, cp, r_pad, st);
+  else if (cp.amode == 1) cross_launch_mode<1>(s, cp, r_pad, st);
+  else cross_launch_mode<2>(s, cp, r_pad, st);
+}
+
 extern "C" {
 
 int nnfac_nmf_plan_destroy(nnfac_nmf_plan* p) {
@@ -430,9 +471,7 @@ static int plan_build(nnfac_ctx* ctx, int64_t m, int64_t n, int r, int sides, vo
     if (!rc) rc = make_map(&s->map_fh, s->fh, p->r_pad, s->C, s->ld, p->r_pad);
     if (!rc) rc = make_map(&s->map_fl, s->fl, p->r_pad, s->C, s->ld, p->r_pad);
     if (rc) { nnfac_nmf_plan_destroy(p); return rc; }
-    cudaError_t e = p->r_pad <= 64
-        ? cudaFuncSetAttribute(tc_cross_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem)
-        : cudaFuncSetAttribute(tc_cross_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem);
+    cudaError_t e = cross_prepare(s, p->r_pad);
     if (e != cudaSuccess) { nnfac_set_error("cudaFuncSetAttribute(smem=%zu): %s", s->smem, cudaGetErrorString(e)); nnfac_nmf_plan_destroy(p); return NNFAC_ERR_CUDA; }
   }
   p->partial = (float*)(base + o_partial);
@@ -488,10 +527,87 @@ int nnfac_nmf_plan_create_sided(nnfac_ctx* ctx, int64_t m, int64_t n, int r, int
   return plan_build(ctx, m, n, r, sides, workspace, workspace_bytes, (cudaStream_t)stream, out, nullptr);
 }
 
+// View plan: the unfolding of another mode of the C-order tensor whose mode-0 unfolding `base` holds (base: I_0 x rest, planes
+// without row padding).  The tensor is (left, I, right) with left * I * right = I_0 * rest; the view is the I x (left * right)
+// unfolding of the middle axis (ntf.py:309-311 makes a COPY of the tensor for it; here it is a TMA map over the same planes):
+//   right == 1 (last mode):   the planes read as [left x I] hold the unfolding transposed -> MN-major operand (amode 1)
+//   otherwise (middle modes): 3-D map {right, I, left}, contraction index c = l * right + rr (amode 2; right % 64 == 0)
+// A view supports nnfac_nmf_plan_set_krao / _cross(which = 0) / _reduce / _info; its workspace holds only the factor planes
+// and the split-K partials.
+static int view_build(nnfac_ctx* ctx, const nnfac_nmf_plan* base, int64_t left, int64_t I, int64_t right, int r, void* buffer,
+                      size_t buffer_bytes, cudaStream_t st, nnfac_nmf_plan** out, size_t* bytes_out) {
+  NNFAC_ARG(ctx && base && left >= 1 && I >= 1 && right >= 1 && r > 0 && r <= 128, "nnfac_nmf_plan_view: bad argument");
+  NNFAC_ARG(!base->base && (base->sides & 1), "nnfac_nmf_plan_view: the base plan must own the planes of side 0");
+  NNFAC_ARG(left * I * right == base->m * base->n, "nnfac_nmf_plan_view: %lld x %lld x %lld is not the base tensor", (long long)left,
+            (long long)I, (long long)right);
+  if (left == 1 || base->side[0].ld != base->n || (right == 1 ? (I % 8 != 0) : (right % 64 != 0)) || left * right >= (1ll << 31) - 256) {
+    nnfac_set_error("nnfac_nmf_plan_view: this unfolding cannot be addressed in place (mode 0, padded planes, or misaligned extents)");
+    return NNFAC_ERR_UNSUPPORTED;
+  }
+  nnfac_nmf_plan* p = (nnfac_nmf_plan*)calloc(1, sizeof(nnfac_nmf_plan));
+  if (!p) return NNFAC_ERR_ALLOC;
+  p->ctx = ctx; p->base = base; p->m = I; p->n = left * right; p->r = r; p->sides = 1;
+  p->r_pad = (int)round_up(r, 16);
+  p->rk = p->r_pad <= 64 ? 64 : 128;
+  p->fused_ok = 0;
+  Side* s = &p->side[0];
+  s->R = I; s->C = left * right; s->ld = round_up(s->C, 64);
+  choose_partition(ctx->sm_count, s->R, s->C, p->r_pad, s);
+  s->cp.amode = right == 1 ? 1 : 2;
+  s->cp.kb_per_slab = right == 1 ? 1 : (int)(right / 64);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t fb = (size_t)p->r_pad * s->ld * sizeof(bf16);
+  const size_t o_fh = take(fb), o_fl = take(fb);
+  const size_t partial_bytes = (size_t)s->cp.splits * p->r_pad * s->cp.ld_partial * sizeof(float);
+  const size_t o_partial = take(partial_bytes);
+  if (bytes_out) *bytes_out = off;
+  if (!out) { free(p); return NNFAC_OK; }
+  if (!buffer || buffer_bytes < off || ((uintptr_t)buffer & 255)) {
+    nnfac_set_error("nnfac_nmf_plan_create_view: workspace of %zu bytes (256-byte aligned) needed, got %zu", off, buffer_bytes);
+    free(p);
+    return NNFAC_ERR_ARG;
+  }
+  p->buffer = buffer; p->buffer_bytes = off; p->owns_buffer = 0;
+  uint8_t* mem = (uint8_t*)buffer;
+  s->xh = base->side[0].xh; s->xl = base->side[0].xl;
+  s->fh = (bf16*)(mem + o_fh); s->fl = (bf16*)(mem + o_fl);
+  p->partial = (float*)(mem + o_partial); p->partial_bytes = partial_bytes;
+  cudaMemsetAsync(s->fh, 0, fb, st);
+  cudaMemsetAsync(s->fl, 0, fb, st);
+  int rc;
+  if (right == 1) {           // planes as [left x I]: box = 64 contraction rows x 64 output rows
+    rc = make_map(&s->map_xh, s->xh, left, I, I, 64);
+    if (!rc) rc = make_map(&s->map_xl, s->xl, left, I, I, 64);
+  } else {
+    rc = make_map_3d(&s->map_xh, s->xh, right, I, left, right, I * right, TILE_ROWS);
+    if (!rc) rc = make_map_3d(&s->map_xl, s->xl, right, I, left, right, I * right, TILE_ROWS);
+  }
+  if (!rc) rc = make_map(&s->map_fh, s->fh, p->r_pad, s->C, s->ld, p->r_pad);
+  if (!rc) rc = make_map(&s->map_fl, s->fl, p->r_pad, s->C, s->ld, p->r_pad);
+  if (!rc && cross_prepare(s, p->r_pad) != cudaSuccess) { nnfac_set_error("cudaFuncSetAttribute failed for a view plan"); rc = NNFAC_ERR_CUDA; }
+  if (!rc && cudaGetLastError() != cudaSuccess) { nnfac_set_error("nnfac_nmf_plan_create_view: clearing the workspace failed"); rc = NNFAC_ERR_CUDA; }
+  if (rc) { free(p); return rc; }
+  *out = p;
+  return NNFAC_OK;
+}
+
+int nnfac_nmf_plan_view_bytes(nnfac_ctx* ctx, const nnfac_nmf_plan* base, int64_t left, int64_t I, int64_t right, int r, size_t* bytes) {
+  NNFAC_ARG(bytes != nullptr, "nnfac_nmf_plan_view_bytes: bytes is NULL");
+  return view_build(ctx, base, left, I, right, r, nullptr, 0, (cudaStream_t)0, nullptr, bytes);
+}
+
+int nnfac_nmf_plan_create_view(nnfac_ctx* ctx, const nnfac_nmf_plan* base, int64_t left, int64_t I, int64_t right, int r,
+                               void* workspace, size_t workspace_bytes, void* stream, nnfac_nmf_plan** out) {
+  NNFAC_ARG(out != nullptr && workspace != nullptr, "nnfac_nmf_plan_create_view: NULL argument");
+  return view_build(ctx, base, left, I, right, r, workspace, workspace_bytes, (cudaStream_t)stream, out, nullptr);
+}
+
 // Rows [row0, row0 + rows) of X (device fp32, `Xrows` points at row row0): both plane orientations of that slab.
 // Lets the host pipeline the upload of X with its ingest (see NMFPlan.load_host in nn_fac/_ops.py).
 int nnfac_nmf_plan_load_x_rows(nnfac_nmf_plan* p, const float* Xrows, int64_t ldx, int64_t row0, int64_t rows, void* stream) {
   NNFAC_ARG(p && Xrows && ldx >= p->n && row0 >= 0 && rows > 0 && row0 + rows <= p->m, "nnfac_nmf_plan_load_x_rows: bad argument");
+  NNFAC_ARG(!p->base, "nnfac_nmf_plan_load_x_rows: a view plan has no planes of its own");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t total = rows * p->n;
   int grid = (int)(ceil_div64(total, 256) < (int64_t)p->ctx->sm_count * 32 ? ceil_div64(total, 256) : (int64_t)p->ctx->sm_count * 32);
@@ -551,10 +667,7 @@ int nnfac_nmf_plan_cross(nnfac_nmf_plan* p, int which, const float* F, int64_t l
   }
   CrossParams cp = s->cp;
   cp.partial = p->partial;
-  if (p->r_pad <= 64)
-    tc_cross_kernel<64><<<s->grid, NTHREADS, s->smem, st>>>(s->map_xh, s->map_xl, s->map_fh, s->map_fl, cp);
-  else
-    tc_cross_kernel<128><<<s->grid, NTHREADS, s->smem, st>>>(s->map_xh, s->map_xl, s->map_fh, s->map_fl, cp);
+  cross_launch(s, cp, p->r_pad, st);
   NNFAC_LAUNCH_CHECK(p->ctx);
   if (!out) return NNFAC_OK;     // the split-K partials stay in the plan (nnfac_nmf_plan_hals_solve / _reduce)
   const int64_t tot2 = (int64_t)p->r * s->R;
@@ -585,7 +698,7 @@ int nnfac_nmf_plan_set_krao(nnfac_nmf_plan* p, const float* At, int64_t lda, int
 int nnfac_nmf_plan_set_krao_rows(nnfac_nmf_plan* p, const float* At, int64_t lda, int64_t I, const float* Bt, int64_t ldb, int64_t J,
                                  void* stream) {
   NNFAC_ARG(p && At && Bt && I > 0 && J > 0 && I * J == p->n && lda >= I && ldb >= J, "nnfac_nmf_plan_set_krao_rows: bad argument");
-  NNFAC_ARG(p->fused_ok, "nnfac_nmf_plan_set_krao_rows: the plan has no row planes");
+  NNFAC_ARG(p->fused_ok && !p->base, "nnfac_nmf_plan_set_krao_rows: the plan has no row planes");
   const int64_t total = I * J;
   const int grid = (int)(ceil_div64(total, 256) < (int64_t)p->ctx->sm_count * 16 ? ceil_div64(total, 256) : (int64_t)p->ctx->sm_count * 16);
   krao_row_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(At, lda, I, Bt, ldb, J, p->r, p->rk, p->rowp_h[1], p->rowp_l[1]);

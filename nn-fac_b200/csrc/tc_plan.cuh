@@ -43,6 +43,22 @@ inline int make_map(CUtensorMap* map, const bf16* base, int64_t rows, int64_t co
   return NNFAC_OK;
 }
 
+// 3-D bf16 tensor [d2][d1][d0] (d0 contiguous; pitches p1, p2 in elements), box = 1 x box_rows x 64, 128B swizzle: the unfolding
+// of a MIDDLE mode of a C-order tensor without a copy (d0 = trailing modes, d1 = the mode, d2 = leading modes).
+inline int make_map_3d(CUtensorMap* map, const bf16* base, int64_t d0, int64_t d1, int64_t d2, int64_t p1, int64_t p2, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { nnfac_set_error("cuTensorMapEncodeTiled is not available from the driver"); return NNFAC_ERR_CUDA; }
+  cuuint64_t gdim[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t gstr[2] = {(cuuint64_t)p1 * sizeof(bf16), (cuuint64_t)p2 * sizeof(bf16)};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) { nnfac_set_error("cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)rc); return NNFAC_ERR_CUDA; }
+  return NNFAC_OK;
+}
+
 // 2-D fp32 row-major [rows x cols], box = 128 rows x 32 columns (128 bytes), 128B swizzle.
 inline int make_map_f32(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld) {
   EncodeTiledFn enc = get_encode();
@@ -66,6 +82,10 @@ struct CrossParams {
   int num_units;        // row_tiles * splits
   int num_stages;       // smem ring depth
   int drain;            // stages per TMEM accumulation chain (the tensor core accumulates with truncation)
+  int amode;            // how the X operand of this side is addressed (see tc_cross_kernel): 0 rows K-major (2-D map);
+                        // 1 MN-major: the planes hold X^T, rows = contraction index, output rows contiguous (last mode of a
+                        // tensor); 2 rows K-major through a 3-D map, contraction index = (slab, position in slab) (middle modes)
+  int kb_per_slab;      // amode 2: 64-wide k-blocks per slab
   int tiles;            // row tiles
   int split_major;      // unit u = split * tiles + tile instead of tile * splits + split: concurrent CTAs then share the factor
                         // columns of one split (the factor planes are re-read per tile; beyond the L2 size that order decides
@@ -102,6 +122,7 @@ struct nnfac_nmf_plan {
   double* cost_part;    // [1024] per-CTA cost partials of a fused pass ([512 + i]: second partial of CTA i)
   double* sums;         // cost_part + 1024: [0] sum of X (as stored in the planes)
   int fused_ok;
+  const nnfac_nmf_plan* base;   // view plans (nnfac_nmf_plan_create_view): the X planes belong to this plan
   int sides;            // bit i: the planes of side i exist (one-sided plans: the MTTKRP of a tensor unfolding only reads side 0)
   void* buffer;         // the one device allocation every pointer above points into
   size_t buffer_bytes;

@@ -56,6 +56,8 @@ SIGNATURES = {
     "nnfac_nmf_plan_create_in": [_P, _I64, _I64, _INT, _P, _c.c_size_t, _P, _c.POINTER(_P)],
     "nnfac_nmf_plan_bytes_sided": [_P, _I64, _I64, _INT, _INT, _c.POINTER(_c.c_size_t)],
     "nnfac_nmf_plan_create_sided": [_P, _I64, _I64, _INT, _INT, _P, _c.c_size_t, _P, _c.POINTER(_P)],
+    "nnfac_nmf_plan_view_bytes": [_P, _P, _I64, _I64, _I64, _INT, _c.POINTER(_c.c_size_t)],
+    "nnfac_nmf_plan_create_view": [_P, _P, _I64, _I64, _I64, _INT, _P, _c.c_size_t, _P, _c.POINTER(_P)],
     "nnfac_nmf_plan_destroy": [_P],
     "nnfac_nmf_plan_load_x": [_P, _P, _I64, _P],
     "nnfac_nmf_plan_load_x_rows": [_P, _P, _I64, _I64, _I64, _P],

@@ -309,6 +309,24 @@ class NMFPlan:
         self._X = None
         return self
 
+    def view(self, left, I, right, r):
+        """The I x (left * right) unfolding of the middle axis of the C-order tensor (left, I, right) whose mode-0 unfolding this
+        plan holds, addressed in place (nnfac_nmf_plan_create_view).  Returns None when the extents do not allow it."""
+        import ctypes
+        nbytes = ctypes.c_size_t()
+        rc = _lib().nnfac_nmf_plan_view_bytes(L.ctx(self.device), self.handle, left, I, right, r, ctypes.byref(nbytes))
+        if rc == L.ERR_UNSUPPORTED:
+            return None
+        L.check(rc)
+        v = NMFPlan.__new__(NMFPlan)
+        v.device, v.m, v.n, v.r, v.sides = self.device, I, left * right, r, 1
+        v._xf32, v._xf32_refused, v._X, v._base = None, True, None, self          # keeps the base plan (and its planes) alive
+        v._workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        v.handle = ctypes.c_void_p()
+        L.check(_lib().nnfac_nmf_plan_create_view(L.ctx(self.device), self.handle, left, I, right, r, L.ptr(v._workspace), nbytes.value,
+                                                  L.stream_ptr(), ctypes.byref(v.handle)))
+        return v
+
     def _load_host(self, host):
         """Double-buffered upload + ingest: copy stream fills slab b while the main stream splits slab 1-b into planes."""
         m, n = self.m, self.n

@@ -334,7 +334,7 @@ def compute_ntd(tensor_in, ranks, core_in, factors_in, n_iter_max=100, tol=1e-6,
             f"The update rule provided is not valid. Please choose between 'hals' and 'mu' (Got {update_rule}).")
     if beta < 0:
         raise err.InvalidArgumentValue("Invalid value for beta: negative one.") from None
-    dt = L.resolve_dtype(tensor_in, core_in, *factors_in)
+    dt, dt_out = L.working_dtype(int(np.prod(np.shape(tensor_in))), tensor_in, core_in, *factors_in)
     state = DeviceNTD(tensor_in, core_in, factors_in, dt)
     cost_fct_vals, toc = [], []
     tic = time.time()
@@ -397,10 +397,11 @@ def compute_ntd(tensor_in, ranks, core_in, factors_in, n_iter_max=100, tol=1e-6,
         host[:nterms].copy_(cost_dev, non_blocking=True)
         pending = torch.cuda.Event()
         pending.record()
-    if isinstance(tensor_in, torch.Tensor):
-        core, factors = state.core, state.factors
-    else:
-        core, factors = state.core.cpu().numpy(), [f.cpu().numpy() for f in state.factors]
+    core, factors = state.core, state.factors
+    if dt_out != dt:                                    # small float32 problems compute in float64 (nn_fac/config.py)
+        core, factors = core.to(dt_out), [f.to(dt_out) for f in factors]
+    if not isinstance(tensor_in, torch.Tensor):
+        core, factors = core.cpu().numpy(), [f.cpu().numpy() for f in factors]
     if return_costs:
         return core, factors, cost_fct_vals, toc
     return core, factors

@@ -64,30 +64,40 @@ class DeviceNTF:
         self.norm_sq = None
         self._grams, self._gram_ok = None, [False] * len(self.factors)      # see _gram
         self.stats = torch.zeros(4, dtype=torch.float64, device=self.T.device)
-        # fp32, rank <= 128: the MTTKRP of every mode runs on tcgen05.  One ONE-SIDED plan per mode holds unfold(T, mode)
-        # (I_mode x rest, C order) as K-major bf16 hi/lo planes -- 4 bytes per element and mode, the same bytes as the fp32
-        # unfolded copies the reference keeps (ntf.py:309-311) -- and the MTTKRP is the plan's cross product F X^T with
-        # F = krao^T.  Not enough memory for the planes: the strided CUDA-core MTTKRP on the tensor itself (self.plans None).
+        # fp32, rank <= 128: the MTTKRP of every mode runs on tcgen05 over ONE copy of the tensor as bf16 hi/lo planes (4 bytes
+        # per element, what the fp32 tensor itself takes): mode 0 reads them as the rows of unfold(T, 0); the last mode reads the
+        # same planes as an MN-major operand, middle modes through a 3-D TMA map (NMFPlan.view) -- the reference copies the
+        # tensor once per mode (ntf.py:309-311).  Extents that cannot be addressed in place (trailing extent not a multiple of
+        # 64 for a middle mode, ...) get a one-sided plan on a copy of that unfolding; not enough memory for the planes at all:
+        # the strided CUDA-core MTTKRP on the tensor itself (self.plans None).
         self.plans = None
         rank = int(self.factors[0].shape[1])
         if dtype == torch.float32 and rank <= 128 and self.T.dim() >= 2 and os.environ.get("NNFAC_NTF_TC", "1") != "0":
             try:
-                self.plans = []
-                for mode in range(self.T.dim()):
-                    Xm = self.T.movedim(mode, 0).reshape(self.shape[mode], -1).contiguous()
-                    self.plans.append(ops.NMFPlan(Xm).bind_rank(rank, sides=1))
-                    del Xm
+                nm = self.T.dim()
+                base = ops.NMFPlan(self.T.reshape(self.shape[0], -1)).bind_rank(rank, sides=1)
+                self.plans = [base]
+                for mode in range(1, nm):
+                    left, I, right = ops._split(list(self.shape), mode)
+                    view = base.view(left, I, right, rank) if os.environ.get("NNFAC_NTF_VIEWS", "1") != "0" else None
+                    if view is None:
+                        Xm = self.T.movedim(mode, 0).reshape(self.shape[mode], -1).contiguous()
+                        view = ops.NMFPlan(Xm).bind_rank(rank, sides=1)
+                        del Xm
+                    self.plans.append(view)
             except torch.cuda.OutOfMemoryError:
                 self.plans = None
                 torch.cuda.empty_cache()
 
-    def direct_cost(self, update_rule):
+    def direct_cost(self, update_rule, fixed_modes=()):
         """fp32 HALS on a 3-way tensor with plans: the objective is the DIRECT residual ||T - [[A, B, C]]||^2 of the state an
         iteration starts from, formed on chip by the fused pass that also yields the first MTTKRP of that iteration (the model
         tile never reaches HBM) -- instead of the reference's ||T||^2 - 2 <F, rhs> + ||F krao^T||^2 (ntf.py:470), which
         subtracts numbers of the size of ||T||^2 and in fp32 keeps an error of ~7e-7 ||T||^2 (the truncation of the tensor
         core's fp32 accumulator biases rhs by -3.5e-7): 1.4e-4 of the objective at C4, more when the fit is better."""
+        free = [m for m in range(len(self.shape)) if m not in fixed_modes]
         return (update_rule == "hals" and self.plans is not None and self.T.dim() == 3 and self.T.dtype == torch.float32
+                and len(free) > 0 and getattr(self.plans[free[0]], "_base", None) is None      # the fused pass needs a full plan
                 and os.environ.get("NNFAC_NTF_DIRECT", "1") != "0")
 
     def _residual_pass(self, mode):
@@ -170,7 +180,7 @@ class DeviceNTF:
         modes = [m for m in range(len(self.shape)) if m not in fixed_modes]
         rhs = krao = cross = None
         mode = None
-        direct = self.direct_cost(update_rule) and len(modes) > 0
+        direct = self.direct_cost(update_rule, fixed_modes)
         lag_terms = None
         if direct:
             lag_terms = []
@@ -252,7 +262,7 @@ class DeviceNTF:
 
     def step(self, rank, norm_tensor, update_rule, beta, sparsity, fixed_modes, normalize):
         terms = self.step_async(rank, norm_tensor, update_rule, beta, sparsity, fixed_modes, normalize)
-        direct = self.direct_cost(update_rule) and len(fixed_modes) < len(self.shape)
+        direct = self.direct_cost(update_rule, fixed_modes)
         if direct:                                      # the terms of the step describe the state it started from
             terms = self.cost_terms_now(sparsity, fixed_modes)
         return self.finish_cost(terms.cpu().numpy(), norm_tensor, update_rule, sparsity, direct)
@@ -282,7 +292,9 @@ class DeviceNTF:
         return ops.mu_apply(F, num, den_mat=contract(Q), gamma=g, floor=mu.epsilon)
 
 
-def _pack(factors, like):
+def _pack(factors, like, dtype=None):
+    if dtype is not None:
+        factors = [f.to(dtype) if f.dtype != dtype else f for f in factors]    # small float32 problems compute in float64 (config.py)
     if isinstance(like, torch.Tensor):
         return factors
     host = [f.cpu().numpy() for f in factors]
@@ -311,7 +323,7 @@ def compute_ntf(tensor_in, rank, factors_in, n_iter_max=100, tol=1e-8,
     _check_step_arguments(update_rule, beta)
     for fixed_value in fixed_modes:
         sparsity_coefficients[fixed_value] = None                           # ntf.py:428-429 (caller's list, as in the reference)
-    dt = L.resolve_dtype(tensor_in, *factors_in)
+    dt, dt_out = L.working_dtype(int(np.prod(np.shape(tensor_in))), tensor_in, *factors_in)
     state = DeviceNTF(tensor_in, factors_in, dt)
     norm_tensor = float(np.sqrt(ops.sq_diff(state.T).item()))              # ntf.py:290
     cost_fct_vals, toc = [], []
@@ -325,7 +337,7 @@ def compute_ntf(tensor_in, rank, factors_in, n_iter_max=100, tol=1e-8,
     # iteration eager.
     graphed = None
     use_graph = n_iter_max >= 4 and state.T.is_cuda and os.environ.get("NNFAC_NTF_GRAPH", "1") != "0"
-    lagged = state.direct_cost(update_rule) and len(fixed_modes) < nb_modes
+    lagged = state.direct_cost(update_rule, fixed_modes)
     step = lambda: state.step_async(rank, norm_tensor, update_rule, beta, sparsity_coefficients, fixed_modes, normalize)  # noqa: E731
 
     def record(cost):
@@ -387,7 +399,7 @@ def compute_ntf(tensor_in, rank, factors_in, n_iter_max=100, tol=1e-8,
                     break
             if stopped:
                 break
-        out = _pack(state.factors, tensor_in)
+        out = _pack(state.factors, tensor_in, dt_out)
         if return_costs:
             return out, cost_fct_vals, toc
         return out
@@ -420,7 +432,7 @@ def compute_ntf(tensor_in, rank, factors_in, n_iter_max=100, tol=1e-8,
         ev = torch.cuda.Event()
         ev.record()
         pending = (ev, terms.numel(), None)
-    out = _pack(state.factors, tensor_in)
+    out = _pack(state.factors, tensor_in, dt_out)
     if return_costs:
         return out, cost_fct_vals, toc
     return out

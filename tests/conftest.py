@@ -24,3 +24,14 @@ def load_golden(name):
 @pytest.fixture(scope="session")
 def golden():
     return load_golden
+
+
+@pytest.fixture
+def fp32_path():
+    """Small float32 problems compute in float64 in "auto" mode (nn_fac/config.py: they are launch-bound, the reference's own
+    arithmetic is free there).  Tests that target the float32 / tensor-core kernels at small sizes switch that off."""
+    import nn_fac.config as config
+    old = config.small_problem_elements
+    config.small_problem_elements = 0
+    yield
+    config.small_problem_elements = old

@@ -5,6 +5,12 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _tensor_core_path(fp32_path):
+    """Everything in this file is about the float32 kernels, whatever the size of the problem."""
+    yield
+
+
 @pytest.mark.parametrize("m,n,r", [(128, 64, 16), (256, 512, 64), (1000, 500, 10), (777, 1300, 33), (4096, 2048, 128),
                                    (130, 70, 9)])
 def test_plan_cross_matches_float64(m, n, r):
@@ -574,3 +580,31 @@ def test_philox_blocks_equal_numpy_restatement_and_tile():
     ops.philox_uniform(100, 200, row0=150, col0=300, seed=1234567890123, stream_id=3, scale=2.0, out=acc, accumulate=True)
     np.testing.assert_allclose(acc.cpu().numpy(), 1.0 + 2.0 * part, rtol=1e-7)
     assert 0.0 <= full.min() and full.max() < 1.0 and abs(full.mean() - 0.5) < 0.01
+
+
+@pytest.mark.parametrize("shape,r", [((64, 48, 128), 16), ((40, 24, 64), 40), ((6, 8, 16, 64), 9), ((130, 70, 192), 100), ((33, 8, 64), 5)])
+def test_mttkrp_of_every_mode_in_place_over_one_copy_of_the_tensor(shape, r):
+    """NMFPlan.view: the unfoldings of the modes >= 1 are TMA maps over the planes of unfold(T, 0) (MN-major operand for the last
+    mode, 3-D map for middle modes) -- no unfolded copy (ntf.py:309-311).  MTTKRP of every mode against float64 numpy."""
+    import torch
+    from nn_fac import _ops as ops
+    rng = np.random.RandomState(sum(shape) + r)
+    T = rng.rand(*shape).astype(np.float32)
+    Td = torch.from_numpy(T).cuda()
+    base = ops.NMFPlan(Td.reshape(shape[0], -1)).bind_rank(r, sides=1)
+    nm = len(shape)
+    for mode in range(nm):
+        left, I, right = ops._split(list(shape), mode)
+        plan = base if mode == 0 else base.view(left, I, right, r)
+        assert plan is not None, (shape, mode)
+        rest = int(np.prod(shape)) // shape[mode]
+        Kt = rng.rand(r, rest).astype(np.float32)                      # any (r x rest) operand; NTF passes the Khatri-Rao product
+        got = plan.cross(0, torch.from_numpy(Kt).cuda()).cpu().numpy()  # (unfold(T, mode) @ Kt^T)^T
+        unf = np.moveaxis(T.astype(np.float64), mode, 0).reshape(shape[mode], -1)
+        ref = Kt.astype(np.float64) @ unf.T
+        np.testing.assert_allclose(got, ref, rtol=2e-5)
+    # extents that cannot be addressed in place are refused, not mis-addressed
+    odd = ops.NMFPlan(torch.rand((10, 6 * 50), device="cuda")).bind_rank(4, sides=1)
+    assert odd.view(10, 6, 50, 4) is None                                 # padded planes (300 % 64 != 0)
+    with pytest.raises(Exception):
+        base.view(shape[0], int(np.prod(shape[1:])), 1, r).set_factor(0, torch.zeros((r, int(np.prod(shape[1:]))), device="cuda"))

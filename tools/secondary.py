@@ -78,11 +78,15 @@ def c4(iters=10, size=512, eager=False, peak_gbs=None):
         step()
         step = GraphedIteration(dev, st.get_state, st.set_state, step).replay
 
+    direct = st.direct_cost("hals")
+
     def run(k):
         terms = None
         for _ in range(k):                           # no host synchronisation between iterations (as compute_ntf does)
             terms = step()
-        return st.finish_cost(terms.cpu().numpy(), norm, "hals", [None] * 3)
+        if direct:                                   # the terms of an iteration describe the state it started from: closing pass
+            terms = st.cost_terms_now([None] * 3)
+        return st.finish_cost(terms.cpu().numpy(), norm, "hals", [None] * 3, direct)
     ms, cost = _timed(run, iters)
     bytes_iter = 3 * I ** 3 * 4
     line = {"config": f"C4: NTF HALS {I}^3 rank {r} (fp32)", "outer_iters_per_s": 1e3 / ms, "ms_per_iter": ms,
