@@ -56,22 +56,25 @@ def parse_args():
 
 def ncu_traffic(phase):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind `phase`, from the committed
-    `ncu --set full` capture (profiles/r1_ncu_full_summaries.json); None when there is no capture of it."""
-    report = {"hals.pass_U": "r1d_fused_res_s0", "mu.pass_U": "r1d_fused_mu_s0_cost", "mu.pass_V": "r1d_fused_mu_s1_nocost",
-              "hals.cross_V": "r1c_cross_s1"}.get(phase)
-    path = os.path.join(ROOT, "profiles", "r1_ncu_full_summaries.json")
-    if report is None or not os.path.exists(path):
+    `ncu --set full` capture of this build at this shape (profiles/r2_ncu_full_summaries.json: the first captured launch of
+    that kernel instantiation is the C2 one); None when there is no capture of it."""
+    kernels = {"hals.pass_U": ["tc_fused_kernel<0, 1, 0, 64>"], "hals.cross_V": ["tc_cross_kernel<64, 0>", "tc_cross_kernel<64>"],
+               "mu.pass_U": ["tc_fused_kernel<1, 1, 1, 64>", "tc_fused_kernel<1, 1, 0, 64>"],
+               "mu.pass_V": ["tc_fused_kernel<1, 0, 1, 64>", "tc_fused_kernel<1, 0, 0, 64>"]}.get(phase)
+    path = os.path.join(ROOT, "profiles", "r2_ncu_full_summaries.json")
+    if kernels is None or not os.path.exists(path):
         return None
     import re
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    for blk in re.findall(r"\{.*?\n\}", open(path).read(), re.S):
-        d = json.loads(blk)
-        if d.get("report", "").startswith(report):
-            tot = 0.0
-            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                val, u = d[key].split()
-                tot += float(val) * unit[u]
-            return tot
+    blocks = [json.loads(blk) for blk in re.findall(r"\{.*?\n\}", open(path).read(), re.S)]
+    for name in kernels:
+        for d in blocks:
+            if name in d.get("kernel", ""):
+                tot = 0.0
+                for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    val, u = d[key].split()
+                    tot += float(val) * unit[u]
+                return tot
     return None
 
 
@@ -449,7 +452,7 @@ def main():
         ach = algo / (phase_ms[dom] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": ncu_traffic(dom) if (m, n, r, world) == (65536, 8192, 64, 1) else None,
-                    "traffic_source": "ncu --set full capture of this kernel at this shape (profiles/r1_ncu_full_summaries.json)",
+                    "traffic_source": "ncu --set full capture of this kernel at this shape (profiles/r2_ncu_full_summaries.json)",
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
                     "ms_per_launch": phase_ms[dom]}
     algo_iter = 2 * m * n * 4 + 4 * (m + n) * r * 4     # bytes per outer iteration (whole job)

@@ -50,6 +50,11 @@ struct Cfg {
   static constexpr uint32_t G_ATOM_BYTES = RP * 128;               // [RP rows x 64 K] bf16
   static constexpr uint32_t G_PLANE_BYTES = KR * G_ATOM_BYTES;     // 8 / 32 KiB
   static constexpr size_t SMEM = NPLANES * G_PLANE_BYTES + (size_t)MAX_TILES * NPLANES * PLANE_BYTES + 512;
+  // blocks of the next sweep that run speculatively while the stop scalar travels: the masters they overwrite are parked in the
+  // idle third operand plane (blocks 0, 1) and in registers (blocks 2 ..).  RP = 64: 3 of 4 blocks (96 of 102 registers are
+  // taken); RP = 128: 6 of 8 (320 threads per CTA leave room for four more register sets) -- a collective solve waits for an
+  // NVLink round trip, which three blocks do not cover.
+  static constexpr int NSPEC = RP == 64 ? 3 : 6;
 };
 
 template <int RP>
@@ -426,7 +431,7 @@ __global__ void __launch_bounds__(Cfg<RP>::NTHREADS, 1) tc_sweep_kernel(const Tc
     // run the in-block recurrence, write the new masters and the operand planes of the 16 steps and hand
     // them to the issuing warp.  Returns the squared step of the block (nnls.py:170).  `keep` receives the
     // masters the block overwrote (needed to undo a speculative block).
-    uint32_t bk2[BLK];                                                  // masters a speculative block 2 overwrote
+    uint32_t bkreg[C::NSPEC - 2][BLK];                                  // masters the speculative blocks 2 .. NSPEC-1 overwrote
     auto block_update = [&](auto Bc, auto Backup) -> float {
       constexpr int B = decltype(Bc)::value;
       constexpr bool BACKUP = decltype(Backup)::value;
@@ -446,9 +451,9 @@ __global__ void __launch_bounds__(Cfg<RP>::NTHREADS, 1) tc_sweep_kernel(const Tc
         for (int c = 0; c < 4; ++c)
           *reinterpret_cast<uint4*>(bkrow + (((B * 4 + c) ^ (row & 7)) << 4)) = make_uint4(keep[4 * c], keep[4 * c + 1], keep[4 * c + 2], keep[4 * c + 3]);
       }
-      if (BACKUP && B == 2) {                                          // ... the third one's stay in registers
+      if (BACKUP && B >= 2 && B < C::NSPEC) {                          // ... the others' stay in registers
 #pragma unroll
-        for (int e = 0; e < BLK; ++e) bk2[e] = keep[e];
+        for (int e = 0; e < BLK; ++e) bkreg[B >= 2 && B < C::NSPEC ? B - 2 : 0][e] = keep[e];
       }
       float u[BLK];
 #pragma unroll
@@ -519,7 +524,7 @@ __global__ void __launch_bounds__(Cfg<RP>::NTHREADS, 1) tc_sweep_kernel(const Tc
     // in a fixed order, so that all CTAs obtain the same bits and take the same decision.  While the partials travel,
     // the first blocks of the coming sweep are run SPECULATIVELY (the masters they overwrite are kept aside), which
     // hides the L2 round trip; if the test ends the solve they are undone.
-    constexpr int NSPEC = 3;
+    constexpr int NSPEC = C::NSPEC;
     int nspec = 0;                                                        // speculative blocks of the current sweep already done
     float nd_spec = 0.f;
     std::integral_constant<bool, false> plain;
@@ -565,16 +570,14 @@ __global__ void __launch_bounds__(Cfg<RP>::NTHREADS, 1) tc_sweep_kernel(const Tc
       nd_spec = 0.f;
       if (cnt + 1 <= a.maxiter) {
         nspec = nblk < NSPEC ? nblk : NSPEC;
-        if (nspec == 1 && poller) early = ld_relaxed_u64(slot);
-        if (active) nd_spec = block_update(std::integral_constant<int, 0>{}, backup);
-        if (nspec > 1) {
-          if (nspec == 2 && poller) early = ld_relaxed_u64(slot);
-          if (active) nd_spec += block_update(std::integral_constant<int, 1>{}, backup);
-        }
-        if (nspec > 2) {
-          if (poller) early = ld_relaxed_u64(slot);
-          if (active) nd_spec += block_update(std::integral_constant<int, 2>{}, backup);
-        }
+        auto spec = [&](auto Bc) {
+          constexpr int B = decltype(Bc)::value;
+          if (B < nspec) {
+            if (B == nspec - 1 && poller) early = ld_relaxed_u64(slot);   // first look, under the last speculative block
+            if (active) nd_spec += block_update(Bc, backup);
+          }
+        };
+        BlockLoop<0, NSPEC>::run(spec);
       }
       // ---- collect the total ----
 #ifdef SWEEP_PROF
@@ -585,16 +588,27 @@ __global__ void __launch_bounds__(Cfg<RP>::NTHREADS, 1) tc_sweep_kernel(const Tc
         // every entry of the local board: thread t adds entries t, t + UPD_THREADS, ... (rank-major), then the usual trees
         float got = 0.f;
         const unsigned long long* board = a.xboard[a.xrank] + xbank;
-        for (int e = threadIdx.x; e < a.xworld * XMAXG; e += UPD_THREADS) {
+        // all loads of a thread are issued before the first one is looked at (independent L2 round trips), then only the
+        // entries that had not arrived yet are polled again
+        constexpr int MAXE = (XMAXW * XMAXG + UPD_THREADS - 1) / UPD_THREADS;
+        unsigned long long bits[MAXE];
+        bool want[MAXE];
+#pragma unroll
+        for (int j = 0; j < MAXE; ++j) {
+          const int e = threadIdx.x + j * UPD_THREADS;
           const int qr = e / XMAXG, c = e - qr * XMAXG;
-          if (c < a.xgrid[qr]) {
-            unsigned long long bits = ld_relaxed_sys_u64(board + e);
+          want[j] = e < a.xworld * XMAXG && c < a.xgrid[qr < XMAXW ? qr : 0];
+          bits[j] = want[j] ? ld_relaxed_sys_u64(board + e) : 0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < MAXE; ++j) {
+          if (want[j]) {
             uint32_t spins = 0;
-            while ((unsigned)(bits >> 32) != tag) {
-              bits = ld_relaxed_sys_u64(board + e);
+            while ((unsigned)(bits[j] >> 32) != tag) {
+              bits[j] = ld_relaxed_sys_u64(board + threadIdx.x + j * UPD_THREADS);
               if (++spins > (1u << 26)) __trap();
             }
-            got += __uint_as_float((unsigned)bits);
+            got += __uint_as_float((unsigned)bits[j]);
           }
         }
         got = warp_sum_f(got);
@@ -660,9 +674,9 @@ __global__ void __launch_bounds__(Cfg<RP>::NTHREADS, 1) tc_sweep_kernel(const Tc
           uint32_t w[16];
           tc::tmem_ld16(t_v + c0, w);
           tc::tmem_ld_wait();
-          if (c0 / BLK == 2 && nspec > 2) {                                   // undo the speculative blocks
+          if (c0 / BLK >= 2 && c0 / BLK < NSPEC && c0 / BLK < nspec) {        // undo the speculative blocks
 #pragma unroll
-            for (int e = 0; e < BLK; ++e) w[e] = bk2[e];
+            for (int e = 0; e < BLK; ++e) w[e] = bkreg[c0 / BLK >= 2 && c0 / BLK < NSPEC ? c0 / BLK - 2 : 0][e];
           } else if (c0 / BLK < 2 && c0 / BLK < nspec) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
