@@ -306,10 +306,16 @@ def run_c3(args, dev, world, rank, group, peak):
             X, U0, V0 = philox_problem(m, n, r, 0, n)
             one = _fast.FusedNMF(X, U0, V0)
             del X
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
             c1 = one.run(args.warmup + args.steps, 0.0, "hals")[0]
+            torch.cuda.synchronize()
+            single_s = time.perf_counter() - t0
             single_sweeps = [[float(v) for v in t.cpu().tolist()] for t in one.sweep_log[-len(sharded_sweeps):]]
             out["parity_vs_n1"] = {"iterations": args.warmup + args.steps, "cost_single": c1[-1], "cost_sharded": costs[-1],
                                    "cost_rel_diff": abs(c1[-1] - costs[-1]) / abs(c1[-1]),
+                                   "single_gpu_outer_iters_per_s": (args.warmup + args.steps) / single_s,
+                                   "speedup_over_single_gpu": its / ((args.warmup + args.steps) / single_s),
                                    "sweeps_equal": single_sweeps == sharded_sweeps,
                                    "sweep_count_max_abs_diff": max((abs(a - b) for x, y in zip(single_sweeps, sharded_sweeps)
                                                                     for a, b in zip(x, y)), default=None)}
@@ -339,6 +345,8 @@ def parity_vs_single_gpu(args, dev, world, rank, X_full, U0, V0_full, sharded_co
             out["hals_sweeps_single_last"] = single
             out["hals_sweeps_sharded_last"] = sharded_sweeps
             out["hals_sweeps_equal"] = single == sharded_sweeps
+            out["hals_sweep_count_max_abs_diff"] = max((abs(a - b) for x, y in zip(single, sharded_sweeps) for a, b in zip(x, y)),
+                                                       default=None)
         del st
         torch.cuda.empty_cache()
     return out

@@ -90,5 +90,5 @@ def test_two_gpus_reproduce_one_gpu(tmp_path, m, n, r):
             # the stop test of nnls.py:156 runs on the squared steps of ALL columns: same sweeps as on one GPU
             np.testing.assert_array_equal(ranks[0]["hals_sweeps"], ranks[0]["hals_sweeps_1"])
             np.testing.assert_array_equal(ranks[0]["hals_sweeps"], ranks[1]["hals_sweeps"])
-        np.testing.assert_allclose(ranks[0][rule + "_U"], ranks[0][rule + "_U_1"], rtol=2e-3, atol=1e-5)
-        np.testing.assert_allclose(V, ranks[0][rule + "_V_1"], rtol=2e-3, atol=1e-5)
+        for got, want in ((ranks[0][rule + "_U"], ranks[0][rule + "_U_1"]), (V, ranks[0][rule + "_V_1"])):
+            assert np.linalg.norm(got - want) <= 1e-3 * np.linalg.norm(want)          # fp32 sums grouped differently
