@@ -71,6 +71,28 @@ int nnfac_ctx_board_attach(nnfac_ctx* ctx, int world, int rank, const void* hand
 int nnfac_ctx_collective(nnfac_ctx* ctx, int on, const int64_t* slice_lengths);
 
 /* ---------------------------------------------------------------------------------------------
+ * Exchange steps of the column-sharded path over peer-mapped memory (new; csrc/peer_xchg.cu).  Every rank owns a region
+ * [flags | stage: r x pitch | send: r x pitch'] in device memory, exported with CUDA IPC and mapped by its peers like the boards
+ * above (create -> export -> exchange handles -> attach).  A rank writes its partial result into its own stage buffer (the X
+ * pass' reduction goes straight there), posts; every rank then pulls and sums ITS columns out of all stages over NVLink
+ * (reduce-scatter + reduction in one kernel, fixed order).  After the slice solves into the send buffers and a second post,
+ * nnfac_nmf_plan_set_factor_pulled reads all slices from the peers' send buffers while it builds the operand planes
+ * (all-gather + install in one kernel).  phase 0 = stage, 1 = send; every rank must make the same sequence of calls.
+ * -------------------------------------------------------------------------------------------*/
+typedef struct nnfac_xchg nnfac_xchg;
+int nnfac_xchg_create(nnfac_ctx* ctx, int64_t stage_floats, int64_t send_floats, nnfac_xchg** out);
+int nnfac_xchg_export(nnfac_xchg* x, void* handle_out);
+int nnfac_xchg_attach(nnfac_xchg* x, int world, int rank, const void* handles);
+int nnfac_xchg_destroy(nnfac_xchg* x);
+void* nnfac_xchg_ptr(nnfac_xchg* x, int which);                 /* local stage (0) / send (1) buffer */
+int nnfac_xchg_post(nnfac_xchg* x, int phase, void* stream);    /* this rank's buffer `phase` is complete (stream-ordered) */
+int nnfac_xchg_wait(nnfac_xchg* x, int phase, void* stream);    /* every rank has posted as often as this rank */
+/* out[k][0:ncols] = sum over ranks of columns [lo, lo+ncols) and out[k][tail_col : tail_col+tail] = sum over ranks of the
+ * `tail` columns behind column `len`, of every rank's buffer `which` ([r x pitch]). */
+int nnfac_xchg_pull_reduce(nnfac_xchg* x, int which, float* out, int64_t ld_out, int r, int64_t pitch, int64_t lo, int64_t ncols,
+                           int64_t len, int tail, int64_t tail_col, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * HALS NNLS solver: replaces nn_fac/update_rules/nnls.py:156-198 (hals_nnls_acc sweep loop with
  * the deterministic stop rule, i.e. alpha = inf).  V (r x n) is updated IN PLACE; the caller
  * makes the copy that nnls.py:147 makes.  Rows k >= r of UtU/V are never touched
@@ -244,6 +266,10 @@ int nnfac_nmf_plan_set_factor(nnfac_nmf_plan* plan, int which, const float* Ft, 
  * [s*chunk, (s+1)*chunk) of the factor); also writes the factor itself, rank-major, into Ft_out (r x len). */
 int nnfac_nmf_plan_set_factor_gathered(nnfac_nmf_plan* plan, int which, const float* G, int64_t chunk, float* Ft_out,
                                        int64_t ld_out, void* stream);
+/* The same straight from the peers' send buffers of an exchange region: slice s is read from rank s's send buffer
+ * ([r x pitch]) over NVLink.  Call after nnfac_xchg_wait(x, 1, stream). */
+int nnfac_nmf_plan_set_factor_pulled(nnfac_nmf_plan* plan, int which, const nnfac_xchg* x, int64_t chunk, int64_t pitch,
+                                     float* Ft_out, int64_t ld_out, void* stream);
 /* HALS solve of factor `which` (nn_fac/update_rules/nnls.py:24-198, deterministic rule, no normalize / nonzero) whose
  * result F_out (r x len, may not alias F_in) is installed in the plan by the sweep kernel itself (no separate pass over
  * the factor).  result: double[4] = {eps, cnt, -1, sweeps}.  Returns NNFAC_ERR_UNSUPPORTED without an error text when

@@ -46,6 +46,8 @@ struct nnfac_ctx {
   unsigned collective_gen;    // collective call counter (advances identically on every rank)
 };
 
+struct nnfac_xchg;      // peer-mapped exchange region (csrc/peer_xchg.cu)
+
 void nnfac_set_error(const char* fmt, ...);
 
 // operand planes the tensor-core HALS sweep can write for the NMF plan (all bf16; see csrc/tc_sweep.cu)

@@ -15,6 +15,8 @@
 // registers because the tensor core accumulates with truncation.
 #include "tc_plan.cuh"
 
+#include <string.h>
+
 namespace {
 using namespace tcplan;
 
@@ -494,10 +496,14 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
 //   else : F = F_in                                                                                 (after a HALS solve)
 // and writes F (fp32, rank-major), its K-major bf16 hi/lo planes [r_pad x ld_plane] (operand of the cross product)
 // and its rank-contiguous planes [R x 64] (operands of the fused pass).  Block = 32 columns x all ranks.
-template <bool APPLY, int RK>
+struct PeerG {                      // PULL: slice s of the factor lives in p[s] ([r x ld_in], the peers' send buffers mapped here)
+  const float* p[NNFAC_MAX_PEERS];
+};
+
+template <bool APPLY, int RK, bool PULL>
 __global__ void __launch_bounds__(256) factor_finish_kernel(const float* __restrict__ partial, int splits, int r, int r_pad, int64_t R,
                                                             int64_t ldp, const float* __restrict__ F_in, int64_t ld_in,
-                                                            int64_t in_chunk, int64_t in_slab,
+                                                            int64_t in_chunk, int64_t in_slab, const PeerG G,
                                                             const float* __restrict__ den, float floor_value, float* __restrict__ F_out,
                                                             int64_t ld_out, bf16* __restrict__ fh, bf16* __restrict__ fl, int64_t ld_plane,
                                                             bf16* __restrict__ rowh, bf16* __restrict__ rowl) {
@@ -509,7 +515,7 @@ __global__ void __launch_bounds__(256) factor_finish_kernel(const float* __restr
   for (int k = ty; k < RK; k += 8) {
     float f = 0.f;
     if (k < r && c < R) {
-      f = F_in[(int64_t)k * ld_in + cin];
+      f = PULL ? __ldcv(G.p[c / in_chunk] + (int64_t)k * ld_in + (c % in_chunk)) : F_in[(int64_t)k * ld_in + cin];
       if (APPLY) {
         float num = 0.f;                            // fixed order; loads issued eight at a time (few blocks, many splits
         int sp = 0;                                 // when the other dimension is short: NTD has 64 splits for 256 rows)
@@ -588,21 +594,27 @@ __global__ void __launch_bounds__(256) planes_to_f32_kernel(const bf16* __restri
 }  // namespace
 
 static int finish_factor(nnfac_nmf_plan* p, int which, bool apply, const float* F_in, int64_t ld_in, int64_t in_chunk, int64_t in_slab,
-                         const float* den, float floor_value, float* F_out, int64_t ld_out, cudaStream_t st) {
+                         const float* den, float floor_value, float* F_out, int64_t ld_out, cudaStream_t st, const PeerG* pulled = nullptr) {
   const int64_t len = which == 0 ? p->m : p->n;
   Side* cs = &p->side[which == 0 ? 1 : 0];        // U^T planes are the Fn operand of side 1, V planes of side 0
   Side* ps = &p->side[which];                     // the pass whose partials feed this factor
   const unsigned grid = (unsigned)ceil_div64(len, 32);
   bf16* rh = p->fused_ok ? p->rowp_h[which] : nullptr;
   bf16* rl = p->fused_ok ? p->rowp_l[which] : nullptr;
+  PeerG none;
+  memset(&none, 0, sizeof(none));
 #define NNFAC_FINISH(RKV)                                                                                                          \
   do {                                                                                                                             \
-    if (apply)                                                                                                                     \
-      factor_finish_kernel<true, RKV><<<grid, 256, 0, st>>>(p->partial, ps->cp.splits, p->r, p->r_pad, len, ps->cp.ld_partial,    \
-          F_in, ld_in, in_chunk, in_slab, den, floor_value, F_out, ld_out, cs->fh, cs->fl, cs->ld, rh, rl);                        \
+    if (pulled)                                                                                                                    \
+      factor_finish_kernel<false, RKV, true><<<grid, 256, 0, st>>>(nullptr, 0, p->r, p->r_pad, len, 0, nullptr, ld_in, in_chunk,  \
+          in_slab, *pulled, nullptr, 0.f, F_out, ld_out, cs->fh, cs->fl, cs->ld, rh, rl);                                          \
+    else if (apply)                                                                                                                \
+      factor_finish_kernel<true, RKV, false><<<grid, 256, 0, st>>>(p->partial, ps->cp.splits, p->r, p->r_pad, len,                \
+          ps->cp.ld_partial, F_in, ld_in, in_chunk, in_slab, none, den, floor_value, F_out, ld_out, cs->fh, cs->fl, cs->ld, rh,    \
+          rl);                                                                                                                     \
     else                                                                                                                           \
-      factor_finish_kernel<false, RKV><<<grid, 256, 0, st>>>(nullptr, 0, p->r, p->r_pad, len, 0, F_in, ld_in, in_chunk, in_slab,  \
-          nullptr, 0.f, F_out, ld_out, cs->fh, cs->fl, cs->ld, rh, rl);                                                            \
+      factor_finish_kernel<false, RKV, false><<<grid, 256, 0, st>>>(nullptr, 0, p->r, p->r_pad, len, 0, F_in, ld_in, in_chunk,    \
+          in_slab, none, nullptr, 0.f, F_out, ld_out, cs->fh, cs->fl, cs->ld, rh, rl);                                             \
   } while (0)
   if (p->rk == 64) NNFAC_FINISH(64); else NNFAC_FINISH(128);
 #undef NNFAC_FINISH
@@ -664,6 +676,24 @@ int nnfac_nmf_plan_set_factor_gathered(nnfac_nmf_plan* p, int which, const float
   const int64_t len = which == 0 ? p->m : p->n;
   NNFAC_ARG(ld_out >= len, "nnfac_nmf_plan_set_factor_gathered: leading dimension too small");
   return finish_factor(p, which, false, G, chunk, chunk, (int64_t)p->r * chunk, nullptr, 0.f, Ft_out, ld_out, (cudaStream_t)stream);
+}
+
+// The same straight from the peers' send buffers of an exchange region (csrc/peer_xchg.cu): slice s = columns
+// [s * chunk, (s + 1) * chunk) of the factor is read from rank s's send buffer ([r x pitch], mapped here) over NVLink -- the
+// all-gather, the un-permute and the construction of the operand planes in one kernel.  Call after nnfac_xchg_wait(x, 1).
+const float* nnfac_xchg_peer_send(const nnfac_xchg* x, int q);
+int nnfac_xchg_world(const nnfac_xchg* x);
+int nnfac_nmf_plan_set_factor_pulled(nnfac_nmf_plan* p, int which, const nnfac_xchg* x, int64_t chunk, int64_t pitch, float* Ft_out,
+                                     int64_t ld_out, void* stream) {
+  NNFAC_ARG(p && x && Ft_out && chunk > 0 && pitch >= chunk && (which == 0 || which == 1), "nnfac_nmf_plan_set_factor_pulled: bad argument");
+  NNFAC_ARG(!p->base, "nnfac_nmf_plan_set_factor_pulled: not available on a view plan");
+  const int64_t len = which == 0 ? p->m : p->n;
+  const int world = nnfac_xchg_world(x);
+  NNFAC_ARG(ld_out >= len && (int64_t)world * chunk >= len, "nnfac_nmf_plan_set_factor_pulled: %d slices of %lld columns do not cover %lld",
+            world, (long long)chunk, (long long)len);
+  PeerG g;
+  for (int q = 0; q < NNFAC_MAX_PEERS; ++q) g.p[q] = nnfac_xchg_peer_send(x, q);
+  return finish_factor(p, which, false, nullptr, pitch, chunk, 0, nullptr, 0.f, Ft_out, ld_out, (cudaStream_t)stream, &g);
 }
 
 // HALS solve of factor `which` (nnls.py:24-198, deterministic rule) that also installs the result in the plan:

@@ -181,6 +181,75 @@ class Comm:
         return Ft
 
 
+class _RawView:
+    """A device pointer owned by libnnfac_b200 as something torch.as_tensor can alias (CUDA array interface v2)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2,
+                                         "strides": None}
+
+
+class PeerExchange:
+    """The U-side exchange of the sharded path over peer-mapped memory instead of NCCL (csrc/peer_xchg.cu): every rank's stage
+    buffer [r x (m + t)] receives its partial cross product / numerator (+ t tail columns: partial Gram or row sums), a pull
+    kernel sums this rank's columns out of all stages over NVLink, the slice results go to the send buffers [r x (chunk + t)],
+    and the install kernel reads all slices from the peers' send buffers.  One region per FusedNMF state."""
+
+    def __init__(self, comm, device, r, m, chunk, tail):
+        lib = L.load_library()
+        self.comm, self.device, self.r, self.m, self.chunk, self.tail = comm, device, r, m, chunk, tail
+        self.handle = ctypes.c_void_p()
+        L.check(lib.nnfac_xchg_create(L.ctx(device), r * (m + tail), r * (chunk + tail), ctypes.byref(self.handle)))
+        mine = (ctypes.c_ubyte * 64)()
+        L.check(lib.nnfac_xchg_export(self.handle, mine))
+        send = torch.tensor(list(mine), dtype=torch.uint8, device=device)
+        recv = torch.empty(comm.world * 64, dtype=torch.uint8, device=device)
+        comm.dist.all_gather_into_tensor(recv, send, group=comm.group)
+        handles = (ctypes.c_ubyte * (64 * comm.world))(*recv.cpu().tolist())
+        L.check(lib.nnfac_xchg_attach(self.handle, comm.world, comm.rank, handles))
+        self.stage = torch.as_tensor(_RawView(lib.nnfac_xchg_ptr(self.handle, 0), (r, m + tail)), device=device)
+        self.send = torch.as_tensor(_RawView(lib.nnfac_xchg_ptr(self.handle, 1), (r, chunk + tail)), device=device)
+        comm.dist.barrier(group=comm.group)              # every region is mapped everywhere before anybody posts
+
+    def post(self, phase):
+        L.check(L.load_library().nnfac_xchg_post(self.handle, phase, L.stream_ptr()))
+
+    def wait(self, phase):
+        L.check(L.load_library().nnfac_xchg_wait(self.handle, phase, L.stream_ptr()))
+
+    def pull_reduce(self, phase, lo, ncols, length):
+        """Sum over the ranks of columns [lo, lo + ncols) and of the tail of every rank's buffer `phase` -> (r x (chunk + tail))
+        with the tail at column chunk (after post + wait)."""
+        out = torch.empty((self.r, self.chunk + self.tail), dtype=torch.float32, device=self.device)
+        pitch = length + self.tail
+        L.check(L.load_library().nnfac_xchg_pull_reduce(self.handle, phase, L.ptr(out), out.stride(0), self.r, pitch, lo, ncols, length,
+                                                        self.tail, self.chunk, L.stream_ptr()))
+        return out
+
+    def pull_tail(self, phase, length):
+        """Only the sum of the tails of every rank's buffer `phase` -> (r x tail)."""
+        out = torch.empty((self.r, self.tail), dtype=torch.float32, device=self.device)
+        L.check(L.load_library().nnfac_xchg_pull_reduce(self.handle, phase, L.ptr(out), out.stride(0), self.r, length + self.tail, 0, 0,
+                                                        length, self.tail, 0, L.stream_ptr()))
+        return out
+
+    def install(self, plan, which, length):
+        """All slices straight from the peers' send buffers -> the factor (r x length) and its operand planes in `plan`."""
+        out = torch.empty((self.r, length), dtype=torch.float32, device=self.device)
+        L.check(L.load_library().nnfac_nmf_plan_set_factor_pulled(plan.handle, which, self.handle, self.chunk, self.chunk + self.tail,
+                                                                  L.ptr(out), out.stride(0), L.stream_ptr()))
+        return out
+
+    def __del__(self):
+        try:
+            if self.handle:
+                torch.cuda.synchronize(self.device)
+                L.load_library().nnfac_xchg_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
 class CudaEngine:
     """The device operators one outer iteration is made of, all in libnnfac_b200 (no torch arithmetic)."""
 
@@ -303,12 +372,24 @@ class FusedNMF:
         self._xbuf = torch.empty(self.r * self.m + self.r * self.r, dtype=self.Ut.dtype, device=self.device)
         self._usend = None
         self._vlens = self.comm.all_lengths(self.n, self.device)
+        self._px = {}
         if self.comm.world > 1 and self._on_gpu and engine is None:
             self.comm.attach_boards(self.device)
 
     def _phase(self, name):
         from nn_fac.nmf import _Phase
         return _Phase(self, name)
+
+    def _exchange(self, tail):
+        """The peer-memory exchange region of this state (tail = r: HALS, partial Gram; tail = 1: MU, partial row sums), or None:
+        one rank, CPU stand-in engine, no peer access, or NNFAC_PEER_EXCHANGE=0 (then the NCCL collectives are used)."""
+        if (self.comm.world == 1 or not self._on_gpu or not hasattr(self.eng, "plan") or self.comm._boards_device is None
+                or os.environ.get("NNFAC_PEER_EXCHANGE", "1") == "0"):
+            return None
+        if tail not in self._px:
+            chunk = self.comm.slice_of(self.m)[0]
+            self._px[tail] = PeerExchange(self.comm, self.device, self.r, self.m, chunk, tail)
+        return self._px[tail]
 
     def _gram_async(self, which, F):
         """F F^T into self._gram[which] on the side stream (it only reads F, which is final by now); returns a
@@ -361,7 +442,20 @@ class FusedNMF:
                     # the U solve is split by rows of U: this rank only needs its own columns of the summed V X^T (and the
                     # summed Gram) -> reduce-scatter
                     chunk, lo, hi = comm.slice_of(m)
-                    if VMt is None:
+                    px = self._exchange(r) if VMt is None else None
+                    if px is not None:
+                        # peer-memory exchange: the split-K partials are summed straight into this rank's stage buffer, the
+                        # partial Gram lands behind them; after the post every rank pulls and sums ITS columns of all stages
+                        eng.plan.reduce(0, out=px.stage[:, :m])
+                        if VVt_join is not None:
+                            px.stage[:, m:].copy_(VVt_join())
+                        else:
+                            eng.gram(V, out=px.stage[:, m:])
+                        px.post(0)
+                        px.wait(0)
+                        recv = px.pull_reduce(0, lo, hi - lo, m)
+                        VMt_slice, VVt = recv[:, :chunk], recv[:, chunk:]
+                    elif VMt is None:
                         # the pass left its split-K partials in the plan: ONE kernel sums them straight into the send layout of the
                         # reduce-scatter and appends the partial Gram (computed under the pass, on the side stream)
                         gram = VVt_join() if VVt_join is not None else eng.gram(V)
@@ -377,6 +471,20 @@ class FusedNMF:
                     Ut = Ut.clone()
                     eng.sweep(VMt, VVt, Ut, r, sparsity[0], normalize[0], self.hals_stats[0])
                     eng.set_factor(0, Ut)
+                elif hasattr(eng, "solve_slice") and self._exchange(r) is not None and VMt is None:
+                    # slice solve straight into this rank's send buffer (the partial Gram of the new slice behind it); after the
+                    # post the install kernel reads every slice from its owner's send buffer while it builds the operand planes
+                    px = self._exchange(r)
+                    eng.solve_slice(VMt_slice[:, :hi - lo], VVt, Ut[:, lo:hi], px.send[:, :hi - lo], r, sparsity[0],
+                                    self.hals_stats[0], comm, comm.slice_lengths(m))
+                    if hi > lo:
+                        eng.gram(px.send[:, :hi - lo], out=px.send[:, chunk:])
+                    else:
+                        px.send[:, chunk:].zero_()
+                    px.post(1)
+                    px.wait(1)
+                    Ut = px.install(eng.plan, 0, m)
+                    self._utu_pulled = px.pull_tail(1, chunk)                        # U^T U = sum of the slices' Grams
                 elif hasattr(eng, "solve_slice"):
                     # every rank solves its slice of the rows of U straight into the send buffer of the all-gather; the
                     # gathered slices become the new U^T and its operand planes in one kernel
@@ -394,10 +502,12 @@ class FusedNMF:
                     eng.set_factor(0, Ut)
         if 1 not in fixed_modes:
             with self._phase("cross_V"):
-                join = self._gram_async(1, Ut) if self._side is not None else None    # nmf.py:432, under the X pass
+                pulled = getattr(self, "_utu_pulled", None)                           # sharded: sum of the slices' Grams
+                self._utu_pulled = None
+                join = self._gram_async(1, Ut) if (self._side is not None and pulled is None) else None    # nmf.py:432, under the X pass
                 keepV = _SPLIT_RHS == "1" and hasattr(eng, "plan") and not normalize[1]   # the V solve adds the split-K partials itself
                 UtM = eng.cross(1, None, keep_partials=True) if keepV else eng.cross(1, None)   # nmf.py:433
-                UtU = join() if join is not None else eng.gram(Ut)
+                UtU = pulled if pulled is not None else (join() if join is not None else eng.gram(Ut))
             with self._phase("sweep_V"):
                 if hasattr(eng, "solve_install"):
                     with comm.collective(self._vlens):       # the columns of V are spread over the ranks: joint stop rule
@@ -437,7 +547,23 @@ class FusedNMF:
         if 0 not in fixed_modes:
             with self._phase("apply_U"):
                 den = den_join() if den_join is not None else eng.row_sums(V)      # mu.py:85-87
-                if comm.world > 1:
+                px = self._exchange(1) if (comm.world > 1 and numU is None) else None
+                if px is not None:
+                    # peer-memory exchange: partial numerator -> stage, partial row sums of V behind it; every rank pulls and
+                    # sums its own rows of U, applies mu.py:84-88 to them, and the install kernel collects the slices
+                    chunk, lo, hi = comm.slice_of(m)
+                    eng.plan.reduce(0, out=px.stage[:, :m])
+                    px.stage[:, m].copy_(den)
+                    px.post(0)
+                    px.wait(0)
+                    recv = px.pull_reduce(0, lo, hi - lo, m)
+                    if hi > lo:
+                        new = eng.mu_apply(Ut[:, lo:hi].contiguous(), recv[:, :hi - lo].contiguous(), recv[:, chunk].contiguous())
+                        px.send[:, :hi - lo].copy_(new)
+                    px.post(1)
+                    px.wait(1)
+                    Ut = px.install(eng.plan, 0, m)
+                elif comm.world > 1:
                     xb = self._xbuf[:r * m + r]
                     if numU.data_ptr() != xb.data_ptr():
                         xb[:r * m].view(r, m).copy_(numU)
@@ -486,7 +612,10 @@ class FusedNMF:
                 keep = keep or (self.comm.world > 1 and mode == MODE_RES and not mu2 and it < n_iter_max and 0 not in fixed_modes
                                 and not normalize[0] and hasattr(self.eng, "plan"))
                 # the cost lands directly in the scalar block that travels to the host
-                if self.comm.world > 1 and mode == MODE_MU and hasattr(self.eng, "plan"):
+                if self.comm.world > 1 and mode == MODE_MU and it < n_iter_max and 0 not in fixed_modes and self._exchange(1) is not None:
+                    # sharded MU over peer memory: the numerator partials stay in the plan and are reduced into the stage buffer
+                    outA, _ = self.eng.fused(0, mode, True, keep_partials=True, cost_out=self._dev_scal[0:1])
+                elif self.comm.world > 1 and mode == MODE_MU and hasattr(self.eng, "plan"):
                     # sharded MU: the partial numerator lands directly in the exchange buffer (no 16.8 MB copy before the sum)
                     outA, _ = self.eng.fused(0, mode, True, cost_out=self._dev_scal[0:1],
                                              out=self._xbuf[:self.r * self.m].view(self.r, self.m))

@@ -30,6 +30,15 @@ SIGNATURES = {
     "nnfac_ctx_board_export": [_P, _P],
     "nnfac_ctx_board_attach": [_P, _INT, _INT, _P],
     "nnfac_ctx_collective": [_P, _INT, _P],
+    "nnfac_xchg_create": [_P, _I64, _I64, _c.POINTER(_P)],
+    "nnfac_xchg_export": [_P, _P],
+    "nnfac_xchg_attach": [_P, _INT, _INT, _P],
+    "nnfac_xchg_destroy": [_P],
+    "nnfac_xchg_ptr": [_P, _INT],
+    "nnfac_xchg_post": [_P, _INT, _P],
+    "nnfac_xchg_wait": [_P, _INT, _P],
+    "nnfac_xchg_pull_reduce": [_P, _INT, _P, _I64, _INT, _I64, _I64, _I64, _I64, _INT, _I64, _P],
+    "nnfac_nmf_plan_set_factor_pulled": [_P, _INT, _P, _I64, _I64, _P, _I64, _P],
     "nnfac_hals_nnls": [_P, _INT, _P, _I64, _P, _I64, _P, _I64, _INT, _I64, _INT, _DBL, _DBL, _U32, _P, _P],
     "nnfac_hals_solve_f32": [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _INT, _I64, _INT, _DBL, _DBL, _P, _P],
     "nnfac_gemm_strided": [_P, _INT, _P, _I64, _I64, _P, _I64, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I64,
@@ -77,7 +86,7 @@ SIGNATURES = {
     "nnfac_nmf_plan_info": [_P, _INT, _c.POINTER(_INT), _c.POINTER(_INT), _c.POINTER(_INT), _c.POINTER(_INT),
                             _c.POINTER(_INT)],
 }
-_RESTYPES = {"nnfac_last_error": _c.c_char_p, "nnfac_ctx_launch_count": _I64}
+_RESTYPES = {"nnfac_last_error": _c.c_char_p, "nnfac_ctx_launch_count": _I64, "nnfac_xchg_ptr": _P}
 
 _lib = None
 _ctxs = {}

@@ -353,10 +353,11 @@ class NMFPlan:
             ingested[b].record(main)
         L.check(_lib().nnfac_nmf_plan_load_x_done(self.handle, L.stream_ptr()))
 
-    def reduce(self, side):
+    def reduce(self, side, out=None):
         """Sum of the split-K partials the last pass over `side` left in the plan (r x rows of that side)."""
         R = self.m if side == 0 else self.n
-        out = torch.empty((self.r, R), dtype=torch.float32, device=self.device)
+        if out is None:
+            out = torch.empty((self.r, R), dtype=torch.float32, device=self.device)
         L.check(_lib().nnfac_nmf_plan_reduce(self.handle, side, L.ptr(out), out.stride(0), L.stream_ptr()))
         return out
 
