@@ -69,6 +69,11 @@ int64_t nnfac_ctx_launch_count(const nnfac_ctx* ctx);
 int nnfac_ctx_board_export(nnfac_ctx* ctx, void* handle_out);
 int nnfac_ctx_board_attach(nnfac_ctx* ctx, int world, int rank, const void* handles);
 int nnfac_ctx_collective(nnfac_ctx* ctx, int on, const int64_t* slice_lengths);
+/* Variant of the tensor-core sweep's stop test (nnls.py:156): 0 = the total of a sweep is collected after three blocks of
+ * the next sweep, 2 = after the WHOLE next sweep (one sweep of lag; one wasted sweep per solve, no exposed exchange) wherever
+ * the shape allows, 1 = chosen per shape (default), -1 = back to the environment (NNFAC_SWEEP_LAG) / default.  Both variants
+ * execute the same sweeps with the same sums; on one GPU their results are bit-identical. */
+int nnfac_ctx_sweep_variant(nnfac_ctx* ctx, int mode);
 
 /* ---------------------------------------------------------------------------------------------
  * Exchange steps of the column-sharded path over peer-mapped memory (new; csrc/peer_xchg.cu).  Every rank owns a region

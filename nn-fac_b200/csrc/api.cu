@@ -48,8 +48,8 @@ int nnfac_guard_enter(nnfac_ctx* ctx, int which, cudaStream_t st) {
   return NNFAC_OK;
 }
 
-// layout of a stop-scalar board: 4 banks x NNFAC_MAX_PEERS ranks x 160 CTAs of 8 bytes (see csrc/tc_sweep.cu)
-static const size_t kBoardBytes = (size_t)4 * NNFAC_MAX_PEERS * 160 * sizeof(unsigned long long);
+// layout of a stop-scalar board: 8 banks x NNFAC_MAX_PEERS ranks x 160 CTAs of 8 bytes (see csrc/tc_sweep.cu)
+static const size_t kBoardBytes = (size_t)8 * NNFAC_MAX_PEERS * 160 * sizeof(unsigned long long);
 
 extern "C" {
 
@@ -70,6 +70,7 @@ int nnfac_ctx_create(int device, nnfac_ctx** out) {
     return NNFAC_ERR_UNSUPPORTED;
   }
   nnfac_ctx* c = (nnfac_ctx*)calloc(1, sizeof(nnfac_ctx));
+  if (c) c->sweep_lag = -1;
   if (!c) return NNFAC_ERR_ALLOC;
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
@@ -107,6 +108,12 @@ int nnfac_ctx_destroy(nnfac_ctx* ctx) {
 // 1. every rank: nnfac_ctx_board_export -> 64-byte IPC handle of its board; 2. exchange the handles (any transport);
 // 3. every rank: nnfac_ctx_board_attach(world, rank, handles); 4. around a solve that is one slice of a joint solve:
 // nnfac_ctx_collective(ctx, 1, slice_lengths) ... nnfac_ctx_collective(ctx, 0, NULL).
+int nnfac_ctx_sweep_variant(nnfac_ctx* ctx, int mode) {
+  NNFAC_ARG(ctx && mode >= -1 && mode <= 2, "nnfac_ctx_sweep_variant: mode must be -1, 0, 1 or 2");
+  ctx->sweep_lag = mode;
+  return NNFAC_OK;
+}
+
 int nnfac_ctx_board_export(nnfac_ctx* ctx, void* handle_out) {
   NNFAC_ARG(ctx && handle_out, "nnfac_ctx_board_export: NULL argument");
   NNFAC_CUDA(cudaSetDevice(ctx->device));

@@ -44,6 +44,7 @@ struct nnfac_ctx {
   int collective;             // the next tensor-core sweeps are collective over `peers`
   int64_t collective_n[NNFAC_MAX_PEERS];   // columns of every rank's slice
   unsigned collective_gen;    // collective call counter (advances identically on every rank)
+  int sweep_lag;              // variant of the tensor-core sweep's stop test: -1 environment / auto, 0 plain, 1 auto, 2 lagged wherever possible
 };
 
 struct nnfac_xchg;      // peer-mapped exchange region (csrc/peer_xchg.cu)

@@ -38,23 +38,29 @@ constexpr int XMAXW = 8;          // ranks of a collective solve (cross-GPU stop
 constexpr int XMAXG = 160;        // board entries per rank (>= CTAs of a solve)
 
 // Per padded rank RP (64 or 128): a tile keeps RP residual + RP master columns in tensor memory, so a CTA carries
-// 256 / RP tiles; the Gram operand planes are RP / 64 K atoms of [RP rows x 128 B].
-template <int RP>
+// up to 256 / RP tiles; the Gram operand planes are RP / 64 K atoms of [RP rows x 128 B].
+// MT = tiles a CTA of this variant carries at most; LAG = the stop test lags one sweep (see the main loop).
+template <int RP, int MT, bool LAG>
 struct Cfg {
+  static_assert(MT * RP <= 256, "512 tensor-memory columns: RP residual + RP master columns per tile");
   static constexpr int NBLK = RP / BLK;
   static constexpr int KR = RP / 64;
-  static constexpr int MAX_TILES = 256 / RP;                       // 4 (RP = 64) or 2 (RP = 128): 512 tensor-memory columns
+  static constexpr int MAX_TILES = MT;
   static constexpr int UPD_THREADS = MAX_TILES * TILE;
   static constexpr int NTHREADS = UPD_THREADS + MAX_TILES * 32;    // + one issuing warp per tile
   static constexpr int TMEM_PER_TILE = 2 * RP;
   static constexpr uint32_t G_ATOM_BYTES = RP * 128;               // [RP rows x 64 K] bf16
   static constexpr uint32_t G_PLANE_BYTES = KR * G_ATOM_BYTES;     // 8 / 32 KiB
-  static constexpr size_t SMEM = NPLANES * G_PLANE_BYTES + (size_t)MAX_TILES * NPLANES * PLANE_BYTES + 512;
-  // blocks of the next sweep that run speculatively while the stop scalar travels: the masters they overwrite are parked in the
-  // idle third operand plane (blocks 0, 1) and in registers (blocks 2 ..).  RP = 64: 3 of 4 blocks (96 of 102 registers are
-  // taken); RP = 128: 6 of 8 (320 threads per CTA leave room for four more register sets) -- a collective solve waits for an
-  // NVLink round trip, which three blocks do not cover.
-  static constexpr int NSPEC = RP == 64 ? 3 : 6;
+  // blocks of the next sweep that run speculatively while the stop scalar travels: the masters they overwrite are parked in
+  // shared memory (blocks 0 .. NSM-1: the idle third operand plane holds two blocks per column, an extra region two more)
+  // and in registers (blocks NSM .. NSPEC-1).  Without lag, RP = 64: 3 of 4 blocks (96 of the 102 registers of a 640-thread
+  // CTA are taken); RP = 128: 6 of 8.  With lag the WHOLE next sweep is speculative (NSPEC = NBLK): RP = 64 with at most two
+  // tiles per CTA (320 threads, 204 registers), RP = 128 with four blocks in shared memory.
+  static constexpr int NSPEC = LAG ? NBLK : (RP == 64 ? 3 : 6);
+  static constexpr int NSM = (LAG && RP == 128) ? 4 : 2;
+  static constexpr uint32_t BK_EXTRA_BYTES = (NSM - 2) * (BLK * 4) * UPD_THREADS;   // 64 B per column and block beyond the first two
+  static constexpr size_t SMEM = NPLANES * G_PLANE_BYTES + (size_t)MAX_TILES * NPLANES * PLANE_BYTES + BK_EXTRA_BYTES + 512;
+  static constexpr int MBANKS = LAG ? 4 : 2;                       // mailbox / board banks per call (by sweep number)
 };
 
 template <int RP>
@@ -244,16 +250,17 @@ struct BlockLoop<N, N> {
   static __device__ __forceinline__ void run(F&) {}
 };
 
-template <int RP>
-__global__ void __launch_bounds__(Cfg<RP>::NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs a) {
-  using C = Cfg<RP>;
+template <int RP, int MT, bool LAG>
+__global__ void __launch_bounds__(Cfg<RP, MT, LAG>::NTHREADS, 1) tc_sweep_kernel(const TcSweepArgs a) {
+  using C = Cfg<RP, MT, LAG>;
   constexpr int MAX_TILES = C::MAX_TILES, UPD_THREADS = C::UPD_THREADS, TMEM_PER_TILE = C::TMEM_PER_TILE, KR = C::KR;
   constexpr uint32_t G_PLANE_BYTES = C::G_PLANE_BYTES, G_ATOM_BYTES = C::G_ATOM_BYTES;
   constexpr uint64_t GP = G_PLANE_BYTES >> 4;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* g_planes = smem;                                            // -UtU / diag: hi | mid | lo, [K atom][row j][128 B]
   uint8_t* v_planes = smem + NPLANES * G_PLANE_BYTES;                  // [tile][hi|mid|lo][16 KiB]
-  uint8_t* tail = v_planes + (size_t)MAX_TILES * NPLANES * PLANE_BYTES;
+  uint8_t* bk_extra = v_planes + (size_t)MAX_TILES * NPLANES * PLANE_BYTES;   // parked masters of blocks 2 .. NSM-1 (LAG, RP = 128)
+  uint8_t* tail = bk_extra + C::BK_EXTRA_BYTES;
   uint64_t* s_full = reinterpret_cast<uint64_t*>(tail);                // [MAX_TILES] MMA batch complete
   uint64_t* s_ready = s_full + MAX_TILES;                              // [MAX_TILES] operand planes of a tile rewritten
   float* redf = reinterpret_cast<float*>(s_ready + MAX_TILES);         // [32]
@@ -419,6 +426,8 @@ __global__ void __launch_bounds__(Cfg<RP>::NTHREADS, 1) tc_sweep_kernel(const Tc
     }
 
     uint8_t* bkrow = vh + 2 * PLANE_BYTES + (uint32_t)row * 128u;       // 128 B: masters of up to 2 speculative blocks
+    uint8_t* bkrow2 = bk_extra + (uint32_t)(tile * TILE + row) * (uint32_t)((C::NSM - 2) * BLK * 4);   // blocks 2 .. NSM-1
+    (void)bkrow2;
 #ifdef SWEEP_PROF
     long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define PROF_T(i) { const long long t__ = clock64(); prof[i] += t__ - tp; tp = t__; }
@@ -431,7 +440,8 @@ __global__ void __launch_bounds__(Cfg<RP>::NTHREADS, 1) tc_sweep_kernel(const Tc
     // run the in-block recurrence, write the new masters and the operand planes of the 16 steps and hand
     // them to the issuing warp.  Returns the squared step of the block (nnls.py:170).  `keep` receives the
     // masters the block overwrote (needed to undo a speculative block).
-    uint32_t bkreg[C::NSPEC - 2][BLK];                                  // masters the speculative blocks 2 .. NSPEC-1 overwrote
+    constexpr int NSM = C::NSM;
+    uint32_t bkreg[C::NSPEC - NSM][BLK];                                // masters the speculative blocks NSM .. NSPEC-1 overwrote
     auto block_update = [&](auto Bc, auto Backup) -> float {
       constexpr int B = decltype(Bc)::value;
       constexpr bool BACKUP = decltype(Backup)::value;
@@ -451,9 +461,14 @@ __global__ void __launch_bounds__(Cfg<RP>::NTHREADS, 1) tc_sweep_kernel(const Tc
         for (int c = 0; c < 4; ++c)
           *reinterpret_cast<uint4*>(bkrow + (((B * 4 + c) ^ (row & 7)) << 4)) = make_uint4(keep[4 * c], keep[4 * c + 1], keep[4 * c + 2], keep[4 * c + 3]);
       }
-      if (BACKUP && B >= 2 && B < C::NSPEC) {                          // ... the others' stay in registers
+      if (BACKUP && B >= 2 && B < NSM) {                               // NSM = 4: 128 B per column in the extra region, same swizzle
 #pragma unroll
-        for (int e = 0; e < BLK; ++e) bkreg[B >= 2 && B < C::NSPEC ? B - 2 : 0][e] = keep[e];
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(bkrow2 + ((((B - 2) * 4 + c) ^ (row & 7)) << 4)) = make_uint4(keep[4 * c], keep[4 * c + 1], keep[4 * c + 2], keep[4 * c + 3]);
+      }
+      if (BACKUP && B >= NSM && B < C::NSPEC) {                        // ... the others' stay in registers
+#pragma unroll
+        for (int e = 0; e < BLK; ++e) bkreg[B >= NSM && B < C::NSPEC ? B - NSM : 0][e] = keep[e];
       }
       float u[BLK];
 #pragma unroll
@@ -529,24 +544,19 @@ __global__ void __launch_bounds__(Cfg<RP>::NTHREADS, 1) tc_sweep_kernel(const Tc
     float nd_spec = 0.f;
     std::integral_constant<bool, false> plain;
     std::integral_constant<bool, true> backup;
-    while (true) {
-      float nd = nd_spec;
-      if (active) {
-        auto body = [&](auto Bc) {
-          constexpr int B = decltype(Bc)::value;
-          if (B < nblk && B >= nspec) nd += block_update(Bc, plain);
-        };
-        BlockLoop<0, C::NBLK>::run(body);
-      }
-      // (fp32 trees: every CTA adds the same numbers in the same order)
+    constexpr unsigned MBANKS = C::MBANKS;
+    // reduce the squared steps of this CTA's columns and post the CTA's partial sum of sweep e + 1 (tag) to every CTA
+    // (fp32 trees: every CTA adds the same numbers in the same order)
+    auto post = [&](float nd, unsigned e) {
       const float t = warp_sum_f(nd);
       if (lane == 0) redf[warp] = t;
       named_bar_sync(1, UPD_THREADS);
-      const unsigned tag = collective ? ((a.xgen & 0xffffu) << 16) | (epoch + 1u) : (gen << 16) | (epoch + 1u);
-      // collective: 4 banks of XMAXW x XMAXG entries, bank = 2 (call parity) + sweep parity, so that a rank that is a
-      // whole sweep (or the start of the next call) ahead never overwrites an entry a slower rank still has to read
-      const size_t xbank = (size_t)(((a.xgen & 1u) << 1) | (epoch & 1u)) * (XMAXW * XMAXG);
+      const unsigned tag = collective ? ((a.xgen & 0xffffu) << 16) | (e + 1u) : (gen << 16) | (e + 1u);
       if (collective) {
+        // 8 banks of XMAXW x XMAXG entries, bank = 4 (call parity) + sweep number mod MBANKS, so that a rank that is ahead
+        // (by up to a sweep, with LAG by up to three, or by the start of the next call) never overwrites an entry a slower
+        // rank still has to read
+        const size_t xbank = (size_t)((a.xgen & 1u) * 4u + (e % MBANKS)) * (XMAXW * XMAXG);
         if (threadIdx.x < (unsigned)a.xworld) {
           float sum = 0.f;
 #pragma unroll
@@ -559,47 +569,47 @@ __global__ void __launch_bounds__(Cfg<RP>::NTHREADS, 1) tc_sweep_kernel(const Tc
 #pragma unroll
         for (int w = 0; w < UPD_THREADS / 32; ++w) sum += redf[w];
         const unsigned long long bits = ((unsigned long long)tag << 32) | __float_as_uint(sum);
-        st_relaxed_u64(a.mail + ((size_t)(epoch & 1u) * nb + threadIdx.x) * nb + blockIdx.x, bits);
+        st_relaxed_u64(a.mail + ((size_t)(e % MBANKS) * nb + threadIdx.x) * nb + blockIdx.x, bits);
       }
-      // ---- speculative blocks of the next sweep; the first look into the mailbox is issued before the last of them,
-      //      so that its L2 round trip runs under that block ----
-      const unsigned long long* slot = a.mail + ((size_t)(epoch & 1u) * nb + blockIdx.x) * nb + threadIdx.x;
-      const bool poller = !collective && nb > 1 && threadIdx.x < nb;
-      unsigned long long early = 0ull;
-      nspec = 0;
-      nd_spec = 0.f;
-      if (cnt + 1 <= a.maxiter) {
-        nspec = nblk < NSPEC ? nblk : NSPEC;
-        auto spec = [&](auto Bc) {
-          constexpr int B = decltype(Bc)::value;
-          if (B < nspec) {
-            if (B == nspec - 1 && poller) early = ld_relaxed_u64(slot);   // first look, under the last speculative block
-            if (active) nd_spec += block_update(Bc, backup);
-          }
-        };
-        BlockLoop<0, NSPEC>::run(spec);
+    };
+    const bool poller = !collective && nb > 1 && threadIdx.x < nb;
+    auto slot_of = [&](unsigned e) { return a.mail + ((size_t)(e % MBANKS) * nb + blockIdx.x) * nb + threadIdx.x; };
+    // collective solves: the entries of the local board this thread adds up (entries t, t + UPD_THREADS, ... rank-major)
+    constexpr int MAXE = (XMAXW * XMAXG + UPD_THREADS - 1) / UPD_THREADS;
+    bool want[MAXE];
+#pragma unroll
+    for (int j = 0; j < MAXE; ++j) {
+      const int en = threadIdx.x + j * UPD_THREADS;
+      const int qr = en / XMAXG, c = en - qr * XMAXG;
+      want[j] = collective && en < a.xworld * XMAXG && c < a.xgrid[qr < XMAXW ? qr : 0];
+    }
+    auto board_of = [&](unsigned e) { return a.xboard[a.xrank] + (size_t)((a.xgen & 1u) * 4u + (e % MBANKS)) * (XMAXW * XMAXG); };
+    // a first look at the partial sums of sweep e + 1 (issued under the last speculative block: the L2 round trip of the
+    // loads runs under that block)
+    unsigned long long early_x[MAXE];
+    auto peek = [&](unsigned e, unsigned long long& early) {
+      if (poller) early = ld_relaxed_u64(slot_of(e));
+      if (collective) {
+        const unsigned long long* board = board_of(e);
+#pragma unroll
+        for (int j = 0; j < MAXE; ++j) early_x[j] = want[j] ? ld_relaxed_sys_u64(board + threadIdx.x + j * UPD_THREADS) : 0ull;
       }
-      // ---- collect the total ----
+    };
+    // the total of sweep e + 1 over all CTAs (and ranks); `early` / early_x: the first look taken by peek(e), if `peeked`
+    auto collect = [&](unsigned e, unsigned long long early, bool peeked) -> float {
 #ifdef SWEEP_PROF
       const long long tg0 = clock64();
 #endif
+      const unsigned tag = collective ? ((a.xgen & 0xffffu) << 16) | (e + 1u) : (gen << 16) | (e + 1u);
       float totf = 0.f;
       if (collective) {
-        // every entry of the local board: thread t adds entries t, t + UPD_THREADS, ... (rank-major), then the usual trees
+        // every entry of the local board, then the usual trees.  All loads of a thread are issued before the first one is
+        // looked at (independent L2 round trips), then only the entries that had not arrived yet are polled again
         float got = 0.f;
-        const unsigned long long* board = a.xboard[a.xrank] + xbank;
-        // all loads of a thread are issued before the first one is looked at (independent L2 round trips), then only the
-        // entries that had not arrived yet are polled again
-        constexpr int MAXE = (XMAXW * XMAXG + UPD_THREADS - 1) / UPD_THREADS;
+        const unsigned long long* board = board_of(e);
         unsigned long long bits[MAXE];
-        bool want[MAXE];
 #pragma unroll
-        for (int j = 0; j < MAXE; ++j) {
-          const int e = threadIdx.x + j * UPD_THREADS;
-          const int qr = e / XMAXG, c = e - qr * XMAXG;
-          want[j] = e < a.xworld * XMAXG && c < a.xgrid[qr < XMAXW ? qr : 0];
-          bits[j] = want[j] ? ld_relaxed_sys_u64(board + e) : 0ull;
-        }
+        for (int j = 0; j < MAXE; ++j) bits[j] = peeked ? early_x[j] : (want[j] ? ld_relaxed_sys_u64(board + threadIdx.x + j * UPD_THREADS) : 0ull);
 #pragma unroll
         for (int j = 0; j < MAXE; ++j) {
           if (want[j]) {
@@ -619,7 +629,8 @@ __global__ void __launch_bounds__(Cfg<RP>::NTHREADS, 1) tc_sweep_kernel(const Tc
       } else if (nb > 1) {
         float got = 0.f;
         if (poller) {
-          unsigned long long bits = early;
+          const unsigned long long* slot = slot_of(e);
+          unsigned long long bits = peeked ? early : ld_relaxed_u64(slot);
           uint32_t spins = 0;
           while ((unsigned)(bits >> 32) != tag) {
             bits = ld_relaxed_u64(slot);
@@ -640,7 +651,10 @@ __global__ void __launch_bounds__(Cfg<RP>::NTHREADS, 1) tc_sweep_kernel(const Tc
 #ifdef SWEEP_PROF
       prof[6] += clock64() - tg0;
 #endif
-      ++epoch;
+      return totf;
+    };
+    // nnls.py:156 after a sweep whose total squared step is totf; returns true when the solve ends
+    auto decide = [&](float totf) -> bool {
       if (cnt == 1) {
         // eps >= delta * eps0 (nnls.py:156, evaluated in double) <=> totf >= thr with thr = delta * eps0 rounded UP to
         // fp32: the per-sweep test then needs no FP64 instruction (scarce on this part)
@@ -658,7 +672,77 @@ __global__ void __launch_bounds__(Cfg<RP>::NTHREADS, 1) tc_sweep_kernel(const Tc
         if (thr == 0.f && cnt < a.maxiter + 1) cnt = a.maxiter + 1;
         stop = true;
       }
-      if (stop) break;
+      return stop;
+    };
+    if constexpr (LAG) {
+      // Stop test with a LAG of one sweep: the partial sums of sweep k are posted, then the WHOLE sweep k + 1 runs
+      // speculatively (every master it overwrites is parked) and is posted too, and only then is the total of sweep k
+      // collected -- it has been travelling for a full sweep, so neither the L2 nor an NVLink round trip (collective solves)
+      // is waited for.  If the test ends the solve after sweep k, sweep k + 1 is undone (one wasted sweep per solve).  Posts
+      // are not gated by collects here: a CTA can be up to three sweeps ahead of the slowest reader, hence four banks.
+      // The host never takes this variant for a single CTA outside a collective solve (nothing to wait for there).
+      float nd = 0.f;
+      if (active) {
+        auto body = [&](auto Bc) {
+          constexpr int B = decltype(Bc)::value;
+          if (B < nblk) nd += block_update(Bc, plain);
+        };
+        BlockLoop<0, C::NBLK>::run(body);
+      }
+      post(nd, 0u);
+      while (true) {
+        // here: sweeps 1 .. cnt are done and posted, the totals up to sweep cnt - 1 are known (epoch = cnt - 1)
+        unsigned long long early = 0ull;
+        nspec = 0;
+        if (cnt + 1 <= a.maxiter) {
+          nspec = nblk;
+          float nd2 = 0.f;
+          auto spec = [&](auto Bc) {
+            constexpr int B = decltype(Bc)::value;
+            if (B < nblk) {
+              if (B == nblk - 1) peek(epoch, early);                                  // first look, under the last block
+              if (active) nd2 += block_update(Bc, backup);
+            }
+          };
+          BlockLoop<0, C::NBLK>::run(spec);
+          post(nd2, epoch + 1u);
+        }
+        const float totf = collect(epoch, early, nspec > 0);
+        ++epoch;
+        if (decide(totf)) break;
+      }
+    } else {
+    while (true) {
+      float nd = nd_spec;
+      if (active) {
+        auto body = [&](auto Bc) {
+          constexpr int B = decltype(Bc)::value;
+          if (B < nblk && B >= nspec) nd += block_update(Bc, plain);
+        };
+        BlockLoop<0, C::NBLK>::run(body);
+      }
+      post(nd, epoch);
+      // ---- speculative blocks of the next sweep; the first look into the mailbox is issued before the last of them,
+      //      so that its L2 round trip runs under that block ----
+      unsigned long long early = 0ull;
+      nspec = 0;
+      nd_spec = 0.f;
+      if (cnt + 1 <= a.maxiter) {
+        nspec = nblk < NSPEC ? nblk : NSPEC;
+        auto spec = [&](auto Bc) {
+          constexpr int B = decltype(Bc)::value;
+          if (B < nspec) {
+            if (B == nspec - 1) peek(epoch, early);                                  // first look, under the last speculative block
+            if (active) nd_spec += block_update(Bc, backup);
+          }
+        };
+        BlockLoop<0, NSPEC>::run(spec);
+      }
+      // ---- collect the total ----
+      const float totf = collect(epoch, early, nspec > 0);
+      ++epoch;
+      if (decide(totf)) break;
+    }
     }
     if (active) {
       tc::mbar_wait(&s_full[tile], s_phase);                              // drain the last rank update
@@ -674,9 +758,15 @@ __global__ void __launch_bounds__(Cfg<RP>::NTHREADS, 1) tc_sweep_kernel(const Tc
           uint32_t w[16];
           tc::tmem_ld16(t_v + c0, w);
           tc::tmem_ld_wait();
-          if (c0 / BLK >= 2 && c0 / BLK < NSPEC && c0 / BLK < nspec) {        // undo the speculative blocks
+          if (c0 / BLK >= NSM && c0 / BLK < NSPEC && c0 / BLK < nspec) {      // undo the speculative blocks
 #pragma unroll
-            for (int e = 0; e < BLK; ++e) w[e] = bkreg[c0 / BLK >= 2 && c0 / BLK < NSPEC ? c0 / BLK - 2 : 0][e];
+            for (int e = 0; e < BLK; ++e) w[e] = bkreg[c0 / BLK >= NSM && c0 / BLK < NSPEC ? c0 / BLK - NSM : 0][e];
+          } else if (c0 / BLK >= 2 && c0 / BLK < NSM && c0 / BLK < nspec) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint4 b4 = *reinterpret_cast<const uint4*>(bkrow2 + ((((c0 / BLK - 2) * 4 + c) ^ (row & 7)) << 4));
+              w[4 * c] = b4.x; w[4 * c + 1] = b4.y; w[4 * c + 2] = b4.z; w[4 * c + 3] = b4.w;
+            }
           } else if (c0 / BLK < 2 && c0 / BLK < nspec) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -742,9 +832,9 @@ __global__ void __launch_bounds__(Cfg<RP>::NTHREADS, 1) tc_sweep_kernel(const Tc
 
 }  // namespace
 
-template <int RP>
+template <int RP, int MT, bool LAG>
 static int sweep_launch(nnfac_ctx* ctx, TcSweepArgs& a, const float* UtU, int64_t ld_utu, int64_t grid, cudaStream_t st) {
-  using C = Cfg<RP>;
+  using C = Cfg<RP, MT, LAG>;
   // the per-call constants are written straight into the __constant__ bank of this device by a one-block kernel (constant
   // caches are invalidated at kernel boundaries, and the stream orders it before the sweep); the bank address is resolved
   // once per context, i.e. per device
@@ -757,11 +847,11 @@ static int sweep_launch(nnfac_ctx* ctx, TcSweepArgs& a, const float* UtU, int64_
   sweep_prep_kernel<RP><<<1, 256, 0, st>>>(UtU, ld_utu, a.r, (SweepConst<RP>*)bank, gen_dev, ctx->mail, ctx->mail_count);
   NNFAC_LAUNCH_CHECK(ctx);
   a.mail = ctx->mail; a.gen = gen_dev;
-  NNFAC_CUDA(cudaFuncSetAttribute(tc_sweep_kernel<RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+  NNFAC_CUDA(cudaFuncSetAttribute(tc_sweep_kernel<RP, MT, LAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
   // every CTA waits for every other one once per sweep: the cooperative launch guarantees that all of them are resident
   // (a plain launch was measured: no difference in launch cost)
   void* params[] = {&a};
-  NNFAC_CUDA(cudaLaunchCooperativeKernel((const void*)tc_sweep_kernel<RP>, dim3((unsigned)grid), dim3(C::NTHREADS), params, C::SMEM, st));
+  NNFAC_CUDA(cudaLaunchCooperativeKernel((const void*)tc_sweep_kernel<RP, MT, LAG>, dim3((unsigned)grid), dim3(C::NTHREADS), params, C::SMEM, st));
   ctx->launches++;
   return NNFAC_OK;
 }
@@ -791,7 +881,7 @@ int nnfac_tc_sweep_run(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const f
   }
   if (cols > max_cols) return NNFAC_ERR_UNSUPPORTED;
   const int64_t grid = ceil_div64(n, cols);
-  if ((size_t)(2 * grid * grid) > ctx->mail_count || maxiter > 65000 || grid > XMAXG) return NNFAC_ERR_UNSUPPORTED;
+  if ((size_t)(4 * grid * grid) > ctx->mail_count || maxiter > 65000 || grid > XMAXG) return NNFAC_ERR_UNSUPPORTED;
   int rc = nnfac_guard_enter(ctx, NNFAC_GUARD_SWEEP, st);
   if (rc) return rc;
   TcSweepArgs a;
@@ -817,7 +907,30 @@ int nnfac_tc_sweep_run(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const f
     if (a.xgrid[pg->rank] != (int)grid) { nnfac_set_error("collective HALS solve: slice length %lld does not match the announced one", (long long)n); return NNFAC_ERR_ARG; }
   }
   // mailbox tags carry a call generation (device-side, see sweep_prep_kernel), so that the slots never need clearing
-  rc = rp == 64 ? sweep_launch<64>(ctx, a, UtU, ld_utu, grid, st) : sweep_launch<128>(ctx, a, UtU, ld_utu, grid, st);
+  // Variant.  The lagged stop test (whole next sweep speculative) needs room to park every master (rank <= 64: at most two
+  // tiles per CTA) and something to wait for (more than one CTA, or a collective solve).  Measured (tools/time_sweeps_lag.py,
+  // tools/time_sweeps_collective.py; results bit-identical to the plain variant on one GPU): one GPU, one tile per CTA,
+  // 128 CTAs: -8 % per sweep at rank 64 (3.42 -> 3.14 us), -4 % at rank 128; two tiles per CTA +5..12 % (issue-bound: parking
+  // the fourth block costs more than the exchange it hides); 16 CTAs +14 %; collective solves on 2 GPUs +0.45..0.6 us per
+  // sweep (the three speculative blocks of the plain variant already cover the NVLink round trip).  So "auto" takes it
+  // for non-collective solves with one tile per CTA on at least 64 CTAs.  Every rank of a collective solve takes the same
+  // variant: the widest slice decides.  NNFAC_SWEEP_LAG = 0 never, 1 auto, 2 wherever possible.
+  static const int lag_env = [] { const char* e = getenv("NNFAC_SWEEP_LAG"); return e ? atoi(e) : 1; }();
+  const int lag_mode = ctx->sweep_lag >= 0 ? ctx->sweep_lag : lag_env;     // nnfac_ctx_sweep_variant overrides the environment
+  int64_t decide_cols = cols;
+  if (pg) {
+    int64_t widest = n;
+    for (int q = 0; q < pg->world; ++q) if (ctx->collective_n[q] > widest) widest = ctx->collective_n[q];
+    decide_cols = ceil_div64(ceil_div64(widest, ctx->sm_count), 32) * 32;
+  }
+  const bool lag_possible = (pg != nullptr || grid > 1) && (rp == 128 || decide_cols <= 2 * TILE);
+  const bool lag_pays = pg == nullptr && decide_cols <= TILE && grid >= 64;
+  const bool lag = lag_possible && (lag_mode >= 2 || (lag_mode == 1 && lag_pays));
+  if (rp == 64) {
+    rc = lag ? sweep_launch<64, 2, true>(ctx, a, UtU, ld_utu, grid, st) : sweep_launch<64, 4, false>(ctx, a, UtU, ld_utu, grid, st);
+  } else {
+    rc = lag ? sweep_launch<128, 2, true>(ctx, a, UtU, ld_utu, grid, st) : sweep_launch<128, 2, false>(ctx, a, UtU, ld_utu, grid, st);
+  }
   return rc;
 }
 

@@ -30,6 +30,7 @@ SIGNATURES = {
     "nnfac_ctx_board_export": [_P, _P],
     "nnfac_ctx_board_attach": [_P, _INT, _INT, _P],
     "nnfac_ctx_collective": [_P, _INT, _P],
+    "nnfac_ctx_sweep_variant": [_P, _INT],
     "nnfac_xchg_create": [_P, _I64, _I64, _c.POINTER(_P)],
     "nnfac_xchg_export": [_P, _P],
     "nnfac_xchg_attach": [_P, _INT, _INT, _P],

@@ -221,6 +221,36 @@ def test_tc_sweep_is_deterministic_and_pure():
     assert torch.equal(outs[0][1], outs[1][1])
 
 
+@pytest.mark.parametrize("r,n,maxiter,delta", [(64, 8192, 100, 0.01), (64, 8192, 60, 0.0), (40, 9000, 100, 0.01), (64, 30000, 100, 0.01),
+                                               (128, 12000, 100, 0.01), (96, 20000, 37, 0.0), (64, 8192, 1, 0.01), (64, 8192, 2, 0.01),
+                                               (64, 300, 100, 0.01), (17, 8192, 3, 0.5)])
+def test_tc_sweep_lagged_stop_test_is_bit_identical(r, n, maxiter, delta):
+    """The stop test of nnls.py:156 evaluated with a lag of one sweep (the whole next sweep runs speculatively and is undone
+    when the test ends the solve, nnfac_ctx_sweep_variant) executes the same sweeps as the plain variant: same bits, same
+    count, same eps -- including maxiter = 1, 2 (nothing to speculate on) and early stops."""
+    import torch
+    from nn_fac import _lib as L
+    from nn_fac import _ops as ops
+    g = torch.Generator(device="cuda"); g.manual_seed(11 * r + n)
+    U = torch.rand((2 * r + 5, r), generator=g, device="cuda")
+    G = (U.T @ U).contiguous()
+    b = (G @ torch.rand((r, n), generator=g, device="cuda") + 0.1 * torch.rand((r, n), generator=g, device="cuda")).contiguous()
+    V0 = torch.rand((r, n), generator=g, device="cuda")
+    lib, ctx = L.load_library(), L.ctx(V0.device)
+    outs = []
+    try:
+        for mode in (0, 2):
+            L.check(lib.nnfac_ctx_sweep_variant(ctx, mode))
+            V = V0.clone()
+            st = ops.hals_nnls(b, G, V, r, maxiter, delta, 0.0, False, False).clone()
+            outs.append((V, st))
+    finally:
+        L.check(lib.nnfac_ctx_sweep_variant(ctx, -1))
+    assert torch.equal(outs[0][1], outs[1][1]), (outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert 2 <= int(outs[0][1][1].item()) <= maxiter + 1
+
+
 # ---------------------------------------------------------------------------------------------
 # plan plumbing: caller workspace, slab-wise ingest of a host array, reuse of installed planes, fp32 copies
 # ---------------------------------------------------------------------------------------------
@@ -608,3 +638,70 @@ def test_mttkrp_of_every_mode_in_place_over_one_copy_of_the_tensor(shape, r):
     assert odd.view(10, 6, 50, 4) is None                                 # padded planes (300 % 64 != 0)
     with pytest.raises(Exception):
         base.view(shape[0], int(np.prod(shape[1:])), 1, r).set_factor(0, torch.zeros((r, int(np.prod(shape[1:]))), device="cuda"))
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs[1] at its FULL size (65536 x 8192, rank 64), through size-independent properties
+# ---------------------------------------------------------------------------------------------
+def _f64_costs_chunked(X, Ut, V, rows=4096):
+    """||X - U V||^2 and KL(X | U V) in float64 with torch, 4096 rows of X at a time (an evaluation that shares nothing with
+    the kernels under test)."""
+    import torch
+    fro = torch.zeros((), dtype=torch.float64, device=X.device)
+    kl = torch.zeros((), dtype=torch.float64, device=X.device)
+    V64 = V.double()
+    for lo in range(0, X.shape[0], rows):
+        x = X[lo:lo + rows].double()
+        k = Ut[:, lo:lo + rows].double().T @ V64
+        fro += ((x - k) ** 2).sum()
+        kl += (x * torch.log(x / k) - x + k).sum()
+    return float(fro), float(kl)
+
+
+@pytest.mark.parametrize("rule", ["hals", "mu"])
+def test_nmf_config2_full_size_against_oracle_on_subsamples(rule):
+    """C2 (the headline configuration) at full size.  An update of U only couples the rows of U through the number of sweeps
+    (nnls.py:156) and not at all for MU, so the float64 oracle restricted to a random subset of rows of X (columns for the V
+    update), run for the sweep count the GPU reports, must reproduce those rows of the GPU result; the reported objective is
+    checked against an independent float64 evaluation over the whole matrix, and must not increase."""
+    import torch
+    from nn_fac import _fast
+    from oracle import nnfac_oracle as orc
+    m, n, r = 65536, 8192, 64
+    g = torch.Generator(device="cuda"); g.manual_seed(2024)
+    W0, H0 = torch.rand((m, r), generator=g, device="cuda"), torch.rand((r, n), generator=g, device="cuda")
+    X = W0 @ H0
+    X += float(X.mean()) * torch.rand((m, n), generator=g, device="cuda") + 1e-3
+    del W0, H0
+    U0, V0 = torch.rand((m, r), generator=g, device="cuda"), torch.rand((r, n), generator=g, device="cuda")
+    beta = 2 if rule == "hals" else 1
+    assert _fast.eligible(torch.float32, r, rule, beta)
+    st = _fast.FusedNMF(X, U0, V0)
+    costs, _ = st.run(3, 0.0, rule, beta=beta)
+    assert len(costs) == 3 and costs[0] >= costs[1] >= costs[2] > 0
+    fro, kl = _f64_costs_chunked(X, st.Ut, st.V)
+    want = fro if rule == "hals" else kl
+    assert abs(costs[-1] - want) <= 1e-5 * want, (costs[-1], want)
+
+    # one outer iteration from (U0, V0): rows of the new U, then columns of the new V, against the oracle on subsamples
+    st = _fast.FusedNMF(X, U0, V0)
+    st.run(1, 0.0, rule, beta=beta)
+    U1t, V1 = st.Ut, st.V
+    rs = np.random.RandomState(5)
+    rows = torch.from_numpy(np.sort(rs.choice(m, 192, replace=False))).cuda()
+    cols = torch.from_numpy(np.sort(rs.choice(n, 192, replace=False))).cuda()
+    Xr, Xc = X[rows].double().cpu().numpy(), X[:, cols].double().cpu().numpy()
+    U0r, V0c = U0[rows].double().cpu().numpy(), V0[:, cols].double().cpu().numpy()
+    V0h, U1h = V0.double().cpu().numpy(), U1t.double().cpu().numpy().T
+    if rule == "hals":
+        cnt_U, cnt_V = [int(c) for c in st.sweep_log[0].cpu().tolist()]
+        assert 2 <= cnt_U <= 100 and 2 <= cnt_V <= 100
+        want_U = orc.hals_nnls_acc(V0h @ Xr.T, V0h @ V0h.T, U0r.T, maxiter=cnt_U, delta=0.0)[0].T      # nmf.py:407-416
+        want_V = orc.hals_nnls_acc(U1h.T @ Xc, U1h.T @ U1h, V0c, maxiter=cnt_V, delta=0.0)[0]          # nmf.py:432-441
+    else:
+        want_U = orc.mu_betadivmin(U0r, V0h, Xr, 1)                                                    # mu.py:84-88
+        want_V = orc.mu_betadivmin(V0c.T, U1h.T, Xc.T, 1).T                                            # mu.py:27
+    got_U, got_V = U1h[rows.cpu().numpy()], V1[:, cols].double().cpu().numpy()
+    assert np.linalg.norm(got_U - want_U) <= 2e-4 * np.linalg.norm(want_U)
+    assert np.linalg.norm(got_V - want_V) <= 2e-4 * np.linalg.norm(want_V)
+    assert (got_U >= 0).all() and (got_V >= 0).all()
