@@ -91,11 +91,22 @@ int nnfac_xchg_attach(nnfac_xchg* x, int world, int rank, const void* handles);
 int nnfac_xchg_destroy(nnfac_xchg* x);
 void* nnfac_xchg_ptr(nnfac_xchg* x, int which);                 /* local stage (0) / send (1) buffer */
 int nnfac_xchg_post(nnfac_xchg* x, int phase, void* stream);    /* this rank's buffer `phase` is complete (stream-ordered) */
-int nnfac_xchg_wait(nnfac_xchg* x, int phase, void* stream);    /* every rank has posted as often as this rank */
+int nnfac_xchg_wait(nnfac_xchg* x, int phase, void* stream);    /* every rank has posted as often as this rank (a kernel of its
+                                                                   own; the consumers below wait by themselves) */
+/* nnfac_xchg_post(x, 0) that first writes column `col` of the stage ([rows x pitch]) from tail_src[0 .. rows): the small partial
+ * sums that travel behind the big ones (row sums of V, mu.py:85-87) without a copy kernel of their own. */
+int nnfac_xchg_post_tail(nnfac_xchg* x, const float* tail_src, int rows, int64_t pitch, int64_t col, void* stream);
 /* out[k][0:ncols] = sum over ranks of columns [lo, lo+ncols) and out[k][tail_col : tail_col+tail] = sum over ranks of the
- * `tail` columns behind column `len`, of every rank's buffer `which` ([r x pitch]). */
+ * `tail` columns behind column `len`, of every rank's buffer `which` ([r x pitch]).  Call after this rank's post on `which`;
+ * the kernel waits until every rank has posted as often (no nnfac_xchg_wait needed). */
 int nnfac_xchg_pull_reduce(nnfac_xchg* x, int which, float* out, int64_t ld_out, int r, int64_t pitch, int64_t lo, int64_t ncols,
                            int64_t len, int tail, int64_t tail_col, void* stream);
+/* The U update of the column-sharded beta = 1 rule (nn_fac/update_rules/mu.py:84-88) in ONE kernel after this rank's post on
+ * phase 0: waits for every rank's post, sums the partial numerators of this rank's rows [lo, lo+ncols) of U and the partial row
+ * sums of V (column `len` of every stage) over NVLink in rank order, and writes max(F[k][lo+c] * num / den[k], floor) into this
+ * rank's send buffer ([r x ld_send]).  F = the current U^T (r x ld_f). */
+int nnfac_xchg_pull_mu_apply(nnfac_xchg* x, const float* F, int64_t ld_f, int r, int64_t pitch, int64_t lo, int64_t ncols,
+                             int64_t len, double floor_value, int64_t ld_send, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * HALS NNLS solver: replaces nn_fac/update_rules/nnls.py:156-198 (hals_nnls_acc sweep loop with
@@ -272,7 +283,8 @@ int nnfac_nmf_plan_set_factor(nnfac_nmf_plan* plan, int which, const float* Ft, 
 int nnfac_nmf_plan_set_factor_gathered(nnfac_nmf_plan* plan, int which, const float* G, int64_t chunk, float* Ft_out,
                                        int64_t ld_out, void* stream);
 /* The same straight from the peers' send buffers of an exchange region: slice s is read from rank s's send buffer
- * ([r x pitch]) over NVLink.  Call after nnfac_xchg_wait(x, 1, stream). */
+ * ([r x pitch]) over NVLink.  Call after this rank's nnfac_xchg_post(x, 1, stream): the kernel waits until every rank has
+ * posted as often. */
 int nnfac_nmf_plan_set_factor_pulled(nnfac_nmf_plan* plan, int which, const nnfac_xchg* x, int64_t chunk, int64_t pitch,
                                      float* Ft_out, int64_t ld_out, void* stream);
 /* HALS solve of factor `which` (nn_fac/update_rules/nnls.py:24-198, deterministic rule, no normalize / nonzero) whose

@@ -41,10 +41,31 @@ struct FlagPtrs {
   unsigned long long* p[NNFAC_MAX_PEERS];
 };
 
-__global__ void xchg_post_kernel(FlagPtrs flags, int world, int phase, int my_rank, unsigned long long seq) {
+// optional: tail_dst[k * tail_pitch] = tail_src[k], k < tail_count (a column of partial sums that travels with the buffer),
+// written by this block before the flags are raised
+__global__ void xchg_post_kernel(FlagPtrs flags, int world, int phase, int my_rank, unsigned long long seq, const float* tail_src,
+                                 float* tail_dst, int64_t tail_pitch, int tail_count) {
+  for (int k = threadIdx.x; k < tail_count; k += blockDim.x) tail_dst[(int64_t)k * tail_pitch] = tail_src[k];
+  __syncthreads();
   if ((int)threadIdx.x < world) {
     __threadfence_system();
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flags.p[threadIdx.x] + phase * NNFAC_MAX_PEERS + my_rank), "l"(seq) : "memory");
+  }
+}
+
+// Block-level wait inside a consumer kernel: every rank has posted `seq` times on `phase` (flags = the local flag block).
+__device__ __forceinline__ void xchg_block_wait(const unsigned long long* flags, int world, int phase, unsigned long long seq) {
+  if (flags != nullptr) {
+    if ((int)threadIdx.x < world) {
+      const unsigned long long* f = flags + phase * NNFAC_MAX_PEERS + threadIdx.x;
+      unsigned long long v;
+      unsigned long long spins = 0;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+        if (++spins > (1ull << 27)) __trap();   // a protocol bug fails the launch instead of hanging the GPU
+      } while (v < seq);
+    }
+    __syncthreads();
   }
 }
 
@@ -62,19 +83,109 @@ __global__ void xchg_wait_kernel(const unsigned long long* flags, int world, int
 
 // out[k][c] = sum_q src_q[k * pitch + lo + c]  (c < ncols; columns ncols .. out_cols-1-tail are zero padding), and
 // out[k][tail_col + j] = sum_q src_q[k * pitch + len + j]  (j < tail); fixed order q = 0 .. world-1.
+// (the kernels wait for every rank's post themselves; the loads of all ranks are issued together -- 16 bytes each where the
+// layout allows -- and added in rank order)
+__device__ __forceinline__ float pull_sum(const PeerPtrs& src, int world, int64_t off) {
+  float v[NNFAC_MAX_PEERS];
+#pragma unroll
+  for (int q = 0; q < NNFAC_MAX_PEERS; ++q) v[q] = q < world ? __ldcv(src.p[q] + off) : 0.f;
+  float s = 0.f;
+#pragma unroll
+  for (int q = 0; q < NNFAC_MAX_PEERS; ++q) if (q < world) s += v[q];
+  return s;
+}
+__device__ __forceinline__ float4 pull_sum4(const PeerPtrs& src, int world, int64_t off) {   // off: multiple of 4 floats
+  float4 v[NNFAC_MAX_PEERS];
+#pragma unroll
+  for (int q = 0; q < NNFAC_MAX_PEERS; ++q)
+    v[q] = q < world ? __ldcv(reinterpret_cast<const float4*>(src.p[q] + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < NNFAC_MAX_PEERS; ++q)
+    if (q < world) { s.x += v[q].x; s.y += v[q].y; s.z += v[q].z; s.w += v[q].w; }
+  return s;
+}
+
+constexpr int PULL_QUADS = 2;      // 4-column groups per thread and step: 2 x world 16-byte loads in flight per thread
+
+// grid = (column blocks, r).  vec: pitch, lo, ld_out and the base pointers allow 16-byte accesses.
 __global__ void __launch_bounds__(256) xchg_pull_reduce_kernel(PeerPtrs src, int world, int r, int64_t pitch, int64_t lo, int64_t ncols,
                                                                int64_t len, int tail, float* __restrict__ out, int64_t ld_out,
-                                                               int64_t tail_col) {
-  const int64_t width = tail_col + tail, total = (int64_t)r * width;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t k = i / width, c = i - k * width;
-    float s = 0.f;
-    if (c < ncols) {
-      for (int q = 0; q < world; ++q) s += __ldcv(src.p[q] + k * pitch + lo + c);
-    } else if (c >= tail_col) {
-      for (int q = 0; q < world; ++q) s += __ldcv(src.p[q] + k * pitch + len + (c - tail_col));
+                                                               int64_t tail_col, const unsigned long long* flags, int phase,
+                                                               unsigned long long seq, int vec) {
+  xchg_block_wait(flags, world, phase, seq);
+  const int64_t k = blockIdx.y;
+  const int64_t row = k * pitch;
+  // tail columns and the zero padding between the slice and the tail: first block of the row
+  if (blockIdx.x == 0) {
+    for (int64_t c = ncols + threadIdx.x; c < tail_col; c += blockDim.x) out[k * ld_out + c] = 0.f;
+    for (int j = threadIdx.x; j < tail; j += blockDim.x) out[k * ld_out + tail_col + j] = pull_sum(src, world, row + len + j);
+  }
+  const int64_t nquad = (ncols + 3) / 4;
+  for (int64_t q0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * PULL_QUADS; q0 < nquad; q0 += (int64_t)gridDim.x * blockDim.x * PULL_QUADS) {
+    float4 acc[PULL_QUADS];
+    bool full[PULL_QUADS];
+#pragma unroll
+    for (int u = 0; u < PULL_QUADS; ++u) {
+      const int64_t c = (q0 + u) * 4;
+      full[u] = vec && c + 4 <= ncols;
+      if (full[u]) acc[u] = pull_sum4(src, world, row + lo + c);
     }
-    out[k * ld_out + c] = s;
+#pragma unroll
+    for (int u = 0; u < PULL_QUADS; ++u) {
+      const int64_t c = (q0 + u) * 4;
+      if (full[u]) {
+        *reinterpret_cast<float4*>(out + k * ld_out + c) = acc[u];
+      } else {
+        for (int64_t cc = c; cc < c + 4 && cc < ncols; ++cc) out[k * ld_out + cc] = pull_sum(src, world, row + lo + cc);
+      }
+    }
+  }
+}
+
+// beta = 1 multiplicative update of this rank's rows of U (mu.py:84-88) straight out of the stages: numerator = sum over the
+// ranks of their partial numerators (columns lo .. lo+ncols of the stage), denominator = sum of their partial row sums of V
+// (column `len`); send[k][c] = max(F[k][lo + c] * (num / den[k]), floor), NaN propagating like numpy.  grid = (column blocks, r).
+__device__ __forceinline__ float mu_rule(float f, float num, float den, float floor_value) {
+  const float v = f * (num / den);
+  return v != v ? v : (v > floor_value ? v : floor_value);
+}
+__global__ void __launch_bounds__(256) xchg_pull_mu_apply_kernel(PeerPtrs src, int world, int r, int64_t pitch, int64_t lo, int64_t ncols,
+                                                                 int64_t len, const float* __restrict__ F, int64_t ld_f, float floor_value,
+                                                                 float* __restrict__ send, int64_t ld_send,
+                                                                 const unsigned long long* flags, unsigned long long seq, int vec) {
+  __shared__ float den_s;
+  xchg_block_wait(flags, world, 0, seq);
+  const int64_t k = blockIdx.y;
+  const int64_t row = k * pitch;
+  if (threadIdx.x == 0) den_s = pull_sum(src, world, row + len);
+  __syncthreads();
+  const float den = den_s;
+  const int64_t nquad = (ncols + 3) / 4;
+  for (int64_t q0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * PULL_QUADS; q0 < nquad; q0 += (int64_t)gridDim.x * blockDim.x * PULL_QUADS) {
+    float4 num[PULL_QUADS], f[PULL_QUADS];
+    bool full[PULL_QUADS];
+#pragma unroll
+    for (int u = 0; u < PULL_QUADS; ++u) {
+      const int64_t c = (q0 + u) * 4;
+      full[u] = vec && c + 4 <= ncols;
+      if (full[u]) {
+        num[u] = pull_sum4(src, world, row + lo + c);
+        f[u] = *reinterpret_cast<const float4*>(F + k * ld_f + lo + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PULL_QUADS; ++u) {
+      const int64_t c = (q0 + u) * 4;
+      if (full[u]) {
+        *reinterpret_cast<float4*>(send + k * ld_send + c) =
+            make_float4(mu_rule(f[u].x, num[u].x, den, floor_value), mu_rule(f[u].y, num[u].y, den, floor_value),
+                        mu_rule(f[u].z, num[u].z, den, floor_value), mu_rule(f[u].w, num[u].w, den, floor_value));
+      } else {
+        for (int64_t cc = c; cc < c + 4 && cc < ncols; ++cc)
+          send[k * ld_send + cc] = mu_rule(F[k * ld_f + lo + cc], pull_sum(src, world, row + lo + cc), den, floor_value);
+      }
+    }
   }
 }
 
@@ -149,9 +260,29 @@ int nnfac_xchg_post(nnfac_xchg* x, int phase, void* stream) {
   NNFAC_ARG(x && (phase == 0 || phase == 1), "nnfac_xchg_post: bad argument");
   FlagPtrs f;
   for (int q = 0; q < NNFAC_MAX_PEERS; ++q) f.p[q] = q < x->world ? (unsigned long long*)x->peer[q] : nullptr;
-  xchg_post_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, x->world, phase, x->rank, ++x->seq[phase]);
+  xchg_post_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, x->world, phase, x->rank, ++x->seq[phase], nullptr, nullptr, 0, 0);
   NNFAC_LAUNCH_CHECK(x->ctx);
   return NNFAC_OK;
+}
+
+// nnfac_xchg_post(x, 0, stream) after writing column `col` of the stage ([rows x pitch]) from tail_src[0 .. rows): the small
+// partial sums that travel behind the big ones (row sums of V for the beta = 1 update) without a copy kernel of their own
+int nnfac_xchg_post_tail(nnfac_xchg* x, const float* tail_src, int rows, int64_t pitch, int64_t col, void* stream) {
+  NNFAC_ARG(x && tail_src && rows > 0 && col >= 0 && col < pitch, "nnfac_xchg_post_tail: bad argument");
+  NNFAC_ARG((size_t)rows * (size_t)pitch * sizeof(float) <= x->send_off - x->stage_off, "nnfac_xchg_post_tail: beyond the stage buffer");
+  FlagPtrs f;
+  for (int q = 0; q < NNFAC_MAX_PEERS; ++q) f.p[q] = q < x->world ? (unsigned long long*)x->peer[q] : nullptr;
+  float* stage = (float*)((char*)x->region + x->stage_off);
+  xchg_post_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(f, x->world, 0, x->rank, ++x->seq[0], tail_src, stage + col, pitch, rows);
+  NNFAC_LAUNCH_CHECK(x->ctx);
+  return NNFAC_OK;
+}
+
+// flag block, world and the number of posts this rank has made on `phase`: what a consumer kernel needs to wait by itself
+void nnfac_xchg_wait_args(const nnfac_xchg* x, int phase, const unsigned long long** flags, int* world, unsigned long long* seq) {
+  *flags = (const unsigned long long*)x->region;
+  *world = x->world;
+  *seq = x->seq[phase];
 }
 
 // every rank has made as many posts on `phase` as this rank (call after the own post)
@@ -163,7 +294,8 @@ int nnfac_xchg_wait(nnfac_xchg* x, int phase, void* stream) {
 }
 
 // Sum over the ranks of the columns [lo, lo + ncols) and of the `tail` columns behind column `len` of every rank's buffer
-// `which` ([r x pitch] each): out (r x ld_out) receives the columns at 0 and the tail at tail_col.  Call after nnfac_xchg_wait.
+// `which` ([r x pitch] each): out (r x ld_out) receives the columns at 0 and the tail at tail_col.  Call after this rank's
+// nnfac_xchg_post(x, which): the kernel itself waits until every rank has posted as often.
 int nnfac_xchg_pull_reduce(nnfac_xchg* x, int which, float* out, int64_t ld_out, int r, int64_t pitch, int64_t lo, int64_t ncols,
                            int64_t len, int tail, int64_t tail_col, void* stream) {
   NNFAC_ARG(x && out && (which == 0 || which == 1) && r > 0 && ncols >= 0 && tail >= 0 && tail_col >= ncols && ld_out >= tail_col + tail &&
@@ -171,10 +303,33 @@ int nnfac_xchg_pull_reduce(nnfac_xchg* x, int which, float* out, int64_t ld_out,
   PeerPtrs src;
   const size_t off = which == 0 ? x->stage_off : x->send_off;
   for (int q = 0; q < NNFAC_MAX_PEERS; ++q) src.p[q] = q < x->world ? (const float*)((const char*)x->peer[q] + off) : nullptr;
-  const int64_t total = (int64_t)r * (tail_col + tail);
-  const int64_t want = ceil_div64(total, 256);
-  const int grid = (int)(want < (int64_t)x->ctx->sm_count * 8 ? (want < 1 ? 1 : want) : (int64_t)x->ctx->sm_count * 8);
-  xchg_pull_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, x->world, r, pitch, lo, ncols, len, tail, out, ld_out, tail_col);
+  int64_t gx = ceil_div64(ceil_div64(ncols, 4 * PULL_QUADS), 256);
+  if (gx < 1) gx = 1;
+  const int vec = pitch % 4 == 0 && lo % 4 == 0 && ld_out % 4 == 0 && ((uintptr_t)out & 15) == 0 && (off & 15) == 0;
+  xchg_pull_reduce_kernel<<<dim3((unsigned)gx, (unsigned)r), 256, 0, (cudaStream_t)stream>>>(
+      src, x->world, r, pitch, lo, ncols, len, tail, out, ld_out, tail_col, (const unsigned long long*)x->region, which, x->seq[which], vec);
+  NNFAC_LAUNCH_CHECK(x->ctx);
+  return NNFAC_OK;
+}
+
+// The U update of the column-sharded beta = 1 rule over peer memory (mu.py:84-88), after this rank's post on phase 0: waits for
+// every rank's post, sums the partial numerators of this rank's rows [lo, lo + ncols) of U and the partial row sums of V
+// (column `len` of every stage, [r x pitch] each) over NVLink in rank order, applies the update to F[:, lo : lo + ncols]
+// (F: r x ld_f, the current U^T) and writes the new slice into this rank's send buffer ([r x ld_send], ld_send = chunk + tail).
+int nnfac_xchg_pull_mu_apply(nnfac_xchg* x, const float* F, int64_t ld_f, int r, int64_t pitch, int64_t lo, int64_t ncols, int64_t len,
+                             double floor_value, int64_t ld_send, void* stream) {
+  NNFAC_ARG(x && F && r > 0 && ncols >= 0 && lo >= 0 && lo + ncols <= len && len < pitch && ld_f >= len && ld_send >= ncols,
+            "nnfac_xchg_pull_mu_apply: bad argument");
+  NNFAC_ARG((size_t)r * (size_t)ld_send * sizeof(float) <= x->bytes - x->send_off, "nnfac_xchg_pull_mu_apply: beyond the send buffer");
+  if (ncols == 0) return NNFAC_OK;
+  PeerPtrs src;
+  for (int q = 0; q < NNFAC_MAX_PEERS; ++q) src.p[q] = q < x->world ? (const float*)((const char*)x->peer[q] + x->stage_off) : nullptr;
+  const int64_t gx = ceil_div64(ceil_div64(ncols, 4 * PULL_QUADS), 256);
+  const int vec = pitch % 4 == 0 && lo % 4 == 0 && ld_f % 4 == 0 && ld_send % 4 == 0 && ((uintptr_t)F & 15) == 0 &&
+                  (x->stage_off & 15) == 0 && (x->send_off & 15) == 0;
+  xchg_pull_mu_apply_kernel<<<dim3((unsigned)gx, (unsigned)r), 256, 0, (cudaStream_t)stream>>>(
+      src, x->world, r, pitch, lo, ncols, len, F, ld_f, (float)floor_value, (float*)((char*)x->region + x->send_off), ld_send,
+      (const unsigned long long*)x->region, x->seq[0], vec);
   NNFAC_LAUNCH_CHECK(x->ctx);
   return NNFAC_OK;
 }

@@ -498,6 +498,9 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
 // and its rank-contiguous planes [R x 64] (operands of the fused pass).  Block = 32 columns x all ranks.
 struct PeerG {                      // PULL: slice s of the factor lives in p[s] ([r x ld_in], the peers' send buffers mapped here)
   const float* p[NNFAC_MAX_PEERS];
+  const unsigned long long* flags;  // local flag block of the exchange region: the kernel waits until every rank's
+  int world;                        // sequence number of phase 1 (send buffer complete) has reached `seq`
+  unsigned long long seq;
 };
 
 template <bool APPLY, int RK, bool PULL>
@@ -509,13 +512,35 @@ __global__ void __launch_bounds__(256) factor_finish_kernel(const float* __restr
                                                             bf16* __restrict__ rowh, bf16* __restrict__ rowl) {
   __shared__ float tile[RK][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (PULL && G.flags != nullptr) {
+    if ((int)threadIdx.x < G.world) {
+      const unsigned long long* f = G.flags + NNFAC_MAX_PEERS + threadIdx.x;      // [phase 1][rank]
+      unsigned long long v, spins = 0;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+        if (++spins > (1ull << 27)) __trap();
+      } while (v < G.seq);
+    }
+    __syncthreads();
+  }
   const int64_t c0 = (int64_t)blockIdx.x * 32, c = c0 + tx;
   // in_chunk > 0: F_in is the output of an all-gather of column slices, [slice][r][in_chunk] with slab pitch in_slab
   const int64_t cin = in_chunk > 0 ? (c / in_chunk) * in_slab + (c % in_chunk) : c;
+  // PULL: this thread's RK / 8 loads from the owner's send buffer (over NVLink) are all issued before the first is used
+  float pulled[PULL ? RK / 8 : 1];
+  if (PULL) {
+    const float* src = c < R ? G.p[c / in_chunk] + (c % in_chunk) : nullptr;
+#pragma unroll
+    for (int i = 0; i < RK / 8; ++i) {
+      const int k = ty + 8 * i;
+      pulled[i] = (k < r && c < R) ? __ldcv(src + (int64_t)k * ld_in) : 0.f;
+    }
+  }
+#pragma unroll
   for (int k = ty; k < RK; k += 8) {
     float f = 0.f;
     if (k < r && c < R) {
-      f = PULL ? __ldcv(G.p[c / in_chunk] + (int64_t)k * ld_in + (c % in_chunk)) : F_in[(int64_t)k * ld_in + cin];
+      f = PULL ? pulled[PULL ? (k - ty) / 8 : 0] : F_in[(int64_t)k * ld_in + cin];
       if (APPLY) {
         float num = 0.f;                            // fixed order; loads issued eight at a time (few blocks, many splits
         int sp = 0;                                 // when the other dimension is short: NTD has 64 splits for 256 rows)
@@ -680,9 +705,11 @@ int nnfac_nmf_plan_set_factor_gathered(nnfac_nmf_plan* p, int which, const float
 
 // The same straight from the peers' send buffers of an exchange region (csrc/peer_xchg.cu): slice s = columns
 // [s * chunk, (s + 1) * chunk) of the factor is read from rank s's send buffer ([r x pitch], mapped here) over NVLink -- the
-// all-gather, the un-permute and the construction of the operand planes in one kernel.  Call after nnfac_xchg_wait(x, 1).
+// all-gather, the un-permute and the construction of the operand planes in one kernel.  Call after this rank's
+// nnfac_xchg_post(x, 1): the kernel itself waits until every rank has posted as often.
 const float* nnfac_xchg_peer_send(const nnfac_xchg* x, int q);
 int nnfac_xchg_world(const nnfac_xchg* x);
+void nnfac_xchg_wait_args(const nnfac_xchg* x, int phase, const unsigned long long** flags, int* world, unsigned long long* seq);
 int nnfac_nmf_plan_set_factor_pulled(nnfac_nmf_plan* p, int which, const nnfac_xchg* x, int64_t chunk, int64_t pitch, float* Ft_out,
                                      int64_t ld_out, void* stream) {
   NNFAC_ARG(p && x && Ft_out && chunk > 0 && pitch >= chunk && (which == 0 || which == 1), "nnfac_nmf_plan_set_factor_pulled: bad argument");
@@ -693,6 +720,7 @@ int nnfac_nmf_plan_set_factor_pulled(nnfac_nmf_plan* p, int which, const nnfac_x
             world, (long long)chunk, (long long)len);
   PeerG g;
   for (int q = 0; q < NNFAC_MAX_PEERS; ++q) g.p[q] = nnfac_xchg_peer_send(x, q);
+  nnfac_xchg_wait_args(x, 1, &g.flags, &g.world, &g.seq);
   return finish_factor(p, which, false, nullptr, pitch, chunk, 0, nullptr, 0.f, Ft_out, ld_out, (cudaStream_t)stream, &g);
 }
 

@@ -198,8 +198,9 @@ class PeerExchange:
     def __init__(self, comm, device, r, m, chunk, tail):
         lib = L.load_library()
         self.comm, self.device, self.r, self.m, self.chunk, self.tail = comm, device, r, m, chunk, tail
+        self.tpad = -(-tail // 4) * 4                 # row pitches stay multiples of 4 floats: 16-byte loads over NVLink
         self.handle = ctypes.c_void_p()
-        L.check(lib.nnfac_xchg_create(L.ctx(device), r * (m + tail), r * (chunk + tail), ctypes.byref(self.handle)))
+        L.check(lib.nnfac_xchg_create(L.ctx(device), r * (m + self.tpad), r * (chunk + self.tpad), ctypes.byref(self.handle)))
         mine = (ctypes.c_ubyte * 64)()
         L.check(lib.nnfac_xchg_export(self.handle, mine))
         send = torch.tensor(list(mine), dtype=torch.uint8, device=device)
@@ -207,21 +208,32 @@ class PeerExchange:
         comm.dist.all_gather_into_tensor(recv, send, group=comm.group)
         handles = (ctypes.c_ubyte * (64 * comm.world))(*recv.cpu().tolist())
         L.check(lib.nnfac_xchg_attach(self.handle, comm.world, comm.rank, handles))
-        self.stage = torch.as_tensor(_RawView(lib.nnfac_xchg_ptr(self.handle, 0), (r, m + tail)), device=device)
-        self.send = torch.as_tensor(_RawView(lib.nnfac_xchg_ptr(self.handle, 1), (r, chunk + tail)), device=device)
+        self.stage = torch.as_tensor(_RawView(lib.nnfac_xchg_ptr(self.handle, 0), (r, m + self.tpad)), device=device)
+        self.send = torch.as_tensor(_RawView(lib.nnfac_xchg_ptr(self.handle, 1), (r, chunk + self.tpad)), device=device)
         comm.dist.barrier(group=comm.group)              # every region is mapped everywhere before anybody posts
 
     def post(self, phase):
         L.check(L.load_library().nnfac_xchg_post(self.handle, phase, L.stream_ptr()))
 
+    def post_tail(self, vec, length):
+        """post(0) that first writes `vec` (r values) into column `length` of the stage (one kernel)."""
+        L.check(L.load_library().nnfac_xchg_post_tail(self.handle, L.ptr(vec), self.r, length + self.tpad, length, L.stream_ptr()))
+
     def wait(self, phase):
+        """A wait kernel of its own -- not needed before pull_reduce / pull_mu_apply / install, which wait by themselves."""
         L.check(L.load_library().nnfac_xchg_wait(self.handle, phase, L.stream_ptr()))
+
+    def pull_mu_apply(self, Ft, lo, ncols, length, floor):
+        """mu.py:84-88 for this rank's rows of U straight out of all stages into the send buffer (after post(0); one kernel:
+        wait + reduce-scatter + reduction + update)."""
+        L.check(L.load_library().nnfac_xchg_pull_mu_apply(self.handle, L.ptr(Ft), Ft.stride(0), self.r, length + self.tpad, lo, ncols,
+                                                          length, float(floor), self.chunk + self.tpad, L.stream_ptr()))
 
     def pull_reduce(self, phase, lo, ncols, length):
         """Sum over the ranks of columns [lo, lo + ncols) and of the tail of every rank's buffer `phase` -> (r x (chunk + tail))
-        with the tail at column chunk (after post + wait)."""
+        with the tail at column chunk (after post; the kernel waits for the other ranks' posts itself)."""
         out = torch.empty((self.r, self.chunk + self.tail), dtype=torch.float32, device=self.device)
-        pitch = length + self.tail
+        pitch = length + self.tpad
         L.check(L.load_library().nnfac_xchg_pull_reduce(self.handle, phase, L.ptr(out), out.stride(0), self.r, pitch, lo, ncols, length,
                                                         self.tail, self.chunk, L.stream_ptr()))
         return out
@@ -229,14 +241,14 @@ class PeerExchange:
     def pull_tail(self, phase, length):
         """Only the sum of the tails of every rank's buffer `phase` -> (r x tail)."""
         out = torch.empty((self.r, self.tail), dtype=torch.float32, device=self.device)
-        L.check(L.load_library().nnfac_xchg_pull_reduce(self.handle, phase, L.ptr(out), out.stride(0), self.r, length + self.tail, 0, 0,
+        L.check(L.load_library().nnfac_xchg_pull_reduce(self.handle, phase, L.ptr(out), out.stride(0), self.r, length + self.tpad, 0, 0,
                                                         length, self.tail, 0, L.stream_ptr()))
         return out
 
     def install(self, plan, which, length):
         """All slices straight from the peers' send buffers -> the factor (r x length) and its operand planes in `plan`."""
         out = torch.empty((self.r, length), dtype=torch.float32, device=self.device)
-        L.check(L.load_library().nnfac_nmf_plan_set_factor_pulled(plan.handle, which, self.handle, self.chunk, self.chunk + self.tail,
+        L.check(L.load_library().nnfac_nmf_plan_set_factor_pulled(plan.handle, which, self.handle, self.chunk, self.chunk + self.tpad,
                                                                   L.ptr(out), out.stride(0), L.stream_ptr()))
         return out
 
@@ -391,20 +403,21 @@ class FusedNMF:
             self._px[tail] = PeerExchange(self.comm, self.device, self.r, self.m, chunk, tail)
         return self._px[tail]
 
-    def _gram_async(self, which, F):
-        """F F^T into self._gram[which] on the side stream (it only reads F, which is final by now); returns a
+    def _gram_async(self, which, F, out=None):
+        """F F^T into `out` (default self._gram[which]) on the side stream (it only reads F, which is final by now); returns a
         function that makes the current stream wait for it."""
+        out = self._gram[which] if out is None else out
         if self._side is None:
-            self.eng.gram(F, out=self._gram[which])
-            return lambda: self._gram[which]
+            self.eng.gram(F, out=out)
+            return lambda: out
         main = torch.cuda.current_stream(self.device)
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side):
-            self.eng.gram(F, out=self._gram[which])
+            self.eng.gram(F, out=out)
 
         def join():
             main.wait_stream(self._side)
-            return self._gram[which]
+            return out
         return join
 
     def _row_sums_async(self, which, F):
@@ -448,11 +461,12 @@ class FusedNMF:
                         # partial Gram lands behind them; after the post every rank pulls and sums ITS columns of all stages
                         eng.plan.reduce(0, out=px.stage[:, :m])
                         if VVt_join is not None:
-                            px.stage[:, m:].copy_(VVt_join())
+                            g = VVt_join()                                         # run() aimed it at the stage tail already
+                            if g.data_ptr() != px.stage[:, m:m + r].data_ptr():
+                                px.stage[:, m:m + r].copy_(g)
                         else:
-                            eng.gram(V, out=px.stage[:, m:])
+                            eng.gram(V, out=px.stage[:, m:m + r])
                         px.post(0)
-                        px.wait(0)
                         recv = px.pull_reduce(0, lo, hi - lo, m)
                         VMt_slice, VVt = recv[:, :chunk], recv[:, chunk:]
                     elif VMt is None:
@@ -478,11 +492,10 @@ class FusedNMF:
                     eng.solve_slice(VMt_slice[:, :hi - lo], VVt, Ut[:, lo:hi], px.send[:, :hi - lo], r, sparsity[0],
                                     self.hals_stats[0], comm, comm.slice_lengths(m))
                     if hi > lo:
-                        eng.gram(px.send[:, :hi - lo], out=px.send[:, chunk:])
+                        eng.gram(px.send[:, :hi - lo], out=px.send[:, chunk:chunk + r])
                     else:
-                        px.send[:, chunk:].zero_()
+                        px.send[:, chunk:chunk + r].zero_()
                     px.post(1)
-                    px.wait(1)
                     Ut = px.install(eng.plan, 0, m)
                     self._utu_pulled = px.pull_tail(1, chunk)                        # U^T U = sum of the slices' Grams
                 elif hasattr(eng, "solve_slice"):
@@ -551,17 +564,13 @@ class FusedNMF:
                 if px is not None:
                     # peer-memory exchange: partial numerator -> stage, partial row sums of V behind it; every rank pulls and
                     # sums its own rows of U, applies mu.py:84-88 to them, and the install kernel collects the slices
+                    # (five kernels: reduction of the split partials into the stage, post with the row sums, pull + update of
+                    # this rank's rows, post, pulled install)
                     chunk, lo, hi = comm.slice_of(m)
                     eng.plan.reduce(0, out=px.stage[:, :m])
-                    px.stage[:, m].copy_(den)
-                    px.post(0)
-                    px.wait(0)
-                    recv = px.pull_reduce(0, lo, hi - lo, m)
-                    if hi > lo:
-                        new = eng.mu_apply(Ut[:, lo:hi].contiguous(), recv[:, :hi - lo].contiguous(), recv[:, chunk].contiguous())
-                        px.send[:, :hi - lo].copy_(new)
+                    px.post_tail(den, m)
+                    px.pull_mu_apply(Ut, lo, hi - lo, m, mu.epsilon)
                     px.post(1)
-                    px.wait(1)
                     Ut = px.install(eng.plan, 0, m)
                 elif comm.world > 1:
                     xb = self._xbuf[:r * m + r]
@@ -600,7 +609,11 @@ class FusedNMF:
             VVt_join = den_join = None
             if mode == MODE_RES and (self.comm.world == 1 or self._side is not None) and it < n_iter_max and 0 not in fixed_modes \
                     and not (self.comm.world > 1 and normalize[0]):
-                VVt_join = self._gram_async(0, self.V)                             # V V^T under the first pass
+                # V V^T under the first pass; sharded over peer memory: straight into the tail of this rank's stage buffer (the
+                # stage is free by now: this stream is behind the install of the previous iteration, which waited for every
+                # peer's second post, hence for every peer's pull)
+                px = self._exchange(self.r) if (self.comm.world > 1 and mode == MODE_RES and not mu2 and hasattr(self.eng, "plan")) else None
+                VVt_join = self._gram_async(0, self.V, out=px.stage[:, self.m:self.m + self.r] if px is not None else None)
             if mode == MODE_MU and self.comm.world == 1 and it < n_iter_max and 0 not in fixed_modes:
                 den_join = self._row_sums_async(0, self.V)                         # row sums of V under the first pass
             with self._phase("pass_U"):
