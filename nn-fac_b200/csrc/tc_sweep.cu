@@ -47,7 +47,11 @@ struct Cfg {
   static constexpr int KR = RP / 64;
   static constexpr int MAX_TILES = MT;
   static constexpr int UPD_THREADS = MAX_TILES * TILE;
-  static constexpr int NTHREADS = UPD_THREADS + MAX_TILES * 32;    // + one issuing warp per tile
+  // The partial sums of a sweep are posted by a warp of their own, except in the four-tile variant (rank <= 64, more than
+  // 256 columns per CTA: 640 threads already sit at the register limit of the update chain; it keeps the update threads
+  // posting after a CTA-wide barrier)
+  static constexpr bool POSTER = !(RP == 64 && MT == 4);
+  static constexpr int NTHREADS = UPD_THREADS + MAX_TILES * 32 + (POSTER ? 32 : 0);   // + one issuing warp per tile (+ the posting warp)
   static constexpr int TMEM_PER_TILE = 2 * RP;
   static constexpr uint32_t G_ATOM_BYTES = RP * 128;               // [RP rows x 64 K] bf16
   static constexpr uint32_t G_PLANE_BYTES = KR * G_ATOM_BYTES;     // 8 / 32 KiB
@@ -263,9 +267,11 @@ __global__ void __launch_bounds__(Cfg<RP, MT, LAG>::NTHREADS, 1) tc_sweep_kernel
   uint8_t* tail = bk_extra + C::BK_EXTRA_BYTES;
   uint64_t* s_full = reinterpret_cast<uint64_t*>(tail);                // [MAX_TILES] MMA batch complete
   uint64_t* s_ready = s_full + MAX_TILES;                              // [MAX_TILES] operand planes of a tile rewritten
-  float* redf = reinterpret_cast<float*>(s_ready + MAX_TILES);         // [32]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(redf + 32);
+  float* redf = reinterpret_cast<float*>(s_ready + MAX_TILES);         // [48]: per-warp partials of a post (2 x 16, by parity), of a collect (16)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(redf + 48);
   volatile uint32_t* s_done = tmem_slot + 1;                            // [MAX_TILES]
+  volatile uint32_t* s_quit = s_done + MAX_TILES;                       // the solve has ended: the posting warp leaves
+  volatile uint32_t* s_posted = s_quit + 1;                             // posts the posting warp has completed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = a.r;
@@ -282,6 +288,8 @@ __global__ void __launch_bounds__(Cfg<RP, MT, LAG>::NTHREADS, 1) tc_sweep_kernel
         tc::mbar_init(&s_ready[t], TILE);
       }
       for (int t = 0; t < MAX_TILES; ++t) s_done[t] = 0;
+      *s_quit = 0;
+      *s_posted = 0;
       tc::fence_barrier_init();
     }
     __syncwarp();
@@ -316,7 +324,39 @@ __global__ void __launch_bounds__(Cfg<RP, MT, LAG>::NTHREADS, 1) tc_sweep_kernel
   // over one operand set: first V (initial residual; one 64-row K atom per hand-over), then one 16-row
   // block of steps each.
   // ------------------------------------------------------------------------------------------------
-  if (warp >= UPD_THREADS / 32) {
+  if (C::POSTER && warp == UPD_THREADS / 32 + MAX_TILES) {
+    // ----------------------------------------------------------------------------------------------
+    // Posting warp: after every sweep the update warps leave their partial sums of squared steps in shared memory and
+    // ARRIVE on named barrier 2 without waiting; this warp adds them up in a fixed order and posts the CTA's partial sum
+    // to every CTA (mailboxes) or, in a collective solve, to the board of every rank (one 8-byte sys-scope store each
+    // over NVLink).  Stores to peer memory can hold the issuing warp for the better part of a microsecond: on a warp of
+    // its own they no longer sit on the update chain (nor does the CTA-wide barrier the update warps used to wait on).
+    // ----------------------------------------------------------------------------------------------
+    constexpr unsigned MB = C::MBANKS;
+    const unsigned nb = gridDim.x;
+    const unsigned gen = *a.gen;
+    const bool collective = a.xworld > 1;
+    for (unsigned e = 0;; ++e) {
+      named_bar_sync(2, UPD_THREADS + 32);
+      if (*s_quit) break;
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < UPD_THREADS / 32; ++w) sum += redf[(e & 1u) * 16 + w];
+      const unsigned tag = collective ? ((a.xgen & 0xffffu) << 16) | (e + 1u) : (gen << 16) | (e + 1u);
+      const unsigned long long bits = ((unsigned long long)tag << 32) | __float_as_uint(sum);
+      if (collective) {
+        // 8 banks of XMAXW x XMAXG entries, bank = 4 (call parity) + sweep number mod MBANKS, so that a rank that is ahead
+        // (by up to a sweep, with LAG by up to three, or by the start of the next call) never overwrites an entry a slower
+        // rank still has to read
+        const size_t xbank = (size_t)((a.xgen & 1u) * 4u + (e % MB)) * (XMAXW * XMAXG);
+        if (lane < a.xworld) st_relaxed_sys_u64(a.xboard[lane] + xbank + (size_t)a.xrank * XMAXG + blockIdx.x, bits);
+      } else if (nb > 1) {
+        for (unsigned t = lane; t < nb; t += 32) st_relaxed_u64(a.mail + ((size_t)(e % MB) * nb + t) * nb + blockIdx.x, bits);
+      }
+      __syncwarp();
+      if (lane == 0) *s_posted = e + 1u;
+    }
+  } else if (warp >= UPD_THREADS / 32) {
     // warp-uniform by construction (shuffle), so that descriptors live in uniform registers
     const int tile = __shfl_sync(0xffffffffu, warp, 0) - UPD_THREADS / 32;
     if (tile < ntiles) {
@@ -545,31 +585,36 @@ __global__ void __launch_bounds__(Cfg<RP, MT, LAG>::NTHREADS, 1) tc_sweep_kernel
     std::integral_constant<bool, false> plain;
     std::integral_constant<bool, true> backup;
     constexpr unsigned MBANKS = C::MBANKS;
-    // reduce the squared steps of this CTA's columns and post the CTA's partial sum of sweep e + 1 (tag) to every CTA
+    // hand the squared steps of this warp's columns in sweep e + 1 to the posting warp (no wait: the barrier is only arrived on)
     // (fp32 trees: every CTA adds the same numbers in the same order)
+    unsigned nposts = 0;
     auto post = [&](float nd, unsigned e) {
       const float t = warp_sum_f(nd);
-      if (lane == 0) redf[warp] = t;
-      named_bar_sync(1, UPD_THREADS);
-      const unsigned tag = collective ? ((a.xgen & 0xffffu) << 16) | (e + 1u) : (gen << 16) | (e + 1u);
-      if (collective) {
-        // 8 banks of XMAXW x XMAXG entries, bank = 4 (call parity) + sweep number mod MBANKS, so that a rank that is ahead
-        // (by up to a sweep, with LAG by up to three, or by the start of the next call) never overwrites an entry a slower
-        // rank still has to read
-        const size_t xbank = (size_t)((a.xgen & 1u) * 4u + (e % MBANKS)) * (XMAXW * XMAXG);
-        if (threadIdx.x < (unsigned)a.xworld) {
+      ++nposts;
+      if constexpr (C::POSTER) {
+        if (lane == 0) {
+          // the posting warp has long finished post e - 1 (a sweep ago); waiting for it makes the double-buffered slots and the
+          // one-phase-at-a-time use of the named barrier safe by construction
+          while (*s_posted < e) {}
+          redf[(e & 1u) * 16 + warp] = t;
+        }
+        __syncwarp();
+        asm volatile("bar.arrive 2, %0;" ::"n"(UPD_THREADS + 32) : "memory");
+      } else {
+        // no posting warp: CTA-wide barrier, then the first threads post (one store each)
+        if (lane == 0) redf[(e & 1u) * 16 + warp] = t;
+        named_bar_sync(1, UPD_THREADS);
+        const unsigned tag = collective ? ((a.xgen & 0xffffu) << 16) | (e + 1u) : (gen << 16) | (e + 1u);
+        if (collective ? threadIdx.x < (unsigned)a.xworld : (nb > 1 && threadIdx.x < nb)) {
           float sum = 0.f;
 #pragma unroll
-          for (int w = 0; w < UPD_THREADS / 32; ++w) sum += redf[w];
+          for (int w = 0; w < UPD_THREADS / 32; ++w) sum += redf[(e & 1u) * 16 + w];
           const unsigned long long bits = ((unsigned long long)tag << 32) | __float_as_uint(sum);
-          st_relaxed_sys_u64(a.xboard[threadIdx.x] + xbank + (size_t)a.xrank * XMAXG + blockIdx.x, bits);
+          if (collective)
+            st_relaxed_sys_u64(a.xboard[threadIdx.x] + (size_t)((a.xgen & 1u) * 4u + (e % MBANKS)) * (XMAXW * XMAXG) + (size_t)a.xrank * XMAXG + blockIdx.x, bits);
+          else
+            st_relaxed_u64(a.mail + ((size_t)(e % MBANKS) * nb + threadIdx.x) * nb + blockIdx.x, bits);
         }
-      } else if (nb > 1 && threadIdx.x < nb) {
-        float sum = 0.f;
-#pragma unroll
-        for (int w = 0; w < UPD_THREADS / 32; ++w) sum += redf[w];
-        const unsigned long long bits = ((unsigned long long)tag << 32) | __float_as_uint(sum);
-        st_relaxed_u64(a.mail + ((size_t)(e % MBANKS) * nb + threadIdx.x) * nb + blockIdx.x, bits);
       }
     };
     const bool poller = !collective && nb > 1 && threadIdx.x < nb;
@@ -622,10 +667,10 @@ __global__ void __launch_bounds__(Cfg<RP, MT, LAG>::NTHREADS, 1) tc_sweep_kernel
           }
         }
         got = warp_sum_f(got);
-        if (lane == 0) redf[16 + warp] = got;
+        if (lane == 0) redf[32 + warp] = got;
         named_bar_sync(1, UPD_THREADS);
 #pragma unroll
-        for (int w = 0; w < UPD_THREADS / 32; ++w) totf += redf[16 + w];
+        for (int w = 0; w < UPD_THREADS / 32; ++w) totf += redf[32 + w];
       } else if (nb > 1) {
         float got = 0.f;
         if (poller) {
@@ -639,14 +684,14 @@ __global__ void __launch_bounds__(Cfg<RP, MT, LAG>::NTHREADS, 1) tc_sweep_kernel
           got = __uint_as_float((unsigned)bits);
         }
         got = warp_sum_f(got);
-        if (lane == 0) redf[16 + warp] = got;
+        if (lane == 0) redf[32 + warp] = got;
         named_bar_sync(1, UPD_THREADS);
 #pragma unroll
-        for (int w = 0; w < UPD_THREADS / 32; ++w) totf += redf[16 + w];
+        for (int w = 0; w < UPD_THREADS / 32; ++w) totf += redf[32 + w];
       } else {
+        if (C::POSTER) named_bar_sync(1, UPD_THREADS);                  // one CTA, no exchange: the partials of post e are all there
 #pragma unroll
-        for (int w = 0; w < UPD_THREADS / 32; ++w) totf += redf[w];
-        named_bar_sync(1, UPD_THREADS);                                 // redf[] is rewritten by the next sweep
+        for (int w = 0; w < UPD_THREADS / 32; ++w) totf += redf[(e & 1u) * 16 + w];
       }
 #ifdef SWEEP_PROF
       prof[6] += clock64() - tg0;
@@ -743,6 +788,14 @@ __global__ void __launch_bounds__(Cfg<RP, MT, LAG>::NTHREADS, 1) tc_sweep_kernel
       ++epoch;
       if (decide(totf)) break;
     }
+    }
+    if constexpr (C::POSTER) {
+      if (lane == 0) {
+        while (*s_posted < nposts) {}                                     // every post has been made: the barrier is between phases
+        if (threadIdx.x == 0) *s_quit = 1;                                // releases the posting warp
+      }
+      __syncwarp();
+      asm volatile("bar.arrive 2, %0;" ::"n"(UPD_THREADS + 32) : "memory");
     }
     if (active) {
       tc::mbar_wait(&s_full[tile], s_phase);                              // drain the last rank update
@@ -908,13 +961,15 @@ int nnfac_tc_sweep_run(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const f
   }
   // mailbox tags carry a call generation (device-side, see sweep_prep_kernel), so that the slots never need clearing
   // Variant.  The lagged stop test (whole next sweep speculative) needs room to park every master (rank <= 64: at most two
-  // tiles per CTA) and something to wait for (more than one CTA, or a collective solve).  Measured (tools/time_sweeps_lag.py,
-  // tools/time_sweeps_collective.py; results bit-identical to the plain variant on one GPU): one GPU, one tile per CTA,
-  // 128 CTAs: -8 % per sweep at rank 64 (3.42 -> 3.14 us), -4 % at rank 128; two tiles per CTA +5..12 % (issue-bound: parking
-  // the fourth block costs more than the exchange it hides); 16 CTAs +14 %; collective solves on 2 GPUs +0.45..0.6 us per
-  // sweep (the three speculative blocks of the plain variant already cover the NVLink round trip).  So "auto" takes it
-  // for non-collective solves with one tile per CTA on at least 64 CTAs.  Every rank of a collective solve takes the same
-  // variant: the widest slice decides.  NNFAC_SWEEP_LAG = 0 never, 1 auto, 2 wherever possible.
+  // tiles per CTA) and something to wait for (more than one CTA, or a collective solve).  Measured with the posting warp
+  // (tools/time_sweeps_lag.py, tools/time_sweeps_collective.py; us per sweep, plain -> lagged; results bit-identical on one
+  // GPU): collective solves on 2 GPUs, rank 64: 5.20 -> 3.63 (8192 columns per rank, one tile per CTA), 5.04 -> 3.57 (4096),
+  // 4.48 -> 4.34 (32768, two tiles); rank 128: 8.59 -> 8.15 -- the lagged variant runs a collective solve at the per-sweep
+  // cost of a single-GPU solve (3.50 / 8.24), the NVLink round trip is off the chain.  One GPU: 3.50 -> 3.47 at one tile
+  // per CTA on 128 CTAs (3.42 -> 3.14 before the posting warp existed), no gain with two tiles per CTA or a handful of
+  // CTAs.  So "auto" takes it for every collective solve and for single-GPU solves with one tile per CTA on at least 64
+  // CTAs.  Every rank of a collective solve takes the same variant: the widest slice decides.
+  // NNFAC_SWEEP_LAG / nnfac_ctx_sweep_variant: 0 never, 1 auto, 2 wherever possible.
   static const int lag_env = [] { const char* e = getenv("NNFAC_SWEEP_LAG"); return e ? atoi(e) : 1; }();
   const int lag_mode = ctx->sweep_lag >= 0 ? ctx->sweep_lag : lag_env;     // nnfac_ctx_sweep_variant overrides the environment
   int64_t decide_cols = cols;
@@ -924,10 +979,12 @@ int nnfac_tc_sweep_run(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const f
     decide_cols = ceil_div64(ceil_div64(widest, ctx->sm_count), 32) * 32;
   }
   const bool lag_possible = (pg != nullptr || grid > 1) && (rp == 128 || decide_cols <= 2 * TILE);
-  const bool lag_pays = pg == nullptr && decide_cols <= TILE && grid >= 64;
+  const bool lag_pays = pg != nullptr || (decide_cols <= TILE && grid >= 64);
   const bool lag = lag_possible && (lag_mode >= 2 || (lag_mode == 1 && lag_pays));
   if (rp == 64) {
-    rc = lag ? sweep_launch<64, 2, true>(ctx, a, UtU, ld_utu, grid, st) : sweep_launch<64, 4, false>(ctx, a, UtU, ld_utu, grid, st);
+    if (lag) rc = sweep_launch<64, 2, true>(ctx, a, UtU, ld_utu, grid, st);
+    else if (decide_cols <= 2 * TILE) rc = sweep_launch<64, 2, false>(ctx, a, UtU, ld_utu, grid, st);
+    else rc = sweep_launch<64, 4, false>(ctx, a, UtU, ld_utu, grid, st);
   } else {
     rc = lag ? sweep_launch<128, 2, true>(ctx, a, UtU, ld_utu, grid, st) : sweep_launch<128, 2, false>(ctx, a, UtU, ld_utu, grid, st);
   }

@@ -16,9 +16,16 @@ for rep in range(3):
     plan = ops.NMFPlan(X); plan.bind_rank(r); t2 = T()
     del plan, X; t3 = T()
     print(f"rep {rep}: upload {1e3*(t1-t0):.1f} ms ({m*n*4/(t1-t0)/1e9:.1f} GB/s)  plan create+ingest {1e3*(t2-t1):.1f} ms  destroy {1e3*(t3-t2):.1f} ms", flush=True)
-for rep in range(3):
-    t0 = T()
-    U, V, cs, toc = nmf.nmf(Xh.numpy(), r, init="custom", U_0=Uh.numpy(), V_0=Vh.numpy(), n_iter_max=20, tol=0, update_rule="mu", beta=1,
-                            return_costs=True, deterministic=True)
-    t1 = T()
-    print(f"nmf mu 20 it: total {1e3*(t1-t0):.1f} ms, loop {1e3*toc[-1]:.1f} ms", flush=True)
+for rule, beta in (("hals", 2), ("mu", 1)):
+    for rep in range(3):
+        t0 = T()
+        U, V, cs, toc = nmf.nmf(Xh.numpy(), r, init="custom", U_0=Uh.numpy(), V_0=Vh.numpy(), n_iter_max=20, tol=0, update_rule=rule, beta=beta,
+                                return_costs=True, deterministic=True)
+        t1 = T()
+        print(f"nmf {rule} 20 it: total {1e3*(t1-t0):.1f} ms, loop {1e3*toc[-1]:.1f} ms (first cost after {1e3*toc[0]:.1f} ms), outside the loop {1e3*(t1-t0-toc[-1]):.1f} ms", flush=True)
+if os.environ.get("E2E_PROFILE"):
+    import cProfile, pstats
+    pr = cProfile.Profile(); pr.enable()
+    nmf.nmf(Xh.numpy(), r, init="custom", U_0=Uh.numpy(), V_0=Vh.numpy(), n_iter_max=20, tol=0, update_rule="hals", beta=2, return_costs=True, deterministic=True)
+    torch.cuda.synchronize(); pr.disable()
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(35)
