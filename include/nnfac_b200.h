@@ -107,6 +107,16 @@ int nnfac_xchg_pull_reduce(nnfac_xchg* x, int which, float* out, int64_t ld_out,
  * rank's send buffer ([r x ld_send]).  F = the current U^T (r x ld_f). */
 int nnfac_xchg_pull_mu_apply(nnfac_xchg* x, const float* F, int64_t ld_f, int r, int64_t pitch, int64_t lo, int64_t ncols,
                              int64_t len, double floor_value, int64_t ld_send, void* stream);
+/* PUSH variant of the U-side exchange (nnfac_nmf_plan_set_push below): the stage buffer of every rank is laid out
+ * [tail block: r x tail_pitch | inbox: (world * splits) slabs of r_pad x chunk]; the fused pass of rank p writes the partial
+ * of every row tile straight into slab (p * splits + split) of the inbox of the rank that owns those rows of U, over NVLink,
+ * from its own epilogue -- the reduce-scatter is part of the X pass.  After its post on phase 0 a rank finds every partial of its
+ * rows in local memory.  nnfac_xchg_inbox_mu_apply = the beta = 1 update (mu.py:84-88) from the inbox: waits for every rank's
+ * post, sums the slabs in slab order and the partial row sums of V (column 0 of every rank's tail block, nnfac_xchg_post_tail
+ * with pitch = tail_pitch, col = 0), writes the new rows [lo, lo + ncols) of U^T into this rank's send buffer. */
+int nnfac_xchg_inbox_mu_apply(nnfac_xchg* x, int64_t inbox_off, int nslabs, int64_t slab_stride, int64_t chunk, int64_t tail_pitch,
+                              const float* F, int64_t ld_f, int r, int64_t lo, int64_t ncols, double floor_value, int64_t ld_send,
+                              void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * HALS NNLS solver: replaces nn_fac/update_rules/nnls.py:156-198 (hals_nnls_acc sweep loop with
@@ -124,6 +134,14 @@ int nnfac_hals_nnls(nnfac_ctx* ctx, int dtype, const void* UtM, int64_t ld_utm, 
 int nnfac_hals_solve_f32(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const float* UtU, int64_t ld_utu,
                          const float* Vin, int64_t ld_vin, float* Vout, int64_t ld_vout, int r, int64_t n, int maxiter,
                          double delta, double sparsity, double* result, void* stream);
+/* The same with the right-hand side given as the sum of nslabs slabs UtM + s * slab_stride ([r_pad x ld_utm] each,
+ * slab_stride = r_pad * ld_utm): split-K partials of an X pass, or the inbox the peers' fused passes pushed their partials into
+ * (nnfac_nmf_plan_set_push).  The tensor-core sweep adds the slabs itself, in slab order; shapes outside it first sum them
+ * into scratch (r x n floats). */
+int nnfac_hals_solve_slabs_f32(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, int nslabs, int64_t slab_stride, int r_pad,
+                               float* scratch, const float* UtU, int64_t ld_utu, const float* Vin, int64_t ld_vin, float* Vout,
+                               int64_t ld_vout, int r, int64_t n, int maxiter, double delta, double sparsity, double* result,
+                               void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Strided, batched, K-blocked GEMM on CUDA cores (fp32 or fp64 accumulate in the operand type):
@@ -287,6 +305,12 @@ int nnfac_nmf_plan_set_factor_gathered(nnfac_nmf_plan* plan, int which, const fl
  * posted as often. */
 int nnfac_nmf_plan_set_factor_pulled(nnfac_nmf_plan* plan, int which, const nnfac_xchg* x, int64_t chunk, int64_t pitch,
                                      float* Ft_out, int64_t ld_out, void* stream);
+/* Column-sharded path, U side (new): from now on a fused pass over side 0 that keeps its partials (out = NULL) writes them into
+ * the inbox of the rank that owns those rows of U -- x's stage buffer on that rank, inbox_off floats in, laid out
+ * [world * splits][r_pad][chunk] (slab = source rank * splits + split; chunk = rows of U per rank, a multiple of 128) -- instead of
+ * the plan's own buffer.  x = NULL switches it off.  slabs / slab_stride (optional) receive world * splits and r_pad * chunk. */
+int nnfac_nmf_plan_set_push(nnfac_nmf_plan* plan, const nnfac_xchg* x, int64_t inbox_off, int64_t chunk, int* slabs,
+                            int64_t* slab_stride);
 /* HALS solve of factor `which` (nn_fac/update_rules/nnls.py:24-198, deterministic rule, no normalize / nonzero) whose
  * result F_out (r x len, may not alias F_in) is installed in the plan by the sweep kernel itself (no separate pass over
  * the factor).  result: double[4] = {eps, cnt, -1, sweeps}.  Returns NNFAC_ERR_UNSUPPORTED without an error text when

@@ -12,6 +12,9 @@ int nnfac_tc_sweep_try(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const f
                        int64_t ld_v, int r, int64_t n, int maxiter, double delta, double sparsity, double* result,
                        cudaStream_t st);
 
+void nnfac_reduce_partials(const float* partial, int splits, int r, int r_pad, int64_t R, int64_t ld_partial, float* out,
+                           int64_t ld_out, int sm_count, cudaStream_t st);       // csrc/tc_nmf.cu
+
 namespace {
 template <typename T>
 hals::SweepArgs<T> make_args(const void* UtM, int64_t ld_utm, const void* UtU, int64_t ld_utu, void* V,
@@ -73,6 +76,33 @@ extern "C" int nnfac_hals_nnls(nnfac_ctx* ctx, int dtype, const void* UtM, int64
 // inside the kernel: the tensor-core sweep reads its start values from Vin and writes the result to Vout).  Used for the
 // slice solves of the sharded path, whose input is a strided view of the full factor and whose output is the contiguous
 // send buffer of the all-gather.  Shapes outside the tensor-core sweep: a strided copy, then the in-place solver.
+//
+// nnfac_hals_solve_slabs_f32: the right-hand side is the sum of `nslabs` slabs UtM + s * slab_stride ([>= r rows x ld_utm] each:
+// split-K partials of an X pass, or the inbox the peers' fused passes pushed their partials into), added up in slab order by the
+// solve itself.  Shapes outside the tensor-core sweep: the slabs are first summed into `scratch` (r x n floats, caller's).
+extern "C" int nnfac_hals_solve_slabs_f32(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, int nslabs, int64_t slab_stride, int r_pad,
+                                          float* scratch, const float* UtU, int64_t ld_utu, const float* Vin, int64_t ld_vin, float* Vout,
+                                          int64_t ld_vout, int r, int64_t n, int maxiter, double delta, double sparsity, double* result,
+                                          void* stream) {
+  NNFAC_ARG(ctx && UtM && UtU && Vin && Vout && result && scratch, "nnfac_hals_solve_slabs_f32: NULL argument");
+  NNFAC_ARG(r > 0 && n > 0 && nslabs >= 1 && r_pad >= r, "nnfac_hals_solve_slabs_f32: empty problem (r=%d, n=%lld, %d slabs)", r, (long long)n, nslabs);
+  NNFAC_ARG(ld_utm >= n && ld_vin >= n && ld_vout >= n && ld_utu >= r && slab_stride == (int64_t)r_pad * ld_utm,
+            "nnfac_hals_solve_slabs_f32: leading dimension too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  static const bool force_fma = getenv("NNFAC_SWEEP") && !strcmp(getenv("NNFAC_SWEEP"), "fma");
+  if (!force_fma) {
+    const int rc = nnfac_tc_sweep_run(ctx, UtM, ld_utm, UtU, ld_utu, Vin, ld_vin, Vout, ld_vout, r, n, maxiter, delta, sparsity,
+                                      result, nullptr, st, nslabs, slab_stride);
+    if (rc != NNFAC_ERR_UNSUPPORTED) return rc;
+  }
+  nnfac_reduce_partials(UtM, nslabs, r, r_pad, n, ld_utm, scratch, n, ctx->sm_count, st);
+  NNFAC_LAUNCH_CHECK(ctx);
+  if (Vin != Vout)
+    NNFAC_CUDA(cudaMemcpy2DAsync(Vout, ld_vout * sizeof(float), Vin, ld_vin * sizeof(float), n * sizeof(float), r,
+                                 cudaMemcpyDeviceToDevice, st));
+  return nnfac_hals_nnls(ctx, NNFAC_F32, scratch, n, UtU, ld_utu, Vout, ld_vout, r, n, maxiter, delta, sparsity, 0u, result, stream);
+}
+
 extern "C" int nnfac_hals_solve_f32(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const float* UtU, int64_t ld_utu,
                                     const float* Vin, int64_t ld_vin, float* Vout, int64_t ld_vout, int r, int64_t n, int maxiter,
                                     double delta, double sparsity, double* result, void* stream) {

@@ -189,6 +189,44 @@ __global__ void __launch_bounds__(256) xchg_pull_mu_apply_kernel(PeerPtrs src, i
   }
 }
 
+// The same update when the partial numerators were PUSHED into this rank's inbox by the peers' fused passes
+// (nnfac_nmf_plan_set_push): numerator = sum of the nslabs local slabs [r_pad x chunk] in slab order (rank-major, then split),
+// denominator = sum over the ranks of column 0 of their tail blocks ([r x tail_pitch] at the start of every stage, read over
+// NVLink: r floats per rank).  grid = (column blocks, r).
+__global__ void __launch_bounds__(256) xchg_inbox_mu_apply_kernel(PeerPtrs stage, int world, const float* __restrict__ inbox, int nslabs,
+                                                                  int64_t slab_stride, int64_t chunk, int64_t tail_pitch, int64_t lo,
+                                                                  int64_t ncols, const float* __restrict__ F, int64_t ld_f,
+                                                                  float floor_value, float* __restrict__ send, int64_t ld_send,
+                                                                  const unsigned long long* flags, unsigned long long seq) {
+  __shared__ float den_s;
+  xchg_block_wait(flags, world, 0, seq);
+  const int64_t k = blockIdx.y;
+  if (threadIdx.x == 0) den_s = pull_sum(stage, world, k * tail_pitch);
+  __syncthreads();
+  const float den = den_s;
+  const float* src = inbox + k * chunk;
+  const int64_t nquad = (ncols + 3) / 4;           // chunk is a multiple of 128: quads never straddle the padding
+  for (int64_t q0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q0 < nquad; q0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = q0 * 4;
+    float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+    int s = 0;
+    for (; s + 4 <= nslabs; s += 4) {             // four slabs in flight, added in slab order
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldcv(reinterpret_cast<const float4*>(src + (int64_t)(s + u) * slab_stride + c));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { num.x += v[u].x; num.y += v[u].y; num.z += v[u].z; num.w += v[u].w; }
+    }
+    for (; s < nslabs; ++s) {
+      const float4 v = __ldcv(reinterpret_cast<const float4*>(src + (int64_t)s * slab_stride + c));
+      num.x += v.x; num.y += v.y; num.z += v.z; num.w += v.w;
+    }
+    const float nv[4] = {num.x, num.y, num.z, num.w};
+    for (int e = 0; e < 4 && c + e < ncols; ++e)
+      send[k * ld_send + c + e] = mu_rule(F[k * ld_f + lo + c + e], nv[e], den, floor_value);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -334,11 +372,42 @@ int nnfac_xchg_pull_mu_apply(nnfac_xchg* x, const float* F, int64_t ld_f, int r,
   return NNFAC_OK;
 }
 
+// The U update of the column-sharded beta = 1 rule when the peers' fused passes pushed their partial numerators into this rank's
+// inbox (nnfac_nmf_plan_set_push; inbox_off floats into the stage buffer, nslabs slabs of slab_stride floats, row pitch chunk),
+// after this rank's post on phase 0 (nnfac_xchg_post_tail with pitch = tail_pitch, col = 0: the partial row sums of V sit in
+// column 0 of the [r x tail_pitch] block at the start of every stage).  Writes the new rows [lo, lo + ncols) of U^T into this
+// rank's send buffer ([r x ld_send]).
+int nnfac_xchg_inbox_mu_apply(nnfac_xchg* x, int64_t inbox_off, int nslabs, int64_t slab_stride, int64_t chunk, int64_t tail_pitch,
+                              const float* F, int64_t ld_f, int r, int64_t lo, int64_t ncols, double floor_value, int64_t ld_send,
+                              void* stream) {
+  NNFAC_ARG(x && F && r > 0 && nslabs > 0 && ncols >= 0 && ncols <= chunk && chunk % 4 == 0 && inbox_off % 4 == 0 && slab_stride % 4 == 0 &&
+                tail_pitch > 0 && inbox_off >= (int64_t)r * tail_pitch && ld_send >= ncols && lo >= 0 && ld_f >= lo + ncols,
+            "nnfac_xchg_inbox_mu_apply: bad argument");
+  NNFAC_ARG((size_t)(inbox_off + (int64_t)nslabs * slab_stride) * sizeof(float) <= x->send_off - x->stage_off,
+            "nnfac_xchg_inbox_mu_apply: beyond the stage buffer");
+  NNFAC_ARG((size_t)r * (size_t)ld_send * sizeof(float) <= x->bytes - x->send_off, "nnfac_xchg_inbox_mu_apply: beyond the send buffer");
+  if (ncols == 0) return NNFAC_OK;
+  PeerPtrs src;
+  for (int q = 0; q < NNFAC_MAX_PEERS; ++q) src.p[q] = q < x->world ? (const float*)((const char*)x->peer[q] + x->stage_off) : nullptr;
+  const int64_t gx = ceil_div64(ceil_div64(ncols, 4), 256);
+  xchg_inbox_mu_apply_kernel<<<dim3((unsigned)gx, (unsigned)r), 256, 0, (cudaStream_t)stream>>>(
+      src, x->world, (const float*)((const char*)x->region + x->stage_off) + inbox_off, nslabs, slab_stride, chunk, tail_pitch, lo, ncols,
+      F, ld_f, (float)floor_value, (float*)((char*)x->region + x->send_off), ld_send, (const unsigned long long*)x->region, x->seq[0]);
+  NNFAC_LAUNCH_CHECK(x->ctx);
+  return NNFAC_OK;
+}
+
 // peer q's send buffer as mapped here (for nnfac_nmf_plan_set_factor_pulled)
 const float* nnfac_xchg_peer_send(const nnfac_xchg* x, int q) {
   if (!x || q < 0 || q >= x->world) return nullptr;
   return (const float*)((const char*)x->peer[q] + x->send_off);
 }
 int nnfac_xchg_world(const nnfac_xchg* x) { return x ? x->world : 0; }
+int nnfac_xchg_rank(const nnfac_xchg* x) { return x ? x->rank : 0; }
+void* nnfac_xchg_peer_stage(const nnfac_xchg* x, int q) {
+  if (!x || q < 0 || q >= x->world) return nullptr;
+  return (char*)x->peer[q] + x->stage_off;
+}
+int64_t nnfac_xchg_stage_floats(const nnfac_xchg* x) { return x ? (int64_t)((x->send_off - x->stage_off) / sizeof(float)) : 0; }
 
 }  // extern "C"

@@ -58,6 +58,12 @@ struct FusedParams {
   double* cost_part;
   const bf16 *a1h, *a1l;   // RK = 128: rank-contiguous planes [R x RK] of the factor aligned with the rows of this side
   int64_t R;               // rows of this side
+  // push_chunk > 0 (column-sharded path, side 0): the partial of row tile t goes to rank q = 128 t / push_chunk, slab
+  // (push_src * splits + split) of its inbox push[q] = [world * splits][r_pad][push_chunk] -- the reduce-scatter of the U side
+  // happens in this kernel's epilogue, tile by tile, over NVLink
+  float* push[NNFAC_MAX_PEERS];
+  int64_t push_chunk;
+  int push_src;
 };
 
 __device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, <= 1 ulp: no IEEE fix-up branch
@@ -465,7 +471,14 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         if (i >= 3 && (i & 1)) { drain_chain(); ++drained; }
       }
       for (; drained < (S + DRAIN - 1) / DRAIN; ++drained) drain_chain();
-      {
+      if (p.push_chunk > 0) {
+        const int64_t row0 = (int64_t)tile * TILE_ROWS;
+        const int q = (int)(row0 / p.push_chunk);                          // owner of these rows of U (warp-uniform)
+        float* out = p.push[q] + (((int64_t)p.push_src * p.splits + split) * p.r_pad + CWD * part) * p.push_chunk + (row0 - q * p.push_chunk) + row;
+#pragma unroll
+        for (int j = 0; j < CWD; ++j)
+          if (CWD * part + j < p.r_pad) out[(int64_t)j * p.push_chunk] = sum[j];
+      } else {
         float* out = p.partial + ((int64_t)split * p.r_pad + CWD * part) * p.ld_partial + (int64_t)tile * TILE_ROWS + row;
 #pragma unroll
         for (int j = 0; j < CWD; ++j)
@@ -753,6 +766,31 @@ int nnfac_nmf_plan_hals_solve(nnfac_nmf_plan* p, int which, const float* UtM, in
                             result, &pl, (cudaStream_t)stream, nsplit, split_stride);
 }
 
+// Column-sharded path, U side: from now on a fused pass over side 0 that keeps its partials (out = NULL) writes them into the
+// inbox of the rank that owns those rows of U instead of the plan's own buffer: x's stage buffer on rank q, `inbox_off`
+// floats in, laid out [world * splits][r_pad][chunk] (slab = source rank * splits + split); chunk = rows of U per rank, a
+// multiple of 128.  x == NULL switches it off.  *slabs / *slab_stride (optional) receive world * splits and r_pad * chunk: what
+// the owner's solve (nnfac_hals_solve_slabs_f32) or update (nnfac_xchg_inbox_mu_apply) needs to add the slabs up.
+void* nnfac_xchg_peer_stage(const nnfac_xchg* x, int q);
+int nnfac_xchg_rank(const nnfac_xchg* x);
+int64_t nnfac_xchg_stage_floats(const nnfac_xchg* x);
+int nnfac_nmf_plan_set_push(nnfac_nmf_plan* p, const nnfac_xchg* x, int64_t inbox_off, int64_t chunk, int* slabs, int64_t* slab_stride) {
+  NNFAC_ARG(p, "nnfac_nmf_plan_set_push: NULL plan");
+  if (!x) { p->push_chunk = 0; return NNFAC_OK; }
+  NNFAC_ARG(!p->base && p->fused_ok, "nnfac_nmf_plan_set_push: needs a plan with the fused pass");
+  const int world = nnfac_xchg_world(x);
+  const int splits = p->side[0].cp.splits;
+  NNFAC_ARG(chunk > 0 && chunk % TILE_ROWS == 0 && (int64_t)world * chunk >= p->m && inbox_off >= 0,
+            "nnfac_nmf_plan_set_push: %d slices of %lld rows (multiple of 128) must cover %lld", world, (long long)chunk, (long long)p->m);
+  NNFAC_ARG(inbox_off + (int64_t)world * splits * p->r_pad * chunk <= nnfac_xchg_stage_floats(x),
+            "nnfac_nmf_plan_set_push: the stage buffer is too small for %d x %d slabs of %d x %lld", world, splits, p->r_pad, (long long)chunk);
+  for (int q = 0; q < world; ++q) p->push[q] = (float*)nnfac_xchg_peer_stage(x, q) + inbox_off;
+  p->push_chunk = chunk; p->push_src = nnfac_xchg_rank(x); p->push_world = world;
+  if (slabs) *slabs = world * splits;
+  if (slab_stride) *slab_stride = (int64_t)p->r_pad * chunk;
+  return NNFAC_OK;
+}
+
 // Sum the split-K partials the last X pass over `side` left in the plan into out (r x R): what nnfac_nmf_plan_fused /
 // _cross do themselves when they are given an output.
 int nnfac_nmf_plan_reduce(nnfac_nmf_plan* p, int side, float* out, int64_t ld_out, void* stream) {
@@ -811,6 +849,12 @@ int nnfac_nmf_plan_fused(nnfac_nmf_plan* p, int side, int mode, int want_cost, f
   fp.tiles = s->cp.tiles; fp.split_major = s->cp.split_major;
   fp.ld_partial = s->cp.ld_partial; fp.partial = p->partial; fp.cost_part = p->cost_part;
   fp.a1h = p->rowp_h[side]; fp.a1l = p->rowp_l[side]; fp.R = s->R;
+  fp.push_chunk = 0; fp.push_src = 0;
+  for (int q = 0; q < NNFAC_MAX_PEERS; ++q) fp.push[q] = nullptr;
+  if (side == 0 && !out && p->push_chunk > 0) {       // sharded U side: partials go straight to their owners' inboxes
+    fp.push_chunk = p->push_chunk; fp.push_src = p->push_src;
+    for (int q = 0; q < p->push_world; ++q) fp.push[q] = p->push[q];
+  }
   const int other = 1 - side;
 #define NNFAC_LAUNCH_FUSED(M, C, XF, RKV, MAPH, MAPL)                                                                             \
   do {                                                                                                                        \

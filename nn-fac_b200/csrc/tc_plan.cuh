@@ -132,6 +132,11 @@ struct nnfac_nmf_plan {
   float* xf[2];
   CUtensorMap map_xf[2];
   int xf_ready;
+  // column-sharded path, U side: the fused pass over side 0 writes its split partials straight into the INBOX of the rank
+  // that owns those rows of U (peer-mapped memory, nnfac_nmf_plan_set_push): [source rank][split][r_pad][push_chunk]
+  float* push[NNFAC_MAX_PEERS];
+  int64_t push_chunk;   // rows of U per rank (multiple of 128); 0: off
+  int push_src, push_world;
 };
 
 

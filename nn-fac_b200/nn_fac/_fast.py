@@ -45,6 +45,24 @@ def eligible(dtype, rank, update_rule, beta):
     return update_rule == "mu" and beta == 1 and rank <= 64
 
 
+# Peer-mapped resources are expensive to set up (cudaMalloc + CUDA IPC export / open on every rank + a barrier: tens of
+# milliseconds on 8 GPUs) and independent of the data, so they are kept for the life of the process and shared by every
+# factorisation of the same group and shape: boards per (group, device), exchange regions per (group, device, r, m, chunk, tail).
+_BOARDS = {}
+_EXCHANGES = {}
+
+
+def release_exchanges():
+    """Free the cached exchange regions (every rank of the group must call it at the same point)."""
+    for px in list(_EXCHANGES.values()):
+        px.close()
+    _EXCHANGES.clear()
+
+
+import atexit  # noqa: E402
+atexit.register(release_exchanges)
+
+
 class Comm:
     """The exchange steps of the column-sharded path over a torch.distributed group (NCCL on GPUs).
     With a single rank every call returns its argument untouched and no collective is issued."""
@@ -101,6 +119,11 @@ class Comm:
             return self._boards_device is not None
         if self.world > 8:
             return False
+        key = (self.group, L.device_index(device))
+        if key in _BOARDS:                            # attached by an earlier factorisation over this group
+            if _BOARDS[key]:
+                self._boards_device = device
+            return _BOARDS[key]
         lib = L.load_library()
         mine = (ctypes.c_ubyte * 64)()
         L.check(lib.nnfac_ctx_board_export(L.ctx(device), mine))
@@ -111,7 +134,8 @@ class Comm:
         rc = lib.nnfac_ctx_board_attach(L.ctx(device), self.world, self.rank, handles)
         ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int64, device=device)
         self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN, group=self.group)      # all ranks or none
-        if int(ok.item()) == 1:
+        _BOARDS[key] = int(ok.item()) == 1
+        if _BOARDS[key]:
             self._boards_device = device
             return True
         import warnings
@@ -195,12 +219,23 @@ class PeerExchange:
     kernel sums this rank's columns out of all stages over NVLink, the slice results go to the send buffers [r x (chunk + t)],
     and the install kernel reads all slices from the peers' send buffers.  One region per FusedNMF state."""
 
-    def __init__(self, comm, device, r, m, chunk, tail):
+    def __init__(self, comm, device, r, m, chunk, tail, push=None):
+        """push = (splits, r_pad): PUSH layout of the stage buffer, [tail block r x tpad | inbox (world * splits) x r_pad x chunk]:
+        the peers' fused passes write their partials of this rank's rows straight into the inbox (nnfac_nmf_plan_set_push); else
+        the stage holds this rank's own r x (m + tpad) partial result and the owners pull their columns out of it."""
         lib = L.load_library()
         self.comm, self.device, self.r, self.m, self.chunk, self.tail = comm, device, r, m, chunk, tail
         self.tpad = -(-tail // 4) * 4                 # row pitches stay multiples of 4 floats: 16-byte loads over NVLink
+        self.push = push
         self.handle = ctypes.c_void_p()
-        L.check(lib.nnfac_xchg_create(L.ctx(device), r * (m + self.tpad), r * (chunk + self.tpad), ctypes.byref(self.handle)))
+        if push is not None:
+            splits, r_pad = push
+            self.nslabs, self.r_pad, self.slab_stride = comm.world * splits, r_pad, r_pad * chunk
+            self.inbox_off = r * self.tpad
+            stage_floats = self.inbox_off + self.nslabs * self.slab_stride
+        else:
+            stage_floats = r * (m + self.tpad)
+        L.check(lib.nnfac_xchg_create(L.ctx(device), stage_floats, r * (chunk + self.tpad), ctypes.byref(self.handle)))
         mine = (ctypes.c_ubyte * 64)()
         L.check(lib.nnfac_xchg_export(self.handle, mine))
         send = torch.tensor(list(mine), dtype=torch.uint8, device=device)
@@ -208,7 +243,14 @@ class PeerExchange:
         comm.dist.all_gather_into_tensor(recv, send, group=comm.group)
         handles = (ctypes.c_ubyte * (64 * comm.world))(*recv.cpu().tolist())
         L.check(lib.nnfac_xchg_attach(self.handle, comm.world, comm.rank, handles))
-        self.stage = torch.as_tensor(_RawView(lib.nnfac_xchg_ptr(self.handle, 0), (r, m + self.tpad)), device=device)
+        if push is not None:
+            base = lib.nnfac_xchg_ptr(self.handle, 0)
+            self.stage = None
+            self.tailblk = torch.as_tensor(_RawView(base, (r, self.tpad)), device=device)
+            self.inbox = torch.as_tensor(_RawView(base + 4 * self.inbox_off, (self.nslabs, self.r_pad, chunk)), device=device)
+            self._scratch = None
+        else:
+            self.stage = torch.as_tensor(_RawView(lib.nnfac_xchg_ptr(self.handle, 0), (r, m + self.tpad)), device=device)
         self.send = torch.as_tensor(_RawView(lib.nnfac_xchg_ptr(self.handle, 1), (r, chunk + self.tpad)), device=device)
         comm.dist.barrier(group=comm.group)              # every region is mapped everywhere before anybody posts
 
@@ -216,8 +258,37 @@ class PeerExchange:
         L.check(L.load_library().nnfac_xchg_post(self.handle, phase, L.stream_ptr()))
 
     def post_tail(self, vec, length):
-        """post(0) that first writes `vec` (r values) into column `length` of the stage (one kernel)."""
-        L.check(L.load_library().nnfac_xchg_post_tail(self.handle, L.ptr(vec), self.r, length + self.tpad, length, L.stream_ptr()))
+        """post(0) that first writes `vec` (r values) into column `length` of the stage -- PUSH layout: into column 0 of the tail
+        block (one kernel)."""
+        if self.push is not None:
+            L.check(L.load_library().nnfac_xchg_post_tail(self.handle, L.ptr(vec), self.r, self.tpad, 0, L.stream_ptr()))
+        else:
+            L.check(L.load_library().nnfac_xchg_post_tail(self.handle, L.ptr(vec), self.r, length + self.tpad, length, L.stream_ptr()))
+
+    def attach_plan(self, plan):
+        """PUSH layout: the fused passes of `plan` over side 0 that keep their partials write them into the owners' inboxes."""
+        slabs, stride = ctypes.c_int(), ctypes.c_int64()
+        L.check(L.load_library().nnfac_nmf_plan_set_push(plan.handle, self.handle, self.inbox_off, self.chunk, ctypes.byref(slabs),
+                                                         ctypes.byref(stride)))
+        assert slabs.value == self.nslabs and stride.value == self.slab_stride, (slabs.value, stride.value, self.nslabs, self.slab_stride)
+
+    def pull_tail0(self):
+        """PUSH layout: sum over the ranks of the first `tail` columns of their tail blocks -> (r x tail) (after post(0); waits)."""
+        out = torch.empty((self.r, self.tail), dtype=torch.float32, device=self.device)
+        L.check(L.load_library().nnfac_xchg_pull_reduce(self.handle, 0, L.ptr(out), out.stride(0), self.r, self.tpad, 0, 0, 0, self.tail, 0,
+                                                        L.stream_ptr()))
+        return out
+
+    def inbox_mu_apply(self, Ft, lo, ncols, floor):
+        """PUSH layout: mu.py:84-88 for this rank's rows of U from the inbox (local) and the peers' tail blocks -> send buffer."""
+        L.check(L.load_library().nnfac_xchg_inbox_mu_apply(self.handle, self.inbox_off, self.nslabs, self.slab_stride, self.chunk, self.tpad,
+                                                           L.ptr(Ft), Ft.stride(0), self.r, lo, ncols, float(floor), self.chunk + self.tpad,
+                                                           L.stream_ptr()))
+
+    def scratch(self, r, n):
+        if self._scratch is None or self._scratch.numel() < r * n:
+            self._scratch = torch.empty(r * n, dtype=torch.float32, device=self.device)
+        return self._scratch
 
     def wait(self, phase):
         """A wait kernel of its own -- not needed before pull_reduce / pull_mu_apply / install, which wait by themselves."""
@@ -252,7 +323,7 @@ class PeerExchange:
                                                                   L.ptr(out), out.stride(0), L.stream_ptr()))
         return out
 
-    def __del__(self):
+    def close(self):
         try:
             if self.handle:
                 torch.cuda.synchronize(self.device)
@@ -260,6 +331,8 @@ class PeerExchange:
                 self.handle = None
         except Exception:
             pass
+
+    __del__ = close
 
 
 class CudaEngine:
@@ -385,6 +458,7 @@ class FusedNMF:
         self._usend = None
         self._vlens = self.comm.all_lengths(self.n, self.device)
         self._px = {}
+        self._pushing = None
         if self.comm.world > 1 and self._on_gpu and engine is None:
             self.comm.attach_boards(self.device)
 
@@ -400,8 +474,20 @@ class FusedNMF:
             return None
         if tail not in self._px:
             chunk = self.comm.slice_of(self.m)[0]
-            self._px[tail] = PeerExchange(self.comm, self.device, self.r, self.m, chunk, tail)
-        return self._px[tail]
+            # PUSH: the fused pass writes its partials straight into the owners' inboxes (needs the fused pass, i.e. rank <= 128;
+            # NNFAC_PEER_PUSH=0: every rank stages its own partial result and the owners pull)
+            push = None
+            if os.environ.get("NNFAC_PEER_PUSH", "1") != "0" and chunk % 128 == 0:
+                push = (self.eng.plan.info(0)["splits"], -(-self.r // 16) * 16)
+            key = (self.comm.group, L.device_index(self.device), self.r, self.m, chunk, tail, push)
+            if key not in _EXCHANGES:
+                _EXCHANGES[key] = PeerExchange(self.comm, self.device, self.r, self.m, chunk, tail, push)
+            self._px[tail] = _EXCHANGES[key]
+        px = self._px[tail]
+        if px.push is not None and self._pushing is not px:
+            px.attach_plan(self.eng.plan)          # the plan pushes into ONE region at a time (HALS: tail r, MU: tail 1)
+            self._pushing = px
+        return px
 
     def _gram_async(self, which, F, out=None):
         """F F^T into `out` (default self._gram[which]) on the side stream (it only reads F, which is final by now); returns a
@@ -456,7 +542,19 @@ class FusedNMF:
                     # summed Gram) -> reduce-scatter
                     chunk, lo, hi = comm.slice_of(m)
                     px = self._exchange(r) if VMt is None else None
-                    if px is not None:
+                    if px is not None and px.push is not None:
+                        # PUSH: the fused pass of every rank has already written its partials of MY rows into my inbox; only the
+                        # partial Grams (r x r) are pulled.  pull_tail0 waits for every rank's post.
+                        if VVt_join is not None:
+                            g = VVt_join()
+                            if g.data_ptr() != px.tailblk.data_ptr():
+                                px.tailblk[:, :r].copy_(g)
+                        else:
+                            eng.gram(V, out=px.tailblk[:, :r])
+                        px.post(0)
+                        VVt = px.pull_tail0()
+                        VMt_slice = None
+                    elif px is not None:
                         # peer-memory exchange: the split-K partials are summed straight into this rank's stage buffer, the
                         # partial Gram lands behind them; after the post every rank pulls and sums ITS columns of all stages
                         eng.plan.reduce(0, out=px.stage[:, :m])
@@ -489,8 +587,15 @@ class FusedNMF:
                     # slice solve straight into this rank's send buffer (the partial Gram of the new slice behind it); after the
                     # post the install kernel reads every slice from its owner's send buffer while it builds the operand planes
                     px = self._exchange(r)
-                    eng.solve_slice(VMt_slice[:, :hi - lo], VVt, Ut[:, lo:hi], px.send[:, :hi - lo], r, sparsity[0],
-                                    self.hals_stats[0], comm, comm.slice_lengths(m))
+                    if px.push is not None:
+                        with comm.collective(comm.slice_lengths(m)):
+                            if hi > lo:
+                                ops.hals_solve_slabs(px.inbox, chunk, px.nslabs, px.slab_stride, px.r_pad, px.scratch(r, hi - lo), VVt,
+                                                     Ut[:, lo:hi], px.send[:, :hi - lo], r, hi - lo, 100, 0.01,
+                                                     0.0 if sparsity[0] is None else float(sparsity[0]), self.hals_stats[0])
+                    else:
+                        eng.solve_slice(VMt_slice[:, :hi - lo], VVt, Ut[:, lo:hi], px.send[:, :hi - lo], r, sparsity[0],
+                                        self.hals_stats[0], comm, comm.slice_lengths(m))
                     if hi > lo:
                         eng.gram(px.send[:, :hi - lo], out=px.send[:, chunk:chunk + r])
                     else:
@@ -567,9 +672,14 @@ class FusedNMF:
                     # (five kernels: reduction of the split partials into the stage, post with the row sums, pull + update of
                     # this rank's rows, post, pulled install)
                     chunk, lo, hi = comm.slice_of(m)
-                    eng.plan.reduce(0, out=px.stage[:, :m])
-                    px.post_tail(den, m)
-                    px.pull_mu_apply(Ut, lo, hi - lo, m, mu.epsilon)
+                    if px.push is not None:
+                        # PUSH: the partial numerators of my rows are already in my inbox (written by every rank's fused pass)
+                        px.post_tail(den, m)
+                        px.inbox_mu_apply(Ut, lo, hi - lo, mu.epsilon)
+                    else:
+                        eng.plan.reduce(0, out=px.stage[:, :m])
+                        px.post_tail(den, m)
+                        px.pull_mu_apply(Ut, lo, hi - lo, m, mu.epsilon)
                     px.post(1)
                     Ut = px.install(eng.plan, 0, m)
                 elif comm.world > 1:
@@ -613,7 +723,10 @@ class FusedNMF:
                 # stage is free by now: this stream is behind the install of the previous iteration, which waited for every
                 # peer's second post, hence for every peer's pull)
                 px = self._exchange(self.r) if (self.comm.world > 1 and mode == MODE_RES and not mu2 and hasattr(self.eng, "plan")) else None
-                VVt_join = self._gram_async(0, self.V, out=px.stage[:, self.m:self.m + self.r] if px is not None else None)
+                gout = None
+                if px is not None:
+                    gout = px.tailblk[:, :self.r] if px.push is not None else px.stage[:, self.m:self.m + self.r]
+                VVt_join = self._gram_async(0, self.V, out=gout)
             if mode == MODE_MU and self.comm.world == 1 and it < n_iter_max and 0 not in fixed_modes:
                 den_join = self._row_sums_async(0, self.V)                         # row sums of V under the first pass
             with self._phase("pass_U"):

@@ -79,6 +79,18 @@ def hals_solve(UtM, UtU, V_in, V_out, r, maxiter, delta, sparsity, result=None):
     return result
 
 
+def hals_solve_slabs(slabs, ld, nslabs, slab_stride, r_pad, scratch, UtU, V_in, V_out, r, n, maxiter, delta, sparsity, result=None):
+    """hals_solve whose right-hand side is the sum of `nslabs` slabs ([r_pad x ld] each, slab_stride floats apart): split-K
+    partials, or the inbox the peers' fused passes pushed their partials into (csrc/hals_sweep.cu)."""
+    if result is None:
+        result = torch.empty(4, dtype=torch.float64, device=V_in.device)
+    L.check(_lib().nnfac_hals_solve_slabs_f32(L.ctx(V_in.device), L.ptr(slabs), int(ld), int(nslabs), int(slab_stride), int(r_pad),
+                                              L.ptr(scratch), L.ptr(UtU), UtU.stride(0), L.ptr(V_in), V_in.stride(0), L.ptr(V_out),
+                                              V_out.stride(0), r, int(n), int(maxiter), float(delta), float(sparsity), L.ptr(result),
+                                              L.stream_ptr()))
+    return result
+
+
 def philox_uniform(rows, cols, row0=0, col0=0, seed=0, stream_id=0, scale=1.0, out=None, accumulate=False, device=None):
     """[rows x cols] float32 block of the synthetic matrix (seed, stream_id): element (i, j) = scale * u(row0 + i, col0 + j)."""
     if out is None:
