@@ -56,13 +56,15 @@ def parse_args():
 
 def ncu_traffic(phase):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind `phase`, from the committed
-    `ncu --set full` capture of this build at this shape (profiles/r2_ncu_full_summaries.json: the first captured launch of
-    that kernel instantiation is the C2 one); None when there is no capture of it."""
+    `ncu --set full` capture of the last build at this shape (profiles/r2_ncu_full_final.json, else the mid-round
+    profiles/r2_ncu_full_summaries.json: the first captured launch of that kernel instantiation is the C2 one); None when
+    there is no capture of it."""
     kernels = {"hals.pass_U": ["tc_fused_kernel<0, 1, 0, 64>"], "hals.cross_V": ["tc_cross_kernel<64, 0>", "tc_cross_kernel<64>"],
                "mu.pass_U": ["tc_fused_kernel<1, 1, 1, 64>", "tc_fused_kernel<1, 1, 0, 64>"],
                "mu.pass_V": ["tc_fused_kernel<1, 0, 1, 64>", "tc_fused_kernel<1, 0, 0, 64>"]}.get(phase)
-    path = os.path.join(ROOT, "profiles", "r2_ncu_full_summaries.json")
-    if kernels is None or not os.path.exists(path):
+    path = next((q for q in (os.path.join(ROOT, "profiles", f) for f in ("r2_ncu_full_final.json", "r2_ncu_full_summaries.json"))
+                 if os.path.exists(q)), None)
+    if kernels is None or path is None:
         return None
     import re
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -460,7 +462,7 @@ def main():
         ach = algo / (phase_ms[dom] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": ncu_traffic(dom) if (m, n, r, world) == (65536, 8192, 64, 1) else None,
-                    "traffic_source": "ncu --set full capture of this kernel at this shape (profiles/r2_ncu_full_summaries.json)",
+                    "traffic_source": "ncu --set full capture of this kernel at this shape (profiles/r2_ncu_full_final.json)",
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
                     "ms_per_launch": phase_ms[dom]}
     algo_iter = 2 * m * n * 4 + 4 * (m + n) * r * 4     # bytes per outer iteration (whole job)
