@@ -34,6 +34,9 @@ constexpr int MODE_RES = 0, MODE_MU = 1;
 #ifndef FUSED_PACKED
 #define FUSED_PACKED 1               // element-wise math on packed fp32 pairs (FADD2 / FMUL2 / FFMA2)
 #endif
+#ifndef FUSED_DEFER_COST
+#define FUSED_DEFER_COST 1           // beta = 1 pass with cost: the log terms are computed AFTER the ratio tile has been handed to the contraction GEMM
+#endif
 constexpr int DRAIN = 2;             // stages per TMEM accumulation chain of the contraction GEMM (the tensor core accumulates with truncation)
 
 // Per padded rank RK (64 or 128).  RK = 128 (ranks 65..128, MODE_RES only): the factor slab of a stage is two 64-rank
@@ -364,6 +367,10 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         uint8_t* xh = ring + (size_t)st * STAGE_BYTES;
         uint8_t* xl = xh + X_BYTES;
         uint32_t qhw[4 * NCHK], qlw[4 * NCHK];
+        // deferred cost (FUSED_DEFER_COST): x and the ratio q of this thread's 16 elements stay in registers until the ratio tile
+        // is on its way to the contraction GEMM; only then are the MUFU.LG2 terms computed (nothing waits for them)
+        constexpr bool DEFER = FUSED_DEFER_COST && FUSED_PACKED && MODE == MODE_MU && COST;
+        float2 xs[DEFER ? 4 * NCHK : 1], qs[DEFER ? 4 * NCHK : 1];
 #pragma unroll
         for (int cc = 0; cc < NCHK; ++cc) {
           float2 xv[4];
@@ -407,8 +414,12 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
               if (COST) {
                 // sum of x log2(x / k) and sum of k (the model tile as the tensor core produced it, so that the two terms
                 // stay consistent); the sum of x is a constant of the plan (see kl_cost_finish_kernel).  x = 0: 0 * log2(1e-30).
-                const float2 qt = __fadd2_rn(q2, tiny2);
-                acc2 = __ffma2_rn(x2, make_float2(lg2_approx(qt.x), lg2_approx(qt.y)), acc2);
+                if (DEFER) {
+                  xs[DEFER ? 4 * cc + w : 0] = x2; qs[DEFER ? 4 * cc + w : 0] = q2;
+                } else {
+                  const float2 qt = __fadd2_rn(q2, tiny2);
+                  acc2 = __ffma2_rn(x2, make_float2(lg2_approx(qt.x), lg2_approx(qt.y)), acc2);
+                }
                 acck2 = __fadd2_rn(acck2, k2);
               }
               const __nv_bfloat162 hq = __floats2bfloat162_rn(q2.x, q2.y);
@@ -445,11 +456,14 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
           }
 #endif
         }
-        if (COST && ((i & 7) == 7 || i == S - 1)) {
-          cost += (double)(acc2.x + acc2.y);
-          acc2 = make_float2(0.f, 0.f);
-          if (MODE == MODE_MU) { costk += (double)(acck2.x + acck2.y); acck2 = make_float2(0.f, 0.f); }
-        }
+        auto flush_cost = [&]() {
+          if (COST && ((i & 7) == 7 || i == S - 1)) {
+            cost += (double)(acc2.x + acc2.y);
+            acc2 = make_float2(0.f, 0.f);
+            if (MODE == MODE_MU) { costk += (double)(acck2.x + acck2.y); acck2 = make_float2(0.f, 0.f); }
+          }
+        };
+        if (!DEFER) flush_cost();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&empty[st]);          // done with the stage's X tile
         if (++st == FSTAGES) { st = 0; ph ^= 1; }
@@ -465,6 +479,14 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&q_ready[qb]);
           if (++qb == 2) { qb = 0; qb_phase ^= 1; }
+          if (DEFER) {
+#pragma unroll
+            for (int e = 0; e < 4 * NCHK; ++e) {
+              const float2 qt = __fadd2_rn(qs[DEFER ? e : 0], tiny2);
+              acc2 = __ffma2_rn(xs[DEFER ? e : 0], make_float2(lg2_approx(qt.x), lg2_approx(qt.y)), acc2);
+            }
+            flush_cost();
+          }
         }
         // drain with a lag of one more stage: chain (i-3)/2 ended with stage i-2, its GEMMs have retired by now, and
         // its TMEM buffer is only needed again by the chain that starts with stage i+1
