@@ -125,6 +125,10 @@ int nnfac_xchg_inbox_mu_apply(nnfac_xchg* x, int64_t inbox_off, int nslabs, int6
  * (tests/nnls_tests.py:40-47).
  *   sparsity : value subtracted in the numerator (0 = no sparsity term, nnls.py:162-167)
  *   result   : device double[4] = { eps, cnt, zero_diag_row (-1 if none, only with NONZERO), sweeps }
+ * Any rank, any n, every option: fp32 without options up to rank 128 runs on the tensor-core sweep, rank <= 128 otherwise on
+ * the register-resident CUDA-core sweep, everything else (rank > 128; normalize / nonzero on more columns than that kernel
+ * keeps resident) on a general sweep that keeps nothing on chip (slow; may synchronise the stream every few sweeps to look at
+ * its device-side stop flag unless the stream is being captured).
  * -------------------------------------------------------------------------------------------*/
 int nnfac_hals_nnls(nnfac_ctx* ctx, int dtype, const void* UtM, int64_t ld_utm, const void* UtU,
                     int64_t ld_utu, void* V, int64_t ld_v, int r, int64_t n, int maxiter,

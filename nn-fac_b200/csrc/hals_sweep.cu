@@ -11,6 +11,10 @@ DECL(f64, double, 16) DECL(f64, double, 32) DECL(f64, double, 64) DECL(f64, doub
 int nnfac_tc_sweep_try(nnfac_ctx* ctx, const float* UtM, int64_t ld_utm, const float* UtU, int64_t ld_utu, float* V,
                        int64_t ld_v, int r, int64_t n, int maxiter, double delta, double sparsity, double* result,
                        cudaStream_t st);
+// any rank, any number of columns, every option (csrc/hals_general.cu): the fallback behind the specialised kernels
+int nnfac_sweep_general(nnfac_ctx* ctx, int dtype, const void* UtM, int64_t ld_utm, const void* UtU, int64_t ld_utu, void* V,
+                        int64_t ld_v, int r, int64_t n, int maxiter, double delta, double sparsity, unsigned flags, double* result,
+                        cudaStream_t st);
 
 void nnfac_reduce_partials(const float* partial, int splits, int r, int r_pad, int64_t R, int64_t ld_partial, float* out,
                            int64_t ld_out, int sm_count, cudaStream_t st);       // csrc/tc_nmf.cu
@@ -36,11 +40,12 @@ extern "C" int nnfac_hals_nnls(nnfac_ctx* ctx, int dtype, const void* UtM, int64
   NNFAC_ARG(ctx && UtM && UtU && V && result, "nnfac_hals_nnls: NULL argument");
   NNFAC_ARG(r > 0 && n > 0, "nnfac_hals_nnls: empty problem (r=%d, n=%lld)", r, (long long)n);
   NNFAC_ARG(ld_utm >= n && ld_v >= n && ld_utu >= r, "nnfac_hals_nnls: leading dimension too small");
-  if (r > 128) {
-    nnfac_set_error("nnfac_hals_nnls: rank %d > 128 is not covered by this build", r);
-    return NNFAC_ERR_UNSUPPORTED;
-  }
+  NNFAC_ARG(dtype == NNFAC_F32 || dtype == NNFAC_F64, "nnfac_hals_nnls: bad dtype %d", dtype);
+  NNFAC_ARG(maxiter >= 0, "nnfac_hals_nnls: negative maxiter");
   cudaStream_t st = (cudaStream_t)stream;
+  static const bool force_general = getenv("NNFAC_SWEEP") && !strcmp(getenv("NNFAC_SWEEP"), "general");
+  if (r > 128 || force_general)       // beyond the specialised kernels (the reference has no rank limit)
+    return nnfac_sweep_general(ctx, dtype, UtM, ld_utm, UtU, ld_utu, V, ld_v, r, n, maxiter, delta, sparsity, flags, result, st);
   const int rp = r <= 16 ? 16 : r <= 32 ? 32 : r <= 64 ? 64 : 128;
   if (dtype == NNFAC_F32 && flags == 0) {
     // tensor-core blocked sweep when the shape fits (rank <= 64, n <= 512 columns per SM); NNFAC_SWEEP=fma disables it
@@ -51,25 +56,29 @@ extern "C" int nnfac_hals_nnls(nnfac_ctx* ctx, int dtype, const void* UtM, int64
       if (rc != NNFAC_ERR_UNSUPPORTED) return rc;
     }
   }
+  int rc;
   if (dtype == NNFAC_F32) {
     auto a = make_args<float>(UtM, ld_utm, UtU, ld_utu, V, ld_v, r, n, maxiter, delta, sparsity, flags, result);
     switch (rp) {
-      case 16: return nnfac_sweep_f32_16(ctx, a, st);
-      case 32: return nnfac_sweep_f32_32(ctx, a, st);
-      case 64: return nnfac_sweep_f32_64(ctx, a, st);
-      default: return nnfac_sweep_f32_128(ctx, a, st);
+      case 16: rc = nnfac_sweep_f32_16(ctx, a, st); break;
+      case 32: rc = nnfac_sweep_f32_32(ctx, a, st); break;
+      case 64: rc = nnfac_sweep_f32_64(ctx, a, st); break;
+      default: rc = nnfac_sweep_f32_128(ctx, a, st); break;
     }
-  } else if (dtype == NNFAC_F64) {
+  } else {
     auto a = make_args<double>(UtM, ld_utm, UtU, ld_utu, V, ld_v, r, n, maxiter, delta, sparsity, flags, result);
     switch (rp) {
-      case 16: return nnfac_sweep_f64_16(ctx, a, st);
-      case 32: return nnfac_sweep_f64_32(ctx, a, st);
-      case 64: return nnfac_sweep_f64_64(ctx, a, st);
-      default: return nnfac_sweep_f64_128(ctx, a, st);
+      case 16: rc = nnfac_sweep_f64_16(ctx, a, st); break;
+      case 32: rc = nnfac_sweep_f64_32(ctx, a, st); break;
+      case 64: rc = nnfac_sweep_f64_64(ctx, a, st); break;
+      default: rc = nnfac_sweep_f64_128(ctx, a, st); break;
     }
   }
-  nnfac_set_error("nnfac_hals_nnls: bad dtype %d", dtype);
-  return NNFAC_ERR_ARG;
+  // outside the register-resident kernel's envelope (row-wise options on more columns than it keeps resident, ...): the
+  // general sweep takes anything
+  if (rc == NNFAC_ERR_UNSUPPORTED)
+    rc = nnfac_sweep_general(ctx, dtype, UtM, ld_utm, UtU, ld_utu, V, ld_v, r, n, maxiter, delta, sparsity, flags, result, st);
+  return rc;
 }
 
 // Out-of-place fp32 solve: Vout (r x n) = hals_nnls_acc(UtM, UtU, Vin) with Vin untouched (the copy of nnls.py:147 happens

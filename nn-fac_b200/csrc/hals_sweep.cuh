@@ -11,7 +11,8 @@
 //     smem hop), a grid barrier, and a fixed-order re-summation so that every CTA (and every
 //     replica on other GPUs) takes the same decision.
 // When n exceeds what the grid can keep in registers the kernel walks column batches and V
-// round-trips through global memory once per sweep.
+// round-trips through global memory once per sweep.  Rank > 128, and row-wise options (normalize / nonzero) on more columns
+// than the grid keeps resident, go to the general sweep of csrc/hals_general.cu.
 #pragma once
 #include "common.cuh"
 
