@@ -1,7 +1,9 @@
-"""The column-sharded path on real GPUs over NCCL (needs >= 2 visible GPUs; skipped otherwise -- the driver's GPU test box has
-one, `gpurun --gpus 2 -- python -m pytest tests/test_gpu_sharded.py -m gpu` runs it): reduce-scatter of the split partials,
-slice solves with the cross-GPU stop scalar (peer-mapped boards), all-gather + one-kernel install, MU all-reduce.  The sharded
-run must reproduce the single-GPU run of the same problem: same sweep counts in every solve, objectives to 1e-6."""
+"""The column-sharded path on real GPUs (needs >= 2 visible GPUs; skipped otherwise -- the driver's GPU test box has one,
+`gpurun --gpus 2 -- python -m pytest tests/test_gpu_sharded.py -m gpu` runs it): the U-side exchange in its three forms --
+"push" (default: the fused pass writes its partials into the owners' inboxes over NVLink, nnfac_nmf_plan_set_push), "pull"
+(NNFAC_PEER_PUSH=0: the owners pull their columns out of every rank's stage) and "nccl" (NNFAC_PEER_EXCHANGE=0: reduce-scatter /
+all-gather / all-reduce) --, slice solves with the cross-GPU stop scalar (peer-mapped boards), the pulled one-kernel install.
+The sharded run must reproduce the single-GPU run of the same problem: same sweep counts in every solve, objectives to 1e-6."""
 import os
 import socket
 import sys
@@ -20,7 +22,11 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_dir, m, n, r, iters):
+def _worker(rank, world, port, out_dir, m, n, r, iters, exchange="push"):
+    if exchange == "pull":
+        os.environ["NNFAC_PEER_PUSH"] = "0"
+    elif exchange == "nccl":
+        os.environ["NNFAC_PEER_EXCHANGE"] = "0"
     for p in (ROOT, os.path.join(ROOT, "nn-fac_b200")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -70,14 +76,15 @@ def _worker(rank, world, port, out_dir, m, n, r, iters):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("m,n,r", [(4096, 2048, 64), (6000, 1500, 40), (8192, 2048, 128)])
-def test_two_gpus_reproduce_one_gpu(tmp_path, m, n, r):
+@pytest.mark.parametrize("m,n,r,exchange", [(4096, 2048, 64, "push"), (6000, 1500, 40, "push"), (8192, 2048, 128, "push"),
+                                            (4096, 2048, 64, "pull"), (6000, 1500, 40, "pull"), (4096, 2048, 64, "nccl")])
+def test_two_gpus_reproduce_one_gpu(tmp_path, m, n, r, exchange):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     iters = 6
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), m, n, r, iters), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), m, n, r, iters, exchange), nprocs=2, join=True)
     ranks = [dict(np.load(os.path.join(str(tmp_path), f"rank{k}.npz"))) for k in range(2)]
     for rule in ("hals", "mu"):
         if rule + "_costs" not in ranks[0]:
