@@ -448,6 +448,7 @@ class FusedNMF:
         self._host = torch.zeros(4, dtype=torch.float64)
         if self._on_gpu:
             self._host = self._host.pin_memory()
+        self._host_np = self._host.numpy()             # same memory: reading a scalar costs no tensor indexing
         self._dev_scal = torch.zeros(4, dtype=torch.float64, device=self.device)
         # Grams of the single-GPU HALS path are computed on a side stream, under the X pass that precedes their use
         self._side = torch.cuda.Stream(self.device) if self._on_gpu else None
@@ -715,7 +716,11 @@ class FusedNMF:
         costs, toc = [], []
         tic = time.time()
         done = torch.cuda.Event() if self._on_gpu else None
+        # every iteration's solves report into their own slot {eps, cnt, zero row, sweeps} x (U, V)
+        stats_log = torch.zeros((n_iter_max + 1, 2, 4), dtype=torch.float64, device=self.device) if (mode == MODE_RES and not mu2) else None
         for it in range(n_iter_max + 1):
+            if stats_log is not None:
+                self.hals_stats = stats_log[it]
             VVt_join = den_join = None
             if mode == MODE_RES and (self.comm.world == 1 or self._side is not None) and it < n_iter_max and 0 not in fixed_modes \
                     and not (self.comm.world > 1 and normalize[0]):
@@ -767,11 +772,11 @@ class FusedNMF:
             if it > 0:
                 if done is not None:
                     done.synchronize()
-                cost = float(self._host[0])
+                cost = float(self._host_np[0])
                 if mu2:
                     cost *= 0.5                         # beta_divergence(., ., 2) = ||X - U V||^2 / 2 (beta_divergence.py:51-52)
                 if with_sparsity:
-                    cost += 2 * (sp[0] * float(self._host[1]) + sp[1] * float(self._host[2]))
+                    cost += 2 * (sp[0] * float(self._host_np[1]) + sp[1] * float(self._host_np[2]))
                 toc.append(time.time() - tic)
                 costs.append(cost)
                 if verbose:
@@ -792,7 +797,7 @@ class FusedNMF:
             if it == n_iter_max:
                 break
             if mode == MODE_RES and not mu2:
-                self.sweep_log.append(self.hals_stats[:, 3].clone())
+                self.sweep_log.append(self.hals_stats[:, 3])       # a view of this iteration's slot of the log: no copy kernel
             self.Ut, self.V = new_Ut, new_V
         return costs, toc
 
