@@ -315,6 +315,10 @@ int nnfac_nmf_plan_set_factor_pulled(nnfac_nmf_plan* plan, int which, const nnfa
  * the plan's own buffer.  x = NULL switches it off.  slabs / slab_stride (optional) receive world * splits and r_pad * chunk. */
 int nnfac_nmf_plan_set_push(nnfac_nmf_plan* plan, const nnfac_xchg* x, int64_t inbox_off, int64_t chunk, int* slabs,
                             int64_t* slab_stride);
+/* out (r x n) = sum of nslabs slabs ([r_pad x ld] each, r_pad * ld floats apart) in slab order: the plain sum of the partials a
+ * rank finds in its inbox (numerator of the beta = 2 update, mu.py:89-91). */
+int nnfac_reduce_slabs_f32(nnfac_ctx* ctx, const float* slabs, int64_t ld, int nslabs, int r, int r_pad, int64_t n, float* out,
+                           int64_t ld_out, void* stream);
 /* HALS solve of factor `which` (nn_fac/update_rules/nnls.py:24-198, deterministic rule, no normalize / nonzero) whose
  * result F_out (r x len, may not alias F_in) is installed in the plan by the sweep kernel itself (no separate pass over
  * the factor).  result: double[4] = {eps, cnt, -1, sweeps}.  Returns NNFAC_ERR_UNSUPPORTED without an error text when

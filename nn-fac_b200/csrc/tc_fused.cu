@@ -813,6 +813,16 @@ int nnfac_nmf_plan_set_push(nnfac_nmf_plan* p, const nnfac_xchg* x, int64_t inbo
   return NNFAC_OK;
 }
 
+// out (r x n) = sum of nslabs slabs ([r_pad x ld] each, r_pad * ld floats apart), in slab order: the partials a rank finds in its
+// inbox (nnfac_nmf_plan_set_push) when a plain sum is what the update needs (beta = 2 numerator)
+int nnfac_reduce_slabs_f32(nnfac_ctx* ctx, const float* slabs, int64_t ld, int nslabs, int r, int r_pad, int64_t n, float* out,
+                           int64_t ld_out, void* stream) {
+  NNFAC_ARG(ctx && slabs && out && nslabs >= 1 && r >= 1 && r_pad >= r && n >= 1 && ld >= n && ld_out >= n, "nnfac_reduce_slabs_f32: bad argument");
+  nnfac_reduce_partials(slabs, nslabs, r, r_pad, n, ld, out, ld_out, ctx->sm_count, (cudaStream_t)stream);
+  NNFAC_LAUNCH_CHECK(ctx);
+  return NNFAC_OK;
+}
+
 // Sum the split-K partials the last X pass over `side` left in the plan into out (r x R): what nnfac_nmf_plan_fused /
 // _cross do themselves when they are given an output.
 int nnfac_nmf_plan_reduce(nnfac_nmf_plan* p, int side, float* out, int64_t ld_out, void* stream) {

@@ -285,6 +285,13 @@ class PeerExchange:
                                                            L.ptr(Ft), Ft.stride(0), self.r, lo, ncols, float(floor), self.chunk + self.tpad,
                                                            L.stream_ptr()))
 
+    def inbox_sum(self, ncols):
+        """PUSH layout: the plain sum of the slabs of the inbox -> (r x ncols) (after a kernel that waited for the posts)."""
+        out = torch.empty((self.r, ncols), dtype=torch.float32, device=self.device)
+        L.check(L.load_library().nnfac_reduce_slabs_f32(L.ctx(self.device), L.ptr(self.inbox), self.chunk, self.nslabs, self.r, self.r_pad,
+                                                        ncols, L.ptr(out), out.stride(0), L.stream_ptr()))
+        return out
+
     def scratch(self, r, n):
         if self._scratch is None or self._scratch.numel() < r * n:
             self._scratch = torch.empty(r * n, dtype=torch.float32, device=self.device)
@@ -645,18 +652,42 @@ class FusedNMF:
         """beta = 2 multiplicative update (mu.py:89-91): U <- U * (X V^T) / (U V V^T), V <- V * (U^T X) / (U^T U V).  The
         denominators never need the model U V: they are small products with the Grams; the numerators are the two cross
         products (first one fused with the cost of the previous iteration)."""
-        Ut, V, eng = self.Ut, self.V, self.eng
+        Ut, V, eng, comm = self.Ut, self.V, self.eng, self.comm
+        UtU_pulled = None
         if 0 not in fixed_modes:
             with self._phase("apply_U"):
-                den = eng.matmul(VVt_join(), Ut)                                   # (V V^T) U^T = (U V V^T)^T
-                Ut = eng.mu_apply_mat(Ut, VXt, den)
-                eng.set_factor(0, Ut)
+                if comm.world > 1:
+                    # column-sharded: X V^T and V V^T are sums over the ranks.  The partial numerators of MY rows of U are in my
+                    # inbox already (pushed by every rank's fused pass); the partial Grams are pulled; every rank updates its own
+                    # rows and the install collects the slices (same exchange as the HALS U side)
+                    r, m = self.r, self.m
+                    px = self._exchange(r)
+                    chunk, lo, hi = comm.slice_of(m)
+                    g = VVt_join()
+                    if g.data_ptr() != px.tailblk.data_ptr():
+                        px.tailblk[:, :r].copy_(g)
+                    px.post(0)
+                    VVt = px.pull_tail0()                                          # waits for every rank's post
+                    if hi > lo:
+                        num = px.inbox_sum(hi - lo)
+                        den = eng.matmul(VVt, Ut[:, lo:hi])
+                        px.send[:, :hi - lo].copy_(eng.mu_apply_mat(Ut[:, lo:hi].contiguous(), num, den))
+                        eng.gram(px.send[:, :hi - lo], out=px.send[:, chunk:chunk + r])
+                    else:
+                        px.send[:, chunk:chunk + r].zero_()
+                    px.post(1)
+                    Ut = px.install(eng.plan, 0, m)
+                    UtU_pulled = px.pull_tail(1, chunk)                            # U^T U = sum of the slices' Grams
+                else:
+                    den = eng.matmul(VVt_join(), Ut)                               # (V V^T) U^T = (U V V^T)^T
+                    Ut = eng.mu_apply_mat(Ut, VXt, den)
+                    eng.set_factor(0, Ut)
         if 1 not in fixed_modes:
             with self._phase("pass_V"):
-                join = self._gram_async(1, Ut)
+                join = self._gram_async(1, Ut) if UtU_pulled is None else None
                 UtX = eng.cross(1, None)
             with self._phase("apply_V"):
-                V = eng.mu_apply_mat(V, UtX, eng.matmul(join(), V))                # (U^T U) V
+                V = eng.mu_apply_mat(V, UtX, eng.matmul(UtU_pulled if UtU_pulled is not None else join(), V))   # (U^T U) V
                 eng.set_factor(1, V)
         return Ut, V
 
@@ -707,7 +738,9 @@ class FusedNMF:
         """The reference's outer loop (nmf.py:298-324).  Returns (costs, toc)."""
         mu2 = update_rule == "mu" and beta == 2       # Frobenius MU: cross products + squared residual, like HALS
         if mu2 and self.comm.world > 1:
-            raise NotImplementedError("the column-sharded path covers update_rule 'hals' and 'mu' with beta = 1")
+            px = self._exchange(self.r) if hasattr(self.eng, "plan") else None
+            if px is None or px.push is None or 0 in fixed_modes:
+                raise NotImplementedError("column-sharded beta = 2 needs the peer-memory exchange in its push form (and a free U)")
         mode = MODE_RES if (update_rule == "hals" or mu2) else MODE_MU
         sp = [0.0 if s is None else float(s) for s in sparsity]
         with_sparsity = update_rule == "hals" and (sp[0] != 0.0 or sp[1] != 0.0)
@@ -727,7 +760,7 @@ class FusedNMF:
                 # V V^T under the first pass; sharded over peer memory: straight into the tail of this rank's stage buffer (the
                 # stage is free by now: this stream is behind the install of the previous iteration, which waited for every
                 # peer's second post, hence for every peer's pull)
-                px = self._exchange(self.r) if (self.comm.world > 1 and mode == MODE_RES and not mu2 and hasattr(self.eng, "plan")) else None
+                px = self._exchange(self.r) if (self.comm.world > 1 and mode == MODE_RES and hasattr(self.eng, "plan")) else None
                 gout = None
                 if px is not None:
                     gout = px.tailblk[:, :self.r] if px.push is not None else px.stage[:, self.m:self.m + self.r]
@@ -740,8 +773,8 @@ class FusedNMF:
                 keep = self.comm.world == 1 and it < n_iter_max and 0 not in fixed_modes and (
                     mode == MODE_MU or (_SPLIT_RHS in ("u", "1") and not mu2 and not normalize[0] and hasattr(self.eng, "plan")))
                 # sharded HALS: the partials stay in the plan too; the reduce-scatter's send buffer is built from them
-                keep = keep or (self.comm.world > 1 and mode == MODE_RES and not mu2 and it < n_iter_max and 0 not in fixed_modes
-                                and not normalize[0] and hasattr(self.eng, "plan"))
+                keep = keep or (self.comm.world > 1 and mode == MODE_RES and it < n_iter_max and 0 not in fixed_modes
+                                and (mu2 or not normalize[0]) and hasattr(self.eng, "plan"))
                 # the cost lands directly in the scalar block that travels to the host
                 if self.comm.world > 1 and mode == MODE_MU and it < n_iter_max and 0 not in fixed_modes and self._exchange(1) is not None:
                     # sharded MU over peer memory: the numerator partials stay in the plan and are reduced into the stage buffer

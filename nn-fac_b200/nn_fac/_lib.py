@@ -47,6 +47,7 @@ SIGNATURES = {
     "nnfac_hals_solve_slabs_f32": [_P, _P, _I64, _INT, _I64, _INT, _P, _P, _I64, _P, _I64, _P, _I64, _INT, _I64, _INT, _DBL, _DBL, _P, _P],
     "nnfac_xchg_inbox_mu_apply": [_P, _I64, _INT, _I64, _I64, _I64, _P, _I64, _INT, _I64, _I64, _DBL, _I64, _P],
     "nnfac_nmf_plan_set_push": [_P, _P, _I64, _I64, _c.POINTER(_INT), _c.POINTER(_I64)],
+    "nnfac_reduce_slabs_f32": [_P, _P, _I64, _INT, _INT, _INT, _I64, _P, _I64, _P],
     "nnfac_gemm_strided": [_P, _INT, _P, _I64, _I64, _P, _I64, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I64,
                            _I64, _I64, _I64, _I64, _I64, _P],
     "nnfac_gram": [_P, _INT, _P, _I64, _P, _I64, _INT, _I64, _P],

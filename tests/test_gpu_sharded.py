@@ -46,16 +46,19 @@ def _worker(rank, world, port, out_dir, m, n, r, iters, exchange="push"):
             ops.philox_uniform(m, c1 - c0, col0=c0, seed=9, stream_id=2, scale=r / 4.0, out=X, accumulate=True)
             return X, ops.philox_uniform(m, r, seed=9, stream_id=3), ops.philox_uniform(r, c1 - c0, col0=c0, seed=9, stream_id=4)
         res = {}
-        for rule, beta in (("hals", 2), ("mu", 1)):
+        for rule, beta in (("hals", 2), ("mu", 1), ("mu2", 2)):
             if rule == "mu" and r > 64:
                 continue
+            if rule == "mu2" and exchange != "push":          # the sharded beta = 2 update needs the push form of the exchange
+                continue
+            tag, rule = rule, rule.rstrip("2")
             X, U0, V0 = block(lo, hi)
             st = _fast.FusedNMF(X, U0, V0, group=dist.group.WORLD)
             costs = st.run(iters, 0.0, rule, beta=beta)[0]
-            res[rule + "_costs"] = np.array(costs)
-            res[rule + "_sweeps"] = np.array([t.cpu().numpy() for t in st.sweep_log])
+            res[tag + "_costs"] = np.array(costs)
+            res[tag + "_sweeps"] = np.array([t.cpu().numpy() for t in st.sweep_log])
             U, V = st.factors()
-            res[rule + "_U"], res[rule + "_V"] = U.cpu().numpy(), V.cpu().numpy()
+            res[tag + "_U"], res[tag + "_V"] = U.cpu().numpy(), V.cpu().numpy()
             del st
             # the public entry point with host arrays
             out = compute_nmf_sharded(X.cpu().numpy(), r, U0.cpu().numpy(), V0.cpu().numpy(), n_iter_max=2, tol=0, update_rule=rule,
@@ -64,10 +67,10 @@ def _worker(rank, world, port, out_dir, m, n, r, iters, exchange="push"):
             if rank == 0:
                 X, U0, V0 = block(0, n)
                 one = _fast.FusedNMF(X, U0, V0)
-                res[rule + "_costs_1"] = np.array(one.run(iters, 0.0, rule, beta=beta)[0])
-                res[rule + "_sweeps_1"] = np.array([t.cpu().numpy() for t in one.sweep_log])
+                res[tag + "_costs_1"] = np.array(one.run(iters, 0.0, rule, beta=beta)[0])
+                res[tag + "_sweeps_1"] = np.array([t.cpu().numpy() for t in one.sweep_log])
                 U1, V1 = one.factors()
-                res[rule + "_U_1"], res[rule + "_V_1"] = U1.cpu().numpy(), V1.cpu().numpy()
+                res[tag + "_U_1"], res[tag + "_V_1"] = U1.cpu().numpy(), V1.cpu().numpy()
                 del one
             dist.barrier()
         res["cols"] = np.array([lo, hi])
@@ -86,7 +89,7 @@ def test_two_gpus_reproduce_one_gpu(tmp_path, m, n, r, exchange):
     iters = 6
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), m, n, r, iters, exchange), nprocs=2, join=True)
     ranks = [dict(np.load(os.path.join(str(tmp_path), f"rank{k}.npz"))) for k in range(2)]
-    for rule in ("hals", "mu"):
+    for rule in ("hals", "mu", "mu2"):
         if rule + "_costs" not in ranks[0]:
             continue
         np.testing.assert_array_equal(ranks[0][rule + "_costs"], ranks[1][rule + "_costs"])      # every rank sees the same objective
