@@ -30,6 +30,9 @@ namespace {
 
 using bf16 = __nv_bfloat16;
 
+#ifndef SWEEP_POSTER4
+#define SWEEP_POSTER4 0          // 1: posting warp in the four-tile variant too (672 threads -> 80 registers, spills: 5.39 against 5.15 us per sweep at n = 65536)
+#endif
 constexpr int BLK = 16;           // rows per Gauss-Seidel block (K extent of the rank update)
 constexpr int TILE = 128;         // columns per tile (UMMA M)
 constexpr uint32_t PLANE_BYTES = TILE * 64 * sizeof(bf16);   // 16 KiB: one 64-wide K atom of an operand plane of a tile
@@ -50,7 +53,7 @@ struct Cfg {
   // The partial sums of a sweep are posted by a warp of their own, except in the four-tile variant (rank <= 64, more than
   // 256 columns per CTA: 640 threads already sit at the register limit of the update chain; it keeps the update threads
   // posting after a CTA-wide barrier)
-  static constexpr bool POSTER = !(RP == 64 && MT == 4);
+  static constexpr bool POSTER = SWEEP_POSTER4 || !(RP == 64 && MT == 4);
   static constexpr int NTHREADS = UPD_THREADS + MAX_TILES * 32 + (POSTER ? 32 : 0);   // + one issuing warp per tile (+ the posting warp)
   static constexpr int TMEM_PER_TILE = 2 * RP;
   static constexpr uint32_t G_ATOM_BYTES = RP * 128;               // [RP rows x 64 K] bf16
